@@ -1,0 +1,183 @@
+/* movierec_b200.h -- C ABI of libmovierec_b200.so: the B200 (sm_100a) NeuMF train / ranking-eval hot
+ * path behind the `movierec` Python API of carlamb/MovieRecommender-TF-TRT.
+ *
+ * The reference has no FFI of its own: its hot path is a Keras graph built in
+ * movierec/model.py:135-215 and driven by Model.fit_generator (model.py:329-333); batches come from
+ * MovieLensDataGenerator.__getitem__ (data_pipeline.py:115-150).  Each entry point below names the
+ * reference code whose work it takes over.  The Python face (movierecommender-tf-trt_b200/movierec)
+ * binds these with ctypes; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless marked [host]; the library never
+ *    allocates or frees device memory; scratch comes through (ws, ws_bytes) sized by the matching
+ *    *_workspace_bytes query (host function, no CUDA work);
+ *  - every compute call enqueues on `stream` (a cudaStream_t passed as void*) and returns without
+ *    synchronising; results are ordered on that stream;
+ *  - return value 0 = MR_OK, negative = error (see MrStatus); mr_last_error() gives a thread-local
+ *    message for the last failing call on this thread; there is no global mutable state;
+ *  - fp32 row-major everywhere; ids are int32; tables are (rows, dim); dense kernels are (in, out)
+ *    exactly as Keras stores them, so weights move to/from the reference without transposes;
+ *  - results are deterministic run to run: no floating-point atomics anywhere.
+ */
+#ifndef MOVIEREC_B200_H_
+#define MOVIEREC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MR_VERSION 100     /* major*100 + minor */
+#define MR_MAX_LAYERS 8    /* len(layers_sizes) <= 8 (model.py:75) */
+#define MR_MAX_WIDTH 1024  /* layers_sizes[i] <= 1024, mf_dim <= 1024 */
+#define MR_MAX_NEGS 1023   /* negatives per positive handled by the sampler / rank kernels */
+
+typedef enum MrStatus {
+  MR_OK = 0,
+  MR_ERR_INVALID = -1,   /* bad argument (null pointer, size, unsupported dimension) */
+  MR_ERR_WORKSPACE = -2, /* ws_bytes smaller than the *_workspace_bytes query */
+  MR_ERR_CUDA = -3,      /* a CUDA runtime call or launch failed; message has cudaGetErrorString */
+  MR_ERR_NO_DEVICE = -4  /* no sm_100 device is current */
+} MrStatus;
+
+typedef enum MrOptimizer { MR_OPT_ADAM = 0, MR_OPT_SGD = 1 } MrOptimizer; /* model.py:36-38 */
+typedef enum MrTableMode {
+  MR_TABLES_DENSE = 0, /* legacy-Keras semantics: every table row is updated every step (reference) */
+  MR_TABLES_SPARSE = 1 /* sparse-row ("lazy") update of the rows touched this step only */
+} MrTableMode;
+
+/* The model of MovierecModel.build_mlp_model (model.py:135-195) plus the optional GMF branch
+ * (mf_dim > 0; absent from the reference, He et al. 2017).  All dense parameters live in ONE
+ * contiguous block `dense` of `dense_count` floats laid out W[1], b[1], ..., W[n-1], b[n-1], w_out,
+ * b_out; the individual pointers point into it. */
+typedef struct MrModel {
+  float* user_mlp; /* (num_users, L[0]/2)            "user_embedding"  model.py:161-165 */
+  float* item_mlp; /* (num_items, L[0]-L[0]/2)       "item_embedding"  model.py:166-170 */
+  float* user_gmf; /* (num_users, mf_dim) or NULL */
+  float* item_gmf; /* (num_items, mf_dim) or NULL */
+  float* dense;    /* contiguous block holding everything below */
+  float* W[MR_MAX_LAYERS]; /* W[l] (L[l-1], L[l]) for l = 1..n_layers-1  "hidden_l" model.py:176-181 */
+  float* b[MR_MAX_LAYERS]; /* b[l] (L[l]) */
+  float* w_out;    /* (mf_dim + L[n_layers-1]) GMF block first   "output" model.py:184-187 */
+  float* b_out;    /* (1) */
+  int64_t dense_count;
+  int32_t num_users, num_items;
+  int32_t n_layers;         /* len(layers_sizes) >= 1 */
+  int32_t L[MR_MAX_LAYERS]; /* layers_sizes */
+  int32_t mf_dim;
+  float l2[MR_MAX_LAYERS];  /* layers_l2reg: l2[0] on the tables, l2[l] on W[l] (model.py:163,168,178) */
+} MrModel;
+
+/* Optimizer hyper-parameters and state (model.py:197-204).  m/v mirror MrModel's tables and dense
+ * block (NULL for SGD).  `iterations` is the number of steps ALREADY applied (Keras' counter). */
+typedef struct MrOptState {
+  int32_t optimizer;  /* MrOptimizer */
+  int32_t table_mode; /* MrTableMode */
+  float lr, beta_1, beta_2, epsilon; /* epsilon = 1e-7 (legacy Keras Adam) */
+  int64_t iterations;
+  float *m_user_mlp, *m_item_mlp, *m_user_gmf, *m_item_gmf, *m_dense;
+  float *v_user_mlp, *v_item_mlp, *v_user_gmf, *v_item_gmf, *v_dense;
+} MrOptState;
+
+/* Gradient buffers, caller-owned so that a data-parallel caller can all-reduce them between
+ * mr_neumf_train_grads and mr_neumf_apply.  Table gradients are full (rows, dim) tables and are
+ * required in MR_TABLES_DENSE mode; in MR_TABLES_SPARSE mode they may be NULL (row gradients are
+ * reduced per touched row and applied straight to the tables). */
+typedef struct MrGrads {
+  float* dense;    /* (dense_count) same layout as MrModel.dense */
+  float* user_mlp; /* (num_users, d_u) */
+  float* item_mlp;
+  float* user_gmf;
+  float* item_gmf;
+} MrGrads;
+
+/* Per-step scalars written by the train step (device floats, MR_STEP_OUT_FLOATS of them). */
+enum { MR_OUT_LOSS_SUM = 0, /* sum over rows of BCE (model.py:213-215), unscaled */
+       MR_OUT_HIT_SUM = 1,  /* sum over groups of hit@k  (model.py:454) */
+       MR_OUT_DCG_SUM = 2,  /* sum over groups of ln2/ln(pos+2)*hit (model.py:414-415) */
+       MR_OUT_L2_PENALTY = 3, /* sum of l2 regulariser terms (0 when all l2 == 0) */
+       MR_OUT_BAD_IDS = 4,  /* non-zero when a user/item id was out of range (row skipped) */
+       MR_STEP_OUT_FLOATS = 8 };
+
+int mr_version(void);
+const char* mr_last_error(void);
+/* Number of SMs of the current device (grid sizing is derived from it); <0 on error. */
+int mr_device_sm_count(void);
+
+/* Embedding lookup out[i,:] = table[idx[i],:]  -- replaces Embedding+Flatten (model.py:161-172). */
+int mr_gather_rows(const float* table, int64_t rows, int32_t dim, const int32_t* idx, int64_t n,
+                   float* out, void* stream);
+
+/* Fused forward: gather -> concat -> Dense/ReLU tower -> GMF product -> head -> sigmoid (-> BCE).
+ * Replaces the forward graph of model.py:154-188 and the loss of model.py:213-215.
+ * Row r uses users[r / user_div] (user_div = 1 for per-row users; = group width when one user id is
+ * given per group) and items[r].  logits/probs/labels/loss_sum may each be NULL.  loss_sum receives
+ * the un-averaged BCE sum over the B rows. */
+size_t mr_forward_workspace_bytes(const MrModel* model, int64_t B);
+int mr_neumf_forward(const MrModel* model, const int32_t* users, const int32_t* items, int64_t B,
+                     int32_t user_div, float* logits, float* probs, const float* labels,
+                     float* loss_sum, void* ws, size_t ws_bytes, void* stream);
+
+/* One optimisation step = Keras train_on_batch inside fit_generator (model.py:329-333):
+ * forward + BCE, analytic backward, deterministic sort + segmented reduction of the embedding row
+ * gradients, optimizer update (model.py:197-204), and the train-batch HR@k / DCG@k that the
+ * compiled metrics report (model.py:207-215).  `group` = num_negs_per_pos + 1 (0 skips metrics),
+ * inv_global_batch = 1 / (rows in the GLOBAL batch) is the gradient scale.  step_out receives
+ * MR_STEP_OUT_FLOATS floats.  opt->iterations is advanced on the host copy. */
+size_t mr_train_workspace_bytes(const MrModel* model, int64_t B);
+int mr_neumf_train_step(MrModel* model, MrOptState* opt, MrGrads* grads, const int32_t* users,
+                        const int32_t* items, const float* labels, int64_t B, int32_t group, int32_t k,
+                        float inv_global_batch, float* step_out, void* ws, size_t ws_bytes, void* stream);
+/* The two halves of the step, for data-parallel callers that all-reduce `grads` in between
+ * (MR_TABLES_DENSE).  In MR_TABLES_SPARSE mode mr_neumf_train_grads already applies the table rows
+ * and mr_neumf_apply only updates the dense block. */
+int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const int32_t* users,
+                         const int32_t* items, const float* labels, int64_t B, int32_t group, int32_t k,
+                         float inv_global_batch, float* step_out, void* ws, size_t ws_bytes, void* stream);
+int mr_neumf_apply(MrModel* model, MrOptState* opt, const MrGrads* grads, void* stream);
+
+/* Ranking evaluation of G groups (one user, `group` candidate items, the positive LAST -- the
+ * generator's layout, data_pipeline.py:113,148): forward scores, position of the positive under
+ * the RankLayer order (descending, lower index first among ties; model.py:344-352), hit@k and DCG@k
+ * sums (model.py:420-455, 361-417).  Replaces Keras validation.
+ * rank (G*group, full permutation) and probs (G*group) may be NULL; pos (G) is always written.
+ * sums receives {hit_sum, dcg_sum}. */
+size_t mr_rank_eval_workspace_bytes(const MrModel* model, int64_t G, int32_t group);
+int mr_rank_eval(const MrModel* model, const int32_t* users, const int32_t* items, int64_t G,
+                 int32_t group, int32_t k, int32_t* rank, int32_t* pos, float* probs, float* sums,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* RankLayer + metrics on caller-supplied scores (model.py:336-455); label_col (G) may be NULL
+ * meaning "last column".  rank may be NULL. */
+size_t mr_rank_scores_workspace_bytes(int64_t G);
+int mr_rank_scores(const float* scores, int64_t G, int32_t group, int32_t k, const int32_t* label_col,
+                   int32_t* rank, int32_t* pos, float* sums, void* ws, size_t ws_bytes, void* stream);
+
+/* On-device negative sampler -- replaces _get_random_negatives_and_positive
+ * (data_pipeline.py:99-113): for positive p (global index first_index + p, user pos_users[p]) draw
+ * `negs` items uniformly from the items NOT in the user's sorted interaction list
+ * csr_items[csr_rowptr[u] .. csr_rowptr[u+1]), without replacement unless there are fewer
+ * candidates than `negs`, then append the positive.  Counter-based Philox4x32-10 keyed by
+ * (seed, epoch, positive index, draw): the output is a pure function of its arguments.
+ * Writes out_users (P*(negs+1), user repeated), out_items (negatives then the positive) and
+ * out_labels ([0]*negs + [1]); each may be NULL. */
+int mr_sample_negatives(const int64_t* csr_rowptr, const int32_t* csr_items, int32_t num_items,
+                        const int32_t* pos_users, const int32_t* pos_items, int64_t P,
+                        int64_t first_index, int32_t negs, uint64_t seed, uint64_t epoch,
+                        int32_t* out_users, int32_t* out_items, float* out_labels, void* stream);
+
+/* Building blocks exposed for tests and for data-parallel callers. */
+/* Stable LSD radix sort of (key, original index) pairs on the low `key_bits` bits. */
+size_t mr_sort_workspace_bytes(int64_t n);
+int mr_sort_pairs(const int32_t* keys, int64_t n, int32_t key_bits, int32_t* sorted_keys,
+                  int32_t* sorted_index, void* ws, size_t ws_bytes, void* stream);
+/* Elementwise legacy-Keras Adam / SGD over a flat buffer (l2 adds 2*l2*p to the gradient). */
+int mr_optimizer_flat(float* p, const float* g, float* m, float* v, int64_t n, int32_t optimizer,
+                      float lr_t, float beta_1, float beta_2, float epsilon, float l2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOVIEREC_B200_H_ */

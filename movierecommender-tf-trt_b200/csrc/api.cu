@@ -1,0 +1,445 @@
+// C-ABI layer of libmovierec_b200.so (declared in include/movierec_b200.h): argument validation,
+// workspace carving and the launch sequence of each entry point.  No device memory is allocated
+// here and nothing synchronises; every launch goes to the caller's stream.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "launchers.h"
+#include "neumf_tile.cuh"
+
+namespace mr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+  return MR_ERR_CUDA;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return kB200Sms;  // sizing queries must work without a device
+  }
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      return kB200Sms;
+    }
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+__global__ void flag_to_float_kernel(const int32_t* flags, float* out) { *out = (float)flags[0]; }
+
+static int bits_for(int32_t n) {
+  int b = 1;
+  while (b < 31 && ((int64_t)1 << b) < n) ++b;
+  return b;
+}
+
+static int check_model(const MrModel* m) {
+  MR_REQUIRE(m != nullptr, "model is NULL");
+  MR_REQUIRE(m->n_layers >= 1 && m->n_layers <= MR_MAX_LAYERS, "n_layers=%d out of [1,%d]", m->n_layers, MR_MAX_LAYERS);
+  MR_REQUIRE(m->L[0] >= 2, "layers_sizes[0]=%d must be >= 2", m->L[0]);
+  for (int l = 0; l < m->n_layers; ++l)
+    MR_REQUIRE(m->L[l] >= 1 && m->L[l] <= MR_MAX_WIDTH, "layers_sizes[%d]=%d out of [1,%d]", l, m->L[l], MR_MAX_WIDTH);
+  MR_REQUIRE(m->mf_dim >= 0 && m->mf_dim <= MR_MAX_WIDTH, "mf_dim=%d out of range", m->mf_dim);
+  MR_REQUIRE(m->num_users > 0 && m->num_items > 0, "num_users/num_items must be > 0");
+  MR_REQUIRE(m->user_mlp && m->item_mlp && m->dense && m->w_out && m->b_out, "model has NULL parameter pointers");
+  if (m->mf_dim > 0) MR_REQUIRE(m->user_gmf && m->item_gmf, "mf_dim > 0 but GMF tables are NULL");
+  // dense block layout: W[1], b[1], ..., w_out, b_out
+  int64_t off = 0;
+  for (int l = 1; l < m->n_layers; ++l) {
+    MR_REQUIRE(m->W[l] == m->dense + off, "W[%d] is not at its offset in the dense block", l);
+    off += (int64_t)m->L[l - 1] * m->L[l];
+    MR_REQUIRE(m->b[l] == m->dense + off, "b[%d] is not at its offset in the dense block", l);
+    off += m->L[l];
+  }
+  MR_REQUIRE(m->w_out == m->dense + off, "w_out is not at its offset in the dense block");
+  off += m->mf_dim + m->L[m->n_layers - 1];
+  MR_REQUIRE(m->b_out == m->dense + off, "b_out is not at its offset in the dense block");
+  off += 1;
+  MR_REQUIRE(m->dense_count == off, "dense_count=%lld, expected %lld", (long long)m->dense_count, (long long)off);
+  MR_REQUIRE(choose_tile_rows(*m, true) > 0, "layer widths too large for the fused kernel's shared memory");
+  return MR_OK;
+}
+
+static bool any_l2(const MrModel& m) {
+  for (int l = 0; l < m.n_layers; ++l)
+    if (m.l2[l] != 0.f) return true;
+  return false;
+}
+
+struct TrainWs {
+  int32_t* flags;
+  float* wt;
+  float* dense_partial;
+  int64_t dense_stride;
+  float* loss_partial;
+  float* probs;
+  float* stage_u;
+  float* stage_i;
+  int32_t* sorted_keys;
+  int32_t* sorted_index;
+  void* sort_ws;
+  size_t sort_ws_bytes;
+  int32_t* pos;
+  float* rank_partials;
+  size_t total;
+};
+
+static TrainWs carve_train(const MrModel& m, int64_t B, void* ws) {
+  TrainWs t;
+  Carver cv(ws);
+  const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
+  const int cap = max_tile_ctas();
+  t.flags = cv.take<int32_t>(64);
+  t.wt = cv.take<float>(m.dense_count);
+  t.dense_stride = (m.dense_count + 3) & ~(int64_t)3;
+  t.dense_partial = cv.take<float>((size_t)cap * t.dense_stride);
+  t.loss_partial = cv.take<float>(cap);
+  t.probs = cv.take<float>(B);
+  t.stage_u = cv.take<float>((size_t)B * (d_u + m.mf_dim));
+  t.stage_i = cv.take<float>((size_t)B * (d_i + m.mf_dim));
+  t.sorted_keys = cv.take<int32_t>(B);
+  t.sorted_index = cv.take<int32_t>(B);
+  t.sort_ws_bytes = sort_workspace_bytes(B);
+  t.sort_ws = cv.take<char>(t.sort_ws_bytes);
+  t.pos = cv.take<int32_t>(B);
+  t.rank_partials = cv.take<float>(rank_partials_count(B));
+  t.total = cv.off;
+  return t;
+}
+
+static float adam_lr_t(const MrOptState& o, int64_t t) {
+  // legacy Keras Adam folds both bias corrections into the step size
+  return (float)((double)o.lr * sqrt(1.0 - pow((double)o.beta_2, (double)t)) / (1.0 - pow((double)o.beta_1, (double)t)));
+}
+
+static int check_opt(const MrModel& m, const MrOptState* o, const MrGrads* g) {
+  MR_REQUIRE(o != nullptr && g != nullptr, "opt/grads is NULL");
+  MR_REQUIRE(o->optimizer == MR_OPT_ADAM || o->optimizer == MR_OPT_SGD, "unknown optimizer %d", o->optimizer);
+  MR_REQUIRE(o->table_mode == MR_TABLES_DENSE || o->table_mode == MR_TABLES_SPARSE, "unknown table_mode %d", o->table_mode);
+  MR_REQUIRE(g->dense != nullptr, "grads.dense is NULL");
+  if (o->optimizer == MR_OPT_ADAM) {
+    MR_REQUIRE(o->m_dense && o->v_dense && o->m_user_mlp && o->v_user_mlp && o->m_item_mlp && o->v_item_mlp,
+               "Adam state pointers are NULL");
+    if (m.mf_dim > 0) MR_REQUIRE(o->m_user_gmf && o->v_user_gmf && o->m_item_gmf && o->v_item_gmf, "Adam GMF state is NULL");
+  }
+  if (o->table_mode == MR_TABLES_DENSE) {
+    MR_REQUIRE(g->user_mlp && g->item_mlp, "dense table mode needs gradient tables");
+    if (m.mf_dim > 0) MR_REQUIRE(g->user_gmf && g->item_gmf, "dense table mode needs GMF gradient tables");
+  } else {
+    MR_REQUIRE(m.l2[0] == 0.f, "layers_l2reg[0] != 0 makes embedding gradients dense; use MR_TABLES_DENSE");
+  }
+  return MR_OK;
+}
+
+}  // namespace mr
+
+using namespace mr;
+
+extern "C" {
+
+int mr_version(void) { return MR_VERSION; }
+
+const char* mr_last_error(void) { return g_err; }
+
+int mr_device_sm_count(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cuda_fail(cudaGetLastError(), "cudaGetDevice");
+    return MR_ERR_NO_DEVICE;
+  }
+  return sm_count();
+}
+
+int mr_gather_rows(const float* table, int64_t rows, int32_t dim, const int32_t* idx, int64_t n, float* out,
+                   void* stream) {
+  MR_REQUIRE(table && idx && out, "gather: NULL pointer");
+  MR_REQUIRE(rows > 0 && dim > 0 && n >= 0, "gather: bad sizes rows=%lld dim=%d n=%lld", (long long)rows, dim, (long long)n);
+  return launch_gather_rows(table, rows, dim, idx, n, out, (cudaStream_t)stream);
+}
+
+size_t mr_forward_workspace_bytes(const MrModel* model, int64_t B) {
+  (void)model;
+  (void)B;
+  return 256 + align_up((size_t)max_tile_ctas() * sizeof(float), 256);
+}
+
+int mr_neumf_forward(const MrModel* model, const int32_t* users, const int32_t* items, int64_t B, int32_t user_div,
+                     float* logits, float* probs, const float* labels, float* loss_sum, void* ws, size_t ws_bytes,
+                     void* stream) {
+  int rc = check_model(model);
+  if (rc != MR_OK) return rc;
+  MR_REQUIRE(users && items && B >= 0, "forward: NULL ids or negative B");
+  MR_REQUIRE(user_div >= 1, "forward: user_div must be >= 1");
+  MR_REQUIRE(ws != nullptr, "forward: workspace is NULL");
+  if (ws_bytes < mr_forward_workspace_bytes(model, B)) {
+    set_error("forward workspace too small: %zu < %zu", ws_bytes, mr_forward_workspace_bytes(model, B));
+    return MR_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(ws);
+  int32_t* flags = cv.take<int32_t>(64);
+  float* loss_partial = cv.take<float>(max_tile_ctas());
+  MR_CUDA(cudaMemsetAsync(flags, 0, 256, st));
+  TileLaunch a{};
+  a.model = model;
+  a.train = false;
+  a.users = users;
+  a.items = items;
+  a.labels = labels;
+  a.B = B;
+  a.user_div = user_div;
+  a.inv_batch = 0.f;
+  a.logits = logits;
+  a.probs = probs;
+  a.loss_partial = loss_partial;
+  a.flags = flags;
+  int grid = 0;
+  rc = launch_neumf_tiles(a, st, &grid);
+  if (rc != MR_OK) return rc;
+  if (loss_sum != nullptr) return launch_sum_partials(loss_partial, grid, loss_sum, st);
+  return MR_OK;
+}
+
+size_t mr_train_workspace_bytes(const MrModel* model, int64_t B) {
+  if (model == nullptr || B < 0 || model->n_layers < 1 || model->n_layers > MR_MAX_LAYERS) return 0;
+  return carve_train(*model, B, nullptr).total + 256;
+}
+
+int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const int32_t* users, const int32_t* items,
+                         const float* labels, int64_t B, int32_t group, int32_t k, float inv_global_batch,
+                         float* step_out, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_model(model);
+  if (rc != MR_OK) return rc;
+  rc = check_opt(*model, opt, grads);
+  if (rc != MR_OK) return rc;
+  MR_REQUIRE(users && items && labels && step_out && ws, "train: NULL pointer");
+  MR_REQUIRE(B > 0 && B < ((int64_t)1 << 31), "train: B=%lld out of range", (long long)B);
+  MR_REQUIRE(group >= 0 && (group == 0 || B % group == 0), "train: B=%lld not divisible by group=%d", (long long)B, group);
+  if (ws_bytes < mr_train_workspace_bytes(model, B)) {
+    set_error("train workspace too small: %zu < %zu", ws_bytes, mr_train_workspace_bytes(model, B));
+    return MR_ERR_WORKSPACE;
+  }
+  const MrModel& m = *model;
+  cudaStream_t st = (cudaStream_t)stream;
+  TrainWs t = carve_train(m, B, ws);
+  const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
+
+  MR_CUDA(cudaMemsetAsync(t.flags, 0, 256, st));
+  MR_CUDA(cudaMemsetAsync(step_out, 0, MR_STEP_OUT_FLOATS * sizeof(float), st));
+  rc = launch_transpose_kernels(m, t.wt, st);
+  if (rc != MR_OK) return rc;
+
+  TileLaunch a{};
+  a.model = model;
+  a.train = true;
+  a.wt = t.wt;
+  a.users = users;
+  a.items = items;
+  a.labels = labels;
+  a.B = B;
+  a.user_div = 1;
+  a.inv_batch = inv_global_batch;
+  a.probs = t.probs;
+  a.loss_partial = t.loss_partial;
+  a.dense_partial = t.dense_partial;
+  a.dense_stride = t.dense_stride;
+  a.stage_u = t.stage_u;
+  a.stage_i = t.stage_i;
+  a.flags = t.flags;
+  int grid = 0;
+  rc = launch_neumf_tiles(a, st, &grid);
+  if (rc != MR_OK) return rc;
+  rc = launch_dense_reduce(m, t.dense_partial, t.dense_stride, grid, grads->dense, st);
+  if (rc != MR_OK) return rc;
+  rc = launch_sum_partials(t.loss_partial, grid, step_out + MR_OUT_LOSS_SUM, st);
+  if (rc != MR_OK) return rc;
+  flag_to_float_kernel<<<1, 1, 0, st>>>(t.flags, step_out + MR_OUT_BAD_IDS);
+  MR_LAUNCH_CHECK("flag_to_float_kernel");
+
+  if (any_l2(m)) {
+    float* pen = step_out + MR_OUT_L2_PENALTY;
+    if (m.l2[0] != 0.f) {
+      rc = launch_l2_penalty(m.user_mlp, (int64_t)m.num_users * d_u, m.l2[0], pen, st);
+      if (rc == MR_OK) rc = launch_l2_penalty(m.item_mlp, (int64_t)m.num_items * d_i, m.l2[0], pen, st);
+      if (rc == MR_OK && m.mf_dim > 0) rc = launch_l2_penalty(m.user_gmf, (int64_t)m.num_users * m.mf_dim, m.l2[0], pen, st);
+      if (rc == MR_OK && m.mf_dim > 0) rc = launch_l2_penalty(m.item_gmf, (int64_t)m.num_items * m.mf_dim, m.l2[0], pen, st);
+      if (rc != MR_OK) return rc;
+    }
+    for (int l = 1; l < m.n_layers; ++l)
+      if (m.l2[l] != 0.f) {
+        rc = launch_l2_penalty(m.W[l], (int64_t)m.L[l - 1] * m.L[l], m.l2[l], pen, st);
+        if (rc != MR_OK) return rc;
+      }
+  }
+
+  if (group > 0) {
+    rc = launch_rank_scores(t.probs, B / group, group, k, nullptr, nullptr, t.pos, step_out + MR_OUT_HIT_SUM,
+                            t.rank_partials, st);
+    if (rc != MR_OK) return rc;
+  }
+
+  // ---- embedding rows: stable sort by row id, segmented reduce in batch order, row update -------
+  const bool dense_mode = opt->table_mode == MR_TABLES_DENSE;
+  RowUpdate u{};
+  u.mode = opt->table_mode;
+  u.optimizer = opt->optimizer;
+  u.lr = opt->lr;
+  u.lr_t = opt->optimizer == MR_OPT_ADAM ? adam_lr_t(*opt, opt->iterations + 1) : opt->lr;
+  u.beta_1 = opt->beta_1;
+  u.beta_2 = opt->beta_2;
+  u.epsilon = opt->epsilon;
+  if (dense_mode) {
+    MR_CUDA(cudaMemsetAsync(grads->user_mlp, 0, (size_t)m.num_users * d_u * sizeof(float), st));
+    MR_CUDA(cudaMemsetAsync(grads->item_mlp, 0, (size_t)m.num_items * d_i * sizeof(float), st));
+    if (m.mf_dim > 0) {
+      MR_CUDA(cudaMemsetAsync(grads->user_gmf, 0, (size_t)m.num_users * m.mf_dim * sizeof(float), st));
+      MR_CUDA(cudaMemsetAsync(grads->item_gmf, 0, (size_t)m.num_items * m.mf_dim * sizeof(float), st));
+    }
+  }
+  // users
+  rc = launch_sort_pairs(users, B, bits_for(m.num_users), t.sorted_keys, t.sorted_index, t.sort_ws, t.sort_ws_bytes, st);
+  if (rc != MR_OK) return rc;
+  u.d0 = d_u;
+  u.d1 = m.mf_dim;
+  u.p0 = m.user_mlp; u.m0 = opt->m_user_mlp; u.v0 = opt->v_user_mlp; u.g0 = grads->user_mlp;
+  u.p1 = m.user_gmf; u.m1 = opt->m_user_gmf; u.v1 = opt->v_user_gmf; u.g1 = grads->user_gmf;
+  rc = launch_segreduce(t.sorted_keys, t.sorted_index, B, t.stage_u, u, st);
+  if (rc != MR_OK) return rc;
+  // items
+  rc = launch_sort_pairs(items, B, bits_for(m.num_items), t.sorted_keys, t.sorted_index, t.sort_ws, t.sort_ws_bytes, st);
+  if (rc != MR_OK) return rc;
+  u.d0 = d_i;
+  u.p0 = m.item_mlp; u.m0 = opt->m_item_mlp; u.v0 = opt->v_item_mlp; u.g0 = grads->item_mlp;
+  u.p1 = m.item_gmf; u.m1 = opt->m_item_gmf; u.v1 = opt->v_item_gmf; u.g1 = grads->item_gmf;
+  rc = launch_segreduce(t.sorted_keys, t.sorted_index, B, t.stage_i, u, st);
+  return rc;
+}
+
+int mr_neumf_apply(MrModel* model, MrOptState* opt, const MrGrads* grads, void* stream) {
+  int rc = check_model(model);
+  if (rc != MR_OK) return rc;
+  rc = check_opt(*model, opt, grads);
+  if (rc != MR_OK) return rc;
+  const MrModel& m = *model;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
+  const bool adam = opt->optimizer == MR_OPT_ADAM;
+  const float lr_t = adam ? adam_lr_t(*opt, opt->iterations + 1) : opt->lr;
+  rc = launch_optimizer_flat(m.dense, grads->dense, opt->m_dense, opt->v_dense, m.dense_count, opt->optimizer, lr_t,
+                             opt->beta_1, opt->beta_2, opt->epsilon, 0.f, st);
+  if (rc != MR_OK) return rc;
+  if (opt->table_mode == MR_TABLES_DENSE) {
+    const float l2 = m.l2[0];
+    rc = launch_optimizer_flat(m.user_mlp, grads->user_mlp, opt->m_user_mlp, opt->v_user_mlp, (int64_t)m.num_users * d_u,
+                               opt->optimizer, lr_t, opt->beta_1, opt->beta_2, opt->epsilon, l2, st);
+    if (rc == MR_OK)
+      rc = launch_optimizer_flat(m.item_mlp, grads->item_mlp, opt->m_item_mlp, opt->v_item_mlp, (int64_t)m.num_items * d_i,
+                                 opt->optimizer, lr_t, opt->beta_1, opt->beta_2, opt->epsilon, l2, st);
+    if (rc == MR_OK && m.mf_dim > 0)
+      rc = launch_optimizer_flat(m.user_gmf, grads->user_gmf, opt->m_user_gmf, opt->v_user_gmf,
+                                 (int64_t)m.num_users * m.mf_dim, opt->optimizer, lr_t, opt->beta_1, opt->beta_2,
+                                 opt->epsilon, l2, st);
+    if (rc == MR_OK && m.mf_dim > 0)
+      rc = launch_optimizer_flat(m.item_gmf, grads->item_gmf, opt->m_item_gmf, opt->v_item_gmf,
+                                 (int64_t)m.num_items * m.mf_dim, opt->optimizer, lr_t, opt->beta_1, opt->beta_2,
+                                 opt->epsilon, l2, st);
+    if (rc != MR_OK) return rc;
+  }
+  opt->iterations += 1;
+  return MR_OK;
+}
+
+int mr_neumf_train_step(MrModel* model, MrOptState* opt, MrGrads* grads, const int32_t* users, const int32_t* items,
+                        const float* labels, int64_t B, int32_t group, int32_t k, float inv_global_batch,
+                        float* step_out, void* ws, size_t ws_bytes, void* stream) {
+  int rc = mr_neumf_train_grads(model, opt, grads, users, items, labels, B, group, k, inv_global_batch, step_out, ws,
+                                ws_bytes, stream);
+  if (rc != MR_OK) return rc;
+  return mr_neumf_apply(model, opt, grads, stream);
+}
+
+size_t mr_rank_eval_workspace_bytes(const MrModel* model, int64_t G, int32_t group) {
+  if (G < 0 || group < 1) return 0;
+  return mr_forward_workspace_bytes(model, G * group) + align_up((size_t)G * group * sizeof(float), 256) +
+         align_up(rank_partials_count(G) * sizeof(float), 256) + 256;
+}
+
+int mr_rank_eval(const MrModel* model, const int32_t* users, const int32_t* items, int64_t G, int32_t group, int32_t k,
+                 int32_t* rank, int32_t* pos, float* probs, float* sums, void* ws, size_t ws_bytes, void* stream) {
+  MR_REQUIRE(G >= 0 && group >= 2 && group <= MR_MAX_NEGS + 1, "rank_eval: bad G=%lld group=%d", (long long)G, group);
+  MR_REQUIRE(pos != nullptr && ws != nullptr, "rank_eval: pos/ws is NULL");
+  if (ws_bytes < mr_rank_eval_workspace_bytes(model, G, group)) {
+    set_error("rank_eval workspace too small: %zu < %zu", ws_bytes, mr_rank_eval_workspace_bytes(model, G, group));
+    return MR_ERR_WORKSPACE;
+  }
+  const size_t fwd_bytes = mr_forward_workspace_bytes(model, G * group);
+  Carver cv(static_cast<char*>(ws) + fwd_bytes);
+  float* probs_buf = cv.take<float>((size_t)G * group);
+  float* partials = cv.take<float>(rank_partials_count(G));
+  float* pr = probs != nullptr ? probs : probs_buf;
+  int rc = mr_neumf_forward(model, users, items, G * group, group, nullptr, pr, nullptr, nullptr, ws, fwd_bytes, stream);
+  if (rc != MR_OK) return rc;
+  return launch_rank_scores(pr, G, group, k, nullptr, rank, pos, sums, partials, (cudaStream_t)stream);
+}
+
+size_t mr_rank_scores_workspace_bytes(int64_t G) { return align_up(rank_partials_count(G < 0 ? 0 : G) * sizeof(float), 256); }
+
+int mr_rank_scores(const float* scores, int64_t G, int32_t group, int32_t k, const int32_t* label_col, int32_t* rank,
+                   int32_t* pos, float* sums, void* ws, size_t ws_bytes, void* stream) {
+  MR_REQUIRE(scores && pos, "rank_scores: NULL pointer");
+  MR_REQUIRE(G >= 0 && group >= 1 && group <= MR_MAX_NEGS + 1, "rank_scores: bad G=%lld group=%d", (long long)G, group);
+  if (sums != nullptr) {
+    MR_REQUIRE(ws != nullptr, "rank_scores: workspace is NULL");
+    if (ws_bytes < mr_rank_scores_workspace_bytes(G)) {
+      set_error("rank_scores workspace too small");
+      return MR_ERR_WORKSPACE;
+    }
+  }
+  return launch_rank_scores(scores, G, group, k, label_col, rank, pos, sums, static_cast<float*>(ws), (cudaStream_t)stream);
+}
+
+int mr_sample_negatives(const int64_t* csr_rowptr, const int32_t* csr_items, int32_t num_items, const int32_t* pos_users,
+                        const int32_t* pos_items, int64_t P, int64_t first_index, int32_t negs, uint64_t seed,
+                        uint64_t epoch, int32_t* out_users, int32_t* out_items, float* out_labels, void* stream) {
+  MR_REQUIRE(csr_rowptr && csr_items && pos_users && pos_items, "sample_negatives: NULL pointer");
+  MR_REQUIRE(P >= 0 && num_items > 0, "sample_negatives: bad sizes");
+  MR_REQUIRE(negs >= 1 && negs <= MR_MAX_NEGS, "sample_negatives: negs=%d out of [1,%d]", negs, MR_MAX_NEGS);
+  return launch_sample_negatives(csr_rowptr, csr_items, num_items, pos_users, pos_items, P, first_index, negs, seed,
+                                 epoch, out_users, out_items, out_labels, (cudaStream_t)stream);
+}
+
+size_t mr_sort_workspace_bytes(int64_t n) { return sort_workspace_bytes(n < 0 ? 0 : n); }
+
+int mr_sort_pairs(const int32_t* keys, int64_t n, int32_t key_bits, int32_t* sorted_keys, int32_t* sorted_index,
+                  void* ws, size_t ws_bytes, void* stream) {
+  MR_REQUIRE(keys && sorted_keys && sorted_index && ws, "sort_pairs: NULL pointer");
+  MR_REQUIRE(n >= 0 && key_bits >= 1 && key_bits <= 32, "sort_pairs: bad n/key_bits");
+  return launch_sort_pairs(keys, n, key_bits, sorted_keys, sorted_index, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int mr_optimizer_flat(float* p, const float* g, float* m, float* v, int64_t n, int32_t optimizer, float lr_t,
+                      float beta_1, float beta_2, float epsilon, float l2, void* stream) {
+  MR_REQUIRE(p && g && n >= 0, "optimizer_flat: NULL pointer");
+  MR_REQUIRE(optimizer == MR_OPT_SGD || (m && v), "optimizer_flat: Adam needs m and v");
+  return launch_optimizer_flat(p, g, m, v, n, optimizer, lr_t, beta_1, beta_2, epsilon, l2, (cudaStream_t)stream);
+}
+
+}  // extern "C"

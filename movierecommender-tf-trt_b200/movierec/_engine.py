@@ -1,0 +1,390 @@
+"""Device-side state of one NeuMF model and the calls into libmovierec_b200.so.
+
+PyTorch is used for what the north star allows it for: allocating device memory, owning streams
+and (in data-parallel runs) the NCCL process group.  All arithmetic of the hot path happens in the
+hand-written CUDA kernels behind the C ABI (`_native`); nothing here computes on tensors except
+trivial bookkeeping (views, zero-fill, scalar accumulation of step outputs).
+"""
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+# Keras weight names of the reference model (model.py:164,169,179,186) + the GMF extension
+K_USER = "user_embedding/embeddings"
+K_ITEM = "item_embedding/embeddings"
+K_GMF_USER = "gmf_user_embedding/embeddings"
+K_GMF_ITEM = "gmf_item_embedding/embeddings"
+K_OUT_W = "output/kernel"
+K_OUT_B = "output/bias"
+ADAM_EPSILON = 1e-7  # legacy Keras Adam: epsilon=None -> K.epsilon()
+
+
+def hidden_names(i):
+    return "hidden_{}/kernel".format(i), "hidden_{}/bias".format(i)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("movierec (B200 build) needs a CUDA device: the hot path has no CPU fallback")
+
+
+def as_device_i32(x, device):
+    """ids -> contiguous int32 device tensor (H2D copy is asynchronous when `x` is pinned)."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x).reshape(-1)))
+    t = t.reshape(-1)
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    return t.to(device, non_blocking=True).contiguous()
+
+
+def as_device_f32(x, device):
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x).reshape(-1)))
+    t = t.reshape(-1)
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t.to(device, non_blocking=True).contiguous()
+
+
+class NeuMFEngine(object):
+    """Parameters, optimizer state, gradient buffers and workspace of one model replica."""
+
+    def __init__(self, num_users, num_items, layers_sizes, layers_l2reg, mf_dim=0, optimizer="adam",
+                 lr=1e-3, beta_1=0.9, beta_2=0.999, table_mode="dense", device=None, seed=None):
+        require_cuda()
+        self.device = torch.device(device if device is not None else "cuda:{}".format(torch.cuda.current_device()))
+        self.num_users, self.num_items = int(num_users), int(num_items)
+        self.L = [int(x) for x in layers_sizes]
+        self.l2 = [float(x) for x in layers_l2reg]
+        self.mf_dim = int(mf_dim)
+        n = len(self.L)
+        if not 1 <= n <= nat.MR_MAX_LAYERS:
+            raise ValueError("layers_sizes must have 1..{} entries, found {}".format(nat.MR_MAX_LAYERS, n))
+        if self.L[0] < 2 or any(not 1 <= w <= nat.MR_MAX_WIDTH for w in self.L) or not 0 <= self.mf_dim <= nat.MR_MAX_WIDTH:
+            raise ValueError("layer widths must be in [1, {}] (first >= 2), found {} mf_dim={}".format(
+                nat.MR_MAX_WIDTH, self.L, self.mf_dim))
+        self.d_u = self.L[0] // 2               # model.py:159
+        self.d_i = self.L[0] - self.d_u         # model.py:160
+        self.optimizer = optimizer
+        self.lr, self.beta_1, self.beta_2 = float(lr), float(beta_1), float(beta_2)
+        self.table_mode = table_mode
+        if table_mode not in ("dense", "sparse"):
+            raise ValueError("table_mode must be 'dense' or 'sparse', found {!r}".format(table_mode))
+        if table_mode == "sparse" and self.l2[0] != 0:
+            raise ValueError("layers_l2reg[0] != 0 makes embedding gradients dense; use table_mode='dense'")
+        self.iterations = 0
+
+        # dense block layout W1,b1,...,w_out,b_out (include/movierec_b200.h: MrModel)
+        self._dense_slices = {}
+        off = 0
+        for i in range(1, n):
+            kn, bn = hidden_names(i)
+            self._dense_slices[kn] = (off, (self.L[i - 1], self.L[i]))
+            off += self.L[i - 1] * self.L[i]
+            self._dense_slices[bn] = (off, (self.L[i],))
+            off += self.L[i]
+        self._dense_slices[K_OUT_W] = (off, (self.mf_dim + self.L[-1], 1))
+        off += self.mf_dim + self.L[-1]
+        self._dense_slices[K_OUT_B] = (off, (1,))
+        off += 1
+        self.dense_count = off
+
+        dev, f32 = self.device, torch.float32
+        self.user_mlp = torch.empty((self.num_users, self.d_u), dtype=f32, device=dev)
+        self.item_mlp = torch.empty((self.num_items, self.d_i), dtype=f32, device=dev)
+        self.user_gmf = torch.empty((self.num_users, self.mf_dim), dtype=f32, device=dev) if self.mf_dim else None
+        self.item_gmf = torch.empty((self.num_items, self.mf_dim), dtype=f32, device=dev) if self.mf_dim else None
+        self.dense = torch.zeros(self.dense_count, dtype=f32, device=dev)
+        self._tables = {K_USER: self.user_mlp, K_ITEM: self.item_mlp}
+        if self.mf_dim:
+            self._tables[K_GMF_USER] = self.user_gmf
+            self._tables[K_GMF_ITEM] = self.item_gmf
+        self.initialize(seed)
+
+        adam = optimizer == "adam"
+        z = lambda t: torch.zeros_like(t) if (t is not None) else None
+        self.m = {k: z(t) for k, t in self._tables.items()} if adam else {}
+        self.v = {k: z(t) for k, t in self._tables.items()} if adam else {}
+        self.m_dense = z(self.dense) if adam else None
+        self.v_dense = z(self.dense) if adam else None
+        self.g_dense = torch.zeros_like(self.dense)
+        self.g_tables = {k: torch.zeros_like(t) for k, t in self._tables.items()} if table_mode == "dense" else {}
+        self.step_out = torch.zeros(nat.MR_STEP_OUT_FLOATS, dtype=f32, device=dev)
+        self._ws = None
+        self._structs()
+
+    # ---- parameters --------------------------------------------------------------------------
+    def weight_names(self):
+        """Keras creation order of the reference model (model.py:161-187), GMF tables last."""
+        names = [K_USER, K_ITEM]
+        for i in range(1, len(self.L)):
+            names.extend(hidden_names(i))
+        names.extend([K_OUT_W, K_OUT_B])
+        if self.mf_dim:
+            names.extend([K_GMF_USER, K_GMF_ITEM])
+        return names
+
+    def _view(self, name, base=None):
+        if name in self._tables:
+            return self._tables[name]
+        off, shape = self._dense_slices[name]
+        base = self.dense if base is None else base
+        return base[off:off + int(np.prod(shape))].view(*shape)
+
+    def initialize(self, seed=None):
+        """Initialisers of model.py:163,168,178,186: glorot-uniform tables and hidden kernels,
+        lecun-uniform head, zero biases (limits per SURVEY App. A-5)."""
+        rng = np.random.default_rng(seed)
+        for name in self.weight_names():
+            t = self._view(name)
+            if name.endswith("bias"):
+                t.zero_()
+                continue
+            if name == K_OUT_W:
+                lim = math.sqrt(3.0 / t.shape[0])
+            else:
+                lim = math.sqrt(6.0 / (t.shape[0] + t.shape[1]))
+            t.copy_(torch.from_numpy(rng.uniform(-lim, lim, size=tuple(t.shape)).astype(np.float32)))
+
+    def get_weights(self):
+        torch.cuda.current_stream(self.device).synchronize()
+        return {k: self._view(k).detach().cpu().numpy().copy() for k in self.weight_names()}
+
+    def set_weights(self, weights):
+        """`weights`: dict keyed by Keras names, or a list in `weight_names()` order."""
+        if not isinstance(weights, dict):
+            weights = dict(zip(self.weight_names(), weights))
+        for k in self.weight_names():
+            t = self._view(k)
+            w = np.asarray(weights[k], dtype=np.float32)
+            if tuple(w.shape) != tuple(t.shape):
+                raise ValueError("weight {} has shape {}, expected {}".format(k, w.shape, tuple(t.shape)))
+            t.copy_(torch.from_numpy(np.ascontiguousarray(w)))
+
+    def get_optimizer_state(self):
+        torch.cuda.current_stream(self.device).synchronize()
+        st = {"iterations": self.iterations}
+        if self.optimizer == "adam":
+            for k in self.weight_names():
+                st["m/" + k] = (self.m[k] if k in self.m else self._view(k, self.m_dense)).detach().cpu().numpy().copy()
+                st["v/" + k] = (self.v[k] if k in self.v else self._view(k, self.v_dense)).detach().cpu().numpy().copy()
+        return st
+
+    def set_optimizer_state(self, st):
+        self.iterations = int(st["iterations"])
+        if self.optimizer == "adam":
+            for k in self.weight_names():
+                for tag, tabs, dense in (("m/", self.m, self.m_dense), ("v/", self.v, self.v_dense)):
+                    dst = tabs[k] if k in tabs else self._view(k, dense)
+                    dst.copy_(torch.from_numpy(np.ascontiguousarray(st[tag + k], dtype=np.float32)).view_as(dst))
+
+    # ---- C structs ------------------------------------------------------------------------------
+    def _structs(self):
+        m = nat.MrModel()
+        m.user_mlp, m.item_mlp = self.user_mlp.data_ptr(), self.item_mlp.data_ptr()
+        m.user_gmf = self.user_gmf.data_ptr() if self.mf_dim else None
+        m.item_gmf = self.item_gmf.data_ptr() if self.mf_dim else None
+        base = self.dense.data_ptr()
+        m.dense = base
+        for i in range(1, len(self.L)):
+            kn, bn = hidden_names(i)
+            m.W[i] = base + 4 * self._dense_slices[kn][0]
+            m.b[i] = base + 4 * self._dense_slices[bn][0]
+        m.w_out = base + 4 * self._dense_slices[K_OUT_W][0]
+        m.b_out = base + 4 * self._dense_slices[K_OUT_B][0]
+        m.dense_count = self.dense_count
+        m.num_users, m.num_items = self.num_users, self.num_items
+        m.n_layers = len(self.L)
+        for i, w in enumerate(self.L):
+            m.L[i] = w
+            m.l2[i] = self.l2[i]
+        m.mf_dim = self.mf_dim
+        self._model = m
+
+        o = nat.MrOptState()
+        o.optimizer = nat.OPT_ADAM if self.optimizer == "adam" else nat.OPT_SGD
+        o.table_mode = nat.TABLES_DENSE if self.table_mode == "dense" else nat.TABLES_SPARSE
+        o.lr, o.beta_1, o.beta_2, o.epsilon = self.lr, self.beta_1, self.beta_2, ADAM_EPSILON
+        o.iterations = self.iterations
+        if self.optimizer == "adam":
+            o.m_user_mlp, o.m_item_mlp = self.m[K_USER].data_ptr(), self.m[K_ITEM].data_ptr()
+            o.v_user_mlp, o.v_item_mlp = self.v[K_USER].data_ptr(), self.v[K_ITEM].data_ptr()
+            if self.mf_dim:
+                o.m_user_gmf, o.m_item_gmf = self.m[K_GMF_USER].data_ptr(), self.m[K_GMF_ITEM].data_ptr()
+                o.v_user_gmf, o.v_item_gmf = self.v[K_GMF_USER].data_ptr(), self.v[K_GMF_ITEM].data_ptr()
+            o.m_dense, o.v_dense = self.m_dense.data_ptr(), self.v_dense.data_ptr()
+        self._opt = o
+
+        g = nat.MrGrads()
+        g.dense = self.g_dense.data_ptr()
+        if self.table_mode == "dense":
+            g.user_mlp, g.item_mlp = self.g_tables[K_USER].data_ptr(), self.g_tables[K_ITEM].data_ptr()
+            if self.mf_dim:
+                g.user_gmf, g.item_gmf = self.g_tables[K_GMF_USER].data_ptr(), self.g_tables[K_GMF_ITEM].data_ptr()
+        self._grads = g
+
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def gradient_tensors(self):
+        """Flat gradient buffers a data-parallel caller all-reduces between train_grads and apply."""
+        return [self.g_dense] + [self.g_tables[k] for k in self._tables if k in self.g_tables]
+
+    # ---- hot path ---------------------------------------------------------------------------------
+    def forward(self, users, items, user_div=1, labels=None, want_logits=True, want_probs=True):
+        """Fused forward (model.py:154-188).  Returns (logits, probs, loss_sum) device tensors
+        (each None when not requested)."""
+        users = as_device_i32(users, self.device)
+        items = as_device_i32(items, self.device)
+        B = items.numel()
+        if users.numel() * user_div != B:
+            raise ValueError("users ({}) x user_div ({}) != items ({})".format(users.numel(), user_div, B))
+        logits = torch.empty(B, dtype=torch.float32, device=self.device) if want_logits else None
+        probs = torch.empty(B, dtype=torch.float32, device=self.device) if want_probs else None
+        lab = as_device_f32(labels, self.device) if labels is not None else None
+        loss = torch.zeros(1, dtype=torch.float32, device=self.device) if labels is not None else None
+        nbytes = nat.lib.mr_forward_workspace_bytes(C.byref(self._model), B)
+        ws = self._workspace(nbytes)
+        nat.check(nat.lib.mr_neumf_forward(C.byref(self._model), _ptr(users), _ptr(items), B, user_div, _ptr(logits),
+                                           _ptr(probs), _ptr(lab), _ptr(loss), _ptr(ws), ws.numel(), self._stream()),
+                  "mr_neumf_forward")
+        return logits, probs, loss
+
+    def _train_args(self, users, items, labels, group, k, inv_global_batch):
+        users = as_device_i32(users, self.device)
+        items = as_device_i32(items, self.device)
+        labels = as_device_f32(labels, self.device)
+        B = items.numel()
+        if users.numel() != B or labels.numel() != B:
+            raise ValueError("users/items/labels must have the same length")
+        inv = 1.0 / B if inv_global_batch is None else float(inv_global_batch)
+        nbytes = nat.lib.mr_train_workspace_bytes(C.byref(self._model), B)
+        ws = self._workspace(nbytes)
+        self._opt.iterations = self.iterations
+        keep = (users, items, labels, ws)
+        args = (C.byref(self._model), C.byref(self._opt), C.byref(self._grads), _ptr(users), _ptr(items), _ptr(labels),
+                B, int(group), int(k), inv, _ptr(self.step_out), _ptr(ws), ws.numel(), self._stream())
+        return args, keep
+
+    def train_step(self, users, items, labels, group=0, k=0, inv_global_batch=None):
+        """One optimisation step (Keras train_on_batch).  Returns a copy of the step outputs
+        [loss_sum, hit_sum, dcg_sum, l2_penalty, bad_ids, ...] as a device tensor."""
+        args, keep = self._train_args(users, items, labels, group, k, inv_global_batch)
+        nat.check(nat.lib.mr_neumf_train_step(*args), "mr_neumf_train_step")
+        self.iterations = int(self._opt.iterations)
+        return self.step_out.clone()
+
+    def train_grads(self, users, items, labels, group=0, k=0, inv_global_batch=None):
+        args, keep = self._train_args(users, items, labels, group, k, inv_global_batch)
+        nat.check(nat.lib.mr_neumf_train_grads(*args), "mr_neumf_train_grads")
+        return self.step_out.clone()
+
+    def apply(self):
+        self._opt.iterations = self.iterations
+        nat.check(nat.lib.mr_neumf_apply(C.byref(self._model), C.byref(self._opt), C.byref(self._grads), self._stream()),
+                  "mr_neumf_apply")
+        self.iterations = int(self._opt.iterations)
+
+    def rank_eval(self, users_per_group, items, group, k, want_rank=False, want_probs=False):
+        """Score G groups (positive last) and rank them (model.py:336-455).  Returns
+        (pos (G,) int32, sums (2,) float [hit_sum, dcg_sum], rank or None, probs or None)."""
+        users = as_device_i32(users_per_group, self.device)
+        items = as_device_i32(items, self.device)
+        G = users.numel()
+        if items.numel() != G * group:
+            raise ValueError("items ({}) != groups ({}) x group ({})".format(items.numel(), G, group))
+        dev = self.device
+        pos = torch.empty(G, dtype=torch.int32, device=dev)
+        sums = torch.zeros(2, dtype=torch.float32, device=dev)
+        rank = torch.empty((G, group), dtype=torch.int32, device=dev) if want_rank else None
+        probs = torch.empty(G * group, dtype=torch.float32, device=dev) if want_probs else None
+        nbytes = nat.lib.mr_rank_eval_workspace_bytes(C.byref(self._model), G, group)
+        ws = self._workspace(nbytes)
+        nat.check(nat.lib.mr_rank_eval(C.byref(self._model), _ptr(users), _ptr(items), G, group, int(k), _ptr(rank),
+                                       _ptr(pos), _ptr(probs), _ptr(sums), _ptr(ws), ws.numel(), self._stream()),
+                  "mr_rank_eval")
+        return pos, sums, rank, probs
+
+
+def rank_scores(scores, group, k, label_col=None, want_rank=True, device=None):
+    """RankLayer + metrics on caller-supplied scores (model.py:336-455), on device."""
+    require_cuda()
+    device = torch.device(device if device is not None else "cuda:{}".format(torch.cuda.current_device()))
+    s = as_device_f32(scores, device)
+    if group < 1 or s.numel() % group:
+        raise ValueError("scores ({}) not divisible by group width {}".format(s.numel(), group))
+    G = s.numel() // group
+    pos = torch.empty(G, dtype=torch.int32, device=device)
+    sums = torch.zeros(2, dtype=torch.float32, device=device)
+    rank = torch.empty((G, group), dtype=torch.int32, device=device) if want_rank else None
+    lc = as_device_i32(label_col, device) if label_col is not None else None
+    nbytes = max(int(nat.lib.mr_rank_scores_workspace_bytes(G)), 256)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    nat.check(nat.lib.mr_rank_scores(_ptr(s), G, int(group), int(k), _ptr(lc), _ptr(rank), _ptr(pos), _ptr(sums), _ptr(ws),
+                                     nbytes, st), "mr_rank_scores")
+    return rank, pos, sums
+
+
+def gather_rows(table, idx):
+    """out[i,:] = table[idx[i],:] through the gather kernel (model.py:161-172)."""
+    require_cuda()
+    idx = as_device_i32(idx, table.device)
+    out = torch.empty((idx.numel(), table.shape[1]), dtype=torch.float32, device=table.device)
+    st = C.c_void_p(torch.cuda.current_stream(table.device).cuda_stream)
+    nat.check(nat.lib.mr_gather_rows(_ptr(table), table.shape[0], table.shape[1], _ptr(idx), idx.numel(), _ptr(out), st),
+              "mr_gather_rows")
+    return out
+
+
+def sort_pairs(keys, key_bits):
+    require_cuda()
+    device = torch.device("cuda:{}".format(torch.cuda.current_device()))
+    keys = as_device_i32(keys, device)
+    n = keys.numel()
+    out_k, out_i = torch.empty_like(keys), torch.empty_like(keys)
+    nbytes = int(nat.lib.mr_sort_workspace_bytes(n))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    nat.check(nat.lib.mr_sort_pairs(_ptr(keys), n, int(key_bits), _ptr(out_k), _ptr(out_i), _ptr(ws), nbytes, st),
+              "mr_sort_pairs")
+    return out_k, out_i
+
+
+def sample_negatives(rowptr, csr_items, num_items, pos_users, pos_items, first_index, negs, seed, epoch):
+    """Device sampler (data_pipeline.py:99-113, 136-150).  Returns (users, items, labels) device
+    tensors of length P*(negs+1) laid out as the reference batches (negatives, then the positive)."""
+    require_cuda()
+    device = rowptr.device
+    pos_users = as_device_i32(pos_users, device)
+    pos_items = as_device_i32(pos_items, device)
+    P = pos_users.numel()
+    n = P * (negs + 1)
+    xu = torch.empty(n, dtype=torch.int32, device=device)
+    xi = torch.empty(n, dtype=torch.int32, device=device)
+    y = torch.empty(n, dtype=torch.float32, device=device)
+    st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    nat.check(nat.lib.mr_sample_negatives(_ptr(rowptr), _ptr(csr_items), int(num_items), _ptr(pos_users), _ptr(pos_items),
+                                          P, int(first_index), int(negs), int(seed) & (2 ** 64 - 1),
+                                          int(epoch) & (2 ** 64 - 1), _ptr(xu), _ptr(xi), _ptr(y), st),
+              "mr_sample_negatives")
+    return xu, xi, y

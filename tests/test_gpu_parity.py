@@ -1,0 +1,346 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle, on a B200.
+
+Tolerances (BASELINE.json north_star): ids / ranks / positions bit-exact given equal scores;
+fp32 logits, loss and updated weights within 1e-5 relative; HR@k / NDCG@k within 1e-3 absolute.
+"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import movierec_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+RTOL = 1e-5  # north_star: fp32 logits, loss, updated weights within 1e-5 relative
+
+
+@pytest.fixture(scope="module")
+def eng_mod():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from movierec import _engine
+    return _engine
+
+
+def make_batch(rng, nu, ni, groups, negs):
+    users = np.repeat(rng.integers(0, nu, groups), negs + 1)
+    items = rng.integers(0, ni, groups * (negs + 1))
+    y = np.tile([0] * negs + [1], groups).astype(np.float32)
+    return users, items, y
+
+
+def rel_close(got, want, rtol=RTOL, what=""):
+    """Relative to the magnitude of the reference tensor (a per-tensor scale keeps entries that
+    cancel to ~0 from demanding absolute precision fp32 cannot give)."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    scale = max(float(np.max(np.abs(want))), 1e-30)
+    err = float(np.max(np.abs(got - want))) / scale
+    assert err <= rtol, "{}: max err / max|ref| = {:.3e} > {:.1e}".format(what, err, rtol)
+
+
+CONFIGS = [
+    # (num_users, num_items, layers, mf_dim, negs, groups)
+    (5, 10, [6, 4], 0, 3, 2),             # reference test params (test/test_model.py:8-26)
+    (5, 10, [5, 4], 0, 2, 7),             # reference toy defaults, odd L0 (model.py:15-34)
+    (37, 53, [7], 0, 1, 9),               # no hidden layer (model.py:175 loop empty)
+    (37, 53, [9, 5, 3], 3, 4, 13),        # odd widths + GMF
+    (200, 300, [64, 32, 16, 8], 0, 4, 50),   # reference trainer defaults (trainer.py:12)
+    (200, 300, [64, 32, 16, 8], 8, 4, 77),   # NeuMF on the ML-1M config
+    (300, 200, [256, 128, 64], 64, 4, 41),   # ML-20M tower
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: "L{}f{}".format("x".join(map(str, c[2])), c[3]))
+def test_forward_matches_oracle(eng_mod, cfg):
+    nu, ni, L, f, negs, groups = cfg
+    rng = np.random.default_rng(11)
+    eng = eng_mod.NeuMFEngine(nu, ni, L, [0] * len(L), mf_dim=f, seed=3)
+    w = eng.get_weights()
+    for k in w:  # non-zero biases
+        if k.endswith("bias"):
+            w[k] = rng.normal(0, 0.1, w[k].shape).astype(np.float32)
+    eng.set_weights(w)
+    users, items, y = make_batch(rng, nu, ni, groups, negs)
+    logits, probs, loss = eng.forward(users, items, labels=y)
+    c = o.forward(w, users, items)
+    rel_close(logits.cpu().numpy(), c["z"], what="logits")
+    rel_close(probs.cpu().numpy(), c["p"], what="probs")
+    want_loss = float(np.sum(o.bce_from_logits(c["z"].astype(np.float64), y.astype(np.float64))))
+    assert abs(float(loss) - want_loss) <= RTOL * abs(want_loss)
+    # float64 oracle: the kernel must be as close to the truth as the fp32 oracle is
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    z64 = o.forward(w64, users, items)["z"]
+    err_gpu = np.max(np.abs(logits.cpu().numpy() - z64))
+    err_cpu = np.max(np.abs(c["z"] - z64))
+    assert err_gpu <= max(4 * err_cpu, 1e-6)
+
+
+def test_forward_user_div_and_tail_tiles(eng_mod):
+    rng = np.random.default_rng(5)
+    eng = eng_mod.NeuMFEngine(30, 40, [16, 8], [0, 0], mf_dim=4, seed=2)
+    w = eng.get_weights()
+    for G, group in ((1, 2), (3, 100), (33, 5), (0, 4)):
+        u = rng.integers(0, 30, G)
+        it = rng.integers(0, 40, G * group)
+        logits, _, _ = eng.forward(u, it, user_div=group)
+        want = o.forward(w, np.repeat(u, group), it)["z"] if G else np.zeros(0)
+        assert logits.numel() == G * group
+        if G:
+            rel_close(logits.cpu().numpy(), want, what="logits G={} group={}".format(G, group))
+
+
+def test_gather_rows_bit_exact(eng_mod):
+    rng = np.random.default_rng(0)
+    for rows, dim in ((943, 32), (1682, 33), (100, 128), (17, 1)):
+        table = torch.from_numpy(rng.normal(size=(rows, dim)).astype(np.float32)).cuda()
+        idx = rng.integers(0, rows, 1000)
+        out = eng_mod.gather_rows(table, idx)
+        assert torch.equal(out, table[torch.from_numpy(idx).cuda()])
+    assert eng_mod.gather_rows(table, np.zeros(0, np.int64)).shape == (0, 1)
+
+
+@pytest.mark.parametrize("n,bits", [(1, 3), (31, 5), (2048, 8), (2049, 9), (100000, 17), (1310720, 18), (70000, 24)])
+def test_sort_pairs_is_a_stable_sort(eng_mod, n, bits):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << bits, n).astype(np.int32)
+    if n > 1000:
+        keys[: n // 3] = keys[0]  # long run of one key: stability is visible
+    k, i = eng_mod.sort_pairs(keys, bits)
+    order = np.argsort(keys, kind="stable")
+    np.testing.assert_array_equal(i.cpu().numpy(), order.astype(np.int32))
+    np.testing.assert_array_equal(k.cpu().numpy(), keys[order])
+
+
+TRAIN_CASES = [
+    # cfg index, optimizer, table mode, l2
+    (0, "adam", "dense", [0.01, 0.01]),   # the reference's test params incl. its l2
+    (1, "sgd", "dense", [0.0, 0.0]),
+    (2, "adam", "dense", [0.0]),
+    (3, "adam", "sparse", [0.0, 0.0, 0.0]),
+    (3, "sgd", "sparse", [0.0, 0.02, 0.0]),
+    (4, "adam", "dense", [0, 0, 0, 0]),
+    (5, "adam", "dense", [0, 0, 0, 0]),
+    (5, "adam", "sparse", [0, 0, 0, 0]),
+    (6, "adam", "dense", [0, 0, 0]),
+]
+
+
+@pytest.mark.parametrize("case", TRAIN_CASES, ids=lambda c: "cfg{}-{}-{}".format(c[0], c[1], c[2]))
+def test_train_steps_match_oracle(eng_mod, case):
+    ci, opt, mode, l2 = case
+    nu, ni, L, f, negs, groups = CONFIGS[ci]
+    rng = np.random.default_rng(100 + ci)
+    params = {"layers_sizes": L, "layers_l2reg": l2, "optimizer": opt, "lr": 0.001, "beta_1": 0.9, "beta_2": 0.999,
+              "num_negs_per_pos": negs, "k": min(2, negs + 1)}
+    eng = eng_mod.NeuMFEngine(nu, ni, L, l2, mf_dim=f, optimizer=opt, lr=0.001, table_mode=mode, seed=7)
+    w = eng.get_weights()
+    st = o.new_opt_state(w)
+    for step in range(3):
+        users, items, y = make_batch(rng, nu, ni, groups, negs)
+        B = len(y)
+        # gradients of this step (dense part), before either side updates
+        c = o.forward(w, users, items)
+        g = o.backward(w, c, y, None, l2)
+        out = eng.train_step(users, items, y, group=negs + 1, k=params["k"]).cpu().numpy().astype(np.float64)
+        assert out[4] == 0
+        for name, (off, shape) in eng._dense_slices.items():
+            got = eng.g_dense[off:off + int(np.prod(shape))].cpu().numpy().reshape(shape)
+            rel_close(got, g[name].reshape(shape), rtol=2e-5, what="grad {} step {}".format(name, step))
+        if mode == "dense":
+            for name, t in eng.g_tables.items():
+                want = g[name] - (2.0 * l2[0]) * w[name] if l2[0] else g[name]  # kernel adds l2 in the update
+                rel_close(t.cpu().numpy(), want, rtol=2e-5, what="table grad {} step {}".format(name, step))
+        loss, hr, dcg = o.train_step(w, st, users, items, y, params, adam_mode="lazy" if mode == "sparse" else "dense")
+        got_loss = out[0] / B + out[3]
+        assert abs(got_loss - loss) <= 2e-5 * max(abs(loss), 1e-3), (got_loss, loss)
+        G = B // (negs + 1)
+        assert abs(out[1] / G - hr) <= 1e-3 and abs(out[2] / G - dcg) <= 1e-3
+        got = eng.get_weights()
+        for k in w:
+            rel_close(got[k], w[k], rtol=RTOL * (step + 1), what="weight {} after step {}".format(k, step + 1))
+    assert eng.iterations == 3
+
+
+def test_train_step_is_deterministic(eng_mod):
+    nu, ni, L, f, negs, groups = CONFIGS[5]
+    rng = np.random.default_rng(1)
+    batches = [make_batch(rng, nu, ni, 400, negs) for _ in range(3)]
+    results = []
+    for _ in range(2):
+        eng = eng_mod.NeuMFEngine(nu, ni, L, [0] * 4, mf_dim=f, seed=9)
+        outs = [eng.train_step(u, i, y, group=negs + 1, k=3).cpu().numpy() for u, i, y in batches]
+        results.append((eng.get_weights(), outs))
+    for k in results[0][0]:
+        assert np.array_equal(results[0][0][k], results[1][0][k]), k
+    for a, b in zip(results[0][1], results[1][1]):
+        assert np.array_equal(a, b)
+
+
+def test_out_of_range_ids_are_flagged(eng_mod):
+    eng = eng_mod.NeuMFEngine(5, 10, [6, 4], [0, 0], seed=1)
+    out = eng.train_step([0, 9], [1, 2], [0.0, 1.0], group=2, k=1).cpu().numpy()
+    assert out[4] != 0
+
+
+# ---- ranking ------------------------------------------------------------------------------------
+
+def test_rank_scores_reference_vectors(eng_mod, golden_dir):
+    with open(os.path.join(golden_dir, "reference_tests.json")) as f:
+        ref = json.load(f)
+    for phase in ("train", "eval"):
+        v = ref["rank_layer"][phase]
+        rank, _, _ = eng_mod.rank_scores(np.array(v["input"], np.float32), v["negs"] + 1, 1)
+        assert rank.cpu().numpy().tolist() == v["expected"]
+    v = ref["ties"]
+    for k in v["zero_for_k"] + [v["hit_k"]]:
+        _, pos, sums = eng_mod.rank_scores(np.array(v["y_pred"], np.float32), 4, k, want_rank=False)
+        assert pos.cpu().numpy().tolist() == [v["hit_position"]]
+        s = sums.cpu().numpy()
+        if k == v["hit_k"]:
+            assert s[0] == 1.0 and abs(s[1] - np.log(2) / np.log(v["hit_position"] + 2)) < 1e-6
+        else:
+            assert s[0] == 0.0 and s[1] == 0.0
+
+
+def test_rank_scores_match_reference_execution(eng_mod, golden_dir):
+    g = np.load(os.path.join(golden_dir, "rank_metrics.npz"))
+    for c in range(int(g["num_cases"])):
+        pre = "c{}_".format(c)
+        s = g[pre + "scores"]
+        G, group = s.shape
+        for k, hr, dcg in zip(g[pre + "ks"], g[pre + "hr"], g[pre + "dcg"]):
+            rank, pos, sums = eng_mod.rank_scores(s, group, int(k))
+            np.testing.assert_array_equal(rank.cpu().numpy(), g[pre + "rank"])
+            np.testing.assert_array_equal(pos.cpu().numpy(), g[pre + "pos"])
+            sm = sums.cpu().numpy()
+            assert abs(sm[0] / G - hr) <= 1e-6 and abs(sm[1] / G - dcg) <= 1e-5
+
+
+def test_rank_scores_nan_and_label_col(eng_mod):
+    s = np.array([[0.3, np.nan, 0.5, 0.4], [0.3, 0.1, 0.2, np.nan]], np.float32)
+    rank, pos, _ = eng_mod.rank_scores(s, 4, 2)
+    assert rank.cpu().numpy().tolist() == o.rank_groups(s, 4).tolist()
+    assert pos.cpu().numpy().tolist() == o.positive_positions(s, 4).tolist()
+    _, pos, _ = eng_mod.rank_scores(s, 4, 2, label_col=np.array([0, 2], np.int32))
+    assert pos.cpu().numpy().tolist() == [2, 1]
+
+
+def test_rank_eval_matches_oracle(eng_mod):
+    nu, ni, L, f = 300, 500, [64, 32, 16, 8], 8
+    rng = np.random.default_rng(4)
+    eng = eng_mod.NeuMFEngine(nu, ni, L, [0] * 4, mf_dim=f, seed=5)
+    w = eng.get_weights()
+    G, group, k = 257, 100, 10
+    users = rng.integers(0, nu, G)
+    items = rng.integers(0, ni, G * group)
+    items[5 * group:6 * group] = items[5 * group]  # a fully tied group: positive must lose
+    pos, sums, rank, probs = eng.rank_eval(users, items, group, k, want_rank=True, want_probs=True)
+    p = probs.cpu().numpy()
+    hr_o, dcg_o, pos_o, p_o = o.evaluate_groups(w, users, items, group, k)
+    rel_close(p, p_o, what="eval probs")
+    # bit-exact given equal scores: rank the kernel's own scores with the oracle's rule
+    np.testing.assert_array_equal(pos.cpu().numpy(), o.positive_positions(p, group))
+    np.testing.assert_array_equal(rank.cpu().numpy(), o.rank_groups(p, group))
+    assert pos.cpu().numpy()[5] == group - 1
+    s = sums.cpu().numpy()
+    assert abs(s[0] / G - hr_o) <= 1e-3 and abs(s[1] / G - dcg_o) <= 1e-3
+    hs, ds = o.metrics_from_positions(pos.cpu().numpy(), k)
+    assert s[0] == hs and abs(s[1] - ds) <= 1e-4 * max(ds, 1)
+
+
+# ---- sampler --------------------------------------------------------------------------------------
+
+def test_sampler_bit_exact_vs_oracle(eng_mod):
+    rng = np.random.default_rng(8)
+    nu, ni = 40, 60
+    users = np.repeat(np.arange(nu), 12)
+    items = np.concatenate([rng.choice(ni, 12, replace=False) for _ in range(nu)])
+    users = np.concatenate([users, np.full(58, 3)])  # user 3 has 2 candidates left -> with replacement
+    items = np.concatenate([items, np.setdiff1d(np.arange(ni), [7, 11])[:58]])
+    rowptr, csr = o.build_csr(nu, users, items)
+    pu = rng.integers(0, nu, 64).astype(np.int32)
+    pu[:4] = 3
+    pi = rng.integers(0, ni, 64).astype(np.int32)
+    d_rowptr, d_csr = torch.from_numpy(rowptr).cuda(), torch.from_numpy(csr).cuda()
+    for negs, seed, epoch, first in ((4, 1, 0, 0), (9, 2 ** 40 + 5, 3, 640), (20, 7, 2 ** 33, 2 ** 32 + 1)):
+        xu, xi, y = eng_mod.sample_negatives(d_rowptr, d_csr, ni, pu, pi, first, negs, seed, epoch)
+        want = o.device_sample_batch(rowptr, csr, ni, pu, pi, first, negs, seed, epoch)
+        np.testing.assert_array_equal(xi.cpu().numpy(), want)
+        np.testing.assert_array_equal(xu.cpu().numpy(), np.repeat(pu, negs + 1))
+        np.testing.assert_array_equal(y.cpu().numpy(), np.tile([0] * negs + [1], 64))
+        got = xi.cpu().numpy().reshape(64, negs + 1)
+        for p in range(64):
+            seen = set(csr[rowptr[pu[p]]:rowptr[pu[p] + 1]].tolist())
+            assert not seen & set(got[p, :negs].tolist())
+            if ni - len(seen) >= negs:
+                assert len(set(got[p, :negs].tolist())) == negs
+
+
+# ---- BASELINE sizes: size-independent properties --------------------------------------------------
+
+def test_full_size_ml20m_properties(eng_mod):
+    """ML-20M shape, 1.3M-row batch: determinism, loss = sum of row losses, dense grads are the
+    sum of two half-batch grads (linearity), untouched rows do not move on step 1."""
+    nu, ni, L, f, negs = 138493, 26744, [256, 128, 64], 64, 4
+    B = 5 * 2 ** 16  # a quarter of the bench batch keeps the test short; tiles, sort and reduce all scale
+    rng = np.random.default_rng(0)
+    users, items, y = make_batch(rng, nu, ni, B // (negs + 1), negs)
+    eng = eng_mod.NeuMFEngine(nu, ni, L, [0, 0, 0], mf_dim=f, seed=1)
+    w0_user = eng.user_mlp.clone()
+    out_full = eng.train_grads(users, items, y, group=negs + 1, k=3, inv_global_batch=1.0 / B)
+    g_full = eng.g_dense.clone()
+    gt_full = eng.g_tables["item_embedding/embeddings"].clone()
+    h = B // 2
+    eng.train_grads(users[:h], items[:h], y[:h], inv_global_batch=1.0 / B)
+    g_a, gt_a = eng.g_dense.clone(), eng.g_tables["item_embedding/embeddings"].clone()
+    eng.train_grads(users[h:], items[h:], y[h:], inv_global_batch=1.0 / B)
+    g_b, gt_b = eng.g_dense.clone(), eng.g_tables["item_embedding/embeddings"].clone()
+    rel_close((g_a + g_b).cpu().numpy(), g_full.cpu().numpy(), rtol=1e-4, what="dense grad linearity")
+    rel_close((gt_a + gt_b).cpu().numpy(), gt_full.cpu().numpy(), rtol=1e-4, what="item grad linearity")
+    # sampled rows against the oracle forward on the same weights
+    w = eng.get_weights()
+    sel = rng.choice(B, 4096, replace=False)
+    logits, _, loss = eng.forward(users, items, labels=y)
+    c = o.forward(w, users[sel], items[sel])
+    rel_close(logits.cpu().numpy()[sel], c["z"], what="logits sample")
+    assert abs(float(loss) - float(out_full[0])) <= 1e-6 * abs(float(loss))
+    # determinism + untouched rows
+    eng.train_grads(users, items, y, group=negs + 1, k=3, inv_global_batch=1.0 / B)
+    assert torch.equal(eng.g_dense, g_full) and torch.equal(eng.g_tables["item_embedding/embeddings"], gt_full)
+    eng.apply()
+    touched = torch.zeros(nu, dtype=torch.bool, device="cuda")
+    touched[torch.from_numpy(users).cuda()] = True
+    assert torch.equal(eng.user_mlp[~touched], w0_user[~touched])
+    assert not torch.equal(eng.user_mlp[touched], w0_user[touched])
+
+
+def test_full_size_eval_sweep_properties(eng_mod):
+    """Config 4 shape: every ML-20M-shaped user, 1 positive + 99 negatives."""
+    nu, ni, L, f = 138493, 26744, [256, 128, 64], 64
+    group, k = 100, 10
+    rng = np.random.default_rng(2)
+    eng = eng_mod.NeuMFEngine(nu, ni, L, [0, 0, 0], mf_dim=f, seed=3)
+    users = np.arange(nu, dtype=np.int32)
+    items = rng.integers(0, ni, nu * group).astype(np.int32)
+    pos, sums, _, probs = eng.rank_eval(users, items, group, k, want_probs=True)
+    p = probs.cpu().numpy()
+    np.testing.assert_array_equal(pos.cpu().numpy(), o.positive_positions(p, group))
+    hs, ds = o.metrics_from_positions(pos.cpu().numpy(), k)
+    s = sums.cpu().numpy()
+    assert s[0] == hs and abs(s[1] - ds) <= 1e-5 * ds
+    # a permutation of the negatives inside each group leaves the position unchanged when scores are distinct
+    sel = rng.choice(nu, 2000, replace=False)
+    it = items.reshape(nu, group)[sel].copy()
+    it[:, :-1] = it[:, :-1][:, ::-1]
+    pos2, _, _, probs2 = eng.rank_eval(users[sel], it.reshape(-1), group, k, want_probs=True)
+    p2 = probs2.cpu().numpy().reshape(-1, group)
+    distinct = np.array([len(np.unique(r)) == group for r in p2])
+    assert np.array_equal(pos2.cpu().numpy()[distinct], pos.cpu().numpy()[sel][distinct])
+    w = eng.get_weights()
+    c = o.forward(w, np.repeat(users[sel[:64]], group), items.reshape(nu, group)[sel[:64]].reshape(-1))
+    rel_close(p.reshape(nu, group)[sel[:64]].reshape(-1), c["p"], what="eval probs sample")

@@ -1,0 +1,230 @@
+"""Host-side logic of the drop-in Python face and the C-ABI surface.  CPU only (no compute calls)."""
+
+import copy
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from movierec import data_pipeline, model, trainer
+from movierec import _native as nat
+from movierec.util import movielens_utils as ml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+TEST_PARAMS = {  # reference test/test_model.py:8-26
+    "num_users": 5, "num_items": 10, "layers_sizes": [6, 4], "layers_l2reg": [0.01, 0.01],
+    "optimizer": "adam", "lr": 0.001, "beta_1": 0.9, "beta_2": 0.999,
+    "batch_size": 8, "num_negs_per_pos": 3, "batch_size_eval": 10, "num_negs_per_pos_eval": 4, "k": 4,
+}
+
+
+@pytest.fixture(scope="module")
+def ref(golden_dir):
+    with open(os.path.join(golden_dir, "reference_tests.json")) as f:
+        return json.load(f)
+
+
+# ---- C ABI --------------------------------------------------------------------------------------
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "movierec_b200.h")).read()
+    declared = set(re.findall(r"\b(mr_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(nat.SIGNATURES), declared ^ set(nat.SIGNATURES)
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert nat.version() == int(re.search(r"#define MR_VERSION (\d+)", header).group(1))
+
+
+def test_struct_layouts_match_header():
+    # sizes follow from the header's field lists (8-byte pointers, natural alignment)
+    assert ctypes.sizeof(nat.MrModel) == 5 * 8 + 8 * 8 * 2 + 2 * 8 + 8 + 3 * 4 + 8 * 4 + 4 + 8 * 4
+    assert ctypes.sizeof(nat.MrOptState) == 2 * 4 + 4 * 4 + 8 + 10 * 8
+    assert ctypes.sizeof(nat.MrGrads) == 5 * 8
+    assert nat.MrModel.dense_count.offset == 5 * 8 + 16 * 8 + 2 * 8
+
+
+def test_workspace_queries_are_host_only():
+    m = nat.MrModel()
+    m.n_layers, m.mf_dim = 3, 64
+    for i, w in enumerate([256, 128, 64]):
+        m.L[i] = w
+    m.dense_count = 256 * 128 + 128 + 128 * 64 + 64 + 128 + 1
+    small = nat.lib.mr_train_workspace_bytes(ctypes.byref(m), 1000)
+    big = nat.lib.mr_train_workspace_bytes(ctypes.byref(m), 100000)
+    assert 0 < small < big
+    assert big - small >= 99000 * 4 * (192 + 192)  # the staged row gradients dominate
+    assert nat.lib.mr_sort_workspace_bytes(1 << 20) >= 2 * 4 * (1 << 20)
+    assert nat.lib.mr_rank_eval_workspace_bytes(ctypes.byref(m), 1000, 100) >= 1000 * 100 * 4
+
+
+def test_compute_without_cuda_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.MovierecModel(copy.deepcopy(TEST_PARAMS), output_dir="/tmp/mr_test_models")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.RankLayer(2, 3, "rank").call(np.array([0.9, 0.8, 0.7, 0.6]))
+
+
+# ---- MovierecModel parameter contract (reference test/test_model.py:31-60) ------------------------
+
+def test_wrong_layers():
+    params = copy.deepcopy(TEST_PARAMS)
+    params["layers_sizes"].append(2)
+    with pytest.raises(ValueError, match="must be equal"):
+        model.MovierecModel(params)
+
+
+def test_missing_param():
+    for key in ("num_users", "num_items", "layers_sizes", "layers_l2reg", "optimizer", "lr", "batch_size",
+                "num_negs_per_pos", "batch_size_eval", "num_negs_per_pos_eval"):
+        params = copy.deepcopy(TEST_PARAMS)
+        del params[key]
+        with pytest.raises(KeyError):
+            model.MovierecModel(params)
+
+
+def test_not_implemented_optimizer():
+    params = copy.deepcopy(TEST_PARAMS)
+    params["optimizer"] = "other"
+    with pytest.raises(NotImplementedError):
+        model.MovierecModel(params)
+
+
+@pytest.mark.parametrize("patch,msg", [
+    ({"num_negs_per_pos": 0}, "num_negs_per_pos must be > 0"),
+    ({"batch_size": 9}, "Batch size must be divisible"),
+    ({"num_negs_per_pos_eval": -1}, "num_negs_per_pos_eval must be > 0"),
+    ({"batch_size_eval": 11}, r"Batch size \(eval\) must be divisible"),
+    ({"k": 5}, "'k' must be lower"),
+])
+def test_value_errors(patch, msg):
+    params = copy.deepcopy(TEST_PARAMS)
+    params.update(patch)
+    with pytest.raises(ValueError, match=msg):
+        model.MovierecModel(params)
+
+
+def test_module_constants():
+    assert model.OPTIMIZERS == ["adam", "sgd"] and model.HIT_RATE == "hr" and model.DCG == "dcg"
+    assert model.OUTPUT_PRED == "output" and model.OUTPUT_RANK == "rank" and model.METRIC_VAL_DCG == "val_output_dcg"
+    assert model.MovierecModel.get_model_weights_path("d", "m") == os.path.join("d", "m_weights.h5")
+    assert model.MovierecModel.get_params_json_path("d", "m") == os.path.join("d", "m_params.json")
+    assert trainer.DEFAULT_PARAMS["layers_sizes"] == [64, 32, 16, 8] and trainer.DEFAULT_PARAMS["k"] == 5
+    assert trainer.DEFAULT_PARAMS["num_negs_per_pos"] == 9 and trainer.DEFAULT_PARAMS["batch_size_eval"] == 200
+    assert ml.NUM_USERS == {"ml-100k": 943, "ml-1m": 6040, "ml-20m": 138493}
+    assert ml.NUM_ITEMS == {"ml-100k": 1682, "ml-1m": 3952, "ml-20m": 27278}
+
+
+def test_callbacks_follow_keras_semantics():
+    class Stub(object):
+        def __init__(self):
+            self.w, self.stop_training, self.saved = [np.zeros(1)], False, []
+
+        def get_weights(self):
+            return [x.copy() for x in self.w]
+
+        def set_weights(self, w):
+            self.w = [x.copy() for x in w]
+
+        def save_weights(self, path):
+            self.saved.append(path)
+
+    stub = Stub()
+    es = model.EarlyStopping(patience=5)
+    ck = model.ModelCheckpoint("/tmp/m-checkpoint-{epoch:02d}-{val_loss:.2f}.h5")
+    for cb in (es, ck):
+        cb.set_model(stub)
+        cb.on_train_begin()
+    values = [0.1, 0.3, 0.2, 0.2, 0.2, 0.2, 0.2, 0.9]
+    ran = 0
+    for epoch, v in enumerate(values):
+        stub.w = [np.array([float(epoch)])]
+        for cb in (es, ck):
+            cb.on_epoch_end(epoch, {"val_output_dcg": v, "val_loss": 0.5})
+        ran += 1
+        if stub.stop_training:
+            break
+    from oracle import movierec_oracle as o
+    assert (ran, 1, True) == o.early_stopping_trace(values, 5)
+    assert stub.w[0][0] == 1.0  # best epoch's weights restored
+    assert stub.saved == ["/tmp/m-checkpoint-01-0.50.h5", "/tmp/m-checkpoint-02-0.50.h5"]
+
+
+# ---- data pipeline (reference test/test_data_pipeline.py) -----------------------------------------
+
+def test_wrong_database_name_load():
+    with pytest.raises(ValueError, match="Invalid dataset name"):
+        data_pipeline.load_ratings_train_test_sets("wrong db", "/tmp/")
+
+
+def test_load_ratings_train_test_sets(ref, monkeypatch):
+    v = ref["split"]
+    df = pd.DataFrame({"userId": v["userId"], "itemId": v["itemId"], "rating": v["rating"]})
+    monkeypatch.setattr(data_pipeline, "load_ratings_data", lambda *a, **k: df)
+    train, validation, test = data_pipeline.load_ratings_train_test_sets("ml-100k", "ml-100k", download=False)
+    for got, name in ((train, "train"), (validation, "validation"), (test, "test")):
+        pd.testing.assert_frame_equal(got, pd.DataFrame(v[name]), check_dtype=False)
+
+
+def test_split_handles_interleaved_users():
+    df = pd.DataFrame({"userId": [1, 0, 1, 0, 1, 0, 2, 2, 2], "itemId": [10, 20, 11, 21, 12, 22, 30, 31, 32],
+                       "rating": np.arange(9, dtype=np.float32)})
+    train, validation, test = data_pipeline.split_leave_last_two_out(df)
+    assert test.itemId.tolist() == [22, 12, 32] and validation.itemId.tolist() == [21, 11, 31]
+    assert train.itemId.tolist() == [20, 10, 30] and train.index.tolist() == [0, 1, 2]
+    from oracle import movierec_oracle as o
+    tr, va, te = o.leave_last_two_out(df.userId.values)
+    assert df.itemId.values[tr].tolist() == train.itemId.tolist()
+    assert df.itemId.values[va].tolist() == validation.itemId.tolist()
+    assert df.itemId.values[te].tolist() == test.itemId.tolist()
+
+
+def test_generator_value_errors(ref):
+    data = pd.DataFrame(ref["generator_duplicated_user"]["data"])
+    msgs = ref["generator_value_errors"]["messages"]
+    with pytest.raises(ValueError, match=msgs[0]):
+        data_pipeline.MovieLensDataGenerator("wrong_name", data, batch_size=6, negatives_per_positive=2)
+    with pytest.raises(ValueError, match=msgs[1]):
+        data_pipeline.MovieLensDataGenerator("ml-100k", data, batch_size=6, negatives_per_positive=0)
+    with pytest.raises(ValueError, match=msgs[2]):
+        data_pipeline.MovieLensDataGenerator("ml-100k", data, batch_size=10, negatives_per_positive=6)
+
+
+def test_generator_len_and_shuffle_follow_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "generator_batches.npz"))
+    df = pd.DataFrame({"userId": g["data_users"], "itemId": g["data_items"]})
+    np.random.seed(int(g["seed"]))
+    gen = data_pipeline.MovieLensDataGenerator("ml-100k", df, int(g["noextra_bs"]), int(g["noextra_negs"]), shuffle=True)
+    np.testing.assert_array_equal(gen.indexes, g["noextra_indexes"])  # same np.random.shuffle call as the reference
+    assert len(gen) == int(g["noextra_len"])
+    assert gen.num_users == 943 and gen.num_items == 1682 and gen.dataset_name == "ml-100k"
+    assert gen.num_positives_per_batch == 4 and gen.num_negatives_per_batch == 16
+
+
+def test_user_csr_matches_oracle():
+    from oracle import movierec_oracle as o
+    rng = np.random.default_rng(0)
+    users, items = rng.integers(0, 20, 300), rng.integers(0, 50, 300)
+    rowptr, csr = data_pipeline.build_user_csr(users, items)
+    rp, it = o.build_csr(int(users.max()) + 1, users, items)
+    np.testing.assert_array_equal(rowptr, rp)
+    np.testing.assert_array_equal(csr, it)
+
+
+def test_load_ratings_data_zero_based(tmp_path):
+    d = tmp_path / "ml-100k"
+    d.mkdir()
+    (d / "u.data").write_text("1\t1\t5\t881250949\n2\t3\t3\t891717742\n")
+    df = ml.load_ratings_data(str(tmp_path), "ml-100k")
+    assert df.userId.tolist() == [0, 1] and df.itemId.tolist() == [0, 2] and df.rating.tolist() == [5.0, 3.0]
+    with pytest.raises(FileNotFoundError):
+        ml.load_ratings_data(str(tmp_path), "ml-1m", download=False)
