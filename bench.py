@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""Benchmark of the NeuMF train step (BASELINE.json metric: NCF train samples/sec) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ml-20m|ml-1m] [--impl reference]
+
+One "step" = one optimisation step (forward + BCE + backward + deterministic embedding-gradient
+reduction + legacy-Keras dense Adam + train-batch HR/DCG) on one synthetic batch.  N > 1 runs under
+torchrun, one rank per GPU, weak scaling (every rank has its own batch of the same size), gradients
+summed with one NCCL all-reduce per step.  Prints ONE JSON line on rank 0.
+
+`--impl reference` times the CPU restatement of the reference's Keras path (oracle/, NumPy fp32,
+all host threads BLAS will use) on a bounded sample of the same workload; TensorFlow is not
+installable here, so this is the "port" kind of baseline.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "movierecommender-tf-trt_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: ML-20M shape, embed dim 64 (GMF), MLP 256-128-64 (C-20M)
+    "ml-20m": dict(num_users=138493, num_items=26744, layers=[256, 128, 64], mf_dim=64, negs=4,
+                   batch=5 * 2 ** 18, eval_negs=99, k_eval=10, cpu_batch=5 * 2 ** 13, cpu_eval_users=2048),
+    # BASELINE.json configs[1]: ML-1M shape, reference default tower + GMF 8
+    "ml-1m": dict(num_users=6040, num_items=3706, layers=[64, 32, 16, 8], mf_dim=8, negs=4,
+                  batch=5 * 2 ** 16, eval_negs=99, k_eval=10, cpu_batch=5 * 2 ** 14, cpu_eval_users=6040),
+}
+METRIC = "ncf_train_samples_per_sec"
+UNIT = "samples/s"
+
+
+def synth_batches(wl, n_batches, seed, rows=None):
+    """MovieLens-shaped synthetic batches: users with a lognormal activity tail, positive
+    items Zipf-distributed over a fixed permutation, negatives uniform, generator layout
+    (users repeated per group, negatives first, positive last, labels [0]*negs+[1])."""
+    rng = np.random.default_rng(seed)
+    nu, ni, negs = wl["num_users"], wl["num_items"], wl["negs"]
+    rows = wl["batch"] if rows is None else rows
+    groups = rows // (negs + 1)
+    act = 20.0 + rng.lognormal(3.0, 1.0, nu)
+    act_cdf = np.cumsum(act / act.sum())
+    zipf = 1.0 / (np.arange(ni) + 1.0)
+    zipf_cdf = np.cumsum(zipf / zipf.sum())
+    perm = rng.permutation(ni)
+    out = []
+    for _ in range(n_batches):
+        u = np.minimum(np.searchsorted(act_cdf, rng.random(groups)), nu - 1).astype(np.int32)
+        pos = perm[np.minimum(np.searchsorted(zipf_cdf, rng.random(groups)), ni - 1)].astype(np.int32)
+        items = rng.integers(0, ni, (groups, negs + 1), dtype=np.int32)
+        items[:, -1] = pos
+        users = np.repeat(u, negs + 1)
+        y = np.tile(np.array([0] * negs + [1], np.float32), groups)
+        out.append((users, items.reshape(-1), y))
+    return out
+
+
+def synth_eval(wl, n_users, seed):
+    rng = np.random.default_rng(seed)
+    group = wl["eval_negs"] + 1
+    users = np.arange(n_users, dtype=np.int32) % wl["num_users"]
+    items = rng.integers(0, wl["num_items"], n_users * group, dtype=np.int32)
+    return users, items, group
+
+
+def model_params(wl, rows):
+    n = len(wl["layers"])
+    return {"num_users": wl["num_users"], "num_items": wl["num_items"], "layers_sizes": wl["layers"],
+            "layers_l2reg": [0] * n, "optimizer": "adam", "lr": 0.001, "beta_1": 0.9, "beta_2": 0.999,
+            "batch_size": rows, "num_negs_per_pos": wl["negs"],
+            "batch_size_eval": (wl["eval_negs"] + 1) * 2, "num_negs_per_pos_eval": wl["eval_negs"],
+            "k": wl["negs"] + 1, "mf_dim": wl["mf_dim"], "adam_mode": "dense", "seed": 1}
+
+
+def algorithmic_bytes(wl, rows):
+    """A_train = B*(4*(d_U+d_I)+12) + 24*(rows of both tables, dense-Adam form) + 24*P_d;
+    the fused tile kernel alone moves the first term."""
+    L, f = wl["layers"], wl["mf_dim"]
+    d_u = L[0] // 2
+    d_i = L[0] - d_u
+    dU, dI = d_u + f, d_i + f
+    p_dense = sum(L[i - 1] * L[i] + L[i] for i in range(1, len(L))) + f + L[-1] + 1
+    tile = rows * (4 * (dU + dI) + 12)
+    step = tile + 24 * (wl["num_users"] * dU + wl["num_items"] * dI) + 24 * p_dense
+    f_fwd = 2 * (sum(L[i - 1] * L[i] for i in range(1, len(L))) + L[-1] + f) + f
+    eval_per_user = 4 * dU + (wl["eval_negs"] + 1) * (4 * dI + 4) + 4
+    return dict(tile=tile, step=step, flops_step=3 * rows * f_fwd, f_fwd=f_fwd, eval_per_user=eval_per_user)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU restatement (oracle) timing: cpu_baseline leg and --impl reference
+# ---------------------------------------------------------------------------------------------------
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        return int(max(n)) if n else 1
+    except Exception:
+        return int(os.cpu_count() or 1)
+
+
+def time_oracle_train(wl, steps, warmup):
+    """Oracle train steps (NumPy fp32: forward, BCE, backward with batch-order scatter, legacy-Keras
+    dense Adam over the full tables, train-batch HR/DCG) on `cpu_batch` rows per step."""
+    from oracle import movierec_oracle as o
+    rows = wl["cpu_batch"]
+    params = model_params(wl, rows)
+    w = o.init_weights(wl["num_users"], wl["num_items"], wl["layers"], wl["mf_dim"], np.random.default_rng(1))
+    st = o.new_opt_state(w)
+    batches = synth_batches(wl, 2, seed=0, rows=rows)
+    for i in range(warmup):
+        o.train_step(w, st, *batches[i % 2], params)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        o.train_step(w, st, *batches[i % 2], params)
+    dt = time.perf_counter() - t0
+    return rows * steps / dt, dt / steps * 1e3, rows
+
+
+def time_oracle_eval(wl, reps=2):
+    from oracle import movierec_oracle as o
+    w = o.init_weights(wl["num_users"], wl["num_items"], wl["layers"], wl["mf_dim"], np.random.default_rng(1))
+    users, items, group = synth_eval(wl, wl["cpu_eval_users"], seed=2)
+    o.evaluate_groups(w, users, items, group, wl["k_eval"])
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        o.evaluate_groups(w, users, items, group, wl["k_eval"])
+    dt = (time.perf_counter() - t0) / reps
+    return len(users) / dt
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, ms, rows = time_oracle_train(wl, args.steps, args.warmup)
+    threads = blas_threads()
+    sample = ("oracle (NumPy fp32 restatement of the reference's Keras train_on_batch, dense Adam over the full "
+              "tables) on {} rows/step of the {} workload, {} steps".format(rows, args.workload, args.steps))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, wl, rows_override=rows),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def config_dict(args, wl, rows_override=None):
+    return {"workload": "{} shape: {} users x {} items, NeuMF layers {} mf_dim {}, {} negatives/positive, "
+                        "Adam (legacy Keras, dense over tables)".format(args.workload, wl["num_users"], wl["num_items"],
+                                                                       wl["layers"], wl["mf_dim"], wl["negs"]),
+            "baseline_config": "BASELINE.json configs[{}]".format(2 if args.workload == "ml-20m" else 1),
+            "rows_per_step_per_gpu": wl["batch"] if rows_override is None else rows_override,
+            "global_rows_per_step": (wl["batch"] if rows_override is None else rows_override) * args.gpus,
+            "parallelism": "dp{} replicated tables, one all-reduce of dense+table gradients".format(args.gpus),
+            "l2_policy": "working set larger than L2: 4 rotating batches; staged row gradients (~{:.1f} GB/step) and "
+                         "tables+Adam state exceed the 126 MB L2".format(wl["batch"] * 4 * (sum(wl["layers"][:1]) + 2 * wl["mf_dim"]) / 1e9)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+
+def run_gpu(args, wl):
+    import torch
+    import torch.distributed as dist
+    from movierec import _native as nat
+    from movierec.model import MovierecModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus {} needs torchrun (one process per GPU); see the module docstring".format(args.gpus))
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dp = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    rows = wl["batch"]
+    group = wl["negs"] + 1
+    out_dir = tempfile.mkdtemp(prefix="movierec_bench_")
+    model = MovierecModel(model_params(wl, rows), "bench", out_dir, verbose=0)
+    eng = model.model.engine
+    if world > 1:
+        from movierec._distributed import DataParallelNeuMF
+        dp = DataParallelNeuMF(eng)
+        dp.broadcast_parameters(0)
+
+    n_batches = 4
+    host = synth_batches(wl, n_batches, seed=1000 + rank)
+    pinned = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in host]
+    resident = [tuple(t.to(dev) for t in b) for b in pinned]
+    global_rows = rows * world
+
+    def step_resident(i):
+        u, it, y = resident[i % n_batches]
+        if dp is None:
+            return eng.train_step(u, it, y, group=group, k=group)
+        return dp.train_step(u, it, y, global_rows, group=group, k=group)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sync_all()
+
+    # ---- timed region: inputs resident in HBM ------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nat.profile_begin()
+    sync_all()
+    ev0.record()
+    last = None
+    for i in range(args.steps):
+        last = step_resident(args.warmup + i)
+    ev1.record()
+    sync_all()
+    phases, launches = nat.profile_end()
+    ms_total = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = global_rows * args.steps / (ms_total / 1e3)
+    final = last.cpu().numpy()
+    if final[4] != 0 or not np.isfinite(final[0]):
+        raise SystemExit("bench produced invalid step outputs: {}".format(final))
+
+    # ---- end to end through the public API: host buffers in, loss out, every step ------------------
+    def step_e2e(i):
+        u, it, y = pinned[i % n_batches]
+        if dp is None:
+            return model.model.train_on_batch([u, it], y)  # uploads, steps, reads the loss back
+        out = dp.train_step(u, it, y, global_rows, group=group, k=group)
+        return out.cpu()
+
+    e2e_steps = 0 if args.lean else max(3, min(args.steps, 20))
+    if not args.lean:
+        step_e2e(0)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step_e2e(i + 1)
+    sync_all()
+    e2e_s = max(time.perf_counter() - t0, 1e-9)
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = global_rows * e2e_steps / float(t.item())
+
+    # ---- ranking eval: HR@10 users/sec (second half of the BASELINE metric), rank 0's replica ------
+    eval_obj = None
+    if rank == 0 and not args.lean:
+        n_eval = wl["num_users"]
+        eu, ei, egroup = synth_eval(wl, n_eval, seed=2)
+        eu_d, ei_d = torch.from_numpy(eu).to(dev), torch.from_numpy(ei).to(dev)
+        for _ in range(2):
+            eng.rank_eval(eu_d, ei_d, egroup, wl["k_eval"])
+        torch.cuda.synchronize(dev)
+        nat.profile_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            pos, sums, _, _ = eng.rank_eval(eu_d, ei_d, egroup, wl["k_eval"])
+        e1.record()
+        torch.cuda.synchronize(dev)
+        eph, _ = nat.profile_end()
+        ems = e0.elapsed_time(e1) / reps
+        ab = algorithmic_bytes(wl, rows)
+        peak, peak_kind = measured_peaks()
+        fwd_ms = eph["tile_forward"][0] / max(eph["tile_forward"][1], 1)
+        ach = ab["eval_per_user"] * n_eval / (fwd_ms / 1e3) / 1e9
+        eval_obj = {"metric": "hr10_eval_users_per_sec", "value": n_eval / (ems / 1e3), "unit": "users/s",
+                    "users": n_eval, "candidates_per_user": egroup, "k": wl["k_eval"], "ms": ems,
+                    "hr_at_k": float(sums[0].item()) / n_eval, "ndcg_at_k": float(sums[1].item()) / n_eval,
+                    "roofline": {"bound": "hbm", "kernel": "neumf_tile_kernel<TM,false>", "achieved": ach, "peak": peak,
+                                 "unit": "GB/s", "frac": ach / peak, "peak_kind": peak_kind, "traffic": None}}
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ab = algorithmic_bytes(wl, rows)
+    peak, peak_kind = measured_peaks()
+    tile_ms, tile_n = phases["tile_train"]
+    tile_avg_ms = tile_ms / max(tile_n, 1)
+    achieved = ab["tile"] / (tile_avg_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {}).get("tile_train_dram_bytes_per_launch")
+    step_ms = ms_total / args.steps
+    if args.lean:
+        cpu_value, cpu_ms, cpu_rows, cpu_eval = None, None, 0, None
+    else:
+        cpu_value, cpu_ms, cpu_rows = time_oracle_train(wl, steps=4, warmup=1)
+        cpu_eval = time_oracle_eval(wl)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(args, wl),
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rows * 12, "d2h_bytes_per_step": 32,
+                "steps": e2e_steps, "api": "MovierecModel.model.train_on_batch([x_users, x_items], y) on pinned host arrays"
+                if dp is None else "DataParallelNeuMF.train_step on pinned host arrays"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "neumf_tile_kernel<TM,true> (fused gather+tower+head+BCE+backward)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_kind": peak_kind, "algorithmic_bytes_per_launch": ab["tile"], "avg_launch_ms": tile_avg_ms,
+                     "launches_timed": tile_n, "share_of_step": tile_avg_ms / step_ms,
+                     "note": "compute-bound on fp32 CUDA cores at this arithmetic intensity (SURVEY 0-7); "
+                             "fp32 TFLOP/s of the step below"},
+        "step_roofline": {"algorithmic_bytes_per_step": ab["step"], "achieved_gbs": ab["step"] / (step_ms / 1e3) / 1e9,
+                          "frac_of_hbm_peak": ab["step"] / (step_ms / 1e3) / 1e9 / peak,
+                          "fp32_tflops": ab["flops_step"] / (step_ms / 1e3) / 1e12},
+        "phase_ms_per_step": {k: v[0] / args.steps for k, v in phases.items() if v[1]},
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+                         "host_cores": os.cpu_count(),
+                         "sample": "oracle NumPy fp32 train step (dense Adam over the full tables) on {} rows/step, "
+                                   "4 steps after 1 warm-up; eval: {} users x {} candidates".format(
+                                       cpu_rows, wl["cpu_eval_users"], wl["eval_negs"] + 1),
+                         "eval_users_per_sec": cpu_eval},
+        "eval": eval_obj,
+        "final_loss": float(final[0]) / rows,
+    }
+    if args.lean:
+        line["lean"] = True
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ml-20m", choices=sorted(WORKLOADS))
+    ap.add_argument("--lean", action="store_true",
+                    help="profiling runs (ncu): skip the e2e, eval and CPU-baseline legs; not a bench value")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_gpu(args, wl)
+
+
+if __name__ == "__main__":
+    main()

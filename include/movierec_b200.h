@@ -168,6 +168,23 @@ int mr_sample_negatives(const int64_t* csr_rowptr, const int32_t* csr_items, int
                         int64_t first_index, int32_t negs, uint64_t seed, uint64_t epoch,
                         int32_t* out_users, int32_t* out_items, float* out_labels, void* stream);
 
+/* Opt-in profiling for benchmarks (thread-local): between mr_profile_begin and mr_profile_end every
+ * entry point records CUDA events on the caller's stream at its phase boundaries.  mr_profile_end
+ * synchronises on the last event and returns, per phase, the summed device time in ms and the
+ * number of intervals, plus the number of kernels this library launched since mr_profile_begin.
+ * All three outputs are [host] arrays/scalars; MR_NUM_PHASES entries each for the first two. */
+enum { MR_PHASE_TILE_TRAIN = 0, /* fused gather+tower+head+BCE+backward kernel */
+       MR_PHASE_MISC = 1,       /* transposes, dense-gradient reduction, loss sum, memsets */
+       MR_PHASE_SORT = 2,       /* radix sort of row ids */
+       MR_PHASE_SEGREDUCE = 3,  /* segmented reduction + row update */
+       MR_PHASE_OPTIMIZER = 4,  /* Adam / SGD sweeps */
+       MR_PHASE_TILE_FORWARD = 5, /* fused forward kernel (predict / eval) */
+       MR_PHASE_RANK = 6,       /* positions + metric sums */
+       MR_PHASE_SAMPLER = 7,
+       MR_NUM_PHASES = 8 };
+int mr_profile_begin(void);
+int mr_profile_end(float* phase_ms, int64_t* phase_count, int64_t* kernel_launches);
+
 /* Building blocks exposed for tests and for data-parallel callers. */
 /* Stable LSD radix sort of (key, original index) pairs on the low `key_bits` bits. */
 size_t mr_sort_workspace_bytes(int64_t n);

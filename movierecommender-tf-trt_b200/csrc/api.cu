@@ -5,6 +5,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "launchers.h"
 #include "neumf_tile.cuh"
 
@@ -41,6 +43,42 @@ int sm_count() {
     cached_dev = dev;
   }
   return cached;
+}
+
+// ---- opt-in profiling (thread-local) -----------------------------------------------------------------
+struct Profiler {
+  bool on = false;
+  bool overflow = false;
+  std::vector<cudaEvent_t> events;
+  std::vector<int> phase;
+  size_t used = 0;
+  int64_t launches = 0;
+};
+static thread_local Profiler g_prof;
+constexpr size_t kMaxProfEvents = 1 << 16;
+
+void count_launch() { g_prof.launches += 1; }
+
+void prof_mark(int phase, cudaStream_t st) {
+  Profiler& p = g_prof;
+  if (!p.on) return;
+  if (p.used >= kMaxProfEvents) {
+    p.overflow = true;
+    return;
+  }
+  if (p.used == p.events.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) {
+      cudaGetLastError();
+      p.overflow = true;
+      return;
+    }
+    p.events.push_back(e);
+    p.phase.push_back(-1);
+  }
+  cudaEventRecord(p.events[p.used], st);
+  p.phase[p.used] = phase;
+  p.used += 1;
 }
 
 __global__ void flag_to_float_kernel(const int32_t* flags, float* out) { *out = (float)flags[0]; }
@@ -170,6 +208,7 @@ int mr_device_sm_count(void) {
 
 int mr_gather_rows(const float* table, int64_t rows, int32_t dim, const int32_t* idx, int64_t n, float* out,
                    void* stream) {
+  if (n == 0) return MR_OK;  // empty batch: nothing to read or write (pointers may be NULL)
   MR_REQUIRE(table && idx && out, "gather: NULL pointer");
   MR_REQUIRE(rows > 0 && dim > 0 && n >= 0, "gather: bad sizes rows=%lld dim=%d n=%lld", (long long)rows, dim, (long long)n);
   return launch_gather_rows(table, rows, dim, idx, n, out, (cudaStream_t)stream);
@@ -186,7 +225,12 @@ int mr_neumf_forward(const MrModel* model, const int32_t* users, const int32_t* 
                      void* stream) {
   int rc = check_model(model);
   if (rc != MR_OK) return rc;
-  MR_REQUIRE(users && items && B >= 0, "forward: NULL ids or negative B");
+  MR_REQUIRE(B >= 0, "forward: negative B");
+  if (B == 0) {  // empty batch (pointers may be NULL): only the loss sum is defined
+    if (loss_sum != nullptr) MR_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(float), (cudaStream_t)stream));
+    return MR_OK;
+  }
+  MR_REQUIRE(users && items, "forward: NULL ids");
   MR_REQUIRE(user_div >= 1, "forward: user_div must be >= 1");
   MR_REQUIRE(ws != nullptr, "forward: workspace is NULL");
   if (ws_bytes < mr_forward_workspace_bytes(model, B)) {
@@ -212,10 +256,12 @@ int mr_neumf_forward(const MrModel* model, const int32_t* users, const int32_t* 
   a.loss_partial = loss_partial;
   a.flags = flags;
   int grid = 0;
+  prof_mark(MR_PHASE_TILE_FORWARD, st);
   rc = launch_neumf_tiles(a, st, &grid);
-  if (rc != MR_OK) return rc;
-  if (loss_sum != nullptr) return launch_sum_partials(loss_partial, grid, loss_sum, st);
-  return MR_OK;
+  prof_mark(MR_PHASE_MISC, st);
+  if (rc == MR_OK && loss_sum != nullptr) rc = launch_sum_partials(loss_partial, grid, loss_sum, st);
+  prof_mark(-1, st);
+  return rc;
 }
 
 size_t mr_train_workspace_bytes(const MrModel* model, int64_t B) {
@@ -242,6 +288,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   TrainWs t = carve_train(m, B, ws);
   const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
 
+  prof_mark(MR_PHASE_MISC, st);
   MR_CUDA(cudaMemsetAsync(t.flags, 0, 256, st));
   MR_CUDA(cudaMemsetAsync(step_out, 0, MR_STEP_OUT_FLOATS * sizeof(float), st));
   rc = launch_transpose_kernels(m, t.wt, st);
@@ -265,7 +312,9 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   a.stage_i = t.stage_i;
   a.flags = t.flags;
   int grid = 0;
+  prof_mark(MR_PHASE_TILE_TRAIN, st);
   rc = launch_neumf_tiles(a, st, &grid);
+  prof_mark(MR_PHASE_MISC, st);
   if (rc != MR_OK) return rc;
   rc = launch_dense_reduce(m, t.dense_partial, t.dense_stride, grid, grads->dense, st);
   if (rc != MR_OK) return rc;
@@ -291,10 +340,12 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   }
 
   if (group > 0) {
+    prof_mark(MR_PHASE_RANK, st);
     rc = launch_rank_scores(t.probs, B / group, group, k, nullptr, nullptr, t.pos, step_out + MR_OUT_HIT_SUM,
                             t.rank_partials, st);
     if (rc != MR_OK) return rc;
   }
+  prof_mark(MR_PHASE_MISC, st);
 
   // ---- embedding rows: stable sort by row id, segmented reduce in batch order, row update -------
   const bool dense_mode = opt->table_mode == MR_TABLES_DENSE;
@@ -315,21 +366,26 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     }
   }
   // users
+  prof_mark(MR_PHASE_SORT, st);
   rc = launch_sort_pairs(users, B, bits_for(m.num_users), t.sorted_keys, t.sorted_index, t.sort_ws, t.sort_ws_bytes, st);
   if (rc != MR_OK) return rc;
   u.d0 = d_u;
   u.d1 = m.mf_dim;
   u.p0 = m.user_mlp; u.m0 = opt->m_user_mlp; u.v0 = opt->v_user_mlp; u.g0 = grads->user_mlp;
   u.p1 = m.user_gmf; u.m1 = opt->m_user_gmf; u.v1 = opt->v_user_gmf; u.g1 = grads->user_gmf;
+  prof_mark(MR_PHASE_SEGREDUCE, st);
   rc = launch_segreduce(t.sorted_keys, t.sorted_index, B, t.stage_u, u, st);
   if (rc != MR_OK) return rc;
   // items
+  prof_mark(MR_PHASE_SORT, st);
   rc = launch_sort_pairs(items, B, bits_for(m.num_items), t.sorted_keys, t.sorted_index, t.sort_ws, t.sort_ws_bytes, st);
   if (rc != MR_OK) return rc;
   u.d0 = d_i;
   u.p0 = m.item_mlp; u.m0 = opt->m_item_mlp; u.v0 = opt->v_item_mlp; u.g0 = grads->item_mlp;
   u.p1 = m.item_gmf; u.m1 = opt->m_item_gmf; u.v1 = opt->v_item_gmf; u.g1 = grads->item_gmf;
+  prof_mark(MR_PHASE_SEGREDUCE, st);
   rc = launch_segreduce(t.sorted_keys, t.sorted_index, B, t.stage_i, u, st);
+  prof_mark(-1, st);
   return rc;
 }
 
@@ -343,6 +399,7 @@ int mr_neumf_apply(MrModel* model, MrOptState* opt, const MrGrads* grads, void* 
   const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
   const bool adam = opt->optimizer == MR_OPT_ADAM;
   const float lr_t = adam ? adam_lr_t(*opt, opt->iterations + 1) : opt->lr;
+  prof_mark(MR_PHASE_OPTIMIZER, st);
   rc = launch_optimizer_flat(m.dense, grads->dense, opt->m_dense, opt->v_dense, m.dense_count, opt->optimizer, lr_t,
                              opt->beta_1, opt->beta_2, opt->epsilon, 0.f, st);
   if (rc != MR_OK) return rc;
@@ -363,6 +420,7 @@ int mr_neumf_apply(MrModel* model, MrOptState* opt, const MrGrads* grads, void* 
                                  opt->epsilon, l2, st);
     if (rc != MR_OK) return rc;
   }
+  prof_mark(-1, st);
   opt->iterations += 1;
   return MR_OK;
 }
@@ -397,7 +455,10 @@ int mr_rank_eval(const MrModel* model, const int32_t* users, const int32_t* item
   float* pr = probs != nullptr ? probs : probs_buf;
   int rc = mr_neumf_forward(model, users, items, G * group, group, nullptr, pr, nullptr, nullptr, ws, fwd_bytes, stream);
   if (rc != MR_OK) return rc;
-  return launch_rank_scores(pr, G, group, k, nullptr, rank, pos, sums, partials, (cudaStream_t)stream);
+  prof_mark(MR_PHASE_RANK, (cudaStream_t)stream);
+  rc = launch_rank_scores(pr, G, group, k, nullptr, rank, pos, sums, partials, (cudaStream_t)stream);
+  prof_mark(-1, (cudaStream_t)stream);
+  return rc;
 }
 
 size_t mr_rank_scores_workspace_bytes(int64_t G) { return align_up(rank_partials_count(G < 0 ? 0 : G) * sizeof(float), 256); }
@@ -422,8 +483,42 @@ int mr_sample_negatives(const int64_t* csr_rowptr, const int32_t* csr_items, int
   MR_REQUIRE(csr_rowptr && csr_items && pos_users && pos_items, "sample_negatives: NULL pointer");
   MR_REQUIRE(P >= 0 && num_items > 0, "sample_negatives: bad sizes");
   MR_REQUIRE(negs >= 1 && negs <= MR_MAX_NEGS, "sample_negatives: negs=%d out of [1,%d]", negs, MR_MAX_NEGS);
-  return launch_sample_negatives(csr_rowptr, csr_items, num_items, pos_users, pos_items, P, first_index, negs, seed,
-                                 epoch, out_users, out_items, out_labels, (cudaStream_t)stream);
+  prof_mark(MR_PHASE_SAMPLER, (cudaStream_t)stream);
+  int rc = launch_sample_negatives(csr_rowptr, csr_items, num_items, pos_users, pos_items, P, first_index, negs, seed,
+                                   epoch, out_users, out_items, out_labels, (cudaStream_t)stream);
+  prof_mark(-1, (cudaStream_t)stream);
+  return rc;
+}
+
+int mr_profile_begin(void) {
+  g_prof.on = true;
+  g_prof.overflow = false;
+  g_prof.used = 0;
+  g_prof.launches = 0;
+  return MR_OK;
+}
+
+int mr_profile_end(float* phase_ms, int64_t* phase_count, int64_t* kernel_launches) {
+  Profiler& p = g_prof;
+  MR_REQUIRE(p.on, "mr_profile_end without mr_profile_begin");
+  p.on = false;
+  for (int i = 0; i < MR_NUM_PHASES; ++i) {
+    if (phase_ms) phase_ms[i] = 0.f;
+    if (phase_count) phase_count[i] = 0;
+  }
+  if (kernel_launches) *kernel_launches = p.launches;
+  if (p.used > 0) MR_CUDA(cudaEventSynchronize(p.events[p.used - 1]));
+  for (size_t i = 0; i + 1 < p.used; ++i) {
+    const int ph = p.phase[i];
+    if (ph < 0 || ph >= MR_NUM_PHASES) continue;
+    float ms = 0.f;
+    MR_CUDA(cudaEventElapsedTime(&ms, p.events[i], p.events[i + 1]));
+    if (phase_ms) phase_ms[ph] += ms;
+    if (phase_count) phase_count[ph] += 1;
+  }
+  p.used = 0;
+  MR_REQUIRE(!p.overflow, "profile event buffer overflowed; profile fewer steps");
+  return MR_OK;
 }
 
 size_t mr_sort_workspace_bytes(int64_t n) { return sort_workspace_bytes(n < 0 ? 0 : n); }

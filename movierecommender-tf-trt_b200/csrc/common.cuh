@@ -35,7 +35,13 @@ int cuda_fail(cudaError_t e, const char* what);
   do {                                                         \
     cudaError_t e__ = cudaGetLastError();                      \
     if (e__ != cudaSuccess) return mr::cuda_fail(e__, name);   \
+    mr::count_launch();                                        \
   } while (0)
+
+// Opt-in, thread-local profiling (mr_profile_begin / mr_profile_end): CUDA events recorded on the
+// caller's stream at phase boundaries, and a count of this library's kernel launches.
+void count_launch();
+void prof_mark(int phase, cudaStream_t st);  // phase < 0 closes the current interval
 
 int sm_count();  // cached per thread; <0 on error
 

@@ -121,8 +121,17 @@ class NeuMFEngine(object):
         self.v = {k: z(t) for k, t in self._tables.items()} if adam else {}
         self.m_dense = z(self.dense) if adam else None
         self.v_dense = z(self.dense) if adam else None
-        self.g_dense = torch.zeros_like(self.dense)
-        self.g_tables = {k: torch.zeros_like(t) for k, t in self._tables.items()} if table_mode == "dense" else {}
+        # one flat gradient buffer [dense | tables...] so a data-parallel caller all-reduces once
+        sizes = [self.dense_count] + ([t.numel() for t in self._tables.values()] if table_mode == "dense" else [])
+        pad = lambda x: (x + 63) // 64 * 64  # keep every slice 256-byte aligned (128-bit kernel accesses)
+        self.g_flat = torch.zeros(sum(pad(x) for x in sizes), dtype=f32, device=dev)
+        self.g_dense = self.g_flat[:self.dense_count]
+        self.g_tables = {}
+        off = pad(self.dense_count)
+        if table_mode == "dense":
+            for k, t in self._tables.items():
+                self.g_tables[k] = self.g_flat[off:off + t.numel()].view_as(t)
+                off += pad(t.numel())
         self.step_out = torch.zeros(nat.MR_STEP_OUT_FLOATS, dtype=f32, device=dev)
         self._ws = None
         self._structs()
@@ -246,8 +255,8 @@ class NeuMFEngine(object):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def gradient_tensors(self):
-        """Flat gradient buffers a data-parallel caller all-reduces between train_grads and apply."""
-        return [self.g_dense] + [self.g_tables[k] for k in self._tables if k in self.g_tables]
+        """The flat gradient buffer a data-parallel caller all-reduces between train_grads and apply."""
+        return [self.g_flat]
 
     # ---- hot path ---------------------------------------------------------------------------------
     def forward(self, users, items, user_div=1, labels=None, want_logits=True, want_probs=True):

@@ -81,6 +81,8 @@ SIGNATURES = {
     "mr_sample_negatives": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i64, _i64, _i32, _u64, _u64, _vp, _vp, _vp, _vp]),
     "mr_sort_workspace_bytes": (_sz, [_i64]),
     "mr_sort_pairs": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "mr_profile_begin": (C.c_int, []),
+    "mr_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mr_optimizer_flat": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _f, _f, _f, _vp]),
 }
 
@@ -109,6 +111,23 @@ def last_error():
 def check(rc, what):
     if rc != 0:
         raise MovierecNativeError("{} failed (status {}): {}".format(what, rc, last_error()))
+
+
+NUM_PHASES = 8
+PHASE_NAMES = ["tile_train", "misc", "sort", "segreduce", "optimizer", "tile_forward", "rank", "sampler"]
+
+
+def profile_begin():
+    check(lib.mr_profile_begin(), "mr_profile_begin")
+
+
+def profile_end():
+    """-> ({phase: (ms, intervals)}, kernel launches since profile_begin)."""
+    ms = (C.c_float * NUM_PHASES)()
+    cnt = (C.c_int64 * NUM_PHASES)()
+    launches = C.c_int64(0)
+    check(lib.mr_profile_end(ms, cnt, C.byref(launches)), "mr_profile_end")
+    return {PHASE_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(NUM_PHASES)}, int(launches.value)
 
 
 def version():
