@@ -135,6 +135,8 @@ struct TrainWs {
   int32_t* sorted_index;
   void* sort_ws;
   size_t sort_ws_bytes;
+  void* seg_ws;
+  size_t seg_ws_bytes;
   int32_t* pos;
   float* rank_partials;
   size_t total;
@@ -157,6 +159,8 @@ static TrainWs carve_train(const MrModel& m, int64_t B, void* ws) {
   t.sorted_index = cv.take<int32_t>(B);
   t.sort_ws_bytes = sort_workspace_bytes(B);
   t.sort_ws = cv.take<char>(t.sort_ws_bytes);
+  t.seg_ws_bytes = segreduce_workspace_bytes(B, (d_u > d_i ? d_u : d_i) + m.mf_dim);
+  t.seg_ws = cv.take<char>(t.seg_ws_bytes);
   t.pos = cv.take<int32_t>(B);
   t.rank_partials = cv.take<float>(rank_partials_count(B));
   t.total = cv.off;
@@ -374,7 +378,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   u.p0 = m.user_mlp; u.m0 = opt->m_user_mlp; u.v0 = opt->v_user_mlp; u.g0 = grads->user_mlp;
   u.p1 = m.user_gmf; u.m1 = opt->m_user_gmf; u.v1 = opt->v_user_gmf; u.g1 = grads->user_gmf;
   prof_mark(MR_PHASE_SEGREDUCE, st);
-  rc = launch_segreduce(t.sorted_keys, t.sorted_index, B, t.stage_u, u, st);
+  rc = launch_segreduce(t.sorted_keys, t.sorted_index, B, t.stage_u, u, t.seg_ws, t.seg_ws_bytes, st);
   if (rc != MR_OK) return rc;
   // items
   prof_mark(MR_PHASE_SORT, st);
@@ -384,7 +388,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   u.p0 = m.item_mlp; u.m0 = opt->m_item_mlp; u.v0 = opt->v_item_mlp; u.g0 = grads->item_mlp;
   u.p1 = m.item_gmf; u.m1 = opt->m_item_gmf; u.v1 = opt->v_item_gmf; u.g1 = grads->item_gmf;
   prof_mark(MR_PHASE_SEGREDUCE, st);
-  rc = launch_segreduce(t.sorted_keys, t.sorted_index, B, t.stage_i, u, st);
+  rc = launch_segreduce(t.sorted_keys, t.sorted_index, B, t.stage_i, u, t.seg_ws, t.seg_ws_bytes, st);
   prof_mark(-1, st);
   return rc;
 }

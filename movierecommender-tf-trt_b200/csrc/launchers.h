@@ -53,8 +53,9 @@ struct RowUpdate {       // what to do with each reduced row gradient
   float *p0, *m0, *v0, *g0;  // table / Adam state / dense gradient table (mode DENSE writes g)
   float *p1, *m1, *v1, *g1;
 };
+size_t segreduce_workspace_bytes(int64_t n, int ld);
 int launch_segreduce(const int32_t* sorted_keys, const int32_t* sorted_index, int64_t n, const float* staged,
-                     const RowUpdate& u, cudaStream_t st);
+                     const RowUpdate& u, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // ---- optimizer.cu ----------------------------------------------------------------------------
 int launch_optimizer_flat(float* p, const float* g, float* m, float* v, int64_t n, int optimizer, float lr_t,

@@ -36,50 +36,69 @@ __global__ void __launch_bounds__(kSortWarps * 32) radix_hist_kernel(const int32
   }
 }
 
-// In-place exclusive scan of `total` counters by one CTA (total = 256 * nwt, a few 100K at most).
-__global__ void __launch_bounds__(1024) radix_scan_kernel(unsigned* __restrict__ hist, int64_t total) {
-  __shared__ unsigned warp_tot[32];
+// Per-digit exclusive scan over the warp tiles: CTA `bin` scans row hist[bin][0..nwt) in place and
+// writes the row total.  256 CTAs run in parallel (a single-CTA scan of the whole matrix cost 0.31 ms
+// per pass at 1.3 M keys); the 256 digit bases are folded into the scatter kernel.
+__global__ void __launch_bounds__(256) radix_rowscan_kernel(unsigned* __restrict__ hist, int64_t nwt,
+                                                            unsigned* __restrict__ totals) {
+  __shared__ unsigned warp_tot[8];
+  __shared__ unsigned carry;
+  unsigned* row = hist + (size_t)blockIdx.x * nwt;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int64_t per = (total + blockDim.x - 1) / blockDim.x;
-  const int64_t lo = min(total, per * tid), hi = min(total, lo + per);
-  unsigned s = 0;
-  for (int64_t i = lo; i < hi; ++i) s += hist[i];
-  unsigned incl = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) warp_tot[w] = incl;
+  if (tid == 0) carry = 0;
   __syncthreads();
-  if (w == 0) {
-    unsigned t = warp_tot[lane];
-    unsigned it = t;
+  for (int64_t t0 = 0; t0 < nwt; t0 += 256) {
+    const int64_t i = t0 + tid;
+    const unsigned v = i < nwt ? row[i] : 0u;
+    unsigned incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned u = __shfl_up_sync(0xffffffffu, it, o);
-      if (lane >= o) it += u;
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    warp_tot[lane] = it - t;  // exclusive prefix of warp totals
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    unsigned before = carry;
+    for (int q = 0; q < w; ++q) before += warp_tot[q];
+    if (i < nwt) row[i] = before + incl - v;
+    __syncthreads();
+    if (tid == 255) carry = before + incl;
+    __syncthreads();
   }
-  __syncthreads();
-  unsigned run = warp_tot[w] + (incl - s);
-  for (int64_t i = lo; i < hi; ++i) {
-    const unsigned v = hist[i];
-    hist[i] = run;
-    run += v;
-  }
+  if (tid == 0) totals[blockIdx.x] = carry;
 }
 
 // Scatter pass: keys (and their payload index) move to their stable position for this digit.
 __global__ void __launch_bounds__(kSortWarps * 32) radix_scatter_kernel(
     const int32_t* __restrict__ keys, const int32_t* __restrict__ index /* null = identity */, int64_t n, int shift,
-    const unsigned* __restrict__ hist, int64_t nwt, int32_t* __restrict__ out_keys, int32_t* __restrict__ out_index) {
+    const unsigned* __restrict__ hist, const unsigned* __restrict__ totals, int64_t nwt,
+    int32_t* __restrict__ out_keys, int32_t* __restrict__ out_index) {
   __shared__ unsigned run[kSortWarps][kBins];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t wt = (int64_t)blockIdx.x * kSortWarps + w;
   if (wt >= nwt) return;
-  for (int b = lane; b < kBins; b += 32) run[w][b] = hist[(size_t)b * nwt + wt];
+  {
+    // digit bases: exclusive scan of the 256 row totals, 8 consecutive digits per lane
+    unsigned t[8], s8 = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      t[q] = __ldg(totals + lane * 8 + q);
+      s8 += t[q];
+    }
+    unsigned incl = s8;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += x;
+    }
+    unsigned basev = incl - s8;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int b = lane * 8 + q;
+      run[w][b] = basev + hist[(size_t)b * nwt + wt];
+      basev += t[q];
+    }
+  }
   __syncwarp();
   const int64_t base = wt * kKeysPerWarp;
   for (int c = 0; c < kKeysPerWarp; c += 32) {
@@ -107,7 +126,7 @@ static int64_t num_warp_tiles(int64_t n) { return (n + kKeysPerWarp - 1) / kKeys
 
 size_t sort_workspace_bytes(int64_t n) {
   const int64_t nwt = num_warp_tiles(n < 1 ? 1 : n);
-  return align_up((size_t)n * 4, 256) * 2 + align_up((size_t)kBins * nwt * 4, 256) + 256;
+  return align_up((size_t)n * 4, 256) * 2 + align_up((size_t)kBins * nwt * 4, 256) + align_up(kBins * 4, 256) + 256;
 }
 
 int launch_sort_pairs(const int32_t* keys, int64_t n, int key_bits, int32_t* out_keys, int32_t* out_index,
@@ -126,6 +145,7 @@ int launch_sort_pairs(const int32_t* keys, int64_t n, int key_bits, int32_t* out
   int32_t* tmp_keys = cv.take<int32_t>(n);
   int32_t* tmp_index = cv.take<int32_t>(n);
   unsigned* hist = cv.take<unsigned>(kBins * nwt);
+  unsigned* totals = cv.take<unsigned>(kBins);
   int passes = (key_bits + 7) / 8;
   if (passes < 1) passes = 1;
   if (passes > 4) passes = 4;
@@ -138,9 +158,9 @@ int launch_sort_pairs(const int32_t* keys, int64_t n, int key_bits, int32_t* out
     int32_t* dst_i = to_out ? out_index : tmp_index;
     radix_hist_kernel<<<blocks, kSortWarps * 32, 0, st>>>(src_k, n, 8 * p, hist, nwt);
     MR_LAUNCH_CHECK("radix_hist_kernel");
-    radix_scan_kernel<<<1, 1024, 0, st>>>(hist, (int64_t)kBins * nwt);
-    MR_LAUNCH_CHECK("radix_scan_kernel");
-    radix_scatter_kernel<<<blocks, kSortWarps * 32, 0, st>>>(src_k, src_i, n, 8 * p, hist, nwt, dst_k, dst_i);
+    radix_rowscan_kernel<<<kBins, 256, 0, st>>>(hist, nwt, totals);
+    MR_LAUNCH_CHECK("radix_rowscan_kernel");
+    radix_scatter_kernel<<<blocks, kSortWarps * 32, 0, st>>>(src_k, src_i, n, 8 * p, hist, totals, nwt, dst_k, dst_i);
     MR_LAUNCH_CHECK("radix_scatter_kernel");
     src_k = dst_k;
     src_i = dst_i;

@@ -1,16 +1,29 @@
 // Deterministic segmented reduction of staged per-sample embedding-row gradients, fused with the
 // row update -- the "segmented-reduce scatter-add, with no atomics, feeding a fused sparse-row Adam
 // update" of the train step.  Input: sample indices stably sorted by row id (radix_sort.cu), so the
-// samples of one row are contiguous and in batch order -- the order in which TensorFlow's
-// IndexedSlices densification sums duplicates.
+// samples of one row are contiguous and in batch order.
 //
-// A warp takes 32 consecutive sorted entries, finds the segments that START among them and owns each
-// of those to its end (which may lie in later chunks).  Lanes span the columns of the row, so every
-// staged row is read with coalesced 128-byte requests, and the samples of a segment are added
-// sequentially -> bit-identical results on every run.
+// Load-balanced by recursive chunking.  Level 0: every warp owns exactly 32 consecutive sorted
+// entries, sums each run of equal row ids inside its chunk (entries added in order), and
+//   * applies the row update at once when the run neither continues from the previous chunk nor
+//     into the next one (the whole segment is inside the chunk), or
+//   * emits a partial sum into one of the chunk's two output slots (slot 0: the run that continues
+//     from the previous chunk, slot 1: the run that continues into the next one).
+// The emitted (row id, partial row) list is again a sequence in which equal ids are contiguous, 16x
+// shorter, and the same kernel reduces it (now reading rows directly); after log32(n) levels one chunk
+// is left and everything has been applied.  Popular rows (MovieLens item popularity is Zipf-like: one
+// item can own 10^4..10^5 samples of a batch) therefore cost a balanced tree instead of one warp's
+// serial loop, and the summation tree depends only on positions -> bit-identical on every run.
+// Unused slots carry the key kSkip; a chunk that is one single continuing run emits (id, sum) and
+// (id, zeros) so that equal ids stay contiguous across chunk boundaries.
 #include "launchers.h"
 
 namespace mr {
+
+constexpr int kSkip = -1;     // empty slot
+constexpr int kPastEnd = -2;  // lane beyond n
+constexpr int kNoNeighbour = -3;
+constexpr int kBatch = 8;     // rows loaded per lane before they are added
 
 __device__ __forceinline__ void apply_row_value(const RowUpdate& u, int row, int c, float g) {
   float *p, *m, *v, *gt;
@@ -34,80 +47,171 @@ __device__ __forceinline__ void apply_row_value(const RowUpdate& u, int row, int
   }
 }
 
-__global__ void __launch_bounds__(256) segreduce_kernel(const int32_t* __restrict__ keys,
-                                                        const int32_t* __restrict__ index, int64_t n,
-                                                        const float* __restrict__ staged, const RowUpdate u) {
-  const int lane = threadIdx.x & 31;
-  const int ld = u.d0 + u.d1;
-  const int64_t nchunks = (n + 31) >> 5;
-  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += warps) {
-    const int64_t e = chunk * 32 + lane;
-    const int key = e < n ? __ldg(keys + e) : -1;
-    const int prev = (e > 0 && e < n) ? __ldg(keys + e - 1) : -2;
-    unsigned starts = __ballot_sync(0xffffffffu, e < n && key != prev);
-    while (starts != 0) {
-      const int sl = __ffs(starts) - 1;
-      starts &= starts - 1;
-      const int row = __shfl_sync(0xffffffffu, key, sl);
-      const int64_t s = chunk * 32 + sl;
-      // end of the segment: first later entry whose key differs (entries past n count as different)
-      int64_t end;
-      const unsigned diff = __ballot_sync(0xffffffffu, lane > sl && key != row);
-      if (diff != 0) {
-        end = chunk * 32 + (__ffs(diff) - 1);
-      } else {
-        int64_t j = (chunk + 1) * 32;
-        for (;;) {
-          const int64_t e2 = j + lane;
-          const int k2 = e2 < n ? __ldg(keys + e2) : -1;
-          const unsigned d2 = __ballot_sync(0xffffffffu, k2 != row);
-          if (d2 != 0) {
-            end = j + (__ffs(d2) - 1);
-            break;
-          }
-          j += 32;
-        }
-      }
-      for (int cb = 0; cb < ld; cb += 32) {
-        const int c = cb + lane;
-        const bool on = c < ld;
-        float acc = 0.f;
-        int64_t j = s;
-        for (; j + 4 <= end; j += 4) {
-          const int i0 = __ldg(index + j), i1 = __ldg(index + j + 1), i2 = __ldg(index + j + 2),
-                    i3 = __ldg(index + j + 3);
-          float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-          if (on) {
-            v0 = __ldg(staged + (size_t)i0 * ld + c);
-            v1 = __ldg(staged + (size_t)i1 * ld + c);
-            v2 = __ldg(staged + (size_t)i2 * ld + c);
-            v3 = __ldg(staged + (size_t)i3 * ld + c);
-          }
-          acc += v0;
-          acc += v1;
-          acc += v2;
-          acc += v3;
-        }
-        for (; j < end; ++j) {
-          const int i0 = __ldg(index + j);
-          if (on) acc += __ldg(staged + (size_t)i0 * ld + c);
-        }
-        if (on) apply_row_value(u, row, c, acc);
-      }
+struct ChunkInfo {
+  int nvalid;       // entries of the chunk that exist
+  bool first_inc;   // run starting at entry 0 continues from the previous chunk
+  bool last_inc;    // run ending at the last entry continues into the next chunk
+  int64_t chunk;
+  int ld;
+  float* out_rows;
+};
+
+// A run [s, t) of row id `key` has been summed into acc (VEC: 4 columns c..c+3, else 1 column c).
+template <bool VEC>
+__device__ __forceinline__ void flush_run(const RowUpdate& u, const ChunkInfo& ci, int key, int s, int t, int c,
+                                          bool on, float4 acc) {
+  if (key == kSkip || !on) return;
+  const bool inc_first = (s == 0) && ci.first_inc;
+  const bool inc_last = (t == ci.nvalid) && ci.last_inc;
+  if (!inc_first && !inc_last) {
+    apply_row_value(u, key, c, acc.x);
+    if (VEC) {
+      apply_row_value(u, key, c + 1, acc.y);
+      apply_row_value(u, key, c + 2, acc.z);
+      apply_row_value(u, key, c + 3, acc.w);
+    }
+    return;
+  }
+  float* slot0 = ci.out_rows + (size_t)(2 * ci.chunk) * ci.ld + c;
+  float* slot1 = slot0 + ci.ld;
+  if (VEC) {
+    if (inc_first) {
+      *reinterpret_cast<float4*>(slot0) = acc;
+      if (inc_last) *reinterpret_cast<float4*>(slot1) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      *reinterpret_cast<float4*>(slot1) = acc;
+    }
+  } else {
+    if (inc_first) {
+      *slot0 = acc.x;
+      if (inc_last) *slot1 = 0.f;
+    } else {
+      *slot1 = acc.x;
     }
   }
 }
 
+// keys[n]; INDIRECT: row of entry e is rows[index[e]], else rows[e].  out_keys/out_rows hold two slots
+// per chunk (may be NULL when there is a single chunk: then nothing can be incomplete).
+template <bool INDIRECT, bool VEC>
+__global__ void __launch_bounds__(256) segreduce_level_kernel(const int32_t* __restrict__ keys,
+                                                              const int32_t* __restrict__ index, int64_t n,
+                                                              const float* __restrict__ rows, int32_t* __restrict__ out_keys,
+                                                              float* __restrict__ out_rows, const RowUpdate u) {
+  const int lane = threadIdx.x & 31;
+  const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t base = chunk * 32;
+  if (base >= n) return;  // warp-uniform
+  const int ld = u.d0 + u.d1;
+  const int64_t e = base + lane;
+  const int key = e < n ? __ldg(keys + e) : kPastEnd;
+  const int64_t src = e < n ? (INDIRECT ? (int64_t)__ldg(index + e) : e) : 0;
+  const bool ok = e < n && key != kSkip;
+  const int kprev = base > 0 ? __ldg(keys + base - 1) : kNoNeighbour;
+  const int knext = base + 32 < n ? __ldg(keys + base + 32) : kNoNeighbour;
+  int kup = __shfl_up_sync(0xffffffffu, key, 1);
+  const unsigned starts = __ballot_sync(0xffffffffu, e < n && (lane == 0 || key != kup));
+
+  ChunkInfo ci;
+  ci.nvalid = (int)min((int64_t)32, n - base);
+  const int key0 = __shfl_sync(0xffffffffu, key, 0);
+  const int keyl = __shfl_sync(0xffffffffu, key, ci.nvalid - 1);
+  ci.first_inc = key0 != kSkip && kprev == key0;
+  ci.last_inc = ci.nvalid == 32 && keyl != kSkip && knext == keyl;
+  ci.chunk = chunk;
+  ci.ld = ld;
+  ci.out_rows = out_rows;
+  if (out_keys != nullptr && lane == 0) {
+    out_keys[2 * chunk] = ci.first_inc ? key0 : kSkip;
+    out_keys[2 * chunk + 1] = ci.last_inc ? keyl : kSkip;
+  }
+
+  constexpr int W = VEC ? 4 : 1;
+  for (int cb = 0; cb < ld; cb += 32 * W) {
+    const int c = cb + lane * W;
+    const bool on = c < ld;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int run_key = key0, run_start = 0;
+    for (int j0 = 0; j0 < ci.nvalid; j0 += kBatch) {
+      float4 v[kBatch];
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q) {
+        const int j = j0 + q;  // j < 32 always (nvalid <= 32, kBatch divides 32)
+        const int64_t sj = __shfl_sync(0xffffffffu, src, j);
+        const bool okj = __shfl_sync(0xffffffffu, (int)ok, j) != 0;
+        v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (okj && on) {
+          if (VEC) v[q] = ld_stream4(rows + (size_t)sj * ld + c);
+          else v[q].x = __ldg(rows + (size_t)sj * ld + c);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kBatch; ++q) {
+        const int j = j0 + q;
+        if (j < ci.nvalid) {
+          if (j > 0 && ((starts >> j) & 1u)) {  // a new run starts: close the previous one
+            flush_run<VEC>(u, ci, run_key, run_start, j, c, on, acc);
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            run_start = j;
+            run_key = __shfl_sync(0xffffffffu, key, j);
+          }
+          acc.x += v[q].x;
+          if (VEC) {
+            acc.y += v[q].y;
+            acc.z += v[q].z;
+            acc.w += v[q].w;
+          }
+        }
+      }
+    }
+    flush_run<VEC>(u, ci, run_key, run_start, ci.nvalid, c, on, acc);
+  }
+}
+
+static int64_t level_entries(int64_t n) { return 2 * ((n + 31) / 32); }
+
+size_t segreduce_workspace_bytes(int64_t n, int ld) {
+  const int64_t n1 = level_entries(n < 1 ? 1 : n), n2 = level_entries(n1);
+  return align_up((size_t)n1 * 4, 256) + align_up((size_t)n2 * 4, 256) + align_up((size_t)n1 * ld * 4, 256) +
+         align_up((size_t)n2 * ld * 4, 256);
+}
+
 int launch_segreduce(const int32_t* sorted_keys, const int32_t* sorted_index, int64_t n, const float* staged,
-                     const RowUpdate& u, cudaStream_t st) {
+                     const RowUpdate& u, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (n == 0) return MR_OK;
-  const int64_t nchunks = (n + 31) / 32;
-  int64_t blocks = (nchunks + 7) / 8;
-  const int64_t cap = (int64_t)sm_count() * 8;
-  if (blocks > cap) blocks = cap;
-  segreduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(sorted_keys, sorted_index, n, staged, u);
-  MR_LAUNCH_CHECK("segreduce_kernel");
+  const int ld = u.d0 + u.d1;
+  if (ws_bytes < segreduce_workspace_bytes(n, ld)) {
+    set_error("segreduce workspace too small: %zu < %zu", ws_bytes, segreduce_workspace_bytes(n, ld));
+    return MR_ERR_WORKSPACE;
+  }
+  const int64_t n1 = level_entries(n), n2 = level_entries(n1);
+  Carver cv(ws);
+  int32_t* kbuf[2] = {cv.take<int32_t>(n1), cv.take<int32_t>(n2)};
+  float* rbuf[2] = {cv.take<float>((size_t)n1 * ld), cv.take<float>((size_t)n2 * ld)};
+  const bool vec = (ld & 3) == 0 && (u.d0 & 3) == 0 && (reinterpret_cast<uintptr_t>(staged) & 15) == 0;
+
+  const int32_t* keys = sorted_keys;
+  const float* rows = staged;
+  int64_t cur = n;
+  for (int level = 0;; ++level) {
+    const int64_t nchunks = (cur + 31) / 32;
+    const bool last = nchunks == 1;
+    int32_t* ok = last ? nullptr : kbuf[level & 1];
+    float* orows = last ? nullptr : rbuf[level & 1];
+    const unsigned blocks = (unsigned)((nchunks + 7) / 8);
+    if (level == 0) {
+      if (vec) segreduce_level_kernel<true, true><<<blocks, 256, 0, st>>>(keys, sorted_index, cur, rows, ok, orows, u);
+      else segreduce_level_kernel<true, false><<<blocks, 256, 0, st>>>(keys, sorted_index, cur, rows, ok, orows, u);
+    } else {
+      if (vec) segreduce_level_kernel<false, true><<<blocks, 256, 0, st>>>(keys, nullptr, cur, rows, ok, orows, u);
+      else segreduce_level_kernel<false, false><<<blocks, 256, 0, st>>>(keys, nullptr, cur, rows, ok, orows, u);
+    }
+    MR_LAUNCH_CHECK("segreduce_level_kernel");
+    if (last) break;
+    keys = ok;
+    rows = orows;
+    cur = 2 * nchunks;
+  }
   return MR_OK;
 }
 

@@ -166,6 +166,34 @@ def test_train_steps_match_oracle(eng_mod, case):
     assert eng.iterations == 3
 
 
+@pytest.mark.parametrize("mode", ["dense", "sparse"])
+def test_hot_rows_span_many_chunks(eng_mod, mode):
+    """Few users/items and a large batch: every segment spans hundreds of 32-entry chunks, so the
+    recursive segmented reduction runs all its levels (incl. whole-chunk runs and empty slots)."""
+    nu, ni, L, f, negs = 50, 30, [64, 32, 16, 8], 8, 4
+    rng = np.random.default_rng(21)
+    groups = 8000
+    users = np.repeat(np.minimum(rng.zipf(1.3, groups) - 1, nu - 1), negs + 1)
+    items = np.minimum(rng.zipf(1.2, groups * (negs + 1)) - 1, ni - 1)
+    y = np.tile([0] * negs + [1], groups).astype(np.float32)
+    params = {"layers_sizes": L, "layers_l2reg": [0] * 4, "optimizer": "adam", "lr": 0.001, "num_negs_per_pos": negs, "k": 3}
+    eng = eng_mod.NeuMFEngine(nu, ni, L, [0] * 4, mf_dim=f, table_mode=mode, seed=4)
+    w = eng.get_weights()
+    st = o.new_opt_state(w)
+    # segments hold ~10^4 samples: the fp32 oracle's own sequential sum is only good to ~1e-4 there,
+    # so the gradient tables are checked against the float64 oracle (the kernel's tree sum is tighter)
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    g64 = o.backward(w64, o.forward(w64, users, items), y.astype(np.float64))
+    eng.train_step(users, items, y, group=negs + 1, k=3)
+    if mode == "dense":
+        for name, t in eng.g_tables.items():
+            rel_close(t.cpu().numpy(), g64[name], rtol=1e-5, what="table grad " + name)
+    o.train_step(w, st, users, items, y, params, adam_mode="lazy" if mode == "sparse" else "dense")
+    got = eng.get_weights()
+    for k in w:
+        rel_close(got[k], w[k], rtol=2e-5, what="weight " + k)
+
+
 def test_train_step_is_deterministic(eng_mod):
     nu, ni, L, f, negs, groups = CONFIGS[5]
     rng = np.random.default_rng(1)
