@@ -186,6 +186,15 @@ int mr_profile_begin(void);
 int mr_profile_end(float* phase_ms, int64_t* phase_count, int64_t* kernel_launches);
 
 /* Building blocks exposed for tests and for data-parallel callers. */
+/* Single-tile tcgen05 GEMM self-test: D[128 x N] = A . B^T on the tensor cores (TF32 or 3xTF32), A given
+ * as [128 x K] (a_mn = 0) or [K x 128] (a_mn = 1), B as [N x K] (b_mn = 0) or [K x N] (b_mn = 1).
+ * Validates the shared-memory operand layout and descriptors the fused kernels rely on. */
+/* Descriptor explorer used by the tests that pin the operand-layout semantics: raw_a (n_words floats) is
+ * the shared-memory image of A, B is the 16x8 identity, one M=128,N=16,K=8 TF32 MMA; D is [128 x 16]. */
+int mr_tc_probe(const float* raw_a, int32_t n_words, int32_t start_off, int32_t lbo, int32_t sbo, int32_t a_mn,
+                float* D, void* stream);
+int mr_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
+                        int32_t three_x, void* stream);
 /* Stable LSD radix sort of (key, original index) pairs on the low `key_bits` bits. */
 size_t mr_sort_workspace_bytes(int64_t n);
 int mr_sort_pairs(const int32_t* keys, int64_t n, int32_t key_bits, int32_t* sorted_keys,

@@ -494,6 +494,18 @@ int mr_sample_negatives(const int64_t* csr_rowptr, const int32_t* csr_items, int
   return rc;
 }
 
+int mr_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
+                        int32_t three_x, void* stream) {
+  MR_REQUIRE(A && B && D, "tc selftest: NULL pointer");
+  return launch_tc_selftest(A, B, D, N, K, a_mn, b_mn, three_x, (cudaStream_t)stream);
+}
+
+int mr_tc_probe(const float* raw_a, int32_t n_words, int32_t start_off, int32_t lbo, int32_t sbo, int32_t a_mn, float* D,
+                void* stream) {
+  MR_REQUIRE(raw_a && D, "tc probe: NULL pointer");
+  return launch_tc_probe(raw_a, n_words, start_off, lbo, sbo, a_mn, D, (cudaStream_t)stream);
+}
+
 int mr_profile_begin(void) {
   g_prof.on = true;
   g_prof.overflow = false;

@@ -72,4 +72,10 @@ int launch_sample_negatives(const int64_t* rowptr, const int32_t* csr_items, int
                             int negs, uint64_t seed, uint64_t epoch, int32_t* out_users, int32_t* out_items,
                             float* out_labels, cudaStream_t st);
 
+// ---- tc_selftest.cu ---------------------------------------------------------------------------
+int launch_tc_probe(const float* raw_a, int n_words, int start_off, int lbo, int sbo, int a_mn, float* D,
+                    cudaStream_t st);
+int launch_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn, int b_mn, int three_x,
+                       cudaStream_t st);
+
 }  // namespace mr
