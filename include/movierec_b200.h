@@ -181,9 +181,20 @@ enum { MR_PHASE_TILE_TRAIN = 0, /* fused gather+tower+head+BCE+backward kernel *
        MR_PHASE_TILE_FORWARD = 5, /* fused forward kernel (predict / eval) */
        MR_PHASE_RANK = 6,       /* positions + metric sums */
        MR_PHASE_SAMPLER = 7,
-       MR_NUM_PHASES = 8 };
+       MR_PHASE_TC_DENSE_FWD = 8,  /* tcgen05 forward layers (gather fused into the first) */
+       MR_PHASE_TC_DENSE_BWD = 9,  /* tcgen05 backward-activation layers */
+       MR_PHASE_TC_WGRAD = 10,     /* tcgen05 weight-gradient layers */
+       MR_PHASE_HEAD = 11,         /* GMF + output unit + BCE (+ their gradients) */
+       MR_NUM_PHASES = 12 };
 int mr_profile_begin(void);
 int mr_profile_end(float* phase_ms, int64_t* phase_count, int64_t* kernel_launches);
+
+/* Two implementations of the tower exist: the tcgen05 (3xTF32 tensor-core) path, used when every layer
+ * width is a multiple of 32 (<= 256), every non-final width a multiple of 128 and layers_sizes[0] a
+ * multiple of 64, and the fp32 SIMT tile kernel for every other shape.  Both are hand-written CUDA; the
+ * selector is thread-local: 0 = automatic (default), 1 = always SIMT, 2 = tensor cores where eligible. */
+int mr_set_compute_path(int32_t path);
+int mr_uses_tensor_cores(const MrModel* model);
 
 /* Building blocks exposed for tests and for data-parallel callers. */
 /* Single-tile tcgen05 GEMM self-test: D[128 x N] = A . B^T on the tensor cores (TF32 or 3xTF32), A given

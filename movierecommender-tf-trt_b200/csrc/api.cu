@@ -122,6 +122,81 @@ static bool any_l2(const MrModel& m) {
   return false;
 }
 
+// ---- tensor-core path (tcgen05 3xTF32): eligibility, workspace and launch sequence ----------------------
+static thread_local int g_path = 0;  // 0 auto, 1 force the SIMT tile kernel, 2 require the tensor-core path
+
+static bool tc_eligible(const MrModel& m) {
+  if (m.n_layers < 2) return false;
+  if (m.L[0] % 64) return false;  // d_u = L0/2 must be a multiple of 32 (K-chunks never straddle the two tables)
+  for (int l = 0; l < m.n_layers; ++l)
+    if (m.L[l] % 32 || m.L[l] > 256) return false;
+  for (int l = 0; l + 1 < m.n_layers; ++l)
+    if (m.L[l] % 128) return false;  // input width of every dense layer = M of the weight-gradient MMAs
+  if (m.mf_dim + m.L[m.n_layers - 1] > 512) return false;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(m.user_mlp) | reinterpret_cast<uintptr_t>(m.item_mlp) |
+                      reinterpret_cast<uintptr_t>(m.dense);
+  return (a & 15) == 0;
+}
+
+static bool use_tc(const MrModel& m) { return g_path != 1 && tc_eligible(m); }
+
+static int64_t tc_sub_batch() { return (int64_t)sm_count() * 128 * 2; }  // two 128-row tiles per SM
+
+struct TcWs {
+  float* pack_f[MR_MAX_LAYERS];  // forward operand of W[l]   (rows = output unit)
+  float* pack_b[MR_MAX_LAYERS];  // backward operand of W[l]  (rows = input unit)
+  float* H[MR_MAX_LAYERS];       // activations of a sub-batch, H[l] (SB x L[l])
+  float* dZ[MR_MAX_LAYERS];      // pre-activation gradients of a sub-batch
+  float* head_partial;
+  size_t total;
+};
+
+static TcWs carve_tc(const MrModel& m, bool train, void* ws) {
+  TcWs t{};
+  Carver cv(ws);
+  const int64_t sb = tc_sub_batch();
+  for (int l = 1; l < m.n_layers; ++l) {
+    const size_t kn = (size_t)m.L[l - 1] * m.L[l];
+    t.pack_f[l] = cv.take<float>(2 * kn);
+    if (train) t.pack_b[l] = cv.take<float>(2 * kn);
+    t.H[l] = cv.take<float>((size_t)sb * m.L[l]);
+    if (train) t.dZ[l] = cv.take<float>((size_t)sb * m.L[l]);
+  }
+  t.head_partial = cv.take<float>(head_partial_floats(m));
+  t.total = cv.off;
+  return t;
+}
+
+// Forward of rows [r0, r1) on the tensor cores; leaves H[1..n-1] of the sub-batch in the workspace.
+static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users, const int32_t* items, int user_div,
+                           int64_t r0, int64_t r1, cudaStream_t st) {
+  const int d_u = m.L[0] / 2;
+  for (int l = 1; l < m.n_layers; ++l) {
+    TcDenseArgs a{};
+    a.gather = (l == 1);
+    a.a_dense = (l == 1) ? nullptr : t.H[l - 1];
+    a.user_tab = m.user_mlp;
+    a.item_tab = m.item_mlp;
+    a.users = users;
+    a.items = items;
+    a.num_users = m.num_users;
+    a.num_items = m.num_items;
+    a.d_u = d_u;
+    a.user_div = user_div;
+    a.b_packed = t.pack_f[l];
+    a.N = m.L[l];
+    a.K = m.L[l - 1];
+    a.rows = r1 - r0;
+    a.row0 = r0;
+    a.epilogue = TC_EPI_BIAS_RELU;
+    a.bias = m.b[l];
+    a.out = t.H[l];
+    int rc = launch_tc_dense(a, st);
+    if (rc != MR_OK) return rc;
+  }
+  return MR_OK;
+}
+
 struct TrainWs {
   int32_t* flags;
   float* wt;
@@ -137,6 +212,8 @@ struct TrainWs {
   size_t sort_ws_bytes;
   void* seg_ws;
   size_t seg_ws_bytes;
+  void* tc_ws;
+  size_t tc_ws_bytes;
   int32_t* pos;
   float* rank_partials;
   size_t total;
@@ -163,6 +240,8 @@ static TrainWs carve_train(const MrModel& m, int64_t B, void* ws) {
   t.seg_ws = cv.take<char>(t.seg_ws_bytes);
   t.pos = cv.take<int32_t>(B);
   t.rank_partials = cv.take<float>(rank_partials_count(B));
+  t.tc_ws_bytes = tc_eligible(m) ? carve_tc(m, true, nullptr).total : 0;
+  t.tc_ws = cv.take<char>(t.tc_ws_bytes);
   t.total = cv.off;
   return t;
 }
@@ -219,9 +298,11 @@ int mr_gather_rows(const float* table, int64_t rows, int32_t dim, const int32_t*
 }
 
 size_t mr_forward_workspace_bytes(const MrModel* model, int64_t B) {
-  (void)model;
   (void)B;
-  return 256 + align_up((size_t)max_tile_ctas() * sizeof(float), 256);
+  size_t n = 256 + align_up((size_t)max_tile_ctas() * sizeof(float), 256);
+  if (model != nullptr && model->n_layers >= 1 && model->n_layers <= MR_MAX_LAYERS && tc_eligible(*model))
+    n += carve_tc(*model, false, nullptr).total;
+  return n;
 }
 
 int mr_neumf_forward(const MrModel* model, const int32_t* users, const int32_t* items, int64_t B, int32_t user_div,
@@ -246,6 +327,38 @@ int mr_neumf_forward(const MrModel* model, const int32_t* users, const int32_t* 
   int32_t* flags = cv.take<int32_t>(64);
   float* loss_partial = cv.take<float>(max_tile_ctas());
   MR_CUDA(cudaMemsetAsync(flags, 0, 256, st));
+  if (use_tc(*model) && labels == nullptr) {  // forward with a loss request is served by the SIMT kernel
+    const MrModel& m = *model;
+    TcWs t = carve_tc(m, false, static_cast<char*>(ws) + cv.off);
+    prof_mark(MR_PHASE_MISC, st);
+    for (int l = 1; l < m.n_layers; ++l) {
+      rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 0, t.pack_f[l], st);
+      if (rc != MR_OK) return rc;
+    }
+    const int64_t sb = tc_sub_batch();
+    for (int64_t r0 = 0; r0 < B; r0 += sb) {
+      const int64_t r1 = r0 + sb < B ? r0 + sb : B;
+      prof_mark(MR_PHASE_TC_DENSE_FWD, st);
+      rc = tc_forward_rows(m, t, users, items, user_div, r0, r1, st);
+      if (rc != MR_OK) return rc;
+      prof_mark(MR_PHASE_HEAD, st);
+      HeadArgs h{};
+      h.model = model;
+      h.h_last = t.H[m.n_layers - 1];
+      h.users = users;
+      h.items = items;
+      h.rows = r1 - r0;
+      h.row0 = r0;
+      h.user_div = user_div;
+      h.logits = logits;
+      h.probs = probs;
+      h.flags = flags;
+      rc = launch_head(h, st);
+      if (rc != MR_OK) return rc;
+    }
+    prof_mark(-1, st);
+    return MR_OK;
+  }
   TileLaunch a{};
   a.model = model;
   a.train = false;
@@ -295,6 +408,96 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   prof_mark(MR_PHASE_MISC, st);
   MR_CUDA(cudaMemsetAsync(t.flags, 0, 256, st));
   MR_CUDA(cudaMemsetAsync(step_out, 0, MR_STEP_OUT_FLOATS * sizeof(float), st));
+  if (use_tc(m)) {
+    // ---- tensor-core path: per sub-batch, forward layers -> head -> per layer weight gradient + backward
+    const int P = sm_count();  // rows of the partial buffer = CTAs of the weight-gradient kernel
+    const int n = m.n_layers, f = m.mf_dim;
+    TcWs tw = carve_tc(m, true, t.tc_ws);
+    MR_CUDA(cudaMemsetAsync(t.dense_partial, 0, (size_t)P * t.dense_stride * sizeof(float), st));
+    for (int l = 1; l < n; ++l) {
+      rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 0, tw.pack_f[l], st);
+      if (rc == MR_OK) rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 1, tw.pack_b[l], st);
+      if (rc != MR_OK) return rc;
+    }
+    const int64_t sb = tc_sub_batch();
+    for (int64_t r0 = 0; r0 < B; r0 += sb) {
+      const int64_t r1 = r0 + sb < B ? r0 + sb : B;
+      prof_mark(MR_PHASE_TC_DENSE_FWD, st);
+      rc = tc_forward_rows(m, tw, users, items, 1, r0, r1, st);
+      if (rc != MR_OK) return rc;
+      prof_mark(MR_PHASE_HEAD, st);
+      HeadArgs h{};
+      h.model = model;
+      h.h_last = tw.H[n - 1];
+      h.users = users;
+      h.items = items;
+      h.labels = labels;
+      h.rows = r1 - r0;
+      h.row0 = r0;
+      h.user_div = 1;
+      h.inv_batch = inv_global_batch;
+      h.probs = t.probs;
+      h.dz_last = tw.dZ[n - 1];
+      h.stage_u = t.stage_u;
+      h.stage_i = t.stage_i;
+      h.head_partial = tw.head_partial;
+      h.d_wout_row0 = t.dense_partial + (m.w_out - m.dense);
+      h.d_bout_row0 = t.dense_partial + (m.b_out - m.dense);
+      h.loss_sum = step_out + MR_OUT_LOSS_SUM;
+      h.flags = t.flags;
+      rc = launch_head(h, st);
+      if (rc != MR_OK) return rc;
+      for (int l = n - 1; l >= 1; --l) {
+        prof_mark(MR_PHASE_TC_WGRAD, st);
+        TcWgradArgs w{};
+        w.gather = (l == 1);
+        w.a_dense = (l == 1) ? nullptr : tw.H[l - 1];
+        w.user_tab = m.user_mlp;
+        w.item_tab = m.item_mlp;
+        w.users = users;
+        w.items = items;
+        w.num_users = m.num_users;
+        w.num_items = m.num_items;
+        w.d_u = d_u;
+        w.z = tw.dZ[l];
+        w.Fa = m.L[l - 1];
+        w.Fb = m.L[l];
+        w.rows = r1 - r0;
+        w.row0 = r0;
+        w.dw_partial = t.dense_partial + (m.W[l] - m.dense);
+        w.db_partial = t.dense_partial + (m.b[l] - m.dense);
+        w.partial_stride = t.dense_stride;
+        rc = launch_tc_wgrad(w, st);
+        if (rc != MR_OK) return rc;
+        prof_mark(MR_PHASE_TC_DENSE_BWD, st);
+        TcDenseArgs a{};
+        a.gather = false;
+        a.a_dense = tw.dZ[l];
+        a.d_u = d_u;
+        a.b_packed = tw.pack_b[l];
+        a.N = m.L[l - 1];
+        a.K = m.L[l];
+        a.rows = r1 - r0;
+        a.row0 = r0;
+        if (l - 1 >= 1) {
+          a.epilogue = TC_EPI_MASK;
+          a.mask_src = tw.H[l - 1];
+          a.out = tw.dZ[l - 1];
+        } else {
+          a.epilogue = TC_EPI_STAGE;
+          a.stage_u = t.stage_u;
+          a.stage_i = t.stage_i;
+          a.su = d_u + f;
+          a.si = d_i + f;
+        }
+        rc = launch_tc_dense(a, st);
+        if (rc != MR_OK) return rc;
+      }
+    }
+    prof_mark(MR_PHASE_MISC, st);
+    rc = launch_dense_reduce(m, t.dense_partial, t.dense_stride, P, grads->dense, st);
+    if (rc != MR_OK) return rc;
+  } else {
   rc = launch_transpose_kernels(m, t.wt, st);
   if (rc != MR_OK) return rc;
 
@@ -324,6 +527,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   if (rc != MR_OK) return rc;
   rc = launch_sum_partials(t.loss_partial, grid, step_out + MR_OUT_LOSS_SUM, st);
   if (rc != MR_OK) return rc;
+  }
   flag_to_float_kernel<<<1, 1, 0, st>>>(t.flags, step_out + MR_OUT_BAD_IDS);
   MR_LAUNCH_CHECK("flag_to_float_kernel");
 
@@ -375,6 +579,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   if (rc != MR_OK) return rc;
   u.d0 = d_u;
   u.d1 = m.mf_dim;
+  u.num_rows = m.num_users;
   u.p0 = m.user_mlp; u.m0 = opt->m_user_mlp; u.v0 = opt->v_user_mlp; u.g0 = grads->user_mlp;
   u.p1 = m.user_gmf; u.m1 = opt->m_user_gmf; u.v1 = opt->v_user_gmf; u.g1 = grads->user_gmf;
   prof_mark(MR_PHASE_SEGREDUCE, st);
@@ -385,6 +590,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   rc = launch_sort_pairs(items, B, bits_for(m.num_items), t.sorted_keys, t.sorted_index, t.sort_ws, t.sort_ws_bytes, st);
   if (rc != MR_OK) return rc;
   u.d0 = d_i;
+  u.num_rows = m.num_items;
   u.p0 = m.item_mlp; u.m0 = opt->m_item_mlp; u.v0 = opt->v_item_mlp; u.g0 = grads->item_mlp;
   u.p1 = m.item_gmf; u.m1 = opt->m_item_gmf; u.v1 = opt->v_item_gmf; u.g1 = grads->item_gmf;
   prof_mark(MR_PHASE_SEGREDUCE, st);
@@ -504,6 +710,17 @@ int mr_tc_probe(const float* raw_a, int32_t n_words, int32_t start_off, int32_t 
                 void* stream) {
   MR_REQUIRE(raw_a && D, "tc probe: NULL pointer");
   return launch_tc_probe(raw_a, n_words, start_off, lbo, sbo, a_mn, D, (cudaStream_t)stream);
+}
+
+int mr_set_compute_path(int32_t path) {
+  MR_REQUIRE(path >= 0 && path <= 2, "compute path must be 0 (auto), 1 (SIMT) or 2 (tensor cores)");
+  g_path = path;
+  return MR_OK;
+}
+
+int mr_uses_tensor_cores(const MrModel* model) {
+  if (model == nullptr || model->n_layers < 1 || model->n_layers > MR_MAX_LAYERS) return 0;
+  return use_tc(*model) ? 1 : 0;
 }
 
 int mr_profile_begin(void) {

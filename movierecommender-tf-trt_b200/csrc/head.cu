@@ -1,0 +1,174 @@
+// NeuMF head (tensor-core path): GMF product, output unit, sigmoid, BCE and their gradients, fused in
+// one HBM-bound pass over the rows (model.py:184-188 and 213-215; GMF branch per He et al. 2017).
+//   z = b_o + w_o[:f].(gu*gi) + w_o[f:].h ,  p = sigmoid(z) ,  loss += bce(z, y)
+//   dz = (p - y) / B_global ;  dh = dz * w_o[f:] * (h > 0)  -> dz_last (enters the tower's backward)
+//   d gu = dz * w_o[:f] * gi , d gi = dz * w_o[:f] * gu     -> GMF columns of the staged row gradients
+//   d w_o = sum_r dz * [gu*gi | h] , d b_o = sum_r dz       -> per-warp partials, reduced in fixed order
+// One warp per row, lanes across columns (every row is read with coalesced 128-byte requests).
+// Algorithmic bytes per row: 4*L_last (h) + 8*f (GMF rows) + 12 (ids, label) read,
+// 4*L_last + 8*f + 8 written.
+#include "launchers.h"
+
+namespace mr {
+
+constexpr int kHeadThreads = 256;
+constexpr int kHeadMaxQ = 16;  // (f + L_last) / 32 columns per lane at most (f, L_last <= 256)
+
+struct HeadParams {
+  MrModel m;
+  const float* h_last;
+  const int32_t* users;
+  const int32_t* items;
+  const float* labels;
+  int64_t rows, row0;
+  int32_t user_div;
+  float inv_batch;
+  float* logits;
+  float* probs;
+  float* dz_last;
+  float* stage_u;
+  float* stage_i;
+  float* head_partial;  // [grid][ncols + 2]: d w_out (ncols), d b_out, loss
+  int32_t* flags;
+};
+
+__global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) {
+  __shared__ float red[kHeadThreads / 32][kHeadMaxQ * 32 + 2];
+  const MrModel& m = p.m;
+  const int f = m.mf_dim, Ln = m.L[m.n_layers - 1], ncols = f + Ln;
+  const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
+  const int su = d_u + f, si = d_i + f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool train = p.labels != nullptr;
+  float accw[kHeadMaxQ];
+#pragma unroll
+  for (int q = 0; q < kHeadMaxQ; ++q) accw[q] = 0.f;
+  float accb = 0.f, accl = 0.f;
+
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t lr = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; lr < p.rows; lr += warps) {
+    const int64_t gr = p.row0 + lr;
+    int u = __ldg(p.users + gr / p.user_div), it = __ldg(p.items + gr);
+    const bool bad = (unsigned)u >= (unsigned)m.num_users || (unsigned)it >= (unsigned)m.num_items;
+    if (bad) {
+      if (lane == 0) atomicOr(p.flags, 1);
+      u = 0;
+      it = 0;
+    }
+    // column j of the head input: j < f -> gu[j]*gi[j], else h[j - f]; lane owns columns lane + 32q
+    float hv[kHeadMaxQ], ga[kHeadMaxQ], gb[kHeadMaxQ];
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < kHeadMaxQ; ++q) {
+      const int j = lane + 32 * q;
+      hv[q] = 0.f;
+      ga[q] = 0.f;
+      gb[q] = 0.f;
+      if (j < f) {
+        ga[q] = __ldg(m.user_gmf + (size_t)u * f + j);
+        gb[q] = __ldg(m.item_gmf + (size_t)it * f + j);
+        hv[q] = ga[q] * gb[q];
+      } else if (j < ncols) {
+        hv[q] = __ldg(p.h_last + (size_t)lr * Ln + (j - f));
+      }
+      if (j < ncols) s = fmaf(__ldg(m.w_out + j), hv[q], s);
+    }
+    s = warp_sum(s);
+    const float z = s + __ldg(m.b_out);
+    const float pr = sigmoidf_stable(z);
+    if (lane == 0) {
+      if (p.logits != nullptr) p.logits[gr] = bad ? nanf("") : z;
+      if (p.probs != nullptr) p.probs[gr] = bad ? nanf("") : pr;
+    }
+    if (train) {
+      const float y = __ldg(p.labels + gr);
+      const float dz = bad ? 0.f : (pr - y) * p.inv_batch;
+      if (!bad) accl += bce_logits(z, y);
+      accb += dz;
+#pragma unroll
+      for (int q = 0; q < kHeadMaxQ; ++q) {
+        const int j = lane + 32 * q;
+        if (j < ncols) {
+          accw[q] = fmaf(dz, hv[q], accw[q]);
+          const float g = dz * __ldg(m.w_out + j);
+          if (j < f) {
+            p.stage_u[(size_t)gr * su + d_u + j] = g * gb[q];
+            p.stage_i[(size_t)gr * si + d_i + j] = g * ga[q];
+          } else {
+            p.dz_last[(size_t)lr * Ln + (j - f)] = hv[q] > 0.f ? g : 0.f;
+          }
+        }
+      }
+    }
+  }
+  if (train) {
+    // per-warp sums -> shared -> this CTA's partial row, warps added in index order
+#pragma unroll
+    for (int q = 0; q < kHeadMaxQ; ++q) red[warp][lane + 32 * q] = accw[q];
+    if (lane == 0) {
+      red[warp][kHeadMaxQ * 32] = accb;  // every lane holds the same accb / accl
+      red[warp][kHeadMaxQ * 32 + 1] = accl;
+    }
+    __syncthreads();
+    float* dst = p.head_partial + (size_t)blockIdx.x * (ncols + 2);
+    for (int j = threadIdx.x; j < ncols + 2; j += blockDim.x) {
+      const int src = j < ncols ? j : kHeadMaxQ * 32 + (j - ncols);
+      float t = 0.f;
+      for (int w = 0; w < kHeadThreads / 32; ++w) t += red[w][src];
+      dst[j] = t;
+    }
+  }
+}
+
+// d w_out / d b_out += sum over CTAs (row 0 of the dense partial buffer), loss_sum += sum of CTA losses.
+__global__ void head_reduce_kernel(const float* __restrict__ head_partial, int grid_ctas, int ncols,
+                                   float* __restrict__ d_wout, float* __restrict__ d_bout, float* __restrict__ loss_sum) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ncols + 2; j += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < grid_ctas; ++c) s += head_partial[(size_t)c * (ncols + 2) + j];
+    if (j < ncols) d_wout[j] += s;
+    else if (j == ncols) *d_bout += s;
+    else *loss_sum += s;
+  }
+}
+
+int head_grid() { return sm_count() * 8; }
+
+size_t head_partial_floats(const MrModel& m) { return (size_t)head_grid() * (m.mf_dim + m.L[m.n_layers - 1] + 2); }
+
+int launch_head(const HeadArgs& a, cudaStream_t st) {
+  const MrModel& m = *a.model;
+  const int ncols = m.mf_dim + m.L[m.n_layers - 1];
+  if (ncols > kHeadMaxQ * 32) {
+    set_error("head kernel: mf_dim + last layer width = %d exceeds %d", ncols, kHeadMaxQ * 32);
+    return MR_ERR_INVALID;
+  }
+  if (a.rows == 0) return MR_OK;
+  HeadParams p{};
+  p.m = m;
+  p.h_last = a.h_last;
+  p.users = a.users;
+  p.items = a.items;
+  p.labels = a.labels;
+  p.rows = a.rows;
+  p.row0 = a.row0;
+  p.user_div = a.user_div < 1 ? 1 : a.user_div;
+  p.inv_batch = a.inv_batch;
+  p.logits = a.logits;
+  p.probs = a.probs;
+  p.dz_last = a.dz_last;
+  p.stage_u = a.stage_u;
+  p.stage_i = a.stage_i;
+  p.head_partial = a.head_partial;
+  p.flags = a.flags;
+  const int grid = head_grid();
+  head_kernel<<<grid, kHeadThreads, 0, st>>>(p);
+  MR_LAUNCH_CHECK("head_kernel");
+  if (a.labels != nullptr) {
+    head_reduce_kernel<<<1, 256, 0, st>>>(a.head_partial, grid, ncols, a.d_wout_row0, a.d_bout_row0, a.loss_sum);
+    MR_LAUNCH_CHECK("head_reduce_kernel");
+  }
+  return MR_OK;
+}
+
+}  // namespace mr

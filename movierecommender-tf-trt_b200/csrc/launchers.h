@@ -50,6 +50,7 @@ struct RowUpdate {       // what to do with each reduced row gradient
   float lr_t, beta_1, beta_2, epsilon, lr;
   // two tables share one staged row: columns [0,d0) -> table 0, [d0,d0+d1) -> table 1
   int d0, d1;
+  int num_rows;          // rows of both tables; ids outside [0, num_rows) are skipped
   float *p0, *m0, *v0, *g0;  // table / Adam state / dense gradient table (mode DENSE writes g)
   float *p1, *m1, *v1, *g1;
 };
@@ -71,6 +72,74 @@ int launch_sample_negatives(const int64_t* rowptr, const int32_t* csr_items, int
                             const int32_t* pos_users, const int32_t* pos_items, int64_t P, int64_t first_index,
                             int negs, uint64_t seed, uint64_t epoch, int32_t* out_users, int32_t* out_items,
                             float* out_labels, cudaStream_t st);
+
+// ---- tc_dense.cu / tc_wgrad.cu / head.cu: tensor-core path of the train step ------------------------
+enum { TC_EPI_BIAS_RELU = 0, TC_EPI_MASK = 1, TC_EPI_STAGE = 2 };
+struct TcDenseArgs {
+  bool gather;            // A = [user row | item row] gathered by id, else a_dense
+  const float* a_dense;
+  const float* user_tab;
+  const float* item_tab;
+  const int32_t* users;
+  const int32_t* items;
+  int32_t num_users, num_items, d_u;
+  int32_t user_div;       // gather: row r uses users[r / user_div]
+  const float* b_packed;  // launch_pack_weights output
+  int32_t N, K;
+  int64_t rows, row0;
+  int epilogue;
+  const float* bias;
+  const float* mask_src;
+  float* out;
+  float* stage_u;
+  float* stage_i;
+  int32_t su, si;
+};
+int launch_tc_dense(const TcDenseArgs& a, cudaStream_t st);
+int launch_pack_weights(const float* W, int K_in, int N_out, int transpose, float* dst, cudaStream_t st);
+
+struct TcWgradArgs {
+  bool gather;            // A rows = [user row | item row] gathered by id, else a_dense [rows x Fa]
+  const float* a_dense;
+  const float* user_tab;
+  const float* item_tab;
+  const int32_t* users;
+  const int32_t* items;
+  int32_t num_users, num_items, d_u;
+  const float* z;         // [rows x Fb] launch-local rows
+  int32_t Fa, Fb;
+  int64_t rows, row0;
+  float* dw_partial;      // per-CTA rows of the dense-gradient partial buffer, this layer's W section
+  float* db_partial;      // same, bias section
+  int64_t partial_stride;
+  bool first;             // overwrite instead of accumulate
+};
+int tc_wgrad_grid();
+int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t st);
+
+struct HeadArgs {
+  const MrModel* model;
+  const float* h_last;    // [rows x L_last] launch-local rows
+  const int32_t* users;
+  const int32_t* items;
+  const float* labels;    // NULL = forward only
+  int64_t rows, row0;
+  int32_t user_div;       // row r uses users[r / user_div]
+  float inv_batch;
+  float* logits;          // global rows, may be NULL
+  float* probs;           // global rows, may be NULL
+  float* dz_last;         // [rows x L_last] launch-local rows (train)
+  float* stage_u;         // GMF row gradients go to columns [d_u, d_u+f) / [d_i, d_i+f) (train)
+  float* stage_i;
+  float* head_partial;    // head_partial_floats() scratch (train)
+  float* d_wout_row0;     // += d w_out  (row 0 of the dense partial buffer)
+  float* d_bout_row0;     // += d b_out
+  float* loss_sum;        // += sum of row losses
+  int32_t* flags;
+};
+int head_grid();
+size_t head_partial_floats(const MrModel& m);
+int launch_head(const HeadArgs& a, cudaStream_t st);
 
 // ---- tc_selftest.cu ---------------------------------------------------------------------------
 int launch_tc_probe(const float* raw_a, int n_words, int start_off, int lbo, int sbo, int a_mn, float* D,

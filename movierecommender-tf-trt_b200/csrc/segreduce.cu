@@ -60,7 +60,7 @@ struct ChunkInfo {
 template <bool VEC>
 __device__ __forceinline__ void flush_run(const RowUpdate& u, const ChunkInfo& ci, int key, int s, int t, int c,
                                           bool on, float4 acc) {
-  if (key == kSkip || !on) return;
+  if (key == kSkip || !on || (unsigned)key >= (unsigned)u.num_rows) return;
   const bool inc_first = (s == 0) && ci.first_inc;
   const bool inc_last = (t == ci.nvalid) && ci.last_inc;
   if (!inc_first && !inc_last) {

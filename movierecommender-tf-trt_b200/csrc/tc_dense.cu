@@ -1,0 +1,341 @@
+// tcgen05 dense-layer kernel of the NeuMF tower (forward layers and backward-activation layers):
+//
+//     OUT[rows x N] = epilogue( A[rows x K] . Bw[N x K]^T )        3xTF32 on the tensor cores, fp32 accumulate
+//
+//   A    : batch rows.  A_GATHER: row r = [user_mlp[u[r]] | item_mlp[i[r]]] (the embedding gather of
+//          model.py:161-172 fused into the first layer); A_DENSE: a row-major fp32 activation matrix.
+//   Bw   : a dense kernel (or its transpose), pre-split into TF32 hi/lo and pre-arranged in core-matrix
+//          order by pack_weights_kernel, so one cp.async.bulk per K-chunk drops it into shared memory.
+//   epilogue: EPI_BIAS_RELU  h = relu(acc + b)          forward Dense/ReLU (model.py:175-181)
+//             EPI_MASK       dz = acc * (h_prev > 0)    backward through the previous ReLU
+//             EPI_STAGE      rows of dL/dx0 split into the user / item staging buffers
+//
+// Persistent, warp-specialised CTA (416 threads), 128 batch rows per tile, K streamed in chunks of 32:
+//   warps 0-7  producers, two groups of four that take alternate K-chunks (twice the loads in flight):
+//              load A fp32 (gather or dense), split x = hi + lo (TF32), st.shared in core-matrix layout;
+//              lane 0 of each group's first warp also issues the bulk copy of the weight chunk
+//   warp  8    one elected thread issues tcgen05.mma: acc += Ahi.Bhi + Alo.Bhi + Ahi.Blo per K-step of 8
+//   warps 9-12 epilogue: tcgen05.ld the accumulator (double-buffered in TMEM so the next tile's MMAs run
+//              under this tile's epilogue), apply the epilogue, store to global
+// Stages are recycled with mbarriers: full[s] (4 producer arrivals + the bulk copy's bytes),
+// empty[s] (tcgen05.commit), acc_full/acc_empty per TMEM buffer.
+#include "launchers.h"
+#include "tc_common.cuh"
+
+namespace mr {
+
+constexpr int kTcThreads = 416;
+constexpr int kTcMmaWarp = 8;
+constexpr int kTcTileRows = 128;
+constexpr int kTcKC = 32;  // K elements per pipeline stage
+
+enum { A_GATHER = 0, A_DENSE = 1 };
+enum { EPI_BIAS_RELU = 0, EPI_MASK = 1, EPI_STAGE = 2 };
+
+struct TcDenseParams {
+  // A operand
+  const float* a_dense;  // [rows x K] (A_DENSE)
+  const float* user_tab; // (A_GATHER) user rows of width d_u, item rows of width K - d_u
+  const float* item_tab;
+  const int32_t* users;
+  const int32_t* items;
+  int32_t num_users, num_items, d_u, user_div;
+  // B operand: packed [K/32 chunks][hi, lo][N x 32] core-matrix order
+  const float* b_packed;
+  int32_t N, K;
+  int64_t rows;          // rows of this launch
+  int64_t row0;          // global index of the first row (ids, staging and outputs are indexed globally)
+  // epilogue
+  const float* bias;     // EPI_BIAS_RELU
+  const float* mask_src; // EPI_MASK: [rows x N], launch-local rows
+  float* out;            // EPI_BIAS_RELU / EPI_MASK: [rows x N], launch-local rows
+  float* stage_u;        // EPI_STAGE: global rows, widths su / si, split at d_u
+  float* stage_i;
+  int32_t su, si;
+  int32_t stages;        // pipeline depth
+};
+
+template <int AMODE, int EPI>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDenseParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[8], empty_bar[8], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, K = p.K, S = p.stages;
+  const int nchunks = K / kTcKC;
+  const uint32_t a_bytes = kTcTileRows * kTcKC * 4;  // one of hi / lo
+  const uint32_t b_bytes = (uint32_t)N * kTcKC * 4;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const int64_t ntiles = (p.rows + kTcTileRows - 1) / kTcTileRows;
+  uint32_t acc_cols = 32;
+  while (acc_cols < (uint32_t)N) acc_cols <<= 1;  // columns per accumulator buffer (power of two)
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      tc::mbar_init(&full_bar[s], 5);
+      tc::mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&acc_full[b], 1);
+      tc::mbar_init(&acc_empty[b], 4);
+    }
+    tc::mbar_init_fence();
+  }
+  if (warp == kTcMmaWarp) tc::tmem_alloc(&tmem_slot, 2 * acc_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 8) {
+    // ================================ producers =================================================
+    const int group = warp >> 2, pw = warp & 3;   // group g fills the chunks whose running index is g mod 2
+    int64_t n = 0;                                // running chunk index of this CTA
+    const int rsub = lane & 7, csub = lane >> 3;  // 8 rows x 4 sixteen-byte chunks per warp instruction
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t trow0 = tile * kTcTileRows;
+      // this lane's 4 rows of the tile: 32*warp + 8*g + rsub, g = 0..3
+      const float* src_u[4];
+      const float* src_i[4];
+      bool ok[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int64_t lr = trow0 + 32 * pw + 8 * g + rsub;  // launch-local row
+        ok[g] = lr < p.rows;
+        src_u[g] = nullptr;
+        src_i[g] = nullptr;
+        if (AMODE == A_GATHER) {
+          if (ok[g]) {
+            const int u = __ldg(p.users + (p.row0 + lr) / p.user_div), it = __ldg(p.items + p.row0 + lr);
+            if ((unsigned)u < (unsigned)p.num_users && (unsigned)it < (unsigned)p.num_items) {
+              src_u[g] = p.user_tab + (size_t)u * p.d_u;
+              src_i[g] = p.item_tab + (size_t)it * (K - p.d_u);
+            } else {
+              ok[g] = false;  // flagged by the head kernel; treated as a zero row here
+            }
+          }
+        } else {
+          src_u[g] = p.a_dense + (size_t)lr * K;
+        }
+      }
+      for (int c = 0; c < nchunks; ++c, ++n) {
+        if ((n & 1) != group) continue;
+        const int stage = (int)(n % S);
+        const uint32_t phase = (uint32_t)((n / S) & 1);
+        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + (size_t)stage * stage_bytes;
+        if (pw == 0 && lane == 0) {
+          tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * b_bytes);
+          tc::bulk_g2s(st + 2 * a_bytes, p.b_packed + (size_t)c * 2 * N * kTcKC, 2 * b_bytes, &full_bar[stage]);
+        }
+        const int col0 = c * kTcKC;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int r = 32 * pw + 8 * g + rsub;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cc = 4 * h + csub;  // 16-byte chunk 0..7 inside the 32-wide K chunk
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[g]) {
+              const int col = col0 + 4 * cc;
+              if (AMODE == A_GATHER) {
+                x = (col < p.d_u) ? ldg4(src_u[g] + col) : ldg4(src_i[g] + (col - p.d_u));
+              } else {
+                x = ldg4(src_u[g] + col);
+              }
+            }
+            float4 hi, lo;
+            tc::split_tf32x4(x, hi, lo);
+            const uint32_t off = (uint32_t)(((r >> 3) * 8 + cc) * 128 + (r & 7) * 16);
+            *reinterpret_cast<float4*>(st + off) = hi;
+            *reinterpret_cast<float4*>(st + a_bytes + off) = lo;
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
+      }
+    }
+  } else if (warp == kTcMmaWarp) {
+    // ================================ MMA issuer ================================================
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t idesc = tc::idesc_tf32(128, N, 0, 0);
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int b = (int)(it & 1);
+      tc::mbar_wait(&acc_empty[b], (uint32_t)((it >> 1) & 1) ^ 1);
+      tc::fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)b * acc_cols;
+      for (int c = 0; c < nchunks; ++c) {
+        tc::mbar_wait(&full_bar[stage], phase);
+        tc::fence_after_sync();
+        if (lane == 0) {
+          const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + 2 * a_bytes;
+#pragma unroll
+          for (int kk = 0; kk < kTcKC / 8; ++kk) {
+            const uint64_t ah = tc::smem_desc(sa + kk * 256, 128, 1024);
+            const uint64_t al = tc::smem_desc(sa + a_bytes + kk * 256, 128, 1024);
+            const uint64_t bh = tc::smem_desc(sb + kk * 256, 128, 1024);
+            const uint64_t bl = tc::smem_desc(sb + b_bytes + kk * 256, 128, 1024);
+            tc::mma_tf32(d_tmem, ah, bh, idesc, (c | kk) != 0);
+            tc::mma_tf32(d_tmem, al, bh, idesc, 1);
+            tc::mma_tf32(d_tmem, ah, bl, idesc, 1);
+          }
+          tc::mma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
+          if (c == nchunks - 1) tc::mma_commit(&acc_full[b]);
+        }
+        __syncwarp();
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue ==================================================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access (warps 9..12 -> 1,2,3,0)
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int b = (int)(it & 1);
+      tc::mbar_wait(&acc_full[b], (uint32_t)((it >> 1) & 1));
+      tc::fence_after_sync();
+      const int64_t lr = tile * kTcTileRows + 32 * quarter + lane;  // launch-local row
+      const bool ok = lr < p.rows;
+      const uint32_t taddr = tmem_base + (uint32_t)b * acc_cols + ((uint32_t)(32 * quarter) << 16);
+      for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(taddr + c0, v);
+        if (!ok) continue;
+        if (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(p.bias + c0 + i), 0.f);
+        } else if (EPI == EPI_MASK) {
+          const float4* m4 = reinterpret_cast<const float4*>(p.mask_src + (size_t)lr * N + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 m = __ldg(m4 + q);
+            if (!(m.x > 0.f)) v[4 * q + 0] = 0.f;
+            if (!(m.y > 0.f)) v[4 * q + 1] = 0.f;
+            if (!(m.z > 0.f)) v[4 * q + 2] = 0.f;
+            if (!(m.w > 0.f)) v[4 * q + 3] = 0.f;
+          }
+        }
+        float* dst;
+        if (EPI == EPI_STAGE) {
+          dst = (c0 < p.d_u) ? p.stage_u + (size_t)(p.row0 + lr) * p.su + c0
+                             : p.stage_i + (size_t)(p.row0 + lr) * p.si + (c0 - p.d_u);
+        } else {
+          dst = p.out + (size_t)lr * N + c0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == kTcMmaWarp) tc::tmem_dealloc(tmem_base, 2 * acc_cols);
+}
+
+// Pre-split a kernel into TF32 hi/lo and lay it out for the bulk copies of tc_dense_kernel.
+//   src: W (K_in x N_out) row-major (Keras layout).
+//   transpose = 0: operand rows n = output unit, cols k = input unit  (forward:  Bw[n][k] = W[k][n])
+//   transpose = 1: operand rows n = input unit,  cols k = output unit (backward: Bw[n][k] = W[n][k])
+//   dst: [Kop/32 chunks][hi, lo][Nop x 32] floats in core-matrix order.
+__global__ void pack_weights_kernel(const float* __restrict__ W, int K_in, int N_out, int transpose,
+                                    float* __restrict__ dst) {
+  const int Nop = transpose ? K_in : N_out, Kop = transpose ? N_out : K_in;
+  const int total = Nop * Kop;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int n = e / Kop, k = e - n * Kop;
+    const float x = transpose ? __ldg(W + (size_t)n * N_out + k) : __ldg(W + (size_t)k * N_out + n);
+    float hi, lo;
+    tc::split_tf32(x, hi, lo);
+    const int c = k / kTcKC, kc = k - c * kTcKC;
+    const size_t base = (size_t)c * 2 * Nop * kTcKC;
+    const uint32_t off = tc::core_off_rg_major(n, kc, kTcKC / 4) / 4;
+    dst[base + off] = hi;
+    dst[base + (size_t)Nop * kTcKC + off] = lo;
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+
+static size_t dense_stage_bytes(int N) { return (size_t)2 * kTcTileRows * kTcKC * 4 + (size_t)2 * N * kTcKC * 4; }
+
+template <int AMODE, int EPI>
+static int launch_dense_t(TcDenseParams p, cudaStream_t st) {
+  const size_t sb = dense_stage_bytes(p.N);
+  int stages = (int)((200 * 1024) / sb);
+  if (stages > 8) stages = 8;
+  if (stages < 2) {
+    set_error("tc dense: N=%d leaves fewer than 2 pipeline stages", p.N);
+    return MR_ERR_INVALID;
+  }
+  p.stages = stages;
+  const size_t smem = sb * stages;
+  auto kern = tc_dense_kernel<AMODE, EPI>;
+  MR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = (p.rows + kTcTileRows - 1) / kTcTileRows;
+  if (ntiles == 0) return MR_OK;
+  int64_t grid = sm_count();
+  if (grid > ntiles) grid = ntiles;
+  kern<<<(unsigned)grid, kTcThreads, smem, st>>>(p);
+  MR_LAUNCH_CHECK("tc_dense_kernel");
+  return MR_OK;
+}
+
+int launch_tc_dense(const TcDenseArgs& a, cudaStream_t st) {
+  TcDenseParams p{};
+  p.a_dense = a.a_dense;
+  p.user_tab = a.user_tab;
+  p.item_tab = a.item_tab;
+  p.users = a.users;
+  p.items = a.items;
+  p.num_users = a.num_users;
+  p.num_items = a.num_items;
+  p.d_u = a.d_u;
+  p.user_div = a.user_div < 1 ? 1 : a.user_div;
+  p.b_packed = a.b_packed;
+  p.N = a.N;
+  p.K = a.K;
+  p.rows = a.rows;
+  p.row0 = a.row0;
+  p.bias = a.bias;
+  p.mask_src = a.mask_src;
+  p.out = a.out;
+  p.stage_u = a.stage_u;
+  p.stage_i = a.stage_i;
+  p.su = a.su;
+  p.si = a.si;
+  if (a.N % 16 || a.N < 16 || a.N > 256 || a.K % kTcKC || a.K < kTcKC) {
+    set_error("tc dense: unsupported N=%d K=%d", a.N, a.K);
+    return MR_ERR_INVALID;
+  }
+  if (a.gather) {
+    if (a.epilogue != TC_EPI_BIAS_RELU) return MR_ERR_INVALID;
+    return launch_dense_t<A_GATHER, EPI_BIAS_RELU>(p, st);
+  }
+  switch (a.epilogue) {
+    case TC_EPI_BIAS_RELU: return launch_dense_t<A_DENSE, EPI_BIAS_RELU>(p, st);
+    case TC_EPI_MASK: return launch_dense_t<A_DENSE, EPI_MASK>(p, st);
+    case TC_EPI_STAGE: return launch_dense_t<A_DENSE, EPI_STAGE>(p, st);
+  }
+  return MR_ERR_INVALID;
+}
+
+int launch_pack_weights(const float* W, int K_in, int N_out, int transpose, float* dst, cudaStream_t st) {
+  const int total = K_in * N_out;
+  pack_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(W, K_in, N_out, transpose, dst);
+  MR_LAUNCH_CHECK("pack_weights_kernel");
+  return MR_OK;
+}
+
+}  // namespace mr

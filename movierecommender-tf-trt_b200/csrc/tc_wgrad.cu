@@ -1,0 +1,255 @@
+// tcgen05 weight-gradient kernel: dW[Fa x Fb] += A^T . Z and db[Fb] += colsum(Z), the reduction running
+// over batch rows (TensorFlow's MatMul-grad / BiasAddGrad of the Dense layers, model.py:175-181).
+//
+// Rows are the K dimension of the MMA, so both operands are MN-major: a row-major [rows x F] chunk goes
+// to shared memory as is (rows of 32 features, SWIZZLE_128B_BASE32B -- tc_common.cuh) and the tensor core
+// transposes it.  A = [user row | item row] gathered by id (first layer) or an activation matrix.
+// Each CTA owns a contiguous slice of 16-row chunks, keeps the whole dW in TMEM (Fa/128 accumulators of
+// Fb columns) for its slice, and adds it to its private row of the partial buffer at the end; the
+// cross-CTA sum happens in dense_reduce_kernel in a fixed order.
+//   warps 0-7  producers (two groups on alternate chunks): load, TF32 hi/lo split, st.shared; the
+//              threads that load Z also keep column sums for db
+//   warp  8    MMA issuer
+//   warps 0-3  epilogue after the last chunk (TMEM -> partial buffer)
+#include "launchers.h"
+#include "tc_common.cuh"
+
+namespace mr {
+
+constexpr int kWgThreads = 288;
+constexpr int kWgMmaWarp = 8;
+constexpr int kWgKC = 16;  // batch rows per pipeline stage
+
+struct TcWgradParams {
+  const float* a_dense;
+  const float* user_tab;
+  const float* item_tab;
+  const int32_t* users;
+  const int32_t* items;
+  int32_t num_users, num_items, d_u;
+  const float* z;
+  int32_t Fa, Fb;
+  int64_t rows, row0;
+  float* dw_partial;
+  float* db_partial;
+  int64_t partial_stride;
+  int32_t stages;
+};
+
+template <bool GATHER>
+__global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[8], empty_bar[8], done_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float db_red[128 * 4];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Fa = p.Fa, Fb = p.Fb, S = p.stages;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = (uint32_t)kWgKC * Fa * 4, z_bytes = (uint32_t)kWgKC * Fb * 4;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * z_bytes;
+  const int halves = Fa / 128;
+  uint32_t acc_cols = 32;
+  while (acc_cols < (uint32_t)(halves * Fb)) acc_cols <<= 1;
+
+  const int64_t total_chunks = (p.rows + kWgKC - 1) / kWgKC;
+  const int64_t per_cta = (total_chunks + gridDim.x - 1) / gridDim.x;
+  const int64_t chunk_lo = min(total_chunks, per_cta * blockIdx.x);
+  const int64_t chunk_hi = min(total_chunks, chunk_lo + per_cta);
+  const int64_t my_chunks = chunk_hi - chunk_lo;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      tc::mbar_init(&full_bar[s], 4);
+      tc::mbar_init(&empty_bar[s], 1);
+    }
+    tc::mbar_init(&done_bar, 1);
+    tc::mbar_init_fence();
+  }
+  if (warp == kWgMmaWarp) tc::tmem_alloc(&tmem_slot, acc_cols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of Z for this thread's fixed float4 column
+  const int zq = Fb >> 2;                          // float4 per Z row (8..64, divides 128)
+
+  if (warp < 8) {
+    const int group = warp >> 2;
+    const int t = tid & 127;  // thread index inside the producer group
+    const int aq = Fa >> 2;   // float4 per A row
+    for (int64_t n = group; n < my_chunks; n += 2) {
+      const int stage = (int)(n % S);
+      const uint32_t phase = (uint32_t)((n / S) & 1);
+      tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* st = smem + (size_t)stage * stage_bytes;
+      const int64_t crow0 = (chunk_lo + n) * kWgKC;  // launch-local first row of the chunk
+      // ---- A chunk: kWgKC rows x Fa
+      for (int idx = t; idx < kWgKC * aq; idx += 128) {
+        const int r = idx / aq, c = (idx - r * aq) << 2;
+        const int64_t lr = crow0 + r;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lr < p.rows) {
+          if (GATHER) {
+            const int u = __ldg(p.users + p.row0 + lr), it = __ldg(p.items + p.row0 + lr);
+            if ((unsigned)u < (unsigned)p.num_users && (unsigned)it < (unsigned)p.num_items)
+              x = (c < p.d_u) ? ldg4(p.user_tab + (size_t)u * p.d_u + c)
+                              : ldg4(p.item_tab + (size_t)it * (Fa - p.d_u) + (c - p.d_u));
+          } else {
+            x = ldg4(p.a_dense + (size_t)lr * Fa + c);
+          }
+        }
+        float4 hi, lo;
+        tc::split_tf32x4(x, hi, lo);
+        const uint32_t off = tc::mn_off(r, c, kWgKC / 4);
+        *reinterpret_cast<float4*>(st + off) = hi;
+        *reinterpret_cast<float4*>(st + a_bytes + off) = lo;
+      }
+      // ---- Z chunk: kWgKC rows x Fb (this thread always sees float4 column t % zq)
+      for (int idx = t; idx < kWgKC * zq; idx += 128) {
+        const int r = idx / zq, c = (idx - r * zq) << 2;
+        const int64_t lr = crow0 + r;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lr < p.rows) x = ldg4(p.z + (size_t)lr * Fb + c);
+        dbacc.x += x.x;
+        dbacc.y += x.y;
+        dbacc.z += x.z;
+        dbacc.w += x.w;
+        float4 hi, lo;
+        tc::split_tf32x4(x, hi, lo);
+        const uint32_t off = tc::mn_off(r, c, kWgKC / 4);
+        *reinterpret_cast<float4*>(st + 2 * a_bytes + off) = hi;
+        *reinterpret_cast<float4*>(st + 2 * a_bytes + z_bytes + off) = lo;
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
+    }
+  } else {
+    // ---- MMA issuer
+    const uint32_t idesc = tc::idesc_tf32(128, Fb, 1, 1);
+    const uint32_t lbo = (kWgKC / 4) * 512, sbo = 512;
+    for (int64_t n = 0; n < my_chunks; ++n) {
+      const int stage = (int)(n % S);
+      const uint32_t phase = (uint32_t)((n / S) & 1);
+      tc::mbar_wait(&full_bar[stage], phase);
+      tc::fence_after_sync();
+      if (lane == 0) {
+        const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t sz = sa + 2 * a_bytes;
+#pragma unroll
+        for (int kk = 0; kk < kWgKC / 8; ++kk) {
+          const uint64_t zh = tc::smem_desc(sz + kk * 1024, lbo, sbo, tc::kLayoutSw128Base32);
+          const uint64_t zl = tc::smem_desc(sz + z_bytes + kk * 1024, lbo, sbo, tc::kLayoutSw128Base32);
+          for (int h = 0; h < halves; ++h) {
+            // features [128h, 128h+128) of A = 4 blocks of 32, each kWgKC/4 groups of 512 bytes
+            const uint32_t aoff = (uint32_t)h * 4 * lbo + kk * 1024;
+            const uint64_t ah = tc::smem_desc(sa + aoff, lbo, sbo, tc::kLayoutSw128Base32);
+            const uint64_t al = tc::smem_desc(sa + a_bytes + aoff, lbo, sbo, tc::kLayoutSw128Base32);
+            const uint32_t d = tmem_base + (uint32_t)h * Fb;
+            tc::mma_tf32(d, ah, zh, idesc, (n | kk) != 0);
+            tc::mma_tf32(d, al, zh, idesc, 1);
+            tc::mma_tf32(d, ah, zl, idesc, 1);
+          }
+        }
+        tc::mma_commit(&empty_bar[stage]);
+        if (n == my_chunks - 1) tc::mma_commit(&done_bar);
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- bias gradient: fold the producer threads' column sums in a fixed order
+  if (warp < 8) {
+    // the two groups hold sums over disjoint chunks; lay them out [group][thread][4]
+    float* slot = db_red;  // 128 threads x 4 floats, group 0 first then group 1 added in order below
+    if ((warp >> 2) == 0) *reinterpret_cast<float4*>(slot + 4 * (tid & 127)) = dbacc;
+  }
+  __syncthreads();
+  if (warp >= 4 && warp < 8) {
+    float4 v = *reinterpret_cast<float4*>(db_red + 4 * (tid & 127));
+    v.x += dbacc.x; v.y += dbacc.y; v.z += dbacc.z; v.w += dbacc.w;
+    *reinterpret_cast<float4*>(db_red + 4 * (tid & 127)) = v;
+  }
+  __syncthreads();
+  if (tid < zq && p.db_partial != nullptr) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = tid; j < 128; j += zq) {
+      const float4 v = *reinterpret_cast<float4*>(db_red + 4 * j);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* dst = p.db_partial + (size_t)blockIdx.x * p.partial_stride + 4 * tid;
+    dst[0] += s.x;
+    dst[1] += s.y;
+    dst[2] += s.z;
+    dst[3] += s.w;
+  }
+
+  // ---- dW: TMEM -> this CTA's row of the partial buffer (accumulated across launches)
+  if (warp < 4 && my_chunks > 0) {
+    tc::mbar_wait(&done_bar, 0);
+    tc::fence_after_sync();
+    float* base = p.dw_partial + (size_t)blockIdx.x * p.partial_stride;
+    for (int h = 0; h < halves; ++h) {
+      const int m = 128 * h + 32 * warp + lane;  // input-feature index = row of dW
+      for (int c0 = 0; c0 < Fb; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem_base + (uint32_t)h * Fb + ((uint32_t)(32 * warp) << 16) + c0, v);
+        float* dst = base + (size_t)m * Fb + c0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dst[i] += v[i];
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == kWgMmaWarp) tc::tmem_dealloc(tmem_base, acc_cols);
+}
+
+int tc_wgrad_grid() { return sm_count(); }
+
+int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
+  if (a.Fa % 128 || a.Fa < 128 || a.Fa > 512 || a.Fb % 32 || a.Fb < 32 || a.Fb > 256 || (a.Fa / 128) * a.Fb > 512) {
+    set_error("tc wgrad: unsupported Fa=%d Fb=%d", a.Fa, a.Fb);
+    return MR_ERR_INVALID;
+  }
+  TcWgradParams p{};
+  p.a_dense = a.a_dense;
+  p.user_tab = a.user_tab;
+  p.item_tab = a.item_tab;
+  p.users = a.users;
+  p.items = a.items;
+  p.num_users = a.num_users;
+  p.num_items = a.num_items;
+  p.d_u = a.d_u;
+  p.z = a.z;
+  p.Fa = a.Fa;
+  p.Fb = a.Fb;
+  p.rows = a.rows;
+  p.row0 = a.row0;
+  p.dw_partial = a.dw_partial;
+  p.db_partial = a.db_partial;
+  p.partial_stride = a.partial_stride;
+  const size_t sb = (size_t)2 * kWgKC * (a.Fa + a.Fb) * 4;
+  int stages = (int)((190 * 1024) / sb);
+  if (stages > 8) stages = 8;
+  if (stages < 2) {
+    set_error("tc wgrad: Fa=%d Fb=%d leave fewer than 2 stages", a.Fa, a.Fb);
+    return MR_ERR_INVALID;
+  }
+  p.stages = stages;
+  const size_t smem = sb * stages + 1024;
+  const int grid = tc_wgrad_grid();
+  if (a.gather) {
+    MR_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_wgrad_kernel<true><<<grid, kWgThreads, smem, st>>>(p);
+  } else {
+    MR_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_wgrad_kernel<false><<<grid, kWgThreads, smem, st>>>(p);
+  }
+  MR_LAUNCH_CHECK("tc_wgrad_kernel");
+  return MR_OK;
+}
+
+}  // namespace mr

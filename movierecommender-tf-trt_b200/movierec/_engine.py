@@ -246,6 +246,9 @@ class NeuMFEngine(object):
                 g.user_gmf, g.item_gmf = self.g_tables[K_GMF_USER].data_ptr(), self.g_tables[K_GMF_ITEM].data_ptr()
         self._grads = g
 
+    def uses_tensor_cores(self):
+        return bool(nat.lib.mr_uses_tensor_cores(C.byref(self._model)))
+
     def _workspace(self, nbytes):
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
@@ -332,6 +335,12 @@ class NeuMFEngine(object):
                                        _ptr(pos), _ptr(probs), _ptr(sums), _ptr(ws), ws.numel(), self._stream()),
                   "mr_rank_eval")
         return pos, sums, rank, probs
+
+
+def set_compute_path(path):
+    """'auto' (tensor cores where the layer widths allow, else the SIMT kernel), 'simt' or 'tc'."""
+    code = {"auto": 0, "simt": 1, "tc": 2}[path]
+    nat.check(nat.lib.mr_set_compute_path(code), "mr_set_compute_path")
 
 
 def rank_scores(scores, group, k, label_col=None, want_rank=True, device=None):

@@ -83,6 +83,8 @@ SIGNATURES = {
     "mr_sort_pairs": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "mr_tc_probe": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mr_tc_gemm_selftest": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mr_set_compute_path": (C.c_int, [_i32]),
+    "mr_uses_tensor_cores": (C.c_int, [_PM]),
     "mr_profile_begin": (C.c_int, []),
     "mr_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mr_optimizer_flat": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _f, _f, _f, _vp]),
@@ -115,8 +117,9 @@ def check(rc, what):
         raise MovierecNativeError("{} failed (status {}): {}".format(what, rc, last_error()))
 
 
-NUM_PHASES = 8
-PHASE_NAMES = ["tile_train", "misc", "sort", "segreduce", "optimizer", "tile_forward", "rank", "sampler"]
+NUM_PHASES = 12
+PHASE_NAMES = ["tile_train", "misc", "sort", "segreduce", "optimizer", "tile_forward", "rank", "sampler",
+               "tc_dense_fwd", "tc_dense_bwd", "tc_wgrad", "head"]
 
 
 def profile_begin():
