@@ -140,7 +140,14 @@ static bool tc_eligible(const MrModel& m) {
 
 static bool use_tc(const MrModel& m) { return g_path != 1 && tc_eligible(m); }
 
-static int64_t tc_sub_batch() { return (int64_t)sm_count() * 128 * 2; }  // two 128-row tiles per SM
+// Rows per launch of the tensor-core kernels: the whole batch up to 2^20 rows (persistent CTAs need many
+// tiles each to reach steady state; intermediates of 1M rows are ~1.5 GB of workspace), split evenly above.
+static int64_t tc_sub_batch(int64_t B) {
+  const int64_t cap = (int64_t)1 << 20;
+  const int64_t parts = B <= cap ? 1 : (B + cap - 1) / cap;
+  const int64_t sb = ((B < 1 ? 1 : B) + parts - 1) / parts;
+  return (sb + 127) / 128 * 128;
+}
 
 struct TcWs {
   float* pack_f[MR_MAX_LAYERS];  // forward operand of W[l]   (rows = output unit)
@@ -151,10 +158,10 @@ struct TcWs {
   size_t total;
 };
 
-static TcWs carve_tc(const MrModel& m, bool train, void* ws) {
+static TcWs carve_tc(const MrModel& m, bool train, int64_t B, void* ws) {
   TcWs t{};
   Carver cv(ws);
-  const int64_t sb = tc_sub_batch();
+  const int64_t sb = tc_sub_batch(B);
   for (int l = 1; l < m.n_layers; ++l) {
     const size_t kn = (size_t)m.L[l - 1] * m.L[l];
     t.pack_f[l] = cv.take<float>(2 * kn);
@@ -240,7 +247,7 @@ static TrainWs carve_train(const MrModel& m, int64_t B, void* ws) {
   t.seg_ws = cv.take<char>(t.seg_ws_bytes);
   t.pos = cv.take<int32_t>(B);
   t.rank_partials = cv.take<float>(rank_partials_count(B));
-  t.tc_ws_bytes = tc_eligible(m) ? carve_tc(m, true, nullptr).total : 0;
+  t.tc_ws_bytes = tc_eligible(m) ? carve_tc(m, true, B, nullptr).total : 0;
   t.tc_ws = cv.take<char>(t.tc_ws_bytes);
   t.total = cv.off;
   return t;
@@ -301,7 +308,7 @@ size_t mr_forward_workspace_bytes(const MrModel* model, int64_t B) {
   (void)B;
   size_t n = 256 + align_up((size_t)max_tile_ctas() * sizeof(float), 256);
   if (model != nullptr && model->n_layers >= 1 && model->n_layers <= MR_MAX_LAYERS && tc_eligible(*model))
-    n += carve_tc(*model, false, nullptr).total;
+    n += carve_tc(*model, false, B, nullptr).total;
   return n;
 }
 
@@ -329,13 +336,13 @@ int mr_neumf_forward(const MrModel* model, const int32_t* users, const int32_t* 
   MR_CUDA(cudaMemsetAsync(flags, 0, 256, st));
   if (use_tc(*model) && labels == nullptr) {  // forward with a loss request is served by the SIMT kernel
     const MrModel& m = *model;
-    TcWs t = carve_tc(m, false, static_cast<char*>(ws) + cv.off);
+    TcWs t = carve_tc(m, false, B, static_cast<char*>(ws) + cv.off);
     prof_mark(MR_PHASE_MISC, st);
     for (int l = 1; l < m.n_layers; ++l) {
       rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 0, t.pack_f[l], st);
       if (rc != MR_OK) return rc;
     }
-    const int64_t sb = tc_sub_batch();
+    const int64_t sb = tc_sub_batch(B);
     for (int64_t r0 = 0; r0 < B; r0 += sb) {
       const int64_t r1 = r0 + sb < B ? r0 + sb : B;
       prof_mark(MR_PHASE_TC_DENSE_FWD, st);
@@ -412,14 +419,15 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     // ---- tensor-core path: per sub-batch, forward layers -> head -> per layer weight gradient + backward
     const int P = sm_count();  // rows of the partial buffer = CTAs of the weight-gradient kernel
     const int n = m.n_layers, f = m.mf_dim;
-    TcWs tw = carve_tc(m, true, t.tc_ws);
+    TcWs tw = carve_tc(m, true, B, t.tc_ws);
     MR_CUDA(cudaMemsetAsync(t.dense_partial, 0, (size_t)P * t.dense_stride * sizeof(float), st));
+    MR_CUDA(cudaMemsetAsync(tw.head_partial, 0, head_partial_floats(m) * sizeof(float), st));
     for (int l = 1; l < n; ++l) {
       rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 0, tw.pack_f[l], st);
       if (rc == MR_OK) rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 1, tw.pack_b[l], st);
       if (rc != MR_OK) return rc;
     }
-    const int64_t sb = tc_sub_batch();
+    const int64_t sb = tc_sub_batch(B);
     for (int64_t r0 = 0; r0 < B; r0 += sb) {
       const int64_t r1 = r0 + sb < B ? r0 + sb : B;
       prof_mark(MR_PHASE_TC_DENSE_FWD, st);
@@ -441,9 +449,6 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       h.stage_u = t.stage_u;
       h.stage_i = t.stage_i;
       h.head_partial = tw.head_partial;
-      h.d_wout_row0 = t.dense_partial + (m.w_out - m.dense);
-      h.d_bout_row0 = t.dense_partial + (m.b_out - m.dense);
-      h.loss_sum = step_out + MR_OUT_LOSS_SUM;
       h.flags = t.flags;
       rc = launch_head(h, st);
       if (rc != MR_OK) return rc;
@@ -495,6 +500,9 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       }
     }
     prof_mark(MR_PHASE_MISC, st);
+    rc = launch_head_reduce(m, tw.head_partial, t.dense_partial + (m.w_out - m.dense),
+                            t.dense_partial + (m.b_out - m.dense), step_out + MR_OUT_LOSS_SUM, st);
+    if (rc != MR_OK) return rc;
     rc = launch_dense_reduce(m, t.dense_partial, t.dense_stride, P, grads->dense, st);
     if (rc != MR_OK) return rc;
   } else {

@@ -12,7 +12,7 @@
 namespace mr {
 
 constexpr int kHeadThreads = 256;
-constexpr int kHeadMaxQ = 16;  // (f + L_last) / 32 columns per lane at most (f, L_last <= 256)
+constexpr int kHeadMaxQ = 16;  // (f + L_last) / 32 columns per lane at most (f + L_last <= 512)
 
 struct HeadParams {
   MrModel m;
@@ -32,17 +32,20 @@ struct HeadParams {
   int32_t* flags;
 };
 
+// MAXQ = columns per lane (compile-time so the per-lane arrays stay in registers and small models get
+// high occupancy: the kernel is latency/HBM bound).
+template <int MAXQ>
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) {
-  __shared__ float red[kHeadThreads / 32][kHeadMaxQ * 32 + 2];
+  __shared__ float red[kHeadThreads / 32][MAXQ * 32 + 2];
   const MrModel& m = p.m;
   const int f = m.mf_dim, Ln = m.L[m.n_layers - 1], ncols = f + Ln;
   const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
   const int su = d_u + f, si = d_i + f;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool train = p.labels != nullptr;
-  float accw[kHeadMaxQ];
+  float accw[MAXQ];
 #pragma unroll
-  for (int q = 0; q < kHeadMaxQ; ++q) accw[q] = 0.f;
+  for (int q = 0; q < MAXQ; ++q) accw[q] = 0.f;
   float accb = 0.f, accl = 0.f;
 
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -56,10 +59,10 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) 
       it = 0;
     }
     // column j of the head input: j < f -> gu[j]*gi[j], else h[j - f]; lane owns columns lane + 32q
-    float hv[kHeadMaxQ], ga[kHeadMaxQ], gb[kHeadMaxQ];
+    float hv[MAXQ], ga[MAXQ], gb[MAXQ];
     float s = 0.f;
 #pragma unroll
-    for (int q = 0; q < kHeadMaxQ; ++q) {
+    for (int q = 0; q < MAXQ; ++q) {
       const int j = lane + 32 * q;
       hv[q] = 0.f;
       ga[q] = 0.f;
@@ -86,7 +89,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) 
       if (!bad) accl += bce_logits(z, y);
       accb += dz;
 #pragma unroll
-      for (int q = 0; q < kHeadMaxQ; ++q) {
+      for (int q = 0; q < MAXQ; ++q) {
         const int j = lane + 32 * q;
         if (j < ncols) {
           accw[q] = fmaf(dz, hv[q], accw[q]);
@@ -104,28 +107,34 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) 
   if (train) {
     // per-warp sums -> shared -> this CTA's partial row, warps added in index order
 #pragma unroll
-    for (int q = 0; q < kHeadMaxQ; ++q) red[warp][lane + 32 * q] = accw[q];
+    for (int q = 0; q < MAXQ; ++q) red[warp][lane + 32 * q] = accw[q];
     if (lane == 0) {
-      red[warp][kHeadMaxQ * 32] = accb;  // every lane holds the same accb / accl
-      red[warp][kHeadMaxQ * 32 + 1] = accl;
+      red[warp][MAXQ * 32] = accb;  // every lane holds the same accb / accl
+      red[warp][MAXQ * 32 + 1] = accl;
     }
     __syncthreads();
     float* dst = p.head_partial + (size_t)blockIdx.x * (ncols + 2);
     for (int j = threadIdx.x; j < ncols + 2; j += blockDim.x) {
-      const int src = j < ncols ? j : kHeadMaxQ * 32 + (j - ncols);
+      const int src = j < ncols ? j : MAXQ * 32 + (j - ncols);
       float t = 0.f;
       for (int w = 0; w < kHeadThreads / 32; ++w) t += red[w][src];
-      dst[j] = t;
+      dst[j] += t;  // the partial rows are zeroed once per step and accumulate over the step's launches
     }
   }
 }
 
-// d w_out / d b_out += sum over CTAs (row 0 of the dense partial buffer), loss_sum += sum of CTA losses.
-__global__ void head_reduce_kernel(const float* __restrict__ head_partial, int grid_ctas, int ncols,
-                                   float* __restrict__ d_wout, float* __restrict__ d_bout, float* __restrict__ loss_sum) {
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ncols + 2; j += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int c = 0; c < grid_ctas; ++c) s += head_partial[(size_t)c * (ncols + 2) + j];
+// d w_out / d b_out / loss: sum of the CTA partial rows, one warp per column, lanes stride over the rows
+// and fold with the fixed shuffle tree (deterministic).  Runs once per step.
+__global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restrict__ head_partial, int grid_ctas,
+                                                          int ncols, float* __restrict__ d_wout,
+                                                          float* __restrict__ d_bout, float* __restrict__ loss_sum) {
+  const int lane = threadIdx.x & 31;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= ncols + 2) return;
+  float s = 0.f;
+  for (int c = lane; c < grid_ctas; c += 32) s += head_partial[(size_t)c * (ncols + 2) + j];
+  s = warp_sum(s);
+  if (lane == 0) {
     if (j < ncols) d_wout[j] += s;
     else if (j == ncols) *d_bout += s;
     else *loss_sum += s;
@@ -162,12 +171,19 @@ int launch_head(const HeadArgs& a, cudaStream_t st) {
   p.head_partial = a.head_partial;
   p.flags = a.flags;
   const int grid = head_grid();
-  head_kernel<<<grid, kHeadThreads, 0, st>>>(p);
+  if (ncols <= 128) head_kernel<4><<<grid, kHeadThreads, 0, st>>>(p);
+  else if (ncols <= 256) head_kernel<8><<<grid, kHeadThreads, 0, st>>>(p);
+  else head_kernel<16><<<grid, kHeadThreads, 0, st>>>(p);
   MR_LAUNCH_CHECK("head_kernel");
-  if (a.labels != nullptr) {
-    head_reduce_kernel<<<1, 256, 0, st>>>(a.head_partial, grid, ncols, a.d_wout_row0, a.d_bout_row0, a.loss_sum);
-    MR_LAUNCH_CHECK("head_reduce_kernel");
-  }
+  return MR_OK;
+}
+
+int launch_head_reduce(const MrModel& m, const float* head_partial, float* d_wout_row0, float* d_bout_row0,
+                       float* loss_sum, cudaStream_t st) {
+  const int ncols = m.mf_dim + m.L[m.n_layers - 1];
+  const int warps = ncols + 2;
+  head_reduce_kernel<<<(warps + 7) / 8, 256, 0, st>>>(head_partial, head_grid(), ncols, d_wout_row0, d_bout_row0, loss_sum);
+  MR_LAUNCH_CHECK("head_reduce_kernel");
   return MR_OK;
 }
 

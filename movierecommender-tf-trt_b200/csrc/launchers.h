@@ -131,12 +131,12 @@ struct HeadArgs {
   float* dz_last;         // [rows x L_last] launch-local rows (train)
   float* stage_u;         // GMF row gradients go to columns [d_u, d_u+f) / [d_i, d_i+f) (train)
   float* stage_i;
-  float* head_partial;    // head_partial_floats() scratch (train)
-  float* d_wout_row0;     // += d w_out  (row 0 of the dense partial buffer)
-  float* d_bout_row0;     // += d b_out
-  float* loss_sum;        // += sum of row losses
+  float* head_partial;    // head_partial_floats() accumulators, zeroed once per step (train)
   int32_t* flags;
 };
+// once per step: d w_out / d b_out (row 0 of the dense partial buffer) and loss_sum += the CTA partials
+int launch_head_reduce(const MrModel& m, const float* head_partial, float* d_wout_row0, float* d_bout_row0,
+                       float* loss_sum, cudaStream_t st);
 int head_grid();
 size_t head_partial_floats(const MrModel& m);
 int launch_head(const HeadArgs& a, cudaStream_t st);
