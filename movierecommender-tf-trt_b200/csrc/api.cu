@@ -132,6 +132,8 @@ static bool tc_eligible(const MrModel& m) {
     if (m.L[l] % 32 || m.L[l] > 256) return false;
   for (int l = 0; l + 1 < m.n_layers; ++l)
     if (m.L[l] % 128) return false;  // input width of every dense layer = M of the weight-gradient MMAs
+  for (int l = 1; l < m.n_layers; ++l)
+    if (m.L[l] & (m.L[l] - 1)) return false;  // output widths 32/64/128/256 (bias-gradient column ownership)
   if (m.mf_dim + m.L[m.n_layers - 1] > 512) return false;
   const uintptr_t a = reinterpret_cast<uintptr_t>(m.user_mlp) | reinterpret_cast<uintptr_t>(m.item_mlp) |
                       reinterpret_cast<uintptr_t>(m.dense);

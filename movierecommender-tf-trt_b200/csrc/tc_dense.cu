@@ -90,72 +90,98 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
 
   if (warp < 8) {
     // ================================ producers =================================================
-    const int group = warp >> 2, pw = warp & 3;   // group g fills the chunks whose running index is g mod 2
-    int64_t n = 0;                                // running chunk index of this CTA
+    // Group g (4 warps) fills the chunks whose running index is g mod 2.  The loads of a group's NEXT
+    // chunk are issued before the current one is converted, so each thread keeps 16 x 16 bytes in flight.
+    const int group = warp >> 2, pw = warp & 3;
     const int rsub = lane & 7, csub = lane >> 3;  // 8 rows x 4 sixteen-byte chunks per warp instruction
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t trow0 = tile * kTcTileRows;
-      // this lane's 4 rows of the tile: 32*warp + 8*g + rsub, g = 0..3
-      const float* src_u[4];
-      const float* src_i[4];
-      bool ok[4];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int64_t lr = trow0 + 32 * pw + 8 * g + rsub;  // launch-local row
-        ok[g] = lr < p.rows;
-        src_u[g] = nullptr;
-        src_i[g] = nullptr;
-        if (AMODE == A_GATHER) {
-          if (ok[g]) {
-            const int u = __ldg(p.users + (p.row0 + lr) / p.user_div), it = __ldg(p.items + p.row0 + lr);
-            if ((unsigned)u < (unsigned)p.num_users && (unsigned)it < (unsigned)p.num_items) {
-              src_u[g] = p.user_tab + (size_t)u * p.d_u;
-              src_i[g] = p.item_tab + (size_t)it * (K - p.d_u);
-            } else {
-              ok[g] = false;  // flagged by the head kernel; treated as a zero row here
-            }
-          }
-        } else {
-          src_u[g] = p.a_dense + (size_t)lr * K;
-        }
-      }
-      for (int c = 0; c < nchunks; ++c, ++n) {
-        if ((n & 1) != group) continue;
-        const int stage = (int)(n % S);
-        const uint32_t phase = (uint32_t)((n / S) & 1);
-        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* st = smem + (size_t)stage * stage_bytes;
-        if (pw == 0 && lane == 0) {
-          tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * b_bytes);
-          tc::bulk_g2s(st + 2 * a_bytes, p.b_packed + (size_t)c * 2 * N * kTcKC, 2 * b_bytes, &full_bar[stage]);
-        }
-        const int col0 = c * kTcKC;
+    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_tiles * nchunks;
+    int64_t cached_tile = -1;
+    const float* src_u[4];
+    const float* src_i[4];
+    bool ok[4];
+
+    auto issue_loads = [&](int64_t n, float4(&x)[8]) {
+      const int64_t tl = n / nchunks;
+      const int c = (int)(n - tl * nchunks);
+      if (tl != cached_tile) {  // this lane's 4 rows of the tile: 32*pw + 8*g + rsub
+        cached_tile = tl;
+        const int64_t trow0 = (blockIdx.x + tl * gridDim.x) * kTcTileRows;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const int r = 32 * pw + 8 * g + rsub;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int cc = 4 * h + csub;  // 16-byte chunk 0..7 inside the 32-wide K chunk
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int64_t lr = trow0 + 32 * pw + 8 * g + rsub;  // launch-local row
+          ok[g] = lr < p.rows;
+          src_u[g] = nullptr;
+          src_i[g] = nullptr;
+          if (AMODE == A_GATHER) {
             if (ok[g]) {
-              const int col = col0 + 4 * cc;
-              if (AMODE == A_GATHER) {
-                x = (col < p.d_u) ? ldg4(src_u[g] + col) : ldg4(src_i[g] + (col - p.d_u));
+              const int u = __ldg(p.users + (p.row0 + lr) / p.user_div), it = __ldg(p.items + p.row0 + lr);
+              if ((unsigned)u < (unsigned)p.num_users && (unsigned)it < (unsigned)p.num_items) {
+                src_u[g] = p.user_tab + (size_t)u * p.d_u;
+                src_i[g] = p.item_tab + (size_t)it * (K - p.d_u);
               } else {
-                x = ldg4(src_u[g] + col);
+                ok[g] = false;  // flagged by the head kernel; treated as a zero row here
               }
             }
-            float4 hi, lo;
-            tc::split_tf32x4(x, hi, lo);
-            const uint32_t off = (uint32_t)(((r >> 3) * 8 + cc) * 128 + (r & 7) * 16);
-            *reinterpret_cast<float4*>(st + off) = hi;
-            *reinterpret_cast<float4*>(st + a_bytes + off) = lo;
+          } else {
+            src_u[g] = p.a_dense + (size_t)lr * K;
           }
         }
-        tc::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
       }
+      const int col0 = c * kTcKC;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = col0 + 4 * (4 * h + csub);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok[g]) {
+            if (AMODE == A_GATHER) v = (col < p.d_u) ? ldg4(src_u[g] + col) : ldg4(src_i[g] + (col - p.d_u));
+            else v = ldg4(src_u[g] + col);
+          }
+          x[2 * g + h] = v;
+        }
+      }
+    };
+    auto store_chunk = [&](int64_t n, const float4(&x)[8]) {
+      const int c = (int)(n % nchunks);
+      const int stage = (int)(n % S);
+      const uint32_t phase = (uint32_t)((n / S) & 1);
+      tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* st = smem + (size_t)stage * stage_bytes;
+      if (pw == 0 && lane == 0) {
+        tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * b_bytes);
+        tc::bulk_g2s(st + 2 * a_bytes, p.b_packed + (size_t)c * 2 * N * kTcKC, 2 * b_bytes, &full_bar[stage]);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int r = 32 * pw + 8 * g + rsub;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int cc = 4 * h + csub;  // 16-byte chunk 0..7 inside the 32-wide K chunk
+          float4 hi, lo;
+          tc::split_tf32x4(x[2 * g + h], hi, lo);
+          const uint32_t off = (uint32_t)(((r >> 3) * 8 + cc) * 128 + (r & 7) * 16);
+          *reinterpret_cast<float4*>(st + off) = hi;
+          *reinterpret_cast<float4*>(st + a_bytes + off) = lo;
+        }
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
+    };
+
+    float4 xa[8], xb[8];
+    int64_t n = group;
+    if (n < total) issue_loads(n, xa);
+    while (n < total) {
+      if (n + 2 < total) issue_loads(n + 2, xb);
+      store_chunk(n, xa);
+      n += 2;
+      if (n >= total) break;
+      if (n + 2 < total) issue_loads(n + 2, xa);
+      store_chunk(n, xb);
+      n += 2;
     }
   } else if (warp == kTcMmaWarp) {
     // ================================ MMA issuer ================================================

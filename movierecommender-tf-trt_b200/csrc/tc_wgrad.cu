@@ -36,7 +36,8 @@ struct TcWgradParams {
   int32_t stages;
 };
 
-template <bool GATHER>
+// NA / NZ: float4 loads per producer thread and chunk for A / Z (Fa / 32 and Fb / 32).
+template <bool GATHER, int NA, int NZ>
 __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[8], empty_bar[8], done_bar;
@@ -76,55 +77,92 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
   const int zq = Fb >> 2;                          // float4 per Z row (8..64, divides 128)
 
   if (warp < 8) {
+    // producers: the loads of a group's next chunk are issued before the current one is converted
     const int group = warp >> 2;
-    const int t = tid & 127;  // thread index inside the producer group
-    const int aq = Fa >> 2;   // float4 per A row
-    for (int64_t n = group; n < my_chunks; n += 2) {
+    const int t = tid & 127;   // thread index inside the producer group
+    const int aq = Fa >> 2;    // float4 per A row
+
+    auto issue_loads = [&](int64_t n, float4(&xa)[NA], float4(&xz)[NZ]) {
+      const int64_t crow0 = (chunk_lo + n) * kWgKC;  // launch-local first row of the chunk
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        {
+          const int idx = t + 128 * i;
+          const int r = idx / aq, c = (idx - r * aq) << 2;
+          const int64_t lr = crow0 + r;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (lr < p.rows) {
+            if (GATHER) {
+              const int u = __ldg(p.users + p.row0 + lr), it = __ldg(p.items + p.row0 + lr);
+              if ((unsigned)u < (unsigned)p.num_users && (unsigned)it < (unsigned)p.num_items)
+                x = (c < p.d_u) ? ldg4(p.user_tab + (size_t)u * p.d_u + c)
+                                : ldg4(p.item_tab + (size_t)it * (Fa - p.d_u) + (c - p.d_u));
+            } else {
+              x = ldg4(p.a_dense + (size_t)lr * Fa + c);
+            }
+          }
+          xa[i] = x;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NZ; ++i) {
+        {
+          const int idx = t + 128 * i;
+          const int r = idx / zq, c = (idx - r * zq) << 2;
+          const int64_t lr = crow0 + r;
+          xz[i] = lr < p.rows ? ldg4(p.z + (size_t)lr * Fb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    auto store_chunk = [&](int64_t n, const float4(&xa)[NA], const float4(&xz)[NZ]) {
       const int stage = (int)(n % S);
       const uint32_t phase = (uint32_t)((n / S) & 1);
       tc::mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* st = smem + (size_t)stage * stage_bytes;
-      const int64_t crow0 = (chunk_lo + n) * kWgKC;  // launch-local first row of the chunk
-      // ---- A chunk: kWgKC rows x Fa
-      for (int idx = t; idx < kWgKC * aq; idx += 128) {
-        const int r = idx / aq, c = (idx - r * aq) << 2;
-        const int64_t lr = crow0 + r;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lr < p.rows) {
-          if (GATHER) {
-            const int u = __ldg(p.users + p.row0 + lr), it = __ldg(p.items + p.row0 + lr);
-            if ((unsigned)u < (unsigned)p.num_users && (unsigned)it < (unsigned)p.num_items)
-              x = (c < p.d_u) ? ldg4(p.user_tab + (size_t)u * p.d_u + c)
-                              : ldg4(p.item_tab + (size_t)it * (Fa - p.d_u) + (c - p.d_u));
-          } else {
-            x = ldg4(p.a_dense + (size_t)lr * Fa + c);
-          }
+#pragma unroll
+      for (int i = 0; i < NA; ++i) {
+        {
+          const int idx = t + 128 * i;
+          const int r = idx / aq, c = (idx - r * aq) << 2;
+          float4 hi, lo;
+          tc::split_tf32x4(xa[i], hi, lo);
+          const uint32_t off = tc::mn_off(r, c, kWgKC / 4);
+          *reinterpret_cast<float4*>(st + off) = hi;
+          *reinterpret_cast<float4*>(st + a_bytes + off) = lo;
         }
-        float4 hi, lo;
-        tc::split_tf32x4(x, hi, lo);
-        const uint32_t off = tc::mn_off(r, c, kWgKC / 4);
-        *reinterpret_cast<float4*>(st + off) = hi;
-        *reinterpret_cast<float4*>(st + a_bytes + off) = lo;
       }
-      // ---- Z chunk: kWgKC rows x Fb (this thread always sees float4 column t % zq)
-      for (int idx = t; idx < kWgKC * zq; idx += 128) {
-        const int r = idx / zq, c = (idx - r * zq) << 2;
-        const int64_t lr = crow0 + r;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lr < p.rows) x = ldg4(p.z + (size_t)lr * Fb + c);
-        dbacc.x += x.x;
-        dbacc.y += x.y;
-        dbacc.z += x.z;
-        dbacc.w += x.w;
-        float4 hi, lo;
-        tc::split_tf32x4(x, hi, lo);
-        const uint32_t off = tc::mn_off(r, c, kWgKC / 4);
-        *reinterpret_cast<float4*>(st + 2 * a_bytes + off) = hi;
-        *reinterpret_cast<float4*>(st + 2 * a_bytes + z_bytes + off) = lo;
+#pragma unroll
+      for (int i = 0; i < NZ; ++i) {
+        {  // this thread always sees float4 column t % zq of Z: keep its column sums for db
+          const int idx = t + 128 * i;
+          const int r = idx / zq, c = (idx - r * zq) << 2;
+          dbacc.x += xz[i].x;
+          dbacc.y += xz[i].y;
+          dbacc.z += xz[i].z;
+          dbacc.w += xz[i].w;
+          float4 hi, lo;
+          tc::split_tf32x4(xz[i], hi, lo);
+          const uint32_t off = tc::mn_off(r, c, kWgKC / 4);
+          *reinterpret_cast<float4*>(st + 2 * a_bytes + off) = hi;
+          *reinterpret_cast<float4*>(st + 2 * a_bytes + z_bytes + off) = lo;
+        }
       }
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
+    };
+
+    float4 a0[NA], z0[NZ], a1[NA], z1[NZ];
+    int64_t n = group;
+    if (n < my_chunks) issue_loads(n, a0, z0);
+    while (n < my_chunks) {
+      if (n + 2 < my_chunks) issue_loads(n + 2, a1, z1);
+      store_chunk(n, a0, z0);
+      n += 2;
+      if (n >= my_chunks) break;
+      if (n + 2 < my_chunks) issue_loads(n + 2, a0, z0);
+      store_chunk(n, a1, z1);
+      n += 2;
     }
   } else {
     // ---- MMA issuer
@@ -210,7 +248,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
 int tc_wgrad_grid() { return sm_count(); }
 
 int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
-  if (a.Fa % 128 || a.Fa < 128 || a.Fa > 512 || a.Fb % 32 || a.Fb < 32 || a.Fb > 256 || (a.Fa / 128) * a.Fb > 512) {
+  if (a.Fa % 128 || a.Fa < 128 || a.Fa > 256 || (a.Fb != 32 && a.Fb != 64 && a.Fb != 128 && a.Fb != 256) || (a.Fa / 128) * a.Fb > 512) {
     set_error("tc wgrad: unsupported Fa=%d Fb=%d", a.Fa, a.Fb);
     return MR_ERR_INVALID;
   }
@@ -241,12 +279,22 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
   p.stages = stages;
   const size_t smem = sb * stages + 1024;
   const int grid = tc_wgrad_grid();
-  if (a.gather) {
-    MR_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_wgrad_kernel<true><<<grid, kWgThreads, smem, st>>>(p);
-  } else {
-    MR_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_wgrad_kernel<false><<<grid, kWgThreads, smem, st>>>(p);
+  const int na = a.Fa / 32, nz = a.Fb / 32;  // kWgKC * (F / 4) / 128
+  int rc = MR_ERR_INVALID;
+#define MR_WG_CASE(G, NA_, NZ_)                                                                          \
+  if (a.gather == G && na == NA_ && nz == NZ_) {                                                         \
+    auto kern = tc_wgrad_kernel<G, NA_, NZ_>;                                                            \
+    MR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    kern<<<grid, kWgThreads, smem, st>>>(p);                                                             \
+    rc = MR_OK;                                                                                          \
+  }
+#define MR_WG_NZ(G, NA_) MR_WG_CASE(G, NA_, 1) MR_WG_CASE(G, NA_, 2) MR_WG_CASE(G, NA_, 4) MR_WG_CASE(G, NA_, 8)
+  MR_WG_NZ(true, 4) MR_WG_NZ(true, 8) MR_WG_NZ(false, 4) MR_WG_NZ(false, 8)
+#undef MR_WG_NZ
+#undef MR_WG_CASE
+  if (rc != MR_OK) {
+    set_error("tc wgrad: no kernel for Fa=%d Fb=%d", a.Fa, a.Fb);
+    return rc;
   }
   MR_LAUNCH_CHECK("tc_wgrad_kernel");
   return MR_OK;
