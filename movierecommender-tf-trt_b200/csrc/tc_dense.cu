@@ -11,7 +11,8 @@
 //             EPI_STAGE      rows of dL/dx0 split into the user / item staging buffers
 //
 // Persistent, warp-specialised CTA (416 threads), 128 batch rows per tile, K streamed in chunks of 32:
-//   warps 0-7  producers, two groups of four that take alternate K-chunks (twice the loads in flight):
+//   warps 0-7  producers, kTcGroups groups of four warps that take K-chunks round-robin; each thread
+//              issues the loads of its group's NEXT chunk before converting the current one:
 //              load A fp32 (gather or dense), split x = hi + lo (TF32), st.shared in core-matrix layout;
 //              lane 0 of each group's first warp also issues the bulk copy of the weight chunk
 //   warp  8    one elected thread issues tcgen05.mma: acc += Ahi.Bhi + Alo.Bhi + Ahi.Blo per K-step of 8
@@ -24,8 +25,9 @@
 
 namespace mr {
 
-constexpr int kTcThreads = 416;
-constexpr int kTcMmaWarp = 8;
+constexpr int kTcGroups = 2;                      // producer groups of 4 warps taking chunks round-robin
+constexpr int kTcMmaWarp = 4 * kTcGroups;
+constexpr int kTcThreads = 32 * (kTcMmaWarp + 5);  // producers + MMA warp + 4 epilogue warps
 constexpr int kTcTileRows = 128;
 constexpr int kTcKC = 32;  // K elements per pipeline stage
 
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      tc::mbar_init(&full_bar[s], 5);
+      tc::mbar_init(&full_bar[s], 5);  // 4 producer warps + the weight copy's expect_tx arrive
       tc::mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -88,9 +90,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
   tc::fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp < 8) {
+  if (warp < kTcMmaWarp) {
     // ================================ producers =================================================
-    // Group g (4 warps) fills the chunks whose running index is g mod 2.  The loads of a group's NEXT
+    // Group g (4 warps) fills the chunks whose running index is g mod kTcGroups.  The loads of a group's NEXT
     // chunk are issued before the current one is converted, so each thread keeps 16 x 16 bytes in flight.
     const int group = warp >> 2, pw = warp & 3;
     const int rsub = lane & 7, csub = lane >> 3;  // 8 rows x 4 sixteen-byte chunks per warp instruction
@@ -175,13 +177,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
     int64_t n = group;
     if (n < total) issue_loads(n, xa);
     while (n < total) {
-      if (n + 2 < total) issue_loads(n + 2, xb);
+      if (n + kTcGroups < total) issue_loads(n + kTcGroups, xb);
       store_chunk(n, xa);
-      n += 2;
+      n += kTcGroups;
       if (n >= total) break;
-      if (n + 2 < total) issue_loads(n + 2, xa);
+      if (n + kTcGroups < total) issue_loads(n + kTcGroups, xa);
       store_chunk(n, xb);
-      n += 2;
+      n += kTcGroups;
     }
   } else if (warp == kTcMmaWarp) {
     // ================================ MMA issuer ================================================
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
     }
   } else {
     // ================================ epilogue ==================================================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access (warps 9..12 -> 1,2,3,0)
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access (the 4 epilogue warps cover 0..3)
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int b = (int)(it & 1);
