@@ -1,0 +1,116 @@
+"""Data-parallel step (movierec._distributed) on CPU: two gloo ranks, the oracle standing in for the
+CUDA engine.  Checks the group-wise sharding and that local grads (scaled by 1/B_global) + ONE
+all-reduce + identical update reproduce the single-process step on the global batch."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist  # noqa: E402
+import torch.multiprocessing as mp  # noqa: E402
+
+from oracle import movierec_oracle as o  # noqa: E402
+
+
+class OracleEngine(object):
+    """Same surface as _engine.NeuMFEngine for the data-parallel wrapper (train_grads /
+    gradient_tensors / apply / dense / _tables), computing with the NumPy oracle."""
+
+    table_mode = "dense"
+
+    def __init__(self, weights, params):
+        self.params = params
+        self.w = {k: v.copy() for k, v in weights.items()}
+        self.state = o.new_opt_state(self.w)
+        self.names = list(self.w)
+        self.sizes = [self.w[k].size for k in self.names]
+        self.g_flat = torch.zeros(sum(self.sizes), dtype=torch.float32)
+        self.dense = torch.zeros(1)
+        self._tables = {}
+
+    def gradient_tensors(self):
+        return [self.g_flat]
+
+    def train_grads(self, users, items, labels, group=0, k=0, inv_global_batch=None):
+        c = o.forward(self.w, users, items)
+        g = o.backward(self.w, c, labels, inv_global_batch, self.params["layers_l2reg"])
+        self.g_flat.copy_(torch.from_numpy(np.concatenate([g[k_].reshape(-1) for k_ in self.names]).astype(np.float32)))
+        y = np.asarray(labels, np.float32)
+        return torch.tensor([float(np.sum(o.bce_from_logits(c["z"], y)))])
+
+    def apply(self):
+        flat = self.g_flat.numpy()
+        g, off = {}, 0
+        for k_, n in zip(self.names, self.sizes):
+            g[k_] = flat[off:off + n].reshape(self.w[k_].shape).copy()
+            off += n
+        p = self.params
+        o.adam_step(self.w, self.state, g, p["lr"], p["beta_1"], p["beta_2"])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+PARAMS = {"layers_sizes": [8, 6, 4], "layers_l2reg": [0.0, 0.0, 0.0], "optimizer": "adam", "lr": 0.01, "beta_1": 0.9,
+          "beta_2": 0.999, "num_negs_per_pos": 3, "k": 2}
+
+
+def _global_batch(step):
+    rng = np.random.default_rng(100 + step)
+    groups, negs = 11, 3  # 11 groups over 2 ranks: uneven split 6 + 5
+    users = np.repeat(rng.integers(0, 9, groups), negs + 1)
+    items = rng.integers(0, 13, groups * (negs + 1))
+    y = np.tile([0] * negs + [1], groups).astype(np.float32)
+    return users, items, y
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from movierec._distributed import DataParallelNeuMF, shard_batch
+    w0 = o.init_weights(9, 13, PARAMS["layers_sizes"], 2, np.random.default_rng(1))
+    dp = DataParallelNeuMF(OracleEngine(w0, PARAMS))
+    loss_local = []
+    for step in range(3):
+        users, items, y = _global_batch(step)
+        u, i, l = shard_batch(users, items, y, 4, world, rank)
+        assert len(l) % 4 == 0 and len(l) in (24, 20)  # whole groups only
+        loss = dp.train_step(u, i, l, global_rows=len(y), group=4, k=2)
+        loss_local.append(float(dp.all_reduce_sums(loss.clone())[0]))
+    if rank == 0:
+        np.savez(out, losses=np.array(loss_local), **dp.engine.w)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_data_parallel_matches_single_process(tmp_path):
+    out = str(tmp_path / "rank0.npz")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    w = o.init_weights(9, 13, PARAMS["layers_sizes"], 2, np.random.default_rng(1))
+    st = o.new_opt_state(w)
+    for step in range(3):
+        users, items, y = _global_batch(step)
+        loss, _, _ = o.train_step(w, st, users, items, y, PARAMS)
+        assert got["losses"][step] / len(y) == pytest.approx(loss, rel=1e-5)
+    for k in w:
+        np.testing.assert_allclose(got[k], w[k], rtol=2e-5, atol=1e-7, err_msg=k)
+
+
+def test_split_groups_covers_everything_once():
+    from movierec._distributed import split_groups
+    for n in (0, 1, 7, 8, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [split_groups(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
