@@ -156,6 +156,7 @@ struct TcWs {
   float* pack_b[MR_MAX_LAYERS];  // backward operand of W[l]  (rows = input unit)
   float* H[MR_MAX_LAYERS];       // activations of a sub-batch, H[l] (SB x L[l])
   float* dZ[MR_MAX_LAYERS];      // pre-activation gradients of a sub-batch
+  uint32_t* bits[MR_MAX_LAYERS]; // ReLU bits (H[l] > 0), one word per 32 units, written by the forward layer
   float* head_partial;
   size_t total;
 };
@@ -170,6 +171,7 @@ static TcWs carve_tc(const MrModel& m, bool train, int64_t B, void* ws) {
     if (train) t.pack_b[l] = cv.take<float>(2 * kn);
     t.H[l] = cv.take<float>((size_t)sb * m.L[l]);
     if (train) t.dZ[l] = cv.take<float>((size_t)sb * m.L[l]);
+    if (train) t.bits[l] = cv.take<uint32_t>((size_t)sb * (m.L[l] / 32));
   }
   t.head_partial = cv.take<float>(head_partial_floats(m));
   t.total = cv.off;
@@ -200,6 +202,7 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     a.epilogue = TC_EPI_BIAS_RELU;
     a.bias = m.b[l];
     a.out = t.H[l];
+    a.bits_out = t.bits[l];  // NULL in forward-only runs
     int rc = launch_tc_dense(a, st);
     if (rc != MR_OK) return rc;
   }
@@ -488,7 +491,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
         a.row0 = r0;
         if (l - 1 >= 1) {
           a.epilogue = TC_EPI_MASK;
-          a.mask_src = tw.H[l - 1];
+          a.mask_bits = tw.bits[l - 1];
           a.out = tw.dZ[l - 1];
         } else {
           a.epilogue = TC_EPI_STAGE;

@@ -89,7 +89,8 @@ struct TcDenseArgs {
   int64_t rows, row0;
   int epilogue;
   const float* bias;
-  const float* mask_src;
+  const uint32_t* mask_bits;  // TC_EPI_MASK: ReLU bits written by the forward layer
+  uint32_t* bits_out;         // TC_EPI_BIAS_RELU, optional
   float* out;
   float* stage_u;
   float* stage_i;

@@ -20,6 +20,8 @@
 //              under this tile's epilogue), apply the epilogue, store to global
 // Stages are recycled with mbarriers: full[s] (4 producer arrivals + the bulk copy's bytes),
 // empty[s] (tcgen05.commit), acc_full/acc_empty per TMEM buffer.
+#include <stdlib.h>
+
 #include "launchers.h"
 #include "tc_common.cuh"
 
@@ -30,6 +32,7 @@ constexpr int kTcMmaWarp = 4 * kTcGroups;
 constexpr int kTcThreads = 32 * (kTcMmaWarp + 5);  // producers + MMA warp + 4 epilogue warps
 constexpr int kTcTileRows = 128;
 constexpr int kTcKC = 32;  // K elements per pipeline stage
+constexpr int kEpiLd = 36;  // floats per row of an epilogue warp's 32x32 staging tile (16-byte aligned, conflict-free)
 
 enum { A_GATHER = 0, A_DENSE = 1 };
 enum { EPI_BIAS_RELU = 0, EPI_MASK = 1, EPI_STAGE = 2 };
@@ -49,12 +52,14 @@ struct TcDenseParams {
   int64_t row0;          // global index of the first row (ids, staging and outputs are indexed globally)
   // epilogue
   const float* bias;     // EPI_BIAS_RELU
-  const float* mask_src; // EPI_MASK: [rows x N], launch-local rows
+  const uint32_t* mask_bits;  // EPI_MASK: [rows x N/32] ReLU bits of the previous layer's output, launch-local rows
+  uint32_t* bits_out;    // EPI_BIAS_RELU, optional: [rows x N/32] bits (h > 0) for the backward pass
   float* out;            // EPI_BIAS_RELU / EPI_MASK: [rows x N], launch-local rows
   float* stage_u;        // EPI_STAGE: global rows, widths su / si, split at d_u
   float* stage_i;
   int32_t su, si;
   int32_t stages;        // pipeline depth
+  int32_t debug;         // MR_TC_DEBUG (diagnostics only): 1 = skip weight copies after the first pass, 2 = skip A loads
 };
 
 template <int AMODE, int EPI>
@@ -69,6 +74,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
   const uint32_t a_bytes = kTcTileRows * kTcKC * 4;  // one of hi / lo
   const uint32_t b_bytes = (uint32_t)N * kTcKC * 4;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  float* epi_smem = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes);  // 4 warps x 32 x kEpiLd floats
   const int64_t ntiles = (p.rows + kTcTileRows - 1) / kTcTileRows;
   uint32_t acc_cols = 32;
   while (acc_cols < (uint32_t)N) acc_cols <<= 1;  // columns per accumulator buffer (power of two)
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
         for (int h = 0; h < 2; ++h) {
           const int col = col0 + 4 * (4 * h + csub);
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok[g]) {
+          if (ok[g] && !(p.debug & 2)) {
             if (AMODE == A_GATHER) v = (col < p.d_u) ? ldg4(src_u[g] + col) : ldg4(src_i[g] + (col - p.d_u));
             else v = ldg4(src_u[g] + col);
           }
@@ -152,9 +158,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       tc::mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* st = smem + (size_t)stage * stage_bytes;
       if (pw == 0 && lane == 0) {
-        tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * b_bytes);
-        tc::bulk_g2s(st + 2 * a_bytes, p.b_packed + (size_t)c * 2 * N * kTcKC, 2 * b_bytes, &full_bar[stage]);
+        if ((p.debug & 1) && n >= S) {
+          tc::mbar_arrive(&full_bar[stage]);
+        } else {
+          tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * b_bytes);
+          tc::bulk_g2s(st + 2 * a_bytes, p.b_packed + (size_t)c * 2 * N * kTcKC, 2 * b_bytes, &full_bar[stage]);
+        }
       }
+      if (!(p.debug & 4))
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int r = 32 * pw + 8 * g + rsub;
@@ -228,39 +239,70 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int b = (int)(it & 1);
+      const int64_t wrow0 = tile * kTcTileRows + 32 * quarter;  // launch-local first row of this warp
+      uint32_t mbits[8];  // EPI_MASK: this thread's row, all N/32 words, fetched before the accumulator is ready
+      if (EPI == EPI_MASK) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          mbits[q] = (q < (N >> 5) && wrow0 + lane < p.rows) ? __ldg(p.mask_bits + (size_t)(wrow0 + lane) * (N >> 5) + q) : 0u;
+      }
       tc::mbar_wait(&acc_full[b], (uint32_t)((it >> 1) & 1));
       tc::fence_after_sync();
-      const int64_t lr = tile * kTcTileRows + 32 * quarter + lane;  // launch-local row
-      const bool ok = lr < p.rows;
       const uint32_t taddr = tmem_base + (uint32_t)b * acc_cols + ((uint32_t)(32 * quarter) << 16);
-      for (int c0 = 0; c0 < N; c0 += 16) {
-        float v[16];
+      // 32 columns per pass: TMEM -> registers (thread = row) -> shared tile -> coalesced global stores
+      // (thread-per-row stores wrote 16-byte pieces of 32 different rows per instruction and made the
+      // epilogue the bottleneck of the backward layers).
+      float* tile_s = epi_smem + (size_t)quarter * (32 * kEpiLd);
+      const int64_t my_lr = wrow0 + lane;  // the row this thread owns while the data is thread-per-row
+      const bool my_ok = my_lr < p.rows;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
         tc::tmem_ld16(taddr + c0, v);
-        if (!ok) continue;
+        tc::tmem_ld16(taddr + c0 + 16, v + 16);
         if (EPI == EPI_BIAS_RELU) {
+          uint32_t bits = 0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(p.bias + c0 + i), 0.f);
+          for (int q = 0; q < 8; ++q) {
+            const float4 bv = ldg4(p.bias + c0 + 4 * q);
+            v[4 * q + 0] = fmaxf(v[4 * q + 0] + bv.x, 0.f);
+            v[4 * q + 1] = fmaxf(v[4 * q + 1] + bv.y, 0.f);
+            v[4 * q + 2] = fmaxf(v[4 * q + 2] + bv.z, 0.f);
+            v[4 * q + 3] = fmaxf(v[4 * q + 3] + bv.w, 0.f);
+          }
+          if (p.bits_out != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
+            if (my_ok) p.bits_out[(size_t)my_lr * (N >> 5) + (c0 >> 5)] = bits;
+          }
         } else if (EPI == EPI_MASK) {
-          const float4* m4 = reinterpret_cast<const float4*>(p.mask_src + (size_t)lr * N + c0);
+          const uint32_t bits = mbits[c0 >> 5];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 m = __ldg(m4 + q);
-            if (!(m.x > 0.f)) v[4 * q + 0] = 0.f;
-            if (!(m.y > 0.f)) v[4 * q + 1] = 0.f;
-            if (!(m.z > 0.f)) v[4 * q + 2] = 0.f;
-            if (!(m.w > 0.f)) v[4 * q + 3] = 0.f;
+          for (int i = 0; i < 32; ++i)
+            if (!((bits >> i) & 1u)) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(tile_s + lane * kEpiLd + 4 * q) =
+              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        if (!(p.debug & 8)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int idx = lane + 32 * j, r = idx >> 3, c = c0 + 4 * (idx & 7);
+            const int64_t lr = wrow0 + r;
+            if (lr >= p.rows) continue;
+            const float4 x = *reinterpret_cast<const float4*>(tile_s + r * kEpiLd + 4 * (idx & 7));
+            float* dst;
+            if (EPI == EPI_STAGE) {
+              dst = (c < p.d_u) ? p.stage_u + (size_t)(p.row0 + lr) * p.su + c
+                                : p.stage_i + (size_t)(p.row0 + lr) * p.si + (c - p.d_u);
+            } else {
+              dst = p.out + (size_t)lr * N + c;
+            }
+            *reinterpret_cast<float4*>(dst) = x;
           }
         }
-        float* dst;
-        if (EPI == EPI_STAGE) {
-          dst = (c0 < p.d_u) ? p.stage_u + (size_t)(p.row0 + lr) * p.su + c0
-                             : p.stage_i + (size_t)(p.row0 + lr) * p.si + (c0 - p.d_u);
-        } else {
-          dst = p.out + (size_t)lr * N + c0;
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -301,14 +343,19 @@ static size_t dense_stage_bytes(int N) { return (size_t)2 * kTcTileRows * kTcKC 
 template <int AMODE, int EPI>
 static int launch_dense_t(TcDenseParams p, cudaStream_t st) {
   const size_t sb = dense_stage_bytes(p.N);
-  int stages = (int)((200 * 1024) / sb);
+  const size_t epi_bytes = (size_t)4 * 32 * kEpiLd * sizeof(float);
+  int stages = (int)((226 * 1024 - epi_bytes - 2048) / sb);
   if (stages > 8) stages = 8;
   if (stages < 2) {
     set_error("tc dense: N=%d leaves fewer than 2 pipeline stages", p.N);
     return MR_ERR_INVALID;
   }
   p.stages = stages;
-  const size_t smem = sb * stages;
+  {
+    const char* dbg = getenv("MR_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
+  const size_t smem = sb * stages + epi_bytes;
   auto kern = tc_dense_kernel<AMODE, EPI>;
   MR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = (p.rows + kTcTileRows - 1) / kTcTileRows;
@@ -337,13 +384,14 @@ int launch_tc_dense(const TcDenseArgs& a, cudaStream_t st) {
   p.rows = a.rows;
   p.row0 = a.row0;
   p.bias = a.bias;
-  p.mask_src = a.mask_src;
+  p.mask_bits = a.mask_bits;
+  p.bits_out = a.bits_out;
   p.out = a.out;
   p.stage_u = a.stage_u;
   p.stage_i = a.stage_i;
   p.su = a.su;
   p.si = a.si;
-  if (a.N % 16 || a.N < 16 || a.N > 256 || a.K % kTcKC || a.K < kTcKC) {
+  if (a.N % 32 || a.N < 32 || a.N > 256 || a.K % kTcKC || a.K < kTcKC) {
     set_error("tc dense: unsupported N=%d K=%d", a.N, a.K);
     return MR_ERR_INVALID;
   }

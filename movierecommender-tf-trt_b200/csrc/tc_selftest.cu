@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(128) tc_gemm_selftest_kernel(const float* __re
     for (int e = tid; e < R * Cc; e += blockDim.x) {
       const int r = e / Cc, c = e - r * Cc;
       float hi, lo;
-      tc::split_tf32(A[e], hi, lo);
+      if (three_x == 2) tc::split_tf32_fast(A[e], hi, lo);  // the activation-path split
+      else tc::split_tf32(A[e], hi, lo);
       const uint32_t off = a_mn ? tc::mn_off(r, c, K >> 2) : tc::core_off_rg_major(r, c, Cc >> 2);
       *reinterpret_cast<float*>(a_hi + off) = hi;
       *reinterpret_cast<float*>(a_lo + off) = lo;

@@ -42,6 +42,16 @@ def test_tc_gemm_3xtf32_is_fp32_accurate(case):
     assert err < 2e-6, "3xTF32 relative error {:.3e} (first row got {} want {})".format(err, got[0, :4], want[0, :4])
 
 
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "N{}K{}a{}b{}".format(*c))
+def test_tc_gemm_fast_activation_split_is_fp32_accurate(case):
+    """three_x = 2: A split by truncation (hi = x & ~0x1fff, lo = x - hi, not re-rounded), B split exactly --
+    the combination the production kernels use (activations x pre-packed weights)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    err, got, want = run_case(*case, three_x=2)
+    assert err < 4e-6, "fast-split 3xTF32 relative error {:.3e}".format(err)
+
+
 @pytest.mark.parametrize("case", CASES[:2] + CASES[4:6], ids=lambda c: "N{}K{}a{}b{}".format(*c))
 def test_tc_gemm_plain_tf32_is_tf32_accurate(case):
     if not torch.cuda.is_available():
