@@ -48,57 +48,92 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) 
   for (int q = 0; q < MAXQ; ++q) accw[q] = 0.f;
   float accb = 0.f, accl = 0.f;
 
+  // kRows rows per warp and iteration, phases interleaved across the rows (ids of all rows, then all
+  // row loads, then the reductions, then the stores): the kernel is latency-bound, so the loads of
+  // several independent rows must be in flight together.  The order in which a warp folds rows into
+  // its d w_out / d b_out / loss sums is fixed (rr = 0..kRows-1), so results stay deterministic.
+  constexpr int kRows = MAXQ <= 4 ? 4 : 2;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t lr = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; lr < p.rows; lr += warps) {
-    const int64_t gr = p.row0 + lr;
-    int u = __ldg(p.users + gr / p.user_div), it = __ldg(p.items + gr);
-    const bool bad = (unsigned)u >= (unsigned)m.num_users || (unsigned)it >= (unsigned)m.num_items;
-    if (bad) {
-      if (lane == 0) atomicOr(p.flags, 1);
-      u = 0;
-      it = 0;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (int64_t base = w0 * kRows; base < p.rows; base += warps * kRows) {
+    int u[kRows], it[kRows];
+    bool live[kRows], bad[kRows];
+#pragma unroll
+    for (int rr = 0; rr < kRows; ++rr) {
+      const int64_t lr = base + rr;
+      live[rr] = lr < p.rows;
+      u[rr] = 0;
+      it[rr] = 0;
+      if (live[rr]) {
+        u[rr] = __ldg(p.users + (p.row0 + lr) / p.user_div);
+        it[rr] = __ldg(p.items + p.row0 + lr);
+      }
     }
     // column j of the head input: j < f -> gu[j]*gi[j], else h[j - f]; lane owns columns lane + 32q
-    float hv[MAXQ], ga[MAXQ], gb[MAXQ];
-    float s = 0.f;
+    float hv[kRows][MAXQ], ga[kRows][MAXQ], gb[kRows][MAXQ];
 #pragma unroll
-    for (int q = 0; q < MAXQ; ++q) {
-      const int j = lane + 32 * q;
-      hv[q] = 0.f;
-      ga[q] = 0.f;
-      gb[q] = 0.f;
-      if (j < f) {
-        ga[q] = __ldg(m.user_gmf + (size_t)u * f + j);
-        gb[q] = __ldg(m.item_gmf + (size_t)it * f + j);
-        hv[q] = ga[q] * gb[q];
-      } else if (j < ncols) {
-        hv[q] = __ldg(p.h_last + (size_t)lr * Ln + (j - f));
+    for (int rr = 0; rr < kRows; ++rr) {
+      bad[rr] = (unsigned)u[rr] >= (unsigned)m.num_users || (unsigned)it[rr] >= (unsigned)m.num_items;
+      if (bad[rr]) {
+        if (lane == 0) atomicOr(p.flags, 1);
+        u[rr] = 0;
+        it[rr] = 0;
       }
-      if (j < ncols) s = fmaf(__ldg(m.w_out + j), hv[q], s);
-    }
-    s = warp_sum(s);
-    const float z = s + __ldg(m.b_out);
-    const float pr = sigmoidf_stable(z);
-    if (lane == 0) {
-      if (p.logits != nullptr) p.logits[gr] = bad ? nanf("") : z;
-      if (p.probs != nullptr) p.probs[gr] = bad ? nanf("") : pr;
-    }
-    if (train) {
-      const float y = __ldg(p.labels + gr);
-      const float dz = bad ? 0.f : (pr - y) * p.inv_batch;
-      if (!bad) accl += bce_logits(z, y);
-      accb += dz;
+      const int64_t lr = base + rr;
 #pragma unroll
       for (int q = 0; q < MAXQ; ++q) {
         const int j = lane + 32 * q;
-        if (j < ncols) {
-          accw[q] = fmaf(dz, hv[q], accw[q]);
-          const float g = dz * __ldg(m.w_out + j);
+        hv[rr][q] = 0.f;
+        ga[rr][q] = 0.f;
+        gb[rr][q] = 0.f;
+        if (live[rr]) {
           if (j < f) {
-            p.stage_u[(size_t)gr * su + d_u + j] = g * gb[q];
-            p.stage_i[(size_t)gr * si + d_i + j] = g * ga[q];
-          } else {
-            p.dz_last[(size_t)lr * Ln + (j - f)] = hv[q] > 0.f ? g : 0.f;
+            ga[rr][q] = __ldg(m.user_gmf + (size_t)u[rr] * f + j);
+            gb[rr][q] = __ldg(m.item_gmf + (size_t)it[rr] * f + j);
+          } else if (j < ncols) {
+            hv[rr][q] = __ldg(p.h_last + (size_t)lr * Ln + (j - f));
+          }
+        }
+      }
+    }
+    float wv[MAXQ];
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) wv[q] = (lane + 32 * q < ncols) ? __ldg(m.w_out + lane + 32 * q) : 0.f;
+    const float b_out = __ldg(m.b_out);
+#pragma unroll
+    for (int rr = 0; rr < kRows; ++rr) {
+      if (!live[rr]) continue;  // warp-uniform
+      const int64_t lr = base + rr, gr = p.row0 + lr;
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < MAXQ; ++q) {
+        if (lane + 32 * q < f) hv[rr][q] = ga[rr][q] * gb[rr][q];
+        s = fmaf(wv[q], hv[rr][q], s);
+      }
+      s = warp_sum(s);
+      const float z = s + b_out;
+      const float pr = sigmoidf_stable(z);
+      if (lane == 0) {
+        if (p.logits != nullptr) p.logits[gr] = bad[rr] ? nanf("") : z;
+        if (p.probs != nullptr) p.probs[gr] = bad[rr] ? nanf("") : pr;
+      }
+      if (train) {
+        const float y = __ldg(p.labels + gr);
+        const float dz = bad[rr] ? 0.f : (pr - y) * p.inv_batch;
+        if (!bad[rr]) accl += bce_logits(z, y);
+        accb += dz;
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q) {
+          const int j = lane + 32 * q;
+          if (j < ncols) {
+            accw[q] = fmaf(dz, hv[rr][q], accw[q]);
+            const float g = dz * wv[q];
+            if (j < f) {
+              p.stage_u[(size_t)gr * su + d_u + j] = g * gb[rr][q];
+              p.stage_i[(size_t)gr * si + d_i + j] = g * ga[rr][q];
+            } else {
+              p.dz_last[(size_t)lr * Ln + (j - f)] = hv[rr][q] > 0.f ? g : 0.f;
+            }
           }
         }
       }

@@ -150,6 +150,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// Pull a line into L2 ahead of use (no register or shared-memory cost; the producers' register prefetch
+// only covers one chunk, L2 prefetch covers the DRAM part of the latency several chunks ahead).
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- operand tile addressing ---------------------------------------------------------------------
 // Byte offset of element (r, c) of a tile stored as core matrices [row group][column chunk]:
 //   ncc = number of 16-byte column chunks per row (cols / 4).

@@ -11,6 +11,8 @@
 //              threads that load Z also keep column sums for db
 //   warp  8    MMA issuer
 //   warps 0-3  epilogue after the last chunk (TMEM -> partial buffer)
+#include <stdlib.h>
+
 #include "launchers.h"
 #include "tc_common.cuh"
 
@@ -34,6 +36,7 @@ struct TcWgradParams {
   float* db_partial;
   int64_t partial_stride;
   int32_t stages;
+  int32_t debug;  // MR_TC_DEBUG (diagnostics only): 2 = skip global loads, 4 = skip convert + shared stores
 };
 
 // NA / NZ: float4 loads per producer thread and chunk for A / Z (Fa / 32 and Fb / 32).
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
           const int r = idx / aq, c = (idx - r * aq) << 2;
           const int64_t lr = crow0 + r;
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (lr < p.rows) {
+          if (lr < p.rows && !(p.debug & 2)) {
             if (GATHER) {
               const int u = __ldg(p.users + p.row0 + lr), it = __ldg(p.items + p.row0 + lr);
               if ((unsigned)u < (unsigned)p.num_users && (unsigned)it < (unsigned)p.num_items)
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
           const int idx = t + 128 * i;
           const int r = idx / zq, c = (idx - r * zq) << 2;
           const int64_t lr = crow0 + r;
-          xz[i] = lr < p.rows ? ldg4(p.z + (size_t)lr * Fb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xz[i] = (lr < p.rows && !(p.debug & 2)) ? ldg4(p.z + (size_t)lr * Fb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     };
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
       const uint32_t phase = (uint32_t)((n / S) & 1);
       tc::mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* st = smem + (size_t)stage * stage_bytes;
+      if (!(p.debug & 4)) {
 #pragma unroll
       for (int i = 0; i < NA; ++i) {
         {
@@ -146,6 +150,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
           *reinterpret_cast<float4*>(st + 2 * a_bytes + off) = hi;
           *reinterpret_cast<float4*>(st + 2 * a_bytes + z_bytes + off) = lo;
         }
+      }
       }
       tc::fence_proxy_async();
       __syncwarp();
@@ -277,6 +282,10 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
     return MR_ERR_INVALID;
   }
   p.stages = stages;
+  {
+    const char* dbg = getenv("MR_TC_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+  }
   const size_t smem = sb * stages + 1024;
   const int grid = tc_wgrad_grid();
   const int na = a.Fa / 32, nz = a.Fb / 32;  // kWgKC * (F / 4) / 128
