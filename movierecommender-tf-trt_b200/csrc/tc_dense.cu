@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       const int c = (int)(n % nchunks);
       const int stage = (int)(n % S);
       const uint32_t phase = (uint32_t)((n / S) & 1);
-      tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (p.debug & 64) tc::mbar_wait_warp(&empty_bar[stage], phase ^ 1); else tc::mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* st = smem + (size_t)stage * stage_bytes;
       if (pw == 0 && lane == 0) {
         if ((p.debug & 1) && n >= S) {
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
           *reinterpret_cast<float4*>(st + a_bytes + off) = lo;
         }
       }
-      tc::fence_proxy_async();
+      if (!(p.debug & 16)) tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
     };
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       tc::fence_after_sync();
       const uint32_t d_tmem = tmem_base + (uint32_t)b * acc_cols;
       for (int c = 0; c < nchunks; ++c) {
-        tc::mbar_wait(&full_bar[stage], phase);
+        if (p.debug & 64) tc::mbar_wait_warp(&full_bar[stage], phase); else tc::mbar_wait(&full_bar[stage], phase);
         tc::fence_after_sync();
         if (lane == 0) {
           const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       float* tile_s = epi_smem + (size_t)quarter * (32 * kEpiLd);
       const int64_t my_lr = wrow0 + lane;  // the row this thread owns while the data is thread-per-row
       const bool my_ok = my_lr < p.rows;
-      for (int c0 = 0; c0 < N; c0 += 32) {
+      for (int c0 = 0; c0 < ((p.debug & 32) ? 0 : N); c0 += 32) {
         float v[32];
         tc::tmem_ld16(taddr + c0, v);
         tc::tmem_ld16(taddr + c0 + 16, v + 16);

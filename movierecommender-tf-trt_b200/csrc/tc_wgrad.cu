@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
     auto store_chunk = [&](int64_t n, const float4(&xa)[NA], const float4(&xz)[NZ]) {
       const int stage = (int)(n % S);
       const uint32_t phase = (uint32_t)((n / S) & 1);
-      tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (p.debug & 64) tc::mbar_wait_warp(&empty_bar[stage], phase ^ 1); else tc::mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* st = smem + (size_t)stage * stage_bytes;
       if (!(p.debug & 4)) {
 #pragma unroll
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
         }
       }
       }
-      tc::fence_proxy_async();
+      if (!(p.debug & 16)) tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
     };
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
     for (int64_t n = 0; n < my_chunks; ++n) {
       const int stage = (int)(n % S);
       const uint32_t phase = (uint32_t)((n / S) & 1);
-      tc::mbar_wait(&full_bar[stage], phase);
+      if (p.debug & 64) tc::mbar_wait_warp(&full_bar[stage], phase); else tc::mbar_wait(&full_bar[stage], phase);
       tc::fence_after_sync();
       if (lane == 0) {
         const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
