@@ -168,6 +168,17 @@ int mr_sample_negatives(const int64_t* csr_rowptr, const int32_t* csr_items, int
                         int64_t first_index, int32_t negs, uint64_t seed, uint64_t epoch,
                         int32_t* out_users, int32_t* out_items, float* out_labels, void* stream);
 
+/* Owner-side update of ROW-SHARDED tables (data-parallel runs whose tables do not fit one GPU): n pairs
+ * (local row id, gradient row [g0 | g1]) received from all ranks, duplicates allowed.  The pairs are
+ * stably sorted by row id, summed per id in arrival order (deterministic, no atomics) and the sparse-row
+ * Adam / SGD update is applied to table0 (num_rows x d0) and table1 (num_rows x d1; d1 may be 0).
+ * lr_t is Adam's bias-corrected step size lr*sqrt(1-b2^t)/(1-b1^t) for the current step. */
+size_t mr_sparse_rows_workspace_bytes(int64_t n, int32_t d0, int32_t d1);
+int mr_sparse_rows_update(float* table0, float* m0, float* v0, int32_t d0, float* table1, float* m1, float* v1,
+                          int32_t d1, int32_t num_rows, const int32_t* row_ids, const float* grad_rows, int64_t n,
+                          int32_t optimizer, float lr, float lr_t, float beta_1, float beta_2, float epsilon,
+                          void* ws, size_t ws_bytes, void* stream);
+
 /* Opt-in profiling for benchmarks (thread-local): between mr_profile_begin and mr_profile_end every
  * entry point records CUDA events on the caller's stream at its phase boundaries.  mr_profile_end
  * synchronises on the last event and returns, per phase, the summed device time in ms and the

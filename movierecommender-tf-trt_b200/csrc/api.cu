@@ -725,6 +725,54 @@ int mr_tc_probe(const float* raw_a, int32_t n_words, int32_t start_off, int32_t 
   return launch_tc_probe(raw_a, n_words, start_off, lbo, sbo, a_mn, D, (cudaStream_t)stream);
 }
 
+size_t mr_sparse_rows_workspace_bytes(int64_t n, int32_t d0, int32_t d1) {
+  if (n < 0) return 0;
+  return align_up((size_t)n * 4, 256) * 2 + sort_workspace_bytes(n) + segreduce_workspace_bytes(n, d0 + d1) + 256;
+}
+
+int mr_sparse_rows_update(float* table0, float* m0, float* v0, int32_t d0, float* table1, float* m1, float* v1,
+                          int32_t d1, int32_t num_rows, const int32_t* row_ids, const float* grad_rows, int64_t n,
+                          int32_t optimizer, float lr, float lr_t, float beta_1, float beta_2, float epsilon,
+                          void* ws, size_t ws_bytes, void* stream) {
+  if (n == 0) return MR_OK;
+  MR_REQUIRE(table0 && row_ids && grad_rows && ws, "sparse_rows_update: NULL pointer");
+  MR_REQUIRE(d0 > 0 && d1 >= 0 && num_rows > 0 && n > 0 && n < ((int64_t)1 << 31), "sparse_rows_update: bad sizes");
+  MR_REQUIRE(optimizer == MR_OPT_SGD || (m0 && v0 && (d1 == 0 || (m1 && v1))), "sparse_rows_update: Adam state is NULL");
+  MR_REQUIRE(d1 == 0 || table1 != nullptr, "sparse_rows_update: table1 is NULL");
+  if (ws_bytes < mr_sparse_rows_workspace_bytes(n, d0, d1)) {
+    set_error("sparse_rows_update workspace too small");
+    return MR_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver cv(ws);
+  int32_t* skeys = cv.take<int32_t>(n);
+  int32_t* sidx = cv.take<int32_t>(n);
+  const size_t sort_bytes = sort_workspace_bytes(n);
+  void* sort_ws = cv.take<char>(sort_bytes);
+  const size_t seg_bytes = segreduce_workspace_bytes(n, d0 + d1);
+  void* seg_ws = cv.take<char>(seg_bytes);
+  prof_mark(MR_PHASE_SORT, st);
+  int rc = launch_sort_pairs(row_ids, n, bits_for(num_rows), skeys, sidx, sort_ws, sort_bytes, st);
+  if (rc != MR_OK) return rc;
+  RowUpdate u{};
+  u.mode = MR_TABLES_SPARSE;
+  u.optimizer = optimizer;
+  u.lr = lr;
+  u.lr_t = lr_t;
+  u.beta_1 = beta_1;
+  u.beta_2 = beta_2;
+  u.epsilon = epsilon;
+  u.d0 = d0;
+  u.d1 = d1;
+  u.num_rows = num_rows;
+  u.p0 = table0; u.m0 = m0; u.v0 = v0;
+  u.p1 = table1; u.m1 = m1; u.v1 = v1;
+  prof_mark(MR_PHASE_SEGREDUCE, st);
+  rc = launch_segreduce(skeys, sidx, n, grad_rows, u, seg_ws, seg_bytes, st);
+  prof_mark(-1, st);
+  return rc;
+}
+
 int mr_set_compute_path(int32_t path) {
   MR_REQUIRE(path >= 0 && path <= 2, "compute path must be 0 (auto), 1 (SIMT) or 2 (tensor cores)");
   g_path = path;

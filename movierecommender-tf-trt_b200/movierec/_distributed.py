@@ -65,3 +65,184 @@ class DataParallelNeuMF(object):
         """Sum metric / loss accumulators over ranks (reporting only)."""
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
+
+
+class ShardedNeuMF(object):
+    """Row-sharded embedding tables for models whose tables do not fit one GPU (BASELINE config 5:
+    10 M users x 1 M items): owner(row) = row % world, local index = row // world; the dense tower is
+    replicated.  One step on every rank:
+
+      1. unique user / item ids of the local batch, grouped by owner;
+      2. all-to-all of the ids, owners gather the rows (gather kernel), all-to-all of the rows back:
+         the rank now holds a compact cache of exactly the rows its batch needs;
+      3. the ordinary fused forward/backward on the cache (ids remapped to cache slots), gradient scale
+         1/B_global -> gradient rows of the cache, dense gradients;
+      4. all-to-all of the gradient rows to the owners, which sort them by row, sum duplicates in a fixed
+         order and apply the sparse-row optimizer (mr_sparse_rows_update); all-reduce of the dense
+         gradients and the identical dense update everywhere.
+
+    The result equals the single-GPU step in sparse-row ("lazy") Adam mode on the global batch up to
+    summation order.  torch.distributed moves bytes (NCCL over NVLink on GPUs); all arithmetic is in the
+    CUDA library."""
+
+    def __init__(self, num_users, num_items, layers_sizes, mf_dim=0, optimizer="adam", lr=1e-3, beta_1=0.9,
+                 beta_2=0.999, max_local_rows=1 << 20, seed=None, process_group=None):
+        import numpy as np
+        from . import _engine
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self._engine_mod = _engine
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        self.num_users, self.num_items = int(num_users), int(num_items)
+        self.optimizer = optimizer
+        # the per-step row cache + the replicated dense tower: an ordinary engine without table state
+        self.cache = _engine.NeuMFEngine(max_local_rows, max_local_rows, layers_sizes, [0.0] * len(layers_sizes),
+                                         mf_dim=mf_dim, optimizer=optimizer, lr=lr, beta_1=beta_1, beta_2=beta_2,
+                                         table_mode="dense", seed=seed, table_state=False)
+        self.capacity = int(max_local_rows)
+        e = self.cache
+        dev = e.device
+        self.f = e.mf_dim
+        rng = np.random.default_rng(None if seed is None else seed + 7919 * (self.rank + 1))
+        self.shard = {}
+        for side, total, d in (("user", self.num_users, e.d_u), ("item", self.num_items, e.d_i)):
+            rows = (total - self.rank + self.world - 1) // self.world if total > self.rank else 0
+            tabs = {}
+            for kind, width, fan_in in (("mlp", d, total), ("gmf", self.f, total)):
+                if width == 0:
+                    tabs[kind] = None
+                    continue
+                lim = (6.0 / (fan_in + width)) ** 0.5  # glorot-uniform of the FULL table (model.py:163)
+                t = torch.empty((max(rows, 1), width), dtype=torch.float32, device=dev)
+                t.uniform_(-lim, lim, generator=None) if seed is None else t.copy_(
+                    torch.from_numpy(rng.uniform(-lim, lim, size=(max(rows, 1), width)).astype("float32")))
+                tabs[kind] = {"p": t, "m": torch.zeros_like(t), "v": torch.zeros_like(t)}
+            self.shard[side] = {"rows": rows, "tabs": tabs, "d": d}
+        self._ws = None
+
+    # ---- helpers --------------------------------------------------------------------------------------
+    def _a2a(self, send, send_counts, recv_counts, width=None):
+        shape = (sum(recv_counts),) if width is None else (sum(recv_counts), width)
+        recv = torch.empty(shape, dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=list(recv_counts),
+                               input_split_sizes=list(send_counts), group=self.group)
+        return recv
+
+    def _route(self, ids):
+        """Unique ids of the batch grouped by owner -> (cache slot of every batch row, unique ids in send
+        order, send counts, ids requested from this rank, their counts)."""
+        uniq, inv = torch.unique(ids, return_inverse=True)
+        owner = uniq % self.world
+        perm = torch.argsort(owner, stable=True)
+        uniq_s = uniq[perm]
+        slot_of_unique = torch.empty_like(perm)
+        slot_of_unique[perm] = torch.arange(perm.numel(), device=perm.device)
+        slots = slot_of_unique[inv].to(torch.int32)
+        send_counts = torch.bincount(owner, minlength=self.world)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()
+        wanted = self._a2a(uniq_s.to(torch.int32), sc, rc)
+        return slots, uniq_s, sc, wanted, rc
+
+    def _fetch(self, side, ids):
+        """Steps 1-2 for one side: fills the cache tables, returns the routing for the way back."""
+        e = self.cache
+        slots, uniq_s, sc, wanted, rc = self._route(ids)
+        n_u = int(uniq_s.numel())
+        if n_u > self.capacity:
+            raise ValueError("batch touches {} distinct {} rows, more than max_local_rows={}".format(n_u, side, self.capacity))
+        local = torch.div(wanted, self.world, rounding_mode="floor").to(torch.int32)
+        tabs = self.shard[side]["tabs"]
+        parts = [self._engine_mod.gather_rows(tabs[k]["p"], local) for k in ("mlp", "gmf") if tabs[k] is not None]
+        rows = self._a2a(torch.cat(parts, dim=1) if len(parts) > 1 else parts[0], rc, sc, width=sum(p.shape[1] for p in parts))
+        d = self.shard[side]["d"]
+        mlp_name = self._engine_mod.K_USER if side == "user" else self._engine_mod.K_ITEM
+        e._tables[mlp_name][:n_u].copy_(rows[:, :d])
+        if self.f:
+            gmf_name = self._engine_mod.K_GMF_USER if side == "user" else self._engine_mod.K_GMF_ITEM
+            e._tables[gmf_name][:n_u].copy_(rows[:, d:])
+        return {"slots": slots, "n": n_u, "send_counts": sc, "recv_counts": rc, "local": local}
+
+    def _push_grads(self, side, route):
+        """Step 4 for one side: gradient rows of the cache -> owners -> sorted, summed, applied."""
+        import ctypes as C
+        nat = self._engine_mod.nat
+        e = self.cache
+        d, n_u = self.shard[side]["d"], route["n"]
+        mlp_name = self._engine_mod.K_USER if side == "user" else self._engine_mod.K_ITEM
+        parts = [e.g_tables[mlp_name][:n_u]]
+        if self.f:
+            parts.append(e.g_tables[self._engine_mod.K_GMF_USER if side == "user" else self._engine_mod.K_GMF_ITEM][:n_u])
+        send = torch.cat(parts, dim=1) if len(parts) > 1 else parts[0]
+        grads = self._a2a(send, route["send_counts"], route["recv_counts"], width=d + self.f)
+        n = int(grads.shape[0])
+        if n == 0:
+            return
+        tabs = self.shard[side]["tabs"]
+        nbytes = int(nat.lib.mr_sparse_rows_workspace_bytes(n, d, self.f))
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=e.device)
+        adam = self.optimizer == "adam"
+        t = e.iterations + 1
+        ptr = lambda x: C.c_void_p(x.data_ptr()) if x is not None else C.c_void_p(0)
+        g = tabs["gmf"]
+        nat.check(nat.lib.mr_sparse_rows_update(
+            ptr(tabs["mlp"]["p"]), ptr(tabs["mlp"]["m"]), ptr(tabs["mlp"]["v"]), d,
+            ptr(g["p"] if g else None), ptr(g["m"] if g else None), ptr(g["v"] if g else None), self.f,
+            self.shard[side]["rows"], ptr(route["local"]), ptr(grads), n, nat.OPT_ADAM if adam else nat.OPT_SGD,
+            e.lr, e.adam_lr_t(t) if adam else e.lr, e.beta_1, e.beta_2, self._engine_mod.ADAM_EPSILON,
+            ptr(self._ws), self._ws.numel(), e._stream()), "mr_sparse_rows_update")
+
+    # ---- the step ---------------------------------------------------------------------------------------
+    def train_step(self, users, items, labels, global_rows, group=0, k=0):
+        e = self.cache
+        dev = e.device
+        users = self._engine_mod.as_device_i32(users, dev).long()
+        items = self._engine_mod.as_device_i32(items, dev).long()
+        ru = self._fetch("user", users)
+        ri = self._fetch("item", items)
+        out = e.train_grads(ru["slots"], ri["slots"], labels, group=group, k=k, inv_global_batch=1.0 / float(global_rows))
+        self._push_grads("user", ru)
+        self._push_grads("item", ri)
+        dist.all_reduce(e.g_dense, op=dist.ReduceOp.SUM, group=self.group)
+        e.apply_dense_only()
+        return out
+
+    def gather_full_tables(self):
+        """All shards reassembled on every rank (tests / small models only): name -> (rows, dim) tensor."""
+        out = {}
+        m = self._engine_mod
+        for side, total in (("user", self.num_users), ("item", self.num_items)):
+            for kind, name in (("mlp", m.K_USER if side == "user" else m.K_ITEM),
+                               ("gmf", m.K_GMF_USER if side == "user" else m.K_GMF_ITEM)):
+                t = self.shard[side]["tabs"][kind]
+                if t is None:
+                    continue
+                full = torch.zeros((total, t["p"].shape[1]), dtype=torch.float32, device=t["p"].device)
+                for r in range(self.world):
+                    rows = (total - r + self.world - 1) // self.world if total > r else 0
+                    buf = t["p"][:rows].clone() if r == self.rank else torch.empty((rows, t["p"].shape[1]), dtype=torch.float32,
+                                                                                 device=t["p"].device)
+                    dist.broadcast(buf, r, group=self.group)
+                    full[r::self.world] = buf
+                out[name] = full
+        return out
+
+    def load_full_tables(self, weights):
+        """Take this rank's rows out of full (rows, dim) arrays keyed by the Keras names; dense block too."""
+        import numpy as np
+        m = self._engine_mod
+        for side in ("user", "item"):
+            for kind, name in (("mlp", m.K_USER if side == "user" else m.K_ITEM),
+                               ("gmf", m.K_GMF_USER if side == "user" else m.K_GMF_ITEM)):
+                t = self.shard[side]["tabs"][kind]
+                if t is None:
+                    continue
+                mine = np.ascontiguousarray(np.asarray(weights[name], dtype=np.float32)[self.rank::self.world])
+                t["p"][:mine.shape[0]].copy_(torch.from_numpy(mine))
+        e = self.cache
+        for name in e._dense_slices:
+            e._view(name).copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(weights[name], dtype=np.float32))).view_as(e._view(name)))

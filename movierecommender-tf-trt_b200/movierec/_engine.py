@@ -64,7 +64,8 @@ class NeuMFEngine(object):
     """Parameters, optimizer state, gradient buffers and workspace of one model replica."""
 
     def __init__(self, num_users, num_items, layers_sizes, layers_l2reg, mf_dim=0, optimizer="adam",
-                 lr=1e-3, beta_1=0.9, beta_2=0.999, table_mode="dense", device=None, seed=None):
+                 lr=1e-3, beta_1=0.9, beta_2=0.999, table_mode="dense", device=None, seed=None,
+                 table_state=True):
         require_cuda()
         self.device = torch.device(device if device is not None else "cuda:{}".format(torch.cuda.current_device()))
         self.num_users, self.num_items = int(num_users), int(num_items)
@@ -117,8 +118,11 @@ class NeuMFEngine(object):
 
         adam = optimizer == "adam"
         z = lambda t: torch.zeros_like(t) if (t is not None) else None
-        self.m = {k: z(t) for k, t in self._tables.items()} if adam else {}
-        self.v = {k: z(t) for k, t in self._tables.items()} if adam else {}
+        # table_state=False: the tables are a per-step cache of rows owned elsewhere (row-sharded runs);
+        # their optimizer state lives with the owner, so none is allocated here and apply() is not used
+        self.table_state = bool(table_state)
+        self.m = {k: z(t) for k, t in self._tables.items()} if (adam and table_state) else {}
+        self.v = {k: z(t) for k, t in self._tables.items()} if (adam and table_state) else {}
         self.m_dense = z(self.dense) if adam else None
         self.v_dense = z(self.dense) if adam else None
         # one flat gradient buffer [dense | tables...] so a data-parallel caller all-reduces once
@@ -230,11 +234,15 @@ class NeuMFEngine(object):
         o.lr, o.beta_1, o.beta_2, o.epsilon = self.lr, self.beta_1, self.beta_2, ADAM_EPSILON
         o.iterations = self.iterations
         if self.optimizer == "adam":
-            o.m_user_mlp, o.m_item_mlp = self.m[K_USER].data_ptr(), self.m[K_ITEM].data_ptr()
-            o.v_user_mlp, o.v_item_mlp = self.v[K_USER].data_ptr(), self.v[K_ITEM].data_ptr()
+            # without table state the struct still needs non-NULL pointers; the gradient tables stand in
+            # (train_grads in dense mode never reads them, and apply() refuses to run -- see apply())
+            ms = self.m if self.table_state else self.g_tables
+            vs = self.v if self.table_state else self.g_tables
+            o.m_user_mlp, o.m_item_mlp = ms[K_USER].data_ptr(), ms[K_ITEM].data_ptr()
+            o.v_user_mlp, o.v_item_mlp = vs[K_USER].data_ptr(), vs[K_ITEM].data_ptr()
             if self.mf_dim:
-                o.m_user_gmf, o.m_item_gmf = self.m[K_GMF_USER].data_ptr(), self.m[K_GMF_ITEM].data_ptr()
-                o.v_user_gmf, o.v_item_gmf = self.v[K_GMF_USER].data_ptr(), self.v[K_GMF_ITEM].data_ptr()
+                o.m_user_gmf, o.m_item_gmf = ms[K_GMF_USER].data_ptr(), ms[K_GMF_ITEM].data_ptr()
+                o.v_user_gmf, o.v_item_gmf = vs[K_GMF_USER].data_ptr(), vs[K_GMF_ITEM].data_ptr()
             o.m_dense, o.v_dense = self.m_dense.data_ptr(), self.v_dense.data_ptr()
         self._opt = o
 
@@ -311,10 +319,27 @@ class NeuMFEngine(object):
         return self.step_out.clone()
 
     def apply(self):
+        if not self.table_state:
+            raise RuntimeError("this engine caches rows owned by other ranks; use apply_dense_only()")
         self._opt.iterations = self.iterations
         nat.check(nat.lib.mr_neumf_apply(C.byref(self._model), C.byref(self._opt), C.byref(self._grads), self._stream()),
                   "mr_neumf_apply")
         self.iterations = int(self._opt.iterations)
+
+    def adam_lr_t(self, t):
+        """Legacy-Keras Adam step size for step t (1-based): lr*sqrt(1-b2^t)/(1-b1^t)."""
+        return self.lr * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
+
+    def apply_dense_only(self):
+        """Optimizer update of the dense block alone from g_dense (row-sharded runs: the table rows are
+        updated by their owners through mr_sparse_rows_update)."""
+        t = self.iterations + 1
+        adam = self.optimizer == "adam"
+        lr_t = self.adam_lr_t(t) if adam else self.lr
+        nat.check(nat.lib.mr_optimizer_flat(_ptr(self.dense), _ptr(self.g_dense), _ptr(self.m_dense), _ptr(self.v_dense),
+                                            self.dense_count, nat.OPT_ADAM if adam else nat.OPT_SGD, lr_t, self.beta_1,
+                                            self.beta_2, ADAM_EPSILON, 0.0, self._stream()), "mr_optimizer_flat")
+        self.iterations = t
 
     def rank_eval(self, users_per_group, items, group, k, want_rank=False, want_probs=False):
         """Score G groups (positive last) and rank them (model.py:336-455).  Returns

@@ -83,6 +83,9 @@ SIGNATURES = {
     "mr_sort_pairs": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "mr_tc_probe": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mr_tc_gemm_selftest": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mr_sparse_rows_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "mr_sparse_rows_update": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i32, _f, _f, _f, _f,
+                                        _f, _vp, _sz, _vp]),
     "mr_set_compute_path": (C.c_int, [_i32]),
     "mr_uses_tensor_cores": (C.c_int, [_PM]),
     "mr_profile_begin": (C.c_int, []),

@@ -114,3 +114,55 @@ def test_split_groups_covers_everything_once():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---- row-sharded tables: routing of ids, rows and gradient rows (BASELINE config 5) --------------------
+def _sharded_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from movierec._distributed import ShardedNeuMF
+    sh = object.__new__(ShardedNeuMF)  # the routing needs no CUDA engine
+    sh.world, sh.rank, sh.group = world, rank, None
+    total, dim = 23, 3
+    full = torch.arange(total * dim, dtype=torch.float32).reshape(total, dim)
+    shard = full[rank::world].clone()  # owner(row) = row % world, local index = row // world
+    rng = np.random.default_rng(40 + rank)
+    ids = torch.from_numpy(rng.integers(0, total, 37)).long()
+    if rank == 1:
+        ids[:5] = 22  # a hot row and a row both ranks ask for
+    slots, uniq_s, sc, wanted, rc = sh._route(ids)
+    assert sum(sc) == uniq_s.numel() and sum(rc) == wanted.numel()
+    assert torch.all(wanted % world == rank)          # only rows this rank owns were requested from it
+    local = torch.div(wanted, world, rounding_mode="floor").long()
+    rows = sh._a2a(shard[local], rc, sc, width=dim)
+    assert torch.equal(rows[slots.long()], full[ids])  # every batch row finds its table row in the cache
+    # way back: one gradient row per distinct id (sum over the batch rows that share it) goes to its owner
+    g_rows = torch.ones(ids.numel(), dim) * (rank + 1)
+    g_unique = torch.zeros(uniq_s.numel(), dim).index_add_(0, slots.long(), g_rows)
+    g_recv = sh._a2a(g_unique, sc, rc, width=dim)
+    acc = torch.zeros_like(shard).index_add_(0, local, g_recv)
+    gathered = [torch.zeros(((total - r + world - 1) // world, dim)) for r in range(world)]
+    all_ids = [torch.zeros(37, dtype=torch.long) for _ in range(world)]
+    dist.all_gather(all_ids, ids)
+    for r in range(world):
+        buf = acc.clone() if r == rank else gathered[r]
+        dist.broadcast(buf, r)
+        gathered[r] = buf
+    if rank == 0:
+        total_g = torch.zeros(total, dim)
+        for r in range(world):
+            total_g[r::world] = gathered[r]
+        want = torch.zeros(total, dim)
+        for r in range(world):
+            want.index_add_(0, all_ids[r], torch.ones(37, dim) * (r + 1))
+        np.savez(out, got=total_g.numpy(), want=want.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_routing_round_trip(tmp_path, world):
+    out = str(tmp_path / "sharded.npz")
+    mp.spawn(_sharded_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    r = np.load(out)
+    assert np.array_equal(r["got"], r["want"])
