@@ -217,6 +217,9 @@ int mr_tc_probe(const float* raw_a, int32_t n_words, int32_t start_off, int32_t 
                 float* D, void* stream);
 int mr_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
                         int32_t three_x, void* stream);
+/* Diagnostics: sustained tcgen05 issue rate of the 3xTF32 stage pattern on static operands (tools/tc_rate.py). */
+int mr_tc_rate(int32_t N, int32_t iters, int32_t nbuf, int32_t flags, int32_t writers, int32_t write_iters,
+               int64_t* out_cycles, int32_t grid, void* stream);
 /* Stable LSD radix sort of (key, original index) pairs on the low `key_bits` bits. */
 size_t mr_sort_workspace_bytes(int64_t n);
 int mr_sort_pairs(const int32_t* keys, int64_t n, int32_t key_bits, int32_t* sorted_keys,

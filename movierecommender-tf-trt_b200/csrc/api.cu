@@ -725,6 +725,13 @@ int mr_tc_probe(const float* raw_a, int32_t n_words, int32_t start_off, int32_t 
   return launch_tc_probe(raw_a, n_words, start_off, lbo, sbo, a_mn, D, (cudaStream_t)stream);
 }
 
+int mr_tc_rate(int32_t N, int32_t iters, int32_t nbuf, int32_t flags, int32_t writers, int32_t write_iters,
+               int64_t* out_cycles, int32_t grid, void* stream) {
+  MR_REQUIRE(out_cycles != nullptr, "tc_rate: NULL output");
+  return launch_tc_rate(N, iters, nbuf, flags, writers, write_iters, reinterpret_cast<long long*>(out_cycles), grid,
+                        (cudaStream_t)stream);
+}
+
 size_t mr_sparse_rows_workspace_bytes(int64_t n, int32_t d0, int32_t d1) {
   if (n < 0) return 0;
   return align_up((size_t)n * 4, 256) * 2 + sort_workspace_bytes(n) + segreduce_workspace_bytes(n, d0 + d1) + 256;

@@ -143,6 +143,8 @@ size_t head_partial_floats(const MrModel& m);
 int launch_head(const HeadArgs& a, cudaStream_t st);
 
 // ---- tc_selftest.cu ---------------------------------------------------------------------------
+int launch_tc_rate(int N, int iters, int nbuf, int flags, int writers, int write_iters, long long* out, int grid,
+                   cudaStream_t st);
 int launch_tc_probe(const float* raw_a, int n_words, int start_off, int lbo, int sbo, int a_mn, float* D,
                     cudaStream_t st);
 int launch_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn, int b_mn, int three_x,

@@ -84,6 +84,21 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a converged warp, chosen by the hardware.  Code under `if (elect_one())` is compiled for the
+// uniform datapath: descriptors live in uniform registers and consecutive tcgen05.mma are 1-2 instructions
+// apart.  Under `if (lane == 0)` the compiler instead wraps EVERY mma in a R2UR + ELECT + BRA.U.ANY waterfall
+// (~14 instructions), and the single issuing thread cannot keep the tensor pipe fed.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // Arrive on an mbarrier when every tcgen05 op issued so far by this thread has completed.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -11,14 +11,15 @@
 //             EPI_STAGE      rows of dL/dx0 split into the user / item staging buffers
 //
 // Persistent, warp-specialised CTA (416 threads), 128 batch rows per tile, K streamed in chunks of 32:
-//   warps 0-7  producers, kTcGroups groups of four warps that take K-chunks round-robin; each thread
-//              issues the loads of its group's NEXT chunk before converting the current one:
+//   warps 0-7  producers: every warp fills a slice of every K-chunk; the global loads of a chunk are issued
+//              kTcLoadAhead chunks before it is converted (rotating register buffers):
 //              load A fp32 (gather or dense), split x = hi + lo (TF32), st.shared in core-matrix layout;
-//              lane 0 of each group's first warp also issues the bulk copy of the weight chunk
+//              lane 0 of warp 0 also issues the bulk copy of the weight chunk
 //   warp  8    one elected thread issues tcgen05.mma: acc += Ahi.Bhi + Alo.Bhi + Ahi.Blo per K-step of 8
 //   warps 9-12 epilogue: tcgen05.ld the accumulator (double-buffered in TMEM so the next tile's MMAs run
 //              under this tile's epilogue), apply the epilogue, store to global
-// Stages are recycled with mbarriers: full[s] (4 producer arrivals + the bulk copy's bytes),
+//   warp 13    L2 prefetch of the A rows two tiles ahead
+// Stages are recycled with mbarriers: full[s] (8 producer arrivals + the bulk copy's bytes),
 // empty[s] (tcgen05.commit), acc_full/acc_empty per TMEM buffer.
 #include <stdlib.h>
 
@@ -27,9 +28,18 @@
 
 namespace mr {
 
-constexpr int kTcGroups = 2;                      // producer groups of 4 warps taking chunks round-robin
-constexpr int kTcMmaWarp = 4 * kTcGroups;
-constexpr int kTcThreads = 32 * (kTcMmaWarp + 5);  // producers + MMA warp + 4 epilogue warps
+constexpr int kTcMmaWarp = 8;                     // warps 0-7 are producers
+#ifndef MR_TC_LOAD_AHEAD
+#define MR_TC_LOAD_AHEAD 1
+#endif
+constexpr int kTcLoadAhead = MR_TC_LOAD_AHEAD;    // group iterations the producers' global loads run ahead of the conversion
+#ifndef MR_TC_GROUPS
+#define MR_TC_GROUPS 2
+#endif
+constexpr int kTcGroups = MR_TC_GROUPS;           // producer groups (8 / kTcGroups warps each) taking chunks round-robin
+constexpr int kTcPrefetchWarp = kTcMmaWarp + 5;
+constexpr int kTcThreads = 32 * (kTcMmaWarp + 6);  // producers + MMA warp + 4 epilogue warps + L2 prefetch warp
+constexpr int kTcPrefetchAhead = 2;                // tiles the prefetch warp runs ahead of the MMA issuer
 constexpr int kTcTileRows = 128;
 constexpr int kTcKC = 32;  // K elements per pipeline stage
 constexpr int kEpiLd = 36;  // floats per row of an epilogue warp's 32x32 staging tile (16-byte aligned, conflict-free)
@@ -67,6 +77,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[8], empty_bar[8], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ int tiles_started;  // written by the MMA issuer, paces the prefetch warp
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.N, K = p.K, S = p.stages;
@@ -81,7 +92,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      tc::mbar_init(&full_bar[s], 5);  // 4 producer warps + the weight copy's expect_tx arrive
+      tc::mbar_init(&full_bar[s], 8 / kTcGroups + 1);  // the group's producer warps + the weight copy's expect_tx arrive
       tc::mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -89,6 +100,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       tc::mbar_init(&acc_empty[b], 4);
     }
     tc::mbar_init_fence();
+    tiles_started = 0;
   }
   if (warp == kTcMmaWarp) tc::tmem_alloc(&tmem_slot, 2 * acc_cols);
   tc::fence_before_sync();
@@ -98,32 +110,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
 
   if (warp < kTcMmaWarp) {
     // ================================ producers =================================================
-    // Group g (4 warps) fills the chunks whose running index is g mod kTcGroups.  The loads of a group's NEXT
-    // chunk are issued before the current one is converted, so each thread keeps 16 x 16 bytes in flight.
-    const int group = warp >> 2, pw = warp & 3;
+    // All eight warps fill every chunk (a thread owns 2 rows x 2 sixteen-byte pieces of it).  The global loads
+    // run kTcLoadAhead chunks ahead of the conversion in a rotating set of register buffers, so 3 x 16 KB per
+    // SM are in flight and a load has three chunk periods to arrive (ncu: the producers of the first version,
+    // one chunk ahead, sat in long-scoreboard stalls for more than half of their samples).
+    constexpr int G = kTcGroups, WPG = 8 / G;     // warps per group
+    constexpr int RG = 2 * G;                     // 8-row groups per thread and chunk (a warp covers 16*G rows)
+    const int group = warp / WPG, pw = warp % WPG;
     const int rsub = lane & 7, csub = lane >> 3;  // 8 rows x 4 sixteen-byte chunks per warp instruction
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total = my_tiles * nchunks;
-    int64_t cached_tile = -1;
-    const float* src_u[4];
-    const float* src_i[4];
-    bool ok[4];
+    // Running positions of the load stream and of the store stream (chunk in tile, tile, stage, phase) are
+    // advanced incrementally: the 64-bit divisions n / nchunks, n % S of the first version kept the XU pipe
+    // 80 % busy (ncu) and were most of the producers' instructions.
+    int64_t ld_tile = 0, cached_tile = -1;
+    int ld_c = group, st_c = group, st_stage = group % S;
+    uint32_t st_phase = (uint32_t)((group / S) & 1);
+    while (ld_c >= nchunks) { ld_c -= nchunks; ++ld_tile; }
+    while (st_c >= nchunks) st_c -= nchunks;
+    const float* src_u[RG];
+    const float* src_i[RG];
+    bool ok[RG];
 
-    auto issue_loads = [&](int64_t n, float4(&x)[8]) {
-      const int64_t tl = n / nchunks;
-      const int c = (int)(n - tl * nchunks);
-      if (tl != cached_tile) {  // this lane's 4 rows of the tile: 32*pw + 8*g + rsub
+    auto issue_loads = [&](float4(&x)[2 * RG]) {
+      const int64_t tl = ld_tile;
+      const int c = ld_c;
+      ld_c += G;
+      while (ld_c >= nchunks) { ld_c -= nchunks; ++ld_tile; }
+      if (tl != cached_tile) {  // this lane's RG rows of the tile: 8*RG*pw + 8*g + rsub
         cached_tile = tl;
         const int64_t trow0 = (blockIdx.x + tl * gridDim.x) * kTcTileRows;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int64_t lr = trow0 + 32 * pw + 8 * g + rsub;  // launch-local row
+        for (int g = 0; g < RG; ++g) {
+          const int64_t lr = trow0 + 8 * RG * pw + 8 * g + rsub;  // launch-local row
           ok[g] = lr < p.rows;
           src_u[g] = nullptr;
           src_i[g] = nullptr;
           if (AMODE == A_GATHER) {
             if (ok[g]) {
-              const int u = __ldg(p.users + (p.row0 + lr) / p.user_div), it = __ldg(p.items + p.row0 + lr);
+              const uint32_t grow = (uint32_t)(p.row0 + lr);  // B < 2^31
+              const int u = __ldg(p.users + (p.user_div == 1 ? grow : grow / (uint32_t)p.user_div)), it = __ldg(p.items + grow);
               if ((unsigned)u < (unsigned)p.num_users && (unsigned)it < (unsigned)p.num_items) {
                 src_u[g] = p.user_tab + (size_t)u * p.d_u;
                 src_i[g] = p.item_tab + (size_t)it * (K - p.d_u);
@@ -138,7 +164,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       }
       const int col0 = c * kTcKC;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int g = 0; g < RG; ++g) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int col = col0 + 4 * (4 * h + csub);
@@ -151,14 +177,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
         }
       }
     };
-    auto store_chunk = [&](int64_t n, const float4(&x)[8]) {
-      const int c = (int)(n % nchunks);
-      const int stage = (int)(n % S);
-      const uint32_t phase = (uint32_t)((n / S) & 1);
-      if (p.debug & 64) tc::mbar_wait_warp(&empty_bar[stage], phase ^ 1); else tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+    auto store_chunk = [&](bool first_pass, const float4(&x)[2 * RG]) {
+      const int c = st_c;
+      const int stage = st_stage;
+      const uint32_t phase = st_phase;
+      st_c += G;
+      while (st_c >= nchunks) st_c -= nchunks;
+      st_stage += G;
+      while (st_stage >= S) { st_stage -= S; st_phase ^= 1; }
+      tc::mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* st = smem + (size_t)stage * stage_bytes;
       if (pw == 0 && lane == 0) {
-        if ((p.debug & 1) && n >= S) {
+        if ((p.debug & 1) && !first_pass) {
           tc::mbar_arrive(&full_bar[stage]);
         } else {
           tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * b_bytes);
@@ -167,8 +197,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       }
       if (!(p.debug & 4))
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int r = 32 * pw + 8 * g + rsub;
+      for (int g = 0; g < RG; ++g) {
+        const int r = 8 * RG * pw + 8 * g + rsub;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int cc = 4 * h + csub;  // 16-byte chunk 0..7 inside the 32-wide K chunk
@@ -184,52 +214,86 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
     };
 
-    float4 xa[8], xb[8];
-    int64_t n = group;
-    if (n < total) issue_loads(n, xa);
-    while (n < total) {
-      if (n + kTcGroups < total) issue_loads(n + kTcGroups, xb);
-      store_chunk(n, xa);
-      n += kTcGroups;
-      if (n >= total) break;
-      if (n + kTcGroups < total) issue_loads(n + kTcGroups, xa);
-      store_chunk(n, xb);
-      n += kTcGroups;
+    constexpr int D = kTcLoadAhead, NB = kTcLoadAhead + 1;
+    float4 buf[NB][2 * RG];
+    const int64_t mine = total > group ? (total - group + G - 1) / G : 0;  // chunks of this group
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+      if (j < mine) issue_loads(buf[j]);
+    for (int64_t i0 = 0; i0 < mine; i0 += NB) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int64_t i = i0 + j;
+        if (i < mine) {
+          if (i + D < mine) issue_loads(buf[(j + D) % NB]);
+          store_chunk(i * G < S, buf[j]);
+        }
+      }
     }
   } else if (warp == kTcMmaWarp) {
     // ================================ MMA issuer ================================================
-    int stage = 0;
-    uint32_t phase = 0;
-    const uint32_t idesc = tc::idesc_tf32(128, N, 0, 0);
-    int64_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int b = (int)(it & 1);
-      tc::mbar_wait(&acc_empty[b], (uint32_t)((it >> 1) & 1) ^ 1);
-      tc::fence_after_sync();
-      const uint32_t d_tmem = tmem_base + (uint32_t)b * acc_cols;
-      for (int c = 0; c < nchunks; ++c) {
-        if (p.debug & 64) tc::mbar_wait_warp(&full_bar[stage], phase); else tc::mbar_wait(&full_bar[stage], phase);
+    // One elected thread runs the whole loop (waits included); see tc::elect_one for why not `lane == 0`.
+    if (tc::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc = tc::idesc_tf32(128, N, 0, 0);
+      const uint64_t dbase = tc::smem_desc(0, 128, 1024);  // address field added per operand (smem < 256 KB: no carry)
+      const uint32_t s0 = tc::smem_u32(smem);
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int b = (int)(it & 1);
+        *reinterpret_cast<volatile int*>(&tiles_started) = (int)it + 1;
+        tc::mbar_wait(&acc_empty[b], (uint32_t)((it >> 1) & 1) ^ 1);
         tc::fence_after_sync();
-        if (lane == 0) {
-          const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t d_tmem = tmem_base + (uint32_t)b * acc_cols;
+        for (int c = 0; c < nchunks; ++c) {
+          tc::mbar_wait(&full_bar[stage], phase);
+          tc::fence_after_sync();
+          const uint32_t sa = s0 + (uint32_t)stage * stage_bytes;
           const uint32_t sb = sa + 2 * a_bytes;
+          const uint64_t ah = dbase + (sa >> 4), al = dbase + ((sa + a_bytes) >> 4);
+          const uint64_t bh = dbase + (sb >> 4), bl = dbase + ((sb + b_bytes) >> 4);
 #pragma unroll
-          for (int kk = 0; kk < kTcKC / 8; ++kk) {
-            const uint64_t ah = tc::smem_desc(sa + kk * 256, 128, 1024);
-            const uint64_t al = tc::smem_desc(sa + a_bytes + kk * 256, 128, 1024);
-            const uint64_t bh = tc::smem_desc(sb + kk * 256, 128, 1024);
-            const uint64_t bl = tc::smem_desc(sb + b_bytes + kk * 256, 128, 1024);
-            tc::mma_tf32(d_tmem, ah, bh, idesc, (c | kk) != 0);
-            tc::mma_tf32(d_tmem, al, bh, idesc, 1);
-            tc::mma_tf32(d_tmem, ah, bl, idesc, 1);
+          for (int kk = 0; kk < kTcKC / 8; ++kk) {  // one K=8 step = two 128-byte core matrices = 256 bytes
+            tc::mma_tf32(d_tmem, ah + 16 * kk, bh + 16 * kk, idesc, (c | kk) != 0);
+            tc::mma_tf32(d_tmem, al + 16 * kk, bh + 16 * kk, idesc, 1);
+            tc::mma_tf32(d_tmem, ah + 16 * kk, bl + 16 * kk, idesc, 1);
           }
           tc::mma_commit(&empty_bar[stage]);  // stage reusable once these MMAs have read it
           if (c == nchunks - 1) tc::mma_commit(&acc_full[b]);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        __syncwarp();
-        if (++stage == S) {
-          stage = 0;
-          phase ^= 1;
+      }
+    }
+  } else if (warp == kTcPrefetchWarp) {
+    // ================================ L2 prefetch ===============================================
+    // The producers keep one chunk per group in flight in registers (32 KB per SM), which covers L2 latency
+    // but not DRAM latency at full bandwidth.  This warp pulls the A rows of the tile kTcPrefetchAhead tiles
+    // ahead of the MMA issuer into L2 (prefetch.global.L2 holds no registers), so the producers' loads hit L2.
+    if (!(p.debug & 128)) {
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        while (it >= (int64_t)*reinterpret_cast<volatile int*>(&tiles_started) + kTcPrefetchAhead) __nanosleep(256);
+#pragma unroll 1
+        for (int rr = 0; rr < kTcTileRows / 32; ++rr) {
+          const int64_t lr = tile * kTcTileRows + 32 * rr + lane;
+          if (lr >= p.rows) continue;
+          if (AMODE == A_GATHER) {
+            const uint32_t grow = (uint32_t)(p.row0 + lr);
+            const int u = __ldg(p.users + (p.user_div == 1 ? grow : grow / (uint32_t)p.user_div)), itm = __ldg(p.items + grow);
+            if ((unsigned)u < (unsigned)p.num_users && (unsigned)itm < (unsigned)p.num_items) {
+              const float* pu = p.user_tab + (size_t)u * p.d_u;
+              const float* pi = p.item_tab + (size_t)itm * (K - p.d_u);
+              for (int c = 0; c < p.d_u; c += 32) tc::prefetch_l2(pu + c);
+              for (int c = 0; c < K - p.d_u; c += 32) tc::prefetch_l2(pi + c);
+            }
+          } else {
+            const float* pa = p.a_dense + (size_t)lr * K;
+            for (int c = 0; c < K; c += 32) tc::prefetch_l2(pa + c);
+          }
         }
       }
     }

@@ -167,3 +167,105 @@ int launch_tc_selftest(const float* A, const float* B, float* D, int N, int K, i
 }
 
 }  // namespace mr
+
+// ---- tensor-pipe rate probe (tools/tc_rate.py; diagnostics only) --------------------------------------------
+// One CTA per SM issues `iters` pipeline stages of 4 k-steps x 3 MMAs (the 3xTF32 pattern of the real kernels)
+// on static operands rotating over `nbuf` shared-memory stage buffers, with no producer handshake, and
+// reports clock64 cycles from the first issue to the completion of the last MMA.
+//   flags bit 0: A operand from TMEM (tcgen05.mma [d], [a], b-desc) instead of shared memory
+//         bit 1: MN-major operands (SWIZZLE_128B_BASE32B descriptors, 16-row K chunks as in tc_wgrad)
+//   writers: extra warps that stream st.shared.v4 into a scratch area while the MMAs run (producer traffic)
+namespace mr {
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(32 * 9, 1) tc_rate_kernel(int N, int iters, int nbuf, int flags, int writers,
+                                                            int write_iters, long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ uint64_t done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = 128 * 32 * 4, b_bytes = (uint32_t)N * 32 * 4;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const uint32_t scratch_off = (uint32_t)nbuf * stage_bytes;
+  for (uint32_t e = tid; e < (scratch_off + 16384) / 16; e += blockDim.x)
+    reinterpret_cast<float4*>(smem)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    tc::mbar_init(&done_bar, 1);
+    tc::mbar_init_fence();
+  }
+  tc::fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  const bool ts = flags & 1, mn = flags & 2;
+  if (tid == 0) {
+    const uint32_t idesc = tc::idesc_tf32(128, N, mn ? 1 : 0, mn ? 1 : 0);
+    const uint32_t lbo = mn ? 8 * 512 : 128, sbo = mn ? 512 : 1024, lt = mn ? tc::kLayoutSw128Base32 : tc::kLayoutNone;
+    const uint32_t kstep = mn ? 1024 : 256;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t sa = tc::smem_u32(smem) + (uint32_t)(it % nbuf) * stage_bytes;
+      const uint32_t sb = sa + 2 * a_bytes;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint64_t bh = tc::smem_desc(sb + kk * kstep, lbo, sbo, lt);
+        const uint64_t bl = tc::smem_desc(sb + b_bytes + kk * kstep, lbo, sbo, lt);
+        if (ts) {
+          const uint32_t ah = tmem_base + 256 + 8 * kk, al = tmem_base + 256 + 32 + 8 * kk;
+          mma_tf32_ts(tmem_base, ah, bh, idesc, 1);
+          mma_tf32_ts(tmem_base, al, bh, idesc, 1);
+          mma_tf32_ts(tmem_base, ah, bl, idesc, 1);
+        } else {
+          const uint64_t ah = tc::smem_desc(sa + kk * kstep, lbo, sbo, lt);
+          const uint64_t al = tc::smem_desc(sa + a_bytes + kk * kstep, lbo, sbo, lt);
+          tc::mma_tf32(tmem_base, ah, bh, idesc, 1);
+          tc::mma_tf32(tmem_base, al, bh, idesc, 1);
+          tc::mma_tf32(tmem_base, ah, bl, idesc, 1);
+        }
+      }
+    }
+    tc::mma_commit(&done_bar);
+    tc::mbar_wait(&done_bar, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  } else if (warp >= 1 && warp <= writers) {
+    float4* dst = reinterpret_cast<float4*>(smem + scratch_off) + (tid & 31) + 32 * ((warp - 1) & 7) * 4;
+    const float4 v = make_float4(1.f, 2.f, 3.f, (float)tid);
+    for (int i = 0; i < write_iters; ++i) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(tc::smem_u32(dst + 32 * q)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
+}
+
+int launch_tc_rate(int N, int iters, int nbuf, int flags, int writers, int write_iters, long long* out, int grid,
+                   cudaStream_t st) {
+  const size_t smem = (size_t)nbuf * (2 * 128 * 32 * 4 + 2 * (size_t)N * 32 * 4) + 16384 + 1024;
+  if (N % 16 || N < 16 || N > 256 || nbuf < 1 || smem > 227 * 1024 || writers < 0 || writers > 8 || grid < 1) {
+    set_error("tc rate: bad arguments");
+    return MR_ERR_INVALID;
+  }
+  MR_CUDA(cudaFuncSetAttribute(tc_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_rate_kernel<<<grid, 32 * 9, smem, st>>>(N, iters, nbuf, flags, writers, write_iters, out);
+  MR_LAUNCH_CHECK("tc_rate_kernel");
+  return MR_OK;
+}
+
+}  // namespace mr

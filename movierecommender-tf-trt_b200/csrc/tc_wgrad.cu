@@ -7,9 +7,11 @@
 // Each CTA owns a contiguous slice of 16-row chunks, keeps the whole dW in TMEM (Fa/128 accumulators of
 // Fb columns) for its slice, and adds it to its private row of the partial buffer at the end; the
 // cross-CTA sum happens in dense_reduce_kernel in a fixed order.
-//   warps 0-7  producers (two groups on alternate chunks): load, TF32 hi/lo split, st.shared; the
-//              threads that load Z also keep column sums for db
+//   warps 0-7  producers (every warp fills a slice of every chunk, global loads kWgLoadAhead chunks ahead in
+//              rotating register buffers): load, TF32 hi/lo split, st.shared; the threads that load Z also
+//              keep column sums for db
 //   warp  8    MMA issuer
+//   warp  9    L2 prefetch of the rows 24 chunks ahead
 //   warps 0-3  epilogue after the last chunk (TMEM -> partial buffer)
 #include <stdlib.h>
 
@@ -18,9 +20,19 @@
 
 namespace mr {
 
-constexpr int kWgThreads = 288;
+constexpr int kWgThreads = 320;  // 8 producer warps + MMA warp + L2 prefetch warp
+constexpr int kWgPrefetchWarp = 9;
+constexpr int kWgPrefetchAhead = 24;  // chunks (of 16 rows) the prefetch warp runs ahead of the MMA issuer
 constexpr int kWgMmaWarp = 8;
 constexpr int kWgKC = 16;  // batch rows per pipeline stage
+#ifndef MR_WG_LOAD_AHEAD
+#define MR_WG_LOAD_AHEAD 1
+#endif
+constexpr int kWgLoadAhead = MR_WG_LOAD_AHEAD;  // group iterations the global loads run ahead of the conversion
+#ifndef MR_WG_GROUPS
+#define MR_WG_GROUPS 2
+#endif
+constexpr int kWgGroups = MR_WG_GROUPS;         // producer groups (8 / kWgGroups warps each) taking chunks round-robin
 
 struct TcWgradParams {
   const float* a_dense;
@@ -45,14 +57,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[8], empty_bar[8], done_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float db_red[128 * 4];
+  __shared__ __align__(16) float db_red[256 * 4];
+  __shared__ int chunks_issued;  // written by the MMA issuer, paces the prefetch warp
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int Fa = p.Fa, Fb = p.Fb, S = p.stages;
+  constexpr int Fa = 32 * NA, Fb = 32 * NZ;  // compile-time widths: index arithmetic folds, no integer divisions
+  const int S = p.stages;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = (uint32_t)kWgKC * Fa * 4, z_bytes = (uint32_t)kWgKC * Fb * 4;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * z_bytes;
-  const int halves = Fa / 128;
+  constexpr int halves = Fa / 128;
   uint32_t acc_cols = 32;
   while (acc_cols < (uint32_t)(halves * Fb)) acc_cols <<= 1;
 
@@ -64,11 +78,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      tc::mbar_init(&full_bar[s], 4);
+      tc::mbar_init(&full_bar[s], 8 / kWgGroups);
       tc::mbar_init(&empty_bar[s], 1);
     }
     tc::mbar_init(&done_bar, 1);
     tc::mbar_init_fence();
+    chunks_issued = 0;
   }
   if (warp == kWgMmaWarp) tc::tmem_alloc(&tmem_slot, acc_cols);
   tc::fence_before_sync();
@@ -77,56 +92,63 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
   const uint32_t tmem_base = tmem_slot;
 
   float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of Z for this thread's fixed float4 column
-  const int zq = Fb >> 2;                          // float4 per Z row (8..64, divides 128)
+  constexpr int zq = Fb >> 2;                      // float4 per Z row (8..64, divides 128)
 
   if (warp < 8) {
-    // producers: the loads of a group's next chunk are issued before the current one is converted
-    const int group = warp >> 2;
-    const int t = tid & 127;   // thread index inside the producer group
-    const int aq = Fa >> 2;    // float4 per A row
+    // producers: all eight warps fill every chunk; global loads run kWgLoadAhead chunks ahead of the
+    // conversion in rotating register buffers (see tc_dense.cu)
+    constexpr int G = kWgGroups, TG = 256 / G;  // threads per group
+    const int group = tid / TG, t = tid % TG;
+    constexpr int aq = Fa >> 2;    // float4 per A row
+    int st_stage = group % S;
+    uint32_t st_phase = (uint32_t)((group / S) & 1);
+    int64_t ld_chunk = chunk_lo + group;  // launch-local chunk index of the next load
+    constexpr int PA = NA * G / 2;                      // float4 of A per thread and chunk (16 rows x Fa/4 over TG threads)
+    constexpr int PZ = NZ * G >= 2 ? NZ * G / 2 : 1;    // float4 of Z per thread and chunk (Fb = 32, G = 1: half of the threads idle)
 
-    auto issue_loads = [&](int64_t n, float4(&xa)[NA], float4(&xz)[NZ]) {
-      const int64_t crow0 = (chunk_lo + n) * kWgKC;  // launch-local first row of the chunk
+    auto issue_loads = [&](float4(&xa)[PA], float4(&xz)[PZ]) {
+      const int64_t crow0 = ld_chunk * kWgKC;  // launch-local first row of the chunk
+      ld_chunk += G;
 #pragma unroll
-      for (int i = 0; i < NA; ++i) {
-        {
-          const int idx = t + 128 * i;
-          const int r = idx / aq, c = (idx - r * aq) << 2;
-          const int64_t lr = crow0 + r;
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (lr < p.rows && !(p.debug & 2)) {
-            if (GATHER) {
-              const int u = __ldg(p.users + p.row0 + lr), it = __ldg(p.items + p.row0 + lr);
-              if ((unsigned)u < (unsigned)p.num_users && (unsigned)it < (unsigned)p.num_items)
-                x = (c < p.d_u) ? ldg4(p.user_tab + (size_t)u * p.d_u + c)
-                                : ldg4(p.item_tab + (size_t)it * (Fa - p.d_u) + (c - p.d_u));
+      for (int i = 0; i < PA; ++i) {
+        const int idx = t + TG * i;
+        const int r = idx / aq, c = (idx - r * aq) << 2;
+        const int64_t lr = crow0 + r;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lr < p.rows && !(p.debug & 2)) {
+          if (GATHER) {
+            if (c < p.d_u) {
+              const int u = __ldg(p.users + p.row0 + lr);
+              if ((unsigned)u < (unsigned)p.num_users) x = ldg4(p.user_tab + (size_t)u * p.d_u + c);
             } else {
-              x = ldg4(p.a_dense + (size_t)lr * Fa + c);
+              const int it = __ldg(p.items + p.row0 + lr);
+              if ((unsigned)it < (unsigned)p.num_items) x = ldg4(p.item_tab + (size_t)it * (Fa - p.d_u) + (c - p.d_u));
             }
+          } else {
+            x = ldg4(p.a_dense + (size_t)lr * Fa + c);
           }
-          xa[i] = x;
         }
+        xa[i] = x;
       }
 #pragma unroll
-      for (int i = 0; i < NZ; ++i) {
-        {
-          const int idx = t + 128 * i;
-          const int r = idx / zq, c = (idx - r * zq) << 2;
-          const int64_t lr = crow0 + r;
-          xz[i] = (lr < p.rows && !(p.debug & 2)) ? ldg4(p.z + (size_t)lr * Fb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+      for (int i = 0; i < PZ; ++i) {
+        const int idx = t + TG * i;
+        const int r = idx / zq, c = (idx - r * zq) << 2;
+        const int64_t lr = crow0 + r;
+        xz[i] = (r < kWgKC && lr < p.rows && !(p.debug & 2)) ? ldg4(p.z + (size_t)lr * Fb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto store_chunk = [&](int64_t n, const float4(&xa)[NA], const float4(&xz)[NZ]) {
-      const int stage = (int)(n % S);
-      const uint32_t phase = (uint32_t)((n / S) & 1);
-      if (p.debug & 64) tc::mbar_wait_warp(&empty_bar[stage], phase ^ 1); else tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+    auto store_chunk = [&](const float4(&xa)[PA], const float4(&xz)[PZ]) {
+      const int stage = st_stage;
+      const uint32_t phase = st_phase;
+      st_stage += G;
+      while (st_stage >= S) { st_stage -= S; st_phase ^= 1; }
+      tc::mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* st = smem + (size_t)stage * stage_bytes;
       if (!(p.debug & 4)) {
 #pragma unroll
-      for (int i = 0; i < NA; ++i) {
-        {
-          const int idx = t + 128 * i;
+        for (int i = 0; i < PA; ++i) {
+          const int idx = t + TG * i;
           const int r = idx / aq, c = (idx - r * aq) << 2;
           float4 hi, lo;
           tc::split_tf32x4(xa[i], hi, lo);
@@ -134,62 +156,95 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
           *reinterpret_cast<float4*>(st + off) = hi;
           *reinterpret_cast<float4*>(st + a_bytes + off) = lo;
         }
-      }
 #pragma unroll
-      for (int i = 0; i < NZ; ++i) {
-        {  // this thread always sees float4 column t % zq of Z: keep its column sums for db
-          const int idx = t + 128 * i;
+        for (int i = 0; i < PZ; ++i) {  // this thread always sees float4 column t % zq of Z: keep its column sums for db
+          const int idx = t + TG * i;
           const int r = idx / zq, c = (idx - r * zq) << 2;
-          dbacc.x += xz[i].x;
-          dbacc.y += xz[i].y;
-          dbacc.z += xz[i].z;
-          dbacc.w += xz[i].w;
-          float4 hi, lo;
-          tc::split_tf32x4(xz[i], hi, lo);
-          const uint32_t off = tc::mn_off(r, c, kWgKC / 4);
-          *reinterpret_cast<float4*>(st + 2 * a_bytes + off) = hi;
-          *reinterpret_cast<float4*>(st + 2 * a_bytes + z_bytes + off) = lo;
+          if (r < kWgKC) {
+            dbacc.x += xz[i].x;
+            dbacc.y += xz[i].y;
+            dbacc.z += xz[i].z;
+            dbacc.w += xz[i].w;
+            float4 hi, lo;
+            tc::split_tf32x4(xz[i], hi, lo);
+            const uint32_t off = tc::mn_off(r, c, kWgKC / 4);
+            *reinterpret_cast<float4*>(st + 2 * a_bytes + off) = hi;
+            *reinterpret_cast<float4*>(st + 2 * a_bytes + z_bytes + off) = lo;
+          }
         }
-      }
       }
       if (!(p.debug & 16)) tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
     };
 
-    float4 a0[NA], z0[NZ], a1[NA], z1[NZ];
-    int64_t n = group;
-    if (n < my_chunks) issue_loads(n, a0, z0);
-    while (n < my_chunks) {
-      if (n + 2 < my_chunks) issue_loads(n + 2, a1, z1);
-      store_chunk(n, a0, z0);
-      n += 2;
-      if (n >= my_chunks) break;
-      if (n + 2 < my_chunks) issue_loads(n + 2, a0, z0);
-      store_chunk(n, a1, z1);
-      n += 2;
+    constexpr int D = kWgLoadAhead, NB = kWgLoadAhead + 1;
+    float4 ba[NB][PA], bz[NB][PZ];
+    const int64_t mine = my_chunks > group ? (my_chunks - group + G - 1) / G : 0;  // chunks of this group
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+      if (j < mine) issue_loads(ba[j], bz[j]);
+    for (int64_t i0 = 0; i0 < mine; i0 += NB) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int64_t i = i0 + j;
+        if (i < mine) {
+          if (i + D < mine) issue_loads(ba[(j + D) % NB], bz[(j + D) % NB]);
+          store_chunk(ba[j], bz[j]);
+        }
+      }
+    }
+  } else if (warp == kWgPrefetchWarp) {
+    // ---- L2 prefetch of the rows kWgPrefetchAhead chunks ahead of the MMA issuer (see tc_dense.cu)
+    if (!(p.debug & 128)) {
+      const int64_t row_lo = chunk_lo * kWgKC, row_hi = min(p.rows, chunk_hi * kWgKC);
+      for (int64_t r0 = row_lo; r0 < row_hi; r0 += 32) {
+        const int64_t n = (r0 - row_lo) / kWgKC;  // chunk this block of 32 rows starts at
+        while (n >= (int64_t)*reinterpret_cast<volatile int*>(&chunks_issued) + kWgPrefetchAhead) __nanosleep(256);
+        const int64_t lr = r0 + lane;
+        if (lr >= row_hi) continue;
+        if (GATHER) {
+          const int u = __ldg(p.users + p.row0 + lr), it = __ldg(p.items + p.row0 + lr);
+          if ((unsigned)u < (unsigned)p.num_users && (unsigned)it < (unsigned)p.num_items) {
+            const float* pu = p.user_tab + (size_t)u * p.d_u;
+            const float* pi = p.item_tab + (size_t)it * (Fa - p.d_u);
+            for (int c = 0; c < p.d_u; c += 32) tc::prefetch_l2(pu + c);
+            for (int c = 0; c < Fa - p.d_u; c += 32) tc::prefetch_l2(pi + c);
+          }
+        } else {
+          const float* pa = p.a_dense + (size_t)lr * Fa;
+          for (int c = 0; c < Fa; c += 32) tc::prefetch_l2(pa + c);
+        }
+        const float* pz = p.z + (size_t)lr * Fb;
+        for (int c = 0; c < Fb; c += 32) tc::prefetch_l2(pz + c);
+      }
     }
   } else {
-    // ---- MMA issuer
-    const uint32_t idesc = tc::idesc_tf32(128, Fb, 1, 1);
-    const uint32_t lbo = (kWgKC / 4) * 512, sbo = 512;
-    for (int64_t n = 0; n < my_chunks; ++n) {
-      const int stage = (int)(n % S);
-      const uint32_t phase = (uint32_t)((n / S) & 1);
-      if (p.debug & 64) tc::mbar_wait_warp(&full_bar[stage], phase); else tc::mbar_wait(&full_bar[stage], phase);
-      tc::fence_after_sync();
-      if (lane == 0) {
-        const uint32_t sa = tc::smem_u32(smem + (size_t)stage * stage_bytes);
+    // ---- MMA issuer: one elected thread runs the whole loop (see tc::elect_one)
+    if (tc::elect_one()) {
+      constexpr int kHalves = NA / 4;  // Fa / 128
+      const uint32_t idesc = tc::idesc_tf32(128, Fb, 1, 1);
+      const uint32_t lbo = (kWgKC / 4) * 512, sbo = 512;
+      const uint64_t dbase = tc::smem_desc(0, lbo, sbo, tc::kLayoutSw128Base32);
+      const uint32_t s0 = tc::smem_u32(smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t n = 0; n < my_chunks; ++n) {
+        *reinterpret_cast<volatile int*>(&chunks_issued) = (int)n + 1;
+        tc::mbar_wait(&full_bar[stage], phase);
+        tc::fence_after_sync();
+        const uint32_t sa = s0 + (uint32_t)stage * stage_bytes;
         const uint32_t sz = sa + 2 * a_bytes;
 #pragma unroll
-        for (int kk = 0; kk < kWgKC / 8; ++kk) {
-          const uint64_t zh = tc::smem_desc(sz + kk * 1024, lbo, sbo, tc::kLayoutSw128Base32);
-          const uint64_t zl = tc::smem_desc(sz + z_bytes + kk * 1024, lbo, sbo, tc::kLayoutSw128Base32);
-          for (int h = 0; h < halves; ++h) {
+        for (int kk = 0; kk < kWgKC / 8; ++kk) {  // one K=8 step spans 1024 bytes
+          const uint64_t zh = dbase + ((sz + kk * 1024) >> 4);
+          const uint64_t zl = dbase + ((sz + z_bytes + kk * 1024) >> 4);
+#pragma unroll
+          for (int h = 0; h < kHalves; ++h) {
             // features [128h, 128h+128) of A = 4 blocks of 32, each kWgKC/4 groups of 512 bytes
             const uint32_t aoff = (uint32_t)h * 4 * lbo + kk * 1024;
-            const uint64_t ah = tc::smem_desc(sa + aoff, lbo, sbo, tc::kLayoutSw128Base32);
-            const uint64_t al = tc::smem_desc(sa + a_bytes + aoff, lbo, sbo, tc::kLayoutSw128Base32);
+            const uint64_t ah = dbase + ((sa + aoff) >> 4);
+            const uint64_t al = dbase + ((sa + a_bytes + aoff) >> 4);
             const uint32_t d = tmem_base + (uint32_t)h * Fb;
             tc::mma_tf32(d, ah, zh, idesc, (n | kk) != 0);
             tc::mma_tf32(d, al, zh, idesc, 1);
@@ -198,27 +253,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
         }
         tc::mma_commit(&empty_bar[stage]);
         if (n == my_chunks - 1) tc::mma_commit(&done_bar);
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
-      __syncwarp();
     }
   }
 
-  // ---- bias gradient: fold the producer threads' column sums in a fixed order
-  if (warp < 8) {
-    // the two groups hold sums over disjoint chunks; lay them out [group][thread][4]
-    float* slot = db_red;  // 128 threads x 4 floats, group 0 first then group 1 added in order below
-    if ((warp >> 2) == 0) *reinterpret_cast<float4*>(slot + 4 * (tid & 127)) = dbacc;
-  }
-  __syncthreads();
-  if (warp >= 4 && warp < 8) {
-    float4 v = *reinterpret_cast<float4*>(db_red + 4 * (tid & 127));
-    v.x += dbacc.x; v.y += dbacc.y; v.z += dbacc.z; v.w += dbacc.w;
-    *reinterpret_cast<float4*>(db_red + 4 * (tid & 127)) = v;
-  }
+  // ---- bias gradient: fold the 256 producer threads' column sums in a fixed order
+  if (warp < 8) *reinterpret_cast<float4*>(db_red + 4 * tid) = dbacc;
   __syncthreads();
   if (tid < zq && p.db_partial != nullptr) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = tid; j < 128; j += zq) {
+    for (int j = tid; j < 256; j += zq) {
       const float4 v = *reinterpret_cast<float4*>(db_red + 4 * j);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }

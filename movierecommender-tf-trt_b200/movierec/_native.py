@@ -18,7 +18,9 @@ OPT_ADAM, OPT_SGD = 0, 1
 TABLES_DENSE, TABLES_SPARSE = 0, 1
 
 LIB_NAME = "libmovierec_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+# MR_LIB_PATH points at another build of the same library (A/B runs of kernel variants); the default is the
+# in-tree build next to this file.
+LIB_PATH = os.environ.get("MR_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
 class MovierecNativeError(RuntimeError):
@@ -83,6 +85,7 @@ SIGNATURES = {
     "mr_sort_pairs": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "mr_tc_probe": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mr_tc_gemm_selftest": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mr_tc_rate": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "mr_sparse_rows_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "mr_sparse_rows_update": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i32, _f, _f, _f, _f,
                                         _f, _vp, _sz, _vp]),
