@@ -311,8 +311,8 @@ def run_gpu(args, wl):
     def step_resident(i):
         u, it, y = resident[i % n_batches]
         if dp is None:
-            return eng.train_step(u, it, y, group=group, k=group)
-        return dp.train_step(u, it, y, global_rows, group=group, k=group)
+            return eng.train_step(u, it, y, group=group, k=group, grouped=True)
+        return dp.train_step(u, it, y, global_rows, group=group, k=group, grouped=True)
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -354,7 +354,7 @@ def run_gpu(args, wl):
         u, it, y = pinned[i % n_batches]
         if dp is None:
             return model.model.train_on_batch([u, it], y)  # uploads, steps, reads the loss back
-        out = dp.train_step(u, it, y, global_rows, group=group, k=group)
+        out = dp.train_step(u, it, y, global_rows, group=group, k=group, grouped=True)
         return out.cpu()
 
     e2e_steps = 0 if args.lean else max(3, min(args.steps, 20))

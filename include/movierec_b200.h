@@ -93,12 +93,21 @@ typedef struct MrGrads {
   float* item_gmf;
 } MrGrads;
 
+/* `flags` of the train step.  MR_TRAIN_USERS_GROUPED: the caller states that the batch has the layout the
+ * reference's generator produces (data_pipeline.py:99-150): `group` consecutive rows (one positive and its
+ * negatives) share one user.  The tensor-core path then computes everything that depends on the user row alone
+ * once per group (user half of the first layer forward, backward and weight gradient on group-summed
+ * gradients, one staged user-gradient row per group).  The statement is verified on the device; a violation
+ * sets bit 1 of step_out[MR_OUT_BAD_IDS].  Without the flag no layout is assumed. */
+enum { MR_TRAIN_USERS_GROUPED = 1 };
+
 /* Per-step scalars written by the train step (device floats, MR_STEP_OUT_FLOATS of them). */
 enum { MR_OUT_LOSS_SUM = 0, /* sum over rows of BCE (model.py:213-215), unscaled */
        MR_OUT_HIT_SUM = 1,  /* sum over groups of hit@k  (model.py:454) */
        MR_OUT_DCG_SUM = 2,  /* sum over groups of ln2/ln(pos+2)*hit (model.py:414-415) */
        MR_OUT_L2_PENALTY = 3, /* sum of l2 regulariser terms (0 when all l2 == 0) */
-       MR_OUT_BAD_IDS = 4,  /* non-zero when a user/item id was out of range (row skipped) */
+       MR_OUT_BAD_IDS = 4,  /* bit 0: a user/item id was out of range (row skipped); bit 1: MR_TRAIN_USERS_GROUPED
+                               was passed but some row's user differs from its group's first row (step invalid) */
        MR_STEP_OUT_FLOATS = 8 };
 
 int mr_version(void);
@@ -129,14 +138,19 @@ int mr_neumf_forward(const MrModel* model, const int32_t* users, const int32_t* 
 size_t mr_train_workspace_bytes(const MrModel* model, int64_t B);
 int mr_neumf_train_step(MrModel* model, MrOptState* opt, MrGrads* grads, const int32_t* users,
                         const int32_t* items, const float* labels, int64_t B, int32_t group, int32_t k,
-                        float inv_global_batch, float* step_out, void* ws, size_t ws_bytes, void* stream);
+                        int32_t flags, float inv_global_batch, float* step_out, void* ws, size_t ws_bytes,
+                        void* stream);
 /* The two halves of the step, for data-parallel callers that all-reduce `grads` in between
  * (MR_TABLES_DENSE).  In MR_TABLES_SPARSE mode mr_neumf_train_grads already applies the table rows
  * and mr_neumf_apply only updates the dense block. */
 int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const int32_t* users,
                          const int32_t* items, const float* labels, int64_t B, int32_t group, int32_t k,
-                         float inv_global_batch, float* step_out, void* ws, size_t ws_bytes, void* stream);
+                         int32_t flags, float inv_global_batch, float* step_out, void* ws, size_t ws_bytes,
+                         void* stream);
 int mr_neumf_apply(MrModel* model, MrOptState* opt, const MrGrads* grads, void* stream);
+/* ORs 1 into *flag (a device int the caller zeroed) when some users[r] != users[r - r % group]: the check a
+ * caller runs before passing MR_TRAIN_USERS_GROUPED for a batch of unknown origin. */
+int mr_users_grouped(const int32_t* users, int64_t n, int32_t group, int32_t* flag, void* stream);
 
 /* Ranking evaluation of G groups (one user, `group` candidate items, the positive LAST -- the
  * generator's layout, data_pipeline.py:113,148): forward scores, position of the positive under

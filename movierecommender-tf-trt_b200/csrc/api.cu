@@ -81,7 +81,10 @@ void prof_mark(int phase, cudaStream_t st) {
   p.used += 1;
 }
 
-__global__ void flag_to_float_kernel(const int32_t* flags, float* out) { *out = (float)flags[0]; }
+// flags[0]: out-of-range id seen, flags[1]: grouped-batch promise violated -> bits 0 and 1 of the output
+__global__ void flag_to_float_kernel(const int32_t* flags, float* out) {
+  *out = (float)((flags[0] ? 1 : 0) | (flags[1] ? 2 : 0));
+}
 
 static int bits_for(int32_t n) {
   int b = 1;
@@ -158,8 +161,28 @@ struct TcWs {
   float* dZ[MR_MAX_LAYERS];      // pre-activation gradients of a sub-batch
   uint32_t* bits[MR_MAX_LAYERS]; // ReLU bits (H[l] > 0), one word per 32 units, written by the forward layer
   float* head_partial;
+  // grouped batches (train): first-layer operands split into the user rows and the item rows of W[1]
+  float* pack_fu;  // forward, user rows   (d_u x L1)
+  float* pack_fi;  // forward, item rows   (d_i x L1)
+  float* pack_bu;  // backward, user rows
+  float* pack_bi;  // backward, item rows
+  float* Zu;       // (sub-batch groups x L1): user half of the first layer + bias, one row per group
+  float* S1;       // (sub-batch groups x L1): dZ[1] summed over the rows of each group
   size_t total;
 };
+
+// Grouped first layer: the user half runs once per group.  Needs whole groups per sub-batch, both halves of
+// the first layer wide enough for the weight-gradient MMAs (M = 128) and the grouped head kernel.
+static bool tc_grouped_ok(const MrModel& m, int64_t B, int group) {
+  if (group < 2 || !tc_eligible(m) || !head_supports_group(m, group)) return false;
+  const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
+  if (d_u % 128 || d_i % 128 || d_u > 256 || d_i > 256) return false;
+  if (B % group) return false;
+  const int64_t cap = (int64_t)1 << 20;
+  const int64_t parts = B <= cap ? 1 : (B + cap - 1) / cap;
+  if (parts > 1 && (tc_sub_batch(B) % group)) return false;  // sub-batch boundaries must not split a group
+  return true;
+}
 
 static TcWs carve_tc(const MrModel& m, bool train, int64_t B, void* ws) {
   TcWs t{};
@@ -174,15 +197,70 @@ static TcWs carve_tc(const MrModel& m, bool train, int64_t B, void* ws) {
     if (train) t.bits[l] = cv.take<uint32_t>((size_t)sb * (m.L[l] / 32));
   }
   t.head_partial = cv.take<float>(head_partial_floats(m));
+  if (train && m.n_layers >= 2) {
+    const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
+    t.pack_fu = cv.take<float>((size_t)2 * d_u * m.L[1]);
+    t.pack_fi = cv.take<float>((size_t)2 * d_i * m.L[1]);
+    t.pack_bu = cv.take<float>((size_t)2 * d_u * m.L[1]);
+    t.pack_bi = cv.take<float>((size_t)2 * d_i * m.L[1]);
+    const int64_t sg = sb / 2 + 1;  // groups per sub-batch (group >= 2)
+    t.Zu = cv.take<float>((size_t)sg * m.L[1]);
+    t.S1 = cv.take<float>((size_t)sg * m.L[1]);
+  }
   t.total = cv.off;
   return t;
 }
 
 // Forward of rows [r0, r1) on the tensor cores; leaves H[1..n-1] of the sub-batch in the workspace.
 static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users, const int32_t* items, int user_div,
-                           int64_t r0, int64_t r1, cudaStream_t st) {
+                           int64_t r0, int64_t r1, cudaStream_t st, int group = 0) {
   const int d_u = m.L[0] / 2;
-  for (int l = 1; l < m.n_layers; ++l) {
+  if (group > 0) {
+    // grouped batch: Zu = E_user[user of the group] . W1[user rows] + b1 once per group, then
+    // H1 = relu(E_item[item] . W1[item rows] + Zu[row / group]) per row
+    const int d_i = m.L[0] - d_u;
+    TcDenseArgs a{};
+    a.gather = true;
+    a.user_tab = m.user_mlp;
+    a.users = users;
+    a.num_users = m.num_users;
+    a.num_items = m.num_items;
+    a.d_u = d_u;
+    a.user_div = 1;
+    a.user_mul = group;
+    a.b_packed = t.pack_fu;
+    a.N = m.L[1];
+    a.K = d_u;
+    a.rows = (r1 - r0) / group;
+    a.row0 = r0 / group;
+    a.epilogue = TC_EPI_BIAS_RELU;
+    a.bias = m.b[1];
+    a.linear = true;
+    a.out = t.Zu;
+    int rc = launch_tc_dense(a, st);
+    if (rc != MR_OK) return rc;
+    TcDenseArgs b{};
+    b.gather = true;
+    b.item_tab = m.item_mlp;
+    b.items = items;
+    b.num_users = m.num_users;
+    b.num_items = m.num_items;
+    b.d_u = 0;
+    b.user_div = 1;
+    b.b_packed = t.pack_fi;
+    b.N = m.L[1];
+    b.K = d_i;
+    b.rows = r1 - r0;
+    b.row0 = r0;
+    b.epilogue = TC_EPI_BIAS_RELU;
+    b.addend = t.Zu;
+    b.addend_div = group;
+    b.out = t.H[1];
+    b.bits_out = t.bits[1];
+    rc = launch_tc_dense(b, st);
+    if (rc != MR_OK) return rc;
+  }
+  for (int l = group > 0 ? 2 : 1; l < m.n_layers; ++l) {
     TcDenseArgs a{};
     a.gather = (l == 1);
     a.a_dense = (l == 1) ? nullptr : t.H[l - 1];
@@ -228,6 +306,7 @@ struct TrainWs {
   size_t tc_ws_bytes;
   int32_t* pos;
   float* rank_partials;
+  int32_t* group_users;  // grouped batches: the user of each group
   size_t total;
 };
 
@@ -252,6 +331,7 @@ static TrainWs carve_train(const MrModel& m, int64_t B, void* ws) {
   t.seg_ws = cv.take<char>(t.seg_ws_bytes);
   t.pos = cv.take<int32_t>(B);
   t.rank_partials = cv.take<float>(rank_partials_count(B));
+  t.group_users = cv.take<int32_t>(B / 2 + 1);
   t.tc_ws_bytes = tc_eligible(m) ? carve_tc(m, true, B, nullptr).total : 0;
   t.tc_ws = cv.take<char>(t.tc_ws_bytes);
   t.total = cv.off;
@@ -399,8 +479,8 @@ size_t mr_train_workspace_bytes(const MrModel* model, int64_t B) {
 }
 
 int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const int32_t* users, const int32_t* items,
-                         const float* labels, int64_t B, int32_t group, int32_t k, float inv_global_batch,
-                         float* step_out, void* ws, size_t ws_bytes, void* stream) {
+                         const float* labels, int64_t B, int32_t group, int32_t k, int32_t flags,
+                         float inv_global_batch, float* step_out, void* ws, size_t ws_bytes, void* stream) {
   int rc = check_model(model);
   if (rc != MR_OK) return rc;
   rc = check_opt(*model, opt, grads);
@@ -420,6 +500,14 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   prof_mark(MR_PHASE_MISC, st);
   MR_CUDA(cudaMemsetAsync(t.flags, 0, 256, st));
   MR_CUDA(cudaMemsetAsync(step_out, 0, MR_STEP_OUT_FLOATS * sizeof(float), st));
+  // grouped batch (MR_TRAIN_USERS_GROUPED): user-only work once per group; the promise is checked on the device
+  const bool grouped = (flags & MR_TRAIN_USERS_GROUPED) && use_tc(m) && tc_grouped_ok(m, B, group);
+  const int gdiv = grouped ? group : 0;
+  if (grouped) {
+    rc = launch_check_grouped(users, B, group, t.flags + 1, st);
+    if (rc == MR_OK) rc = launch_group_heads(users, B / group, group, t.group_users, st);
+    if (rc != MR_OK) return rc;
+  }
   if (use_tc(m)) {
     // ---- tensor-core path: per sub-batch, forward layers -> head -> per layer weight gradient + backward
     const int P = sm_count();  // rows of the partial buffer = CTAs of the weight-gradient kernel
@@ -427,16 +515,25 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     TcWs tw = carve_tc(m, true, B, t.tc_ws);
     MR_CUDA(cudaMemsetAsync(t.dense_partial, 0, (size_t)P * t.dense_stride * sizeof(float), st));
     MR_CUDA(cudaMemsetAsync(tw.head_partial, 0, head_partial_floats(m) * sizeof(float), st));
-    for (int l = 1; l < n; ++l) {
+    for (int l = grouped ? 2 : 1; l < n; ++l) {
       rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 0, tw.pack_f[l], st);
       if (rc == MR_OK) rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 1, tw.pack_b[l], st);
+      if (rc != MR_OK) return rc;
+    }
+    if (grouped) {  // W[1] is (L0, L1) row-major: rows [0, d_u) multiply the user row, rows [d_u, L0) the item row
+      const float* Wu = m.W[1];
+      const float* Wi = m.W[1] + (size_t)d_u * m.L[1];
+      rc = launch_pack_weights(Wu, d_u, m.L[1], 0, tw.pack_fu, st);
+      if (rc == MR_OK) rc = launch_pack_weights(Wi, d_i, m.L[1], 0, tw.pack_fi, st);
+      if (rc == MR_OK) rc = launch_pack_weights(Wu, d_u, m.L[1], 1, tw.pack_bu, st);
+      if (rc == MR_OK) rc = launch_pack_weights(Wi, d_i, m.L[1], 1, tw.pack_bi, st);
       if (rc != MR_OK) return rc;
     }
     const int64_t sb = tc_sub_batch(B);
     for (int64_t r0 = 0; r0 < B; r0 += sb) {
       const int64_t r1 = r0 + sb < B ? r0 + sb : B;
       prof_mark(MR_PHASE_TC_DENSE_FWD, st);
-      rc = tc_forward_rows(m, tw, users, items, 1, r0, r1, st);
+      rc = tc_forward_rows(m, tw, users, items, 1, r0, r1, st, gdiv);
       if (rc != MR_OK) return rc;
       prof_mark(MR_PHASE_HEAD, st);
       HeadArgs h{};
@@ -448,6 +545,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       h.rows = r1 - r0;
       h.row0 = r0;
       h.user_div = 1;
+      h.group = gdiv;
       h.inv_batch = inv_global_batch;
       h.probs = t.probs;
       h.dz_last = tw.dZ[n - 1];
@@ -458,6 +556,81 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       rc = launch_head(h, st);
       if (rc != MR_OK) return rc;
       for (int l = n - 1; l >= 1; --l) {
+        if (grouped && l == 1) {
+          // first layer of a grouped batch: item half per row, user half per group on S1 = group sums of dZ[1]
+          const int64_t ng = (r1 - r0) / group, g0 = r0 / group;
+          prof_mark(MR_PHASE_MISC, st);
+          rc = launch_group_sum_rows(tw.dZ[1], ng, group, m.L[1], tw.S1, st);
+          if (rc != MR_OK) return rc;
+          prof_mark(MR_PHASE_TC_WGRAD, st);
+          TcWgradArgs wi{};
+          wi.gather = true;
+          wi.item_tab = m.item_mlp;
+          wi.items = items;
+          wi.num_users = m.num_users;
+          wi.num_items = m.num_items;
+          wi.d_u = 0;
+          wi.z = tw.dZ[1];
+          wi.Fa = d_i;
+          wi.Fb = m.L[1];
+          wi.rows = r1 - r0;
+          wi.row0 = r0;
+          wi.dw_partial = t.dense_partial + (m.W[1] - m.dense) + (size_t)d_u * m.L[1];
+          wi.db_partial = t.dense_partial + (m.b[1] - m.dense);
+          wi.partial_stride = t.dense_stride;
+          rc = launch_tc_wgrad(wi, st);
+          if (rc != MR_OK) return rc;
+          TcWgradArgs wu{};
+          wu.gather = true;
+          wu.user_tab = m.user_mlp;
+          wu.users = users;
+          wu.num_users = m.num_users;
+          wu.num_items = m.num_items;
+          wu.d_u = d_u;
+          wu.user_mul = group;
+          wu.z = tw.S1;
+          wu.Fa = d_u;
+          wu.Fb = m.L[1];
+          wu.rows = ng;
+          wu.row0 = g0;
+          wu.dw_partial = t.dense_partial + (m.W[1] - m.dense);
+          wu.db_partial = nullptr;  // the bias gradient came with the item half (column sums of dZ[1])
+          wu.partial_stride = t.dense_stride;
+          rc = launch_tc_wgrad(wu, st);
+          if (rc != MR_OK) return rc;
+          prof_mark(MR_PHASE_TC_DENSE_BWD, st);
+          TcDenseArgs bi{};
+          bi.a_dense = tw.dZ[1];
+          bi.d_u = 0;  // every output column belongs to the item row
+          bi.b_packed = tw.pack_bi;
+          bi.N = d_i;
+          bi.K = m.L[1];
+          bi.rows = r1 - r0;
+          bi.row0 = r0;
+          bi.epilogue = TC_EPI_STAGE;
+          bi.stage_u = t.stage_u;
+          bi.stage_i = t.stage_i;
+          bi.su = d_u + f;
+          bi.si = d_i + f;
+          rc = launch_tc_dense(bi, st);
+          if (rc != MR_OK) return rc;
+          TcDenseArgs bu{};
+          bu.a_dense = tw.S1;
+          bu.d_u = d_u;  // every output column belongs to the user row of the group
+          bu.b_packed = tw.pack_bu;
+          bu.N = d_u;
+          bu.K = m.L[1];
+          bu.rows = ng;
+          bu.row0 = g0;
+          bu.epilogue = TC_EPI_STAGE;
+          bu.stage_u = t.stage_u;
+          bu.stage_i = t.stage_i;
+          bu.su = d_u + f;
+          bu.si = d_i + f;
+          rc = launch_tc_dense(bu, st);
+          if (rc != MR_OK) return rc;
+          continue;
+        }
         prof_mark(MR_PHASE_TC_WGRAD, st);
         TcWgradArgs w{};
         w.gather = (l == 1);
@@ -588,7 +761,9 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   }
   // users
   prof_mark(MR_PHASE_SORT, st);
-  rc = launch_sort_pairs(users, B, bits_for(m.num_users), t.sorted_keys, t.sorted_index, t.sort_ws, t.sort_ws_bytes, st);
+  const int64_t n_user_rows = grouped ? B / group : B;  // staged user-gradient rows: one per group or one per row
+  rc = launch_sort_pairs(grouped ? t.group_users : users, n_user_rows, bits_for(m.num_users), t.sorted_keys, t.sorted_index,
+                         t.sort_ws, t.sort_ws_bytes, st);
   if (rc != MR_OK) return rc;
   u.d0 = d_u;
   u.d1 = m.mf_dim;
@@ -596,7 +771,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   u.p0 = m.user_mlp; u.m0 = opt->m_user_mlp; u.v0 = opt->v_user_mlp; u.g0 = grads->user_mlp;
   u.p1 = m.user_gmf; u.m1 = opt->m_user_gmf; u.v1 = opt->v_user_gmf; u.g1 = grads->user_gmf;
   prof_mark(MR_PHASE_SEGREDUCE, st);
-  rc = launch_segreduce(t.sorted_keys, t.sorted_index, B, t.stage_u, u, t.seg_ws, t.seg_ws_bytes, st);
+  rc = launch_segreduce(t.sorted_keys, t.sorted_index, n_user_rows, t.stage_u, u, t.seg_ws, t.seg_ws_bytes, st);
   if (rc != MR_OK) return rc;
   // items
   prof_mark(MR_PHASE_SORT, st);
@@ -649,10 +824,10 @@ int mr_neumf_apply(MrModel* model, MrOptState* opt, const MrGrads* grads, void* 
 }
 
 int mr_neumf_train_step(MrModel* model, MrOptState* opt, MrGrads* grads, const int32_t* users, const int32_t* items,
-                        const float* labels, int64_t B, int32_t group, int32_t k, float inv_global_batch,
+                        const float* labels, int64_t B, int32_t group, int32_t k, int32_t flags, float inv_global_batch,
                         float* step_out, void* ws, size_t ws_bytes, void* stream) {
-  int rc = mr_neumf_train_grads(model, opt, grads, users, items, labels, B, group, k, inv_global_batch, step_out, ws,
-                                ws_bytes, stream);
+  int rc = mr_neumf_train_grads(model, opt, grads, users, items, labels, B, group, k, flags, inv_global_batch, step_out,
+                                ws, ws_bytes, stream);
   if (rc != MR_OK) return rc;
   return mr_neumf_apply(model, opt, grads, stream);
 }
@@ -723,6 +898,12 @@ int mr_tc_probe(const float* raw_a, int32_t n_words, int32_t start_off, int32_t 
                 void* stream) {
   MR_REQUIRE(raw_a && D, "tc probe: NULL pointer");
   return launch_tc_probe(raw_a, n_words, start_off, lbo, sbo, a_mn, D, (cudaStream_t)stream);
+}
+
+int mr_users_grouped(const int32_t* users, int64_t n, int32_t group, int32_t* flag, void* stream) {
+  MR_REQUIRE(users != nullptr && flag != nullptr, "users_grouped: NULL pointer");
+  MR_REQUIRE(n >= 0 && group >= 1, "users_grouped: bad sizes");
+  return launch_check_grouped(users, n, group, flag, (cudaStream_t)stream);
 }
 
 int mr_tc_rate(int32_t N, int32_t iters, int32_t nbuf, int32_t flags, int32_t writers, int32_t write_iters,

@@ -39,4 +39,74 @@ int launch_gather_rows(const float* table, int64_t rows, int dim, const int32_t*
   return MR_OK;
 }
 
+// ---- grouped batches --------------------------------------------------------------------------------------
+// The reference's generator lays a batch out as groups of one positive and its negatives, all of one user
+// (data_pipeline.py:99-150).  Everything the tower computes from the user row alone is therefore shared by
+// the rows of a group: the user half of the first layer in the forward pass, and -- after summing the
+// pre-activation gradients of the group -- the user half of the backward pass and of the weight gradient.
+
+// out[g] = sum_{j < group} in[g * group + j], rows of `width` floats, added in order j = 0, 1, ...
+// HBM-bound: (group + 1) * width * 4 bytes per group.
+__global__ void __launch_bounds__(256) group_sum_rows_kernel(const float* __restrict__ in, int64_t groups, int group,
+                                                             int width4, float* __restrict__ out) {
+  const int64_t total = groups * width4;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = e / width4;
+    const int c = (int)(e - g * width4);
+    const float4* src = reinterpret_cast<const float4*>(in) + g * group * width4 + c;
+    float4 s = ld_stream4(reinterpret_cast<const float*>(src));
+    for (int j = 1; j < group; ++j) {
+      const float4 v = ld_stream4(reinterpret_cast<const float*>(src + (int64_t)j * width4));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[e] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) group_heads_kernel(const int32_t* __restrict__ ids, int64_t groups, int group,
+                                                          int32_t* __restrict__ out) {
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x)
+    out[g] = __ldg(ids + g * group);
+}
+
+__global__ void __launch_bounds__(256) check_grouped_kernel(const int32_t* __restrict__ ids, int64_t n, int group,
+                                                            int32_t* __restrict__ flag) {
+  bool bad = false;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+    bad |= __ldg(ids + r) != __ldg(ids + (r - r % group));
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+static unsigned grid_for(int64_t work_items) {
+  int64_t blocks = (work_items + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+int launch_group_sum_rows(const float* in, int64_t groups, int group, int width, float* out, cudaStream_t st) {
+  if (groups == 0) return MR_OK;
+  if (width % 4 || group < 1 || ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)) {
+    set_error("group_sum_rows: width=%d must be a multiple of 4 and the buffers 16-byte aligned", width);
+    return MR_ERR_INVALID;
+  }
+  group_sum_rows_kernel<<<grid_for(groups * (width / 4)), 256, 0, st>>>(in, groups, group, width / 4, out);
+  MR_LAUNCH_CHECK("group_sum_rows_kernel");
+  return MR_OK;
+}
+
+int launch_group_heads(const int32_t* ids, int64_t groups, int group, int32_t* out, cudaStream_t st) {
+  if (groups == 0) return MR_OK;
+  group_heads_kernel<<<grid_for(groups), 256, 0, st>>>(ids, groups, group, out);
+  MR_LAUNCH_CHECK("group_heads_kernel");
+  return MR_OK;
+}
+
+int launch_check_grouped(const int32_t* ids, int64_t n, int group, int32_t* flag, cudaStream_t st) {
+  if (n == 0 || group <= 1) return MR_OK;
+  check_grouped_kernel<<<grid_for(n), 256, 0, st>>>(ids, n, group, flag);
+  MR_LAUNCH_CHECK("check_grouped_kernel");
+  return MR_OK;
+}
+
 }  // namespace mr

@@ -22,6 +22,7 @@ struct HeadParams {
   const float* labels;
   int64_t rows, row0;
   int32_t user_div;
+  int32_t group;  // > 0: grouped batch -- a warp takes whole groups and stages ONE GMF user-gradient row per group
   float inv_batch;
   float* logits;
   float* probs;
@@ -33,9 +34,11 @@ struct HeadParams {
 };
 
 // MAXQ = columns per lane (compile-time so the per-lane arrays stay in registers and small models get
-// high occupancy: the kernel is latency/HBM bound).
-template <int MAXQ>
-__global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) {
+// high occupancy: the kernel is latency/HBM bound).  KR = rows per warp and iteration.  GROUPED: the KR rows
+// are one group of a grouped batch (same user): the GMF user row is read once and its gradient, summed over
+// the group in row order, is staged once at row (row0 / KR + group index) of stage_u.
+template <int MAXQ, int KR, bool GROUPED>
+__global__ void __launch_bounds__(kHeadThreads, MAXQ <= 4 ? 2 : 1) head_kernel(const HeadParams p) {
   __shared__ float red[kHeadThreads / 32][MAXQ * 32 + 2];
   const MrModel& m = p.m;
   const int f = m.mf_dim, Ln = m.L[m.n_layers - 1], ncols = f + Ln;
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) 
   // row loads, then the reductions, then the stores): the kernel is latency-bound, so the loads of
   // several independent rows must be in flight together.  The order in which a warp folds rows into
   // its d w_out / d b_out / loss sums is fixed (rr = 0..kRows-1), so results stay deterministic.
-  constexpr int kRows = MAXQ <= 4 ? 4 : 2;
+  constexpr int kRows = KR;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   for (int64_t base = w0 * kRows; base < p.rows; base += warps * kRows) {
@@ -65,10 +68,13 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) 
       u[rr] = 0;
       it[rr] = 0;
       if (live[rr]) {
-        u[rr] = __ldg(p.users + (p.row0 + lr) / p.user_div);
+        u[rr] = __ldg(p.users + (GROUPED ? p.row0 + base : (p.row0 + lr) / p.user_div));
         it[rr] = __ldg(p.items + p.row0 + lr);
       }
     }
+    float gu_acc[MAXQ];  // GROUPED: gradient of the group's GMF user row
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) gu_acc[q] = 0.f;
     // column j of the head input: j < f -> gu[j]*gi[j], else h[j - f]; lane owns columns lane + 32q
     float hv[kRows][MAXQ], ga[kRows][MAXQ], gb[kRows][MAXQ];
 #pragma unroll
@@ -88,7 +94,7 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) 
         gb[rr][q] = 0.f;
         if (live[rr]) {
           if (j < f) {
-            ga[rr][q] = __ldg(m.user_gmf + (size_t)u[rr] * f + j);
+            ga[rr][q] = (GROUPED && rr > 0) ? ga[0][q] : __ldg(m.user_gmf + (size_t)u[rr] * f + j);
             gb[rr][q] = __ldg(m.item_gmf + (size_t)it[rr] * f + j);
           } else if (j < ncols) {
             hv[rr][q] = __ldg(p.h_last + (size_t)lr * Ln + (j - f));
@@ -129,13 +135,22 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) 
             accw[q] = fmaf(dz, hv[rr][q], accw[q]);
             const float g = dz * wv[q];
             if (j < f) {
-              p.stage_u[(size_t)gr * su + d_u + j] = g * gb[rr][q];
+              if (GROUPED) gu_acc[q] = fmaf(g, gb[rr][q], gu_acc[q]);
+              else p.stage_u[(size_t)gr * su + d_u + j] = g * gb[rr][q];
               p.stage_i[(size_t)gr * si + d_i + j] = g * ga[rr][q];
             } else {
               p.dz_last[(size_t)lr * Ln + (j - f)] = hv[rr][q] > 0.f ? g : 0.f;
             }
           }
         }
+      }
+    }
+    if (GROUPED && train && live[0]) {
+      const int64_t grp = (p.row0 + base) / kRows;
+#pragma unroll
+      for (int q = 0; q < MAXQ; ++q) {
+        const int j = lane + 32 * q;
+        if (j < f) p.stage_u[(size_t)grp * su + d_u + j] = gu_acc[q];
       }
     }
   }
@@ -178,6 +193,10 @@ __global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restric
 
 int head_grid() { return sm_count() * 8; }
 
+bool head_supports_group(const MrModel& m, int group) {
+  return group >= 2 && group <= 8 && m.mf_dim + m.L[m.n_layers - 1] <= 128;
+}
+
 size_t head_partial_floats(const MrModel& m) { return (size_t)head_grid() * (m.mf_dim + m.L[m.n_layers - 1] + 2); }
 
 int launch_head(const HeadArgs& a, cudaStream_t st) {
@@ -205,10 +224,25 @@ int launch_head(const HeadArgs& a, cudaStream_t st) {
   p.stage_i = a.stage_i;
   p.head_partial = a.head_partial;
   p.flags = a.flags;
+  p.group = a.group;
   const int grid = head_grid();
-  if (ncols <= 128) head_kernel<4><<<grid, kHeadThreads, 0, st>>>(p);
-  else if (ncols <= 256) head_kernel<8><<<grid, kHeadThreads, 0, st>>>(p);
-  else head_kernel<16><<<grid, kHeadThreads, 0, st>>>(p);
+  if (a.group > 0) {
+    if (!head_supports_group(m, a.group) || a.rows % a.group || a.row0 % a.group || p.user_div != 1) {
+      set_error("head kernel: grouped mode needs group <= 8, mf_dim + last width <= 128 and whole groups");
+      return MR_ERR_INVALID;
+    }
+    switch (a.group) {
+      case 2: head_kernel<4, 2, true><<<grid, kHeadThreads, 0, st>>>(p); break;
+      case 3: head_kernel<4, 3, true><<<grid, kHeadThreads, 0, st>>>(p); break;
+      case 4: head_kernel<4, 4, true><<<grid, kHeadThreads, 0, st>>>(p); break;
+      case 5: head_kernel<4, 5, true><<<grid, kHeadThreads, 0, st>>>(p); break;
+      case 6: head_kernel<4, 6, true><<<grid, kHeadThreads, 0, st>>>(p); break;
+      case 7: head_kernel<4, 7, true><<<grid, kHeadThreads, 0, st>>>(p); break;
+      default: head_kernel<4, 8, true><<<grid, kHeadThreads, 0, st>>>(p); break;
+    }
+  } else if (ncols <= 128) head_kernel<4, 4, false><<<grid, kHeadThreads, 0, st>>>(p);
+  else if (ncols <= 256) head_kernel<8, 2, false><<<grid, kHeadThreads, 0, st>>>(p);
+  else head_kernel<16, 2, false><<<grid, kHeadThreads, 0, st>>>(p);
   MR_LAUNCH_CHECK("head_kernel");
   return MR_OK;
 }

@@ -84,11 +84,15 @@ struct TcDenseArgs {
   const int32_t* items;
   int32_t num_users, num_items, d_u;
   int32_t user_div;       // gather: row r uses users[r / user_div]
+  int32_t user_mul;       // gather (user_div == 1): row r uses users[r * user_mul] (one row per group of a grouped batch)
   const float* b_packed;  // launch_pack_weights output
   int32_t N, K;
   int64_t rows, row0;
   int epilogue;
-  const float* bias;
+  const float* bias;          // TC_EPI_BIAS_RELU, optional
+  const float* addend;        // TC_EPI_BIAS_RELU, optional: row r adds addend[r / addend_div] (launch-local rows x N)
+  int32_t addend_div;
+  bool linear;                // TC_EPI_BIAS_RELU without the ReLU
   const uint32_t* mask_bits;  // TC_EPI_MASK: ReLU bits written by the forward layer
   uint32_t* bits_out;         // TC_EPI_BIAS_RELU, optional
   float* out;
@@ -107,6 +111,7 @@ struct TcWgradArgs {
   const int32_t* users;
   const int32_t* items;
   int32_t num_users, num_items, d_u;
+  int32_t user_mul;       // gather: user rows read users[(row0 + r) * user_mul]; d_u = 0 / Fa selects one table
   const float* z;         // [rows x Fb] launch-local rows
   int32_t Fa, Fb;
   int64_t rows, row0;
@@ -126,6 +131,7 @@ struct HeadArgs {
   const float* labels;    // NULL = forward only
   int64_t rows, row0;
   int32_t user_div;       // row r uses users[r / user_div]
+  int32_t group;          // > 0 (train): grouped batch, stage_u holds ONE row per group (index row / group)
   float inv_batch;
   float* logits;          // global rows, may be NULL
   float* probs;           // global rows, may be NULL
@@ -139,8 +145,17 @@ struct HeadArgs {
 int launch_head_reduce(const MrModel& m, const float* head_partial, float* d_wout_row0, float* d_bout_row0,
                        float* loss_sum, cudaStream_t st);
 int head_grid();
+bool head_supports_group(const MrModel& m, int group);
 size_t head_partial_floats(const MrModel& m);
 int launch_head(const HeadArgs& a, cudaStream_t st);
+
+// ---- grouped batches (gather.cu): one positive and its negatives share the user ----------------------------
+// out[g] = sum_{j < group} in[g * group + j]  (rows of `width` floats, width % 4 == 0), fixed order
+int launch_group_sum_rows(const float* in, int64_t groups, int group, int width, float* out, cudaStream_t st);
+// out[g] = ids[g * group]
+int launch_group_heads(const int32_t* ids, int64_t groups, int group, int32_t* out, cudaStream_t st);
+// *flag = 1 when some ids[r] != ids[r - r % group]
+int launch_check_grouped(const int32_t* ids, int64_t n, int group, int32_t* flag, cudaStream_t st);
 
 // ---- tc_selftest.cu ---------------------------------------------------------------------------
 int launch_tc_rate(int N, int iters, int nbuf, int flags, int writers, int write_iters, long long* out, int grid,

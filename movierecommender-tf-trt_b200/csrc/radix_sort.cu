@@ -7,7 +7,12 @@
 
 namespace mr {
 
-constexpr int kKeysPerWarp = 2048;
+// Keys per warp tile.  A warp walks its tile 32 keys at a time IN ORDER (that is what makes the sort stable), so
+// the tile length is the serial depth of the kernel: at 2048 keys a launch took ~50 us however few keys there
+// were (64 dependent iterations, 4 warps per SM at 1.3 M keys).  256 keys = 8 iterations whose loads are all
+// issued up front.
+constexpr int kKeysPerWarp = 256;
+constexpr int kTileIters = kKeysPerWarp / 32;
 constexpr int kSortWarps = 4;  // warps per CTA
 constexpr int kBins = 256;
 
@@ -24,10 +29,17 @@ __global__ void __launch_bounds__(kSortWarps * 32) radix_hist_kernel(const int32
   __syncwarp();
   if (wt < nwt) {
     const int64_t base = wt * kKeysPerWarp;
-    for (int c = 0; c < kKeysPerWarp && base + c < n; c += 32) {
-      const int64_t i = base + c + lane;
+    int32_t kreg[kTileIters];
+#pragma unroll
+    for (int q = 0; q < kTileIters; ++q) {
+      const int64_t i = base + 32 * q + lane;
+      kreg[q] = i < n ? __ldg(keys + i) : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < kTileIters; ++q) {
+      const int64_t i = base + 32 * q + lane;
       const bool valid = i < n;
-      const unsigned d = valid ? digit_of(__ldg(keys + i), shift) : (0x100u | lane);
+      const unsigned d = valid ? digit_of(kreg[q], shift) : (0x100u | lane);
       const unsigned peers = __match_any_sync(0xffffffffu, d);
       if (valid && (peers & ((1u << lane) - 1)) == 0) cnt[w][d] += __popc(peers);
       __syncwarp();
@@ -101,12 +113,20 @@ __global__ void __launch_bounds__(kSortWarps * 32) radix_scatter_kernel(
   }
   __syncwarp();
   const int64_t base = wt * kKeysPerWarp;
-  for (int c = 0; c < kKeysPerWarp; c += 32) {
-    const int64_t i = base + c + lane;
-    if (base + c >= n) break;  // warp-uniform
+  int32_t kreg[kTileIters], vreg[kTileIters];
+#pragma unroll
+  for (int q = 0; q < kTileIters; ++q) {
+    const int64_t i = base + 32 * q + lane;
+    kreg[q] = i < n ? __ldg(keys + i) : 0;
+    vreg[q] = i < n ? (index != nullptr ? __ldg(index + i) : (int32_t)i) : 0;
+  }
+#pragma unroll
+  for (int q = 0; q < kTileIters; ++q) {
+    const int64_t i = base + 32 * q + lane;
+    if (base + 32 * q >= n) break;  // warp-uniform
     const bool valid = i < n;
-    const int32_t key = valid ? __ldg(keys + i) : 0;
-    const int32_t val = valid ? (index != nullptr ? __ldg(index + i) : (int32_t)i) : 0;
+    const int32_t key = kreg[q];
+    const int32_t val = vreg[q];
     const unsigned d = valid ? digit_of(key, shift) : (0x100u | lane);
     const unsigned peers = __match_any_sync(0xffffffffu, d);
     const int rank = __popc(peers & ((1u << lane) - 1));

@@ -54,14 +54,17 @@ struct TcDenseParams {
   const float* item_tab;
   const int32_t* users;
   const int32_t* items;
-  int32_t num_users, num_items, d_u, user_div;
+  int32_t num_users, num_items, d_u, user_div, user_mul;  // row r reads users[r * user_mul / user_div]; d_u = 0 or K: one table only
   // B operand: packed [K/32 chunks][hi, lo][N x 32] core-matrix order
   const float* b_packed;
   int32_t N, K;
   int64_t rows;          // rows of this launch
   int64_t row0;          // global index of the first row (ids, staging and outputs are indexed globally)
   // epilogue
-  const float* bias;     // EPI_BIAS_RELU
+  const float* bias;     // EPI_BIAS_RELU, optional
+  const float* addend;   // EPI_BIAS_RELU, optional: [rows / addend_div x N] added before the activation (launch-local rows)
+  int32_t addend_div;
+  int32_t relu;          // EPI_BIAS_RELU: apply the ReLU (0 = linear output)
   const uint32_t* mask_bits;  // EPI_MASK: [rows x N/32] ReLU bits of the previous layer's output, launch-local rows
   uint32_t* bits_out;    // EPI_BIAS_RELU, optional: [rows x N/32] bits (h > 0) for the backward pass
   float* out;            // EPI_BIAS_RELU / EPI_MASK: [rows x N], launch-local rows
@@ -149,7 +152,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
           if (AMODE == A_GATHER) {
             if (ok[g]) {
               const uint32_t grow = (uint32_t)(p.row0 + lr);  // B < 2^31
-              const int u = __ldg(p.users + (p.user_div == 1 ? grow : grow / (uint32_t)p.user_div)), it = __ldg(p.items + grow);
+              const bool has_u = p.d_u > 0, has_i = p.d_u < K;
+              const int u = has_u ? __ldg(p.users + (p.user_div == 1 ? grow * (uint32_t)p.user_mul : grow / (uint32_t)p.user_div)) : 0;
+              const int it = has_i ? __ldg(p.items + grow) : 0;
               if ((unsigned)u < (unsigned)p.num_users && (unsigned)it < (unsigned)p.num_items) {
                 src_u[g] = p.user_tab + (size_t)u * p.d_u;
                 src_i[g] = p.item_tab + (size_t)it * (K - p.d_u);
@@ -283,7 +288,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
           if (lr >= p.rows) continue;
           if (AMODE == A_GATHER) {
             const uint32_t grow = (uint32_t)(p.row0 + lr);
-            const int u = __ldg(p.users + (p.user_div == 1 ? grow : grow / (uint32_t)p.user_div)), itm = __ldg(p.items + grow);
+            const bool has_u = p.d_u > 0, has_i = p.d_u < K;
+            const int u = has_u ? __ldg(p.users + (p.user_div == 1 ? grow * (uint32_t)p.user_mul : grow / (uint32_t)p.user_div)) : 0;
+            const int itm = has_i ? __ldg(p.items + grow) : 0;
             if ((unsigned)u < (unsigned)p.num_users && (unsigned)itm < (unsigned)p.num_items) {
               const float* pu = p.user_tab + (size_t)u * p.d_u;
               const float* pi = p.item_tab + (size_t)itm * (K - p.d_u);
@@ -319,19 +326,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       float* tile_s = epi_smem + (size_t)quarter * (32 * kEpiLd);
       const int64_t my_lr = wrow0 + lane;  // the row this thread owns while the data is thread-per-row
       const bool my_ok = my_lr < p.rows;
+      // optional per-group addend row of this thread's row (the rows of a group read the same line)
+      const float* arow = (EPI == EPI_BIAS_RELU && p.addend != nullptr && my_ok)
+                              ? p.addend + (size_t)((uint32_t)my_lr / (uint32_t)p.addend_div) * N : nullptr;
       for (int c0 = 0; c0 < ((p.debug & 32) ? 0 : N); c0 += 32) {
         float v[32];
         tc::tmem_ld16(taddr + c0, v);
         tc::tmem_ld16(taddr + c0 + 16, v + 16);
         if (EPI == EPI_BIAS_RELU) {
           uint32_t bits = 0;
+          if (p.bias != nullptr) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 bv = ldg4(p.bias + c0 + 4 * q);
-            v[4 * q + 0] = fmaxf(v[4 * q + 0] + bv.x, 0.f);
-            v[4 * q + 1] = fmaxf(v[4 * q + 1] + bv.y, 0.f);
-            v[4 * q + 2] = fmaxf(v[4 * q + 2] + bv.z, 0.f);
-            v[4 * q + 3] = fmaxf(v[4 * q + 3] + bv.w, 0.f);
+            for (int q = 0; q < 8; ++q) {
+              const float4 bv = ldg4(p.bias + c0 + 4 * q);
+              v[4 * q + 0] += bv.x; v[4 * q + 1] += bv.y; v[4 * q + 2] += bv.z; v[4 * q + 3] += bv.w;
+            }
+          }
+          if (arow != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 av = ldg4(arow + c0 + 4 * q);
+              v[4 * q + 0] += av.x; v[4 * q + 1] += av.y; v[4 * q + 2] += av.z; v[4 * q + 3] += av.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           }
           if (p.bits_out != nullptr) {
 #pragma unroll
@@ -442,6 +462,10 @@ int launch_tc_dense(const TcDenseArgs& a, cudaStream_t st) {
   p.num_items = a.num_items;
   p.d_u = a.d_u;
   p.user_div = a.user_div < 1 ? 1 : a.user_div;
+  p.user_mul = a.user_mul < 1 ? 1 : a.user_mul;
+  p.addend = a.addend;
+  p.addend_div = a.addend_div < 1 ? 1 : a.addend_div;
+  p.relu = a.linear ? 0 : 1;
   p.b_packed = a.b_packed;
   p.N = a.N;
   p.K = a.K;

@@ -40,7 +40,7 @@ struct TcWgradParams {
   const float* item_tab;
   const int32_t* users;
   const int32_t* items;
-  int32_t num_users, num_items, d_u;
+  int32_t num_users, num_items, d_u, user_mul;  // d_u = 0 or Fa: one table only; user rows read users[r * user_mul]
   const float* z;
   int32_t Fa, Fb;
   int64_t rows, row0;
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
         if (lr < p.rows && !(p.debug & 2)) {
           if (GATHER) {
             if (c < p.d_u) {
-              const int u = __ldg(p.users + p.row0 + lr);
+              const int u = __ldg(p.users + (p.row0 + lr) * p.user_mul);
               if ((unsigned)u < (unsigned)p.num_users) x = ldg4(p.user_tab + (size_t)u * p.d_u + c);
             } else {
               const int it = __ldg(p.items + p.row0 + lr);
@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
         const int64_t lr = r0 + lane;
         if (lr >= row_hi) continue;
         if (GATHER) {
-          const int u = __ldg(p.users + p.row0 + lr), it = __ldg(p.items + p.row0 + lr);
+          const int u = p.d_u > 0 ? __ldg(p.users + (p.row0 + lr) * p.user_mul) : 0;
+          const int it = p.d_u < Fa ? __ldg(p.items + p.row0 + lr) : 0;
           if ((unsigned)u < (unsigned)p.num_users && (unsigned)it < (unsigned)p.num_items) {
             const float* pu = p.user_tab + (size_t)u * p.d_u;
             const float* pi = p.item_tab + (size_t)it * (Fa - p.d_u);
@@ -314,6 +315,7 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
   p.num_users = a.num_users;
   p.num_items = a.num_items;
   p.d_u = a.d_u;
+  p.user_mul = a.user_mul < 1 ? 1 : a.user_mul;
   p.z = a.z;
   p.Fa = a.Fa;
   p.Fb = a.Fb;

@@ -51,11 +51,13 @@ class DataParallelNeuMF(object):
         for t in [e.dense] + list(e._tables.values()):
             dist.broadcast(t, src, group=self.group)
 
-    def train_step(self, users, items, labels, global_rows, group=0, k=0):
+    def train_step(self, users, items, labels, global_rows, group=0, k=0, grouped=False):
         """Local forward/backward -> all-reduce(sum) of the flat gradients -> identical update.
-        Returns the rank-local step outputs (loss/hit/dcg sums over the local rows)."""
+        Returns the rank-local step outputs (loss/hit/dcg sums over the local rows).
+        grouped: see NeuMFEngine.train_step (batches are split by whole groups, so the layout survives)."""
         e = self.engine
-        out = e.train_grads(users, items, labels, group=group, k=k, inv_global_batch=1.0 / float(global_rows))
+        out = e.train_grads(users, items, labels, group=group, k=k, inv_global_batch=1.0 / float(global_rows),
+                            grouped=grouped)
         for t in e.gradient_tensors():
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         e.apply()
@@ -197,14 +199,15 @@ class ShardedNeuMF(object):
             ptr(self._ws), self._ws.numel(), e._stream()), "mr_sparse_rows_update")
 
     # ---- the step ---------------------------------------------------------------------------------------
-    def train_step(self, users, items, labels, global_rows, group=0, k=0):
+    def train_step(self, users, items, labels, global_rows, group=0, k=0, grouped=False):
         e = self.cache
         dev = e.device
         users = self._engine_mod.as_device_i32(users, dev).long()
         items = self._engine_mod.as_device_i32(items, dev).long()
         ru = self._fetch("user", users)
         ri = self._fetch("item", items)
-        out = e.train_grads(ru["slots"], ri["slots"], labels, group=group, k=k, inv_global_batch=1.0 / float(global_rows))
+        out = e.train_grads(ru["slots"], ri["slots"], labels, group=group, k=k, inv_global_batch=1.0 / float(global_rows),
+                            grouped=grouped)  # cache slots are a function of the id, so equal users stay equal
         self._push_grads("user", ru)
         self._push_grads("item", ri)
         dist.all_reduce(e.g_dense, op=dist.ReduceOp.SUM, group=self.group)

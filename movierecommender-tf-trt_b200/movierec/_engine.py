@@ -289,7 +289,18 @@ class NeuMFEngine(object):
                   "mr_neumf_forward")
         return logits, probs, loss
 
-    def _train_args(self, users, items, labels, group, k, inv_global_batch):
+    def users_grouped(self, users, group):
+        """True when every `group` consecutive entries of `users` are equal (the generator's layout,
+        data_pipeline.py:99-150).  One small kernel and a 4-byte read-back."""
+        users = as_device_i32(users, self.device)
+        if group < 2 or users.numel() % group:
+            return False
+        flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        nat.check(nat.lib.mr_users_grouped(_ptr(users), users.numel(), int(group), _ptr(flag), self._stream()),
+                  "mr_users_grouped")
+        return int(flag.item()) == 0
+
+    def _train_args(self, users, items, labels, group, k, inv_global_batch, grouped=False):
         users = as_device_i32(users, self.device)
         items = as_device_i32(items, self.device)
         labels = as_device_f32(labels, self.device)
@@ -301,20 +312,24 @@ class NeuMFEngine(object):
         ws = self._workspace(nbytes)
         self._opt.iterations = self.iterations
         keep = (users, items, labels, ws)
+        flags = nat.TRAIN_USERS_GROUPED if (grouped and group > 1) else 0
         args = (C.byref(self._model), C.byref(self._opt), C.byref(self._grads), _ptr(users), _ptr(items), _ptr(labels),
-                B, int(group), int(k), inv, _ptr(self.step_out), _ptr(ws), ws.numel(), self._stream())
+                B, int(group), int(k), flags, inv, _ptr(self.step_out), _ptr(ws), ws.numel(), self._stream())
         return args, keep
 
-    def train_step(self, users, items, labels, group=0, k=0, inv_global_batch=None):
+    def train_step(self, users, items, labels, group=0, k=0, inv_global_batch=None, grouped=False):
         """One optimisation step (Keras train_on_batch).  Returns a copy of the step outputs
-        [loss_sum, hit_sum, dcg_sum, l2_penalty, bad_ids, ...] as a device tensor."""
-        args, keep = self._train_args(users, items, labels, group, k, inv_global_batch)
+        [loss_sum, hit_sum, dcg_sum, l2_penalty, bad_ids, ...] as a device tensor.
+        grouped=True states that every `group` consecutive rows share one user (the generator's layout): the
+        tensor-core path then does the user-only work once per group.  The statement is verified on the device;
+        a violation sets bit 1 of the bad_ids output and makes the step invalid."""
+        args, keep = self._train_args(users, items, labels, group, k, inv_global_batch, grouped)
         nat.check(nat.lib.mr_neumf_train_step(*args), "mr_neumf_train_step")
         self.iterations = int(self._opt.iterations)
         return self.step_out.clone()
 
-    def train_grads(self, users, items, labels, group=0, k=0, inv_global_batch=None):
-        args, keep = self._train_args(users, items, labels, group, k, inv_global_batch)
+    def train_grads(self, users, items, labels, group=0, k=0, inv_global_batch=None, grouped=False):
+        args, keep = self._train_args(users, items, labels, group, k, inv_global_batch, grouped)
         nat.check(nat.lib.mr_neumf_train_grads(*args), "mr_neumf_train_grads")
         return self.step_out.clone()
 

@@ -14,6 +14,7 @@ MR_MAX_WIDTH = 1024
 MR_MAX_NEGS = 1023
 MR_STEP_OUT_FLOATS = 8
 OUT_LOSS_SUM, OUT_HIT_SUM, OUT_DCG_SUM, OUT_L2_PENALTY, OUT_BAD_IDS = 0, 1, 2, 3, 4
+TRAIN_USERS_GROUPED = 1  # MR_TRAIN_USERS_GROUPED
 OPT_ADAM, OPT_SGD = 0, 1
 TABLES_DENSE, TABLES_SPARSE = 0, 1
 
@@ -73,8 +74,9 @@ SIGNATURES = {
     "mr_forward_workspace_bytes": (_sz, [_PM, _i64]),
     "mr_neumf_forward": (C.c_int, [_PM, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mr_train_workspace_bytes": (_sz, [_PM, _i64]),
-    "mr_neumf_train_step": (C.c_int, [_PM, _PO, _PG, _vp, _vp, _vp, _i64, _i32, _i32, _f, _vp, _vp, _sz, _vp]),
-    "mr_neumf_train_grads": (C.c_int, [_PM, _PO, _PG, _vp, _vp, _vp, _i64, _i32, _i32, _f, _vp, _vp, _sz, _vp]),
+    "mr_neumf_train_step": (C.c_int, [_PM, _PO, _PG, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f, _vp, _vp, _sz, _vp]),
+    "mr_neumf_train_grads": (C.c_int, [_PM, _PO, _PG, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f, _vp, _vp, _sz, _vp]),
+    "mr_users_grouped": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "mr_neumf_apply": (C.c_int, [_PM, _PO, _PG, _vp]),
     "mr_rank_eval_workspace_bytes": (_sz, [_PM, _i64, _i32]),
     "mr_rank_eval": (C.c_int, [_PM, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -27,6 +27,9 @@ COL_LABEL = 'label'
 
 
 class MovieLensDataGenerator(object):
+    # every batch is made of groups of one user: negatives first, the positive last (reference
+    # data_pipeline.py:99-150); the trainer passes this on so the kernels can share the user-only work
+    grouped_batches = True
 
     def __init__(self, dataset_name, data_df, batch_size, negatives_per_positive, extra_data_df=None, shuffle=True,
                  seed=None):

@@ -140,8 +140,13 @@ class NeuMFModel(object):
         x_users, x_items = x
         o = self._owner
         group = o._num_negs_per_pos + 1
-        out = self.engine.train_step(x_users, x_items, y, group=group, k=o._k).cpu().numpy().astype(np.float64)
-        if out[4] != 0:
+        # the reference accepts any users per row; the once-per-group fast path is taken only when the batch
+        # really has the generator's layout (checked on the device before the step: one tiny kernel)
+        eng = self.engine
+        x_users = _engine_module().as_device_i32(x_users, eng.device)
+        grouped = eng.users_grouped(x_users, group)
+        out = eng.train_step(x_users, x_items, y, group=group, k=o._k, grouped=grouped).cpu().numpy().astype(np.float64)
+        if int(out[4]) & 1:
             raise IndexError("user/item id out of range in batch (num_users={}, num_items={})".format(
                 o._num_users, o._num_items))
         logs = self._step_logs(out, int(np.asarray(y).size if not hasattr(y, "numel") else y.numel()), group)
@@ -226,7 +231,7 @@ class NeuMFModel(object):
             rows = 0
             for b in order:
                 x, y = _device_batch(generator, b)
-                out = eng.train_step(x[0], x[1], y, group=group, k=o._k)
+                out = eng.train_step(x[0], x[1], y, group=group, k=o._k, grouped=_is_grouped(generator, eng, x[0], group))
                 acc[:3] += out[:3].double()
                 acc[3] += out[3].double() * y.numel()
                 acc[4] += out[4].double()
@@ -234,8 +239,9 @@ class NeuMFModel(object):
             logs = {}
             if rows:
                 a = acc.cpu().numpy()
-                if a[4] != 0:
-                    raise IndexError("user/item id out of range during training")
+                if a[4] != 0:  # sum over steps of the per-step flag word (bit 0 bad id, bit 1 group layout broken)
+                    raise IndexError("user/item id out of range (or a generator that declares grouped batches "
+                                     "produced a group with more than one user) during training")
                 logs = self._step_logs([a[0], a[1], a[2], a[3] / rows], rows, group)
             if validation_data is not None:
                 vals = self.evaluate_generator(validation_data)
@@ -254,6 +260,15 @@ class NeuMFModel(object):
         for cb in callbacks:
             cb.on_train_end()
         return history
+
+
+def _is_grouped(generator, engine, x_users, group):
+    """Whether a training batch has one user per group.  Generators of this package say so themselves
+    (`grouped_batches`: MovieLensDataGenerator always builds groups of one user, data_pipeline.py:99-150, and
+    the device verifies it during the step); batches of any other Sequence are checked on the device first."""
+    if getattr(generator, "grouped_batches", False):
+        return True
+    return engine.users_grouped(x_users, group)
 
 
 def _device_batch(generator, b):

@@ -34,7 +34,7 @@ class OracleEngine(object):
     def gradient_tensors(self):
         return [self.g_flat]
 
-    def train_grads(self, users, items, labels, group=0, k=0, inv_global_batch=None):
+    def train_grads(self, users, items, labels, group=0, k=0, inv_global_batch=None, grouped=False):
         c = o.forward(self.w, users, items)
         g = o.backward(self.w, c, labels, inv_global_batch, self.params["layers_l2reg"])
         self.g_flat.copy_(torch.from_numpy(np.concatenate([g[k_].reshape(-1) for k_ in self.names]).astype(np.float32)))

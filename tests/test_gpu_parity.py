@@ -138,6 +138,20 @@ TRAIN_CASES = [
 
 @pytest.mark.parametrize("case", TRAIN_CASES, ids=lambda c: "cfg{}-{}-{}".format(c[0], c[1], c[2]))
 def test_train_steps_match_oracle(eng_mod, case):
+    _train_steps_vs_oracle(eng_mod, case, grouped=False)
+
+
+# the grouped-batch path (user-only work once per group) on the tensor-core configs, plus configs that are not
+# eligible for it (the flag must then be harmless): same oracle, same tolerances
+GROUPED_CASES = [c for c in TRAIN_CASES if c[0] in (4, 6, 7, 8)]
+
+
+@pytest.mark.parametrize("case", GROUPED_CASES, ids=lambda c: "cfg{}-{}-{}".format(c[0], c[1], c[2]))
+def test_grouped_train_steps_match_oracle(eng_mod, case):
+    _train_steps_vs_oracle(eng_mod, case, grouped=True)
+
+
+def _train_steps_vs_oracle(eng_mod, case, grouped):
     ci, opt, mode, l2 = case
     nu, ni, L, f, negs, groups = CONFIGS[ci]
     rng = np.random.default_rng(100 + ci)
@@ -152,7 +166,7 @@ def test_train_steps_match_oracle(eng_mod, case):
         # gradients of this step (dense part), before either side updates
         c = o.forward(w, users, items)
         g = o.backward(w, c, y, None, l2)
-        out = eng.train_step(users, items, y, group=negs + 1, k=params["k"]).cpu().numpy().astype(np.float64)
+        out = eng.train_step(users, items, y, group=negs + 1, k=params["k"], grouped=grouped).cpu().numpy().astype(np.float64)
         assert out[4] == 0
         for name, (off, shape) in eng._dense_slices.items():
             got = eng.g_dense[off:off + int(np.prod(shape))].cpu().numpy().reshape(shape)
@@ -243,6 +257,47 @@ def test_train_step_is_deterministic(eng_mod):
         assert np.array_equal(results[0][0][k], results[1][0][k]), k
     for a, b in zip(results[0][1], results[1][1]):
         assert np.array_equal(a, b)
+
+
+def test_grouped_promise_is_verified(eng_mod):
+    """grouped=True with a batch whose groups hold several users: bit 1 of the flag word is raised."""
+    nu, ni, L, f, negs = 300, 200, [256, 128, 64], 64, 4
+    rng = np.random.default_rng(3)
+    users, items, y = make_batch(rng, nu, ni, 64, negs)
+    eng = eng_mod.NeuMFEngine(nu, ni, L, [0, 0, 0], mf_dim=f, seed=2)
+    assert eng.users_grouped(users, negs + 1)
+    assert int(eng.train_step(users, items, y, group=negs + 1, k=3, grouped=True).cpu().numpy()[4]) == 0
+    broken = users.copy()
+    broken[7] = (broken[7] + 1) % nu
+    assert not eng.users_grouped(broken, negs + 1)
+    assert not eng.users_grouped(users[:-1], negs + 1)
+    assert int(eng.train_step(broken, items, y, group=negs + 1, k=3, grouped=True).cpu().numpy()[4]) & 2
+    assert int(eng.train_step(broken, items, y, group=negs + 1, k=3).cpu().numpy()[4]) == 0  # no promise, no assumption
+
+
+def test_grouped_and_ungrouped_steps_agree(eng_mod):
+    """Same batches through both launch sequences of the tensor-core path: Zipf-hot users and items, three
+    steps, dense and sparse tables."""
+    nu, ni, L, f, negs, groups = 5000, 3000, [256, 128, 64], 64, 4, 6000
+    for mode in ("dense", "sparse"):
+        weights = {}
+        for grouped in (False, True):
+            rng = np.random.default_rng(17)
+            eng = eng_mod.NeuMFEngine(nu, ni, L, [0, 0, 0], mf_dim=f, table_mode=mode, optimizer="sgd", lr=0.5, seed=6)
+            assert eng.uses_tensor_cores()
+            outs = []
+            for _ in range(3):
+                users = np.repeat(np.minimum(rng.zipf(1.3, groups) - 1, nu - 1), negs + 1)
+                items = np.minimum(rng.zipf(1.2, groups * (negs + 1)) - 1, ni - 1)
+                y = np.tile([0] * negs + [1], groups).astype(np.float32)
+                outs.append(eng.train_step(users, items, y, group=negs + 1, k=3, grouped=grouped).cpu().numpy())
+            weights[grouped] = (eng.get_weights(), outs)
+        for a, b in zip(weights[False][1], weights[True][1]):
+            assert abs(a[0] - b[0]) <= 1e-5 * abs(a[0]) and a[1] == b[1] and a[4] == 0 and b[4] == 0
+        # SGD: the update is linear in the gradients; three steps at lr 0.5 let a 1e-6 difference of the first
+        # step's gradients feed back through the weights, hence 1e-4 after the third step
+        for k in weights[False][0]:
+            rel_close(weights[True][0][k], weights[False][0][k], rtol=1e-4, what="{} grouped vs ungrouped {}".format(mode, k))
 
 
 def test_out_of_range_ids_are_flagged(eng_mod):
