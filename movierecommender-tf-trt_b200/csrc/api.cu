@@ -3,6 +3,7 @@
 // here and nothing synchronises; every launch goes to the caller's stream.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -82,6 +83,37 @@ void prof_mark(int phase, cudaStream_t st) {
 }
 
 // flags[0]: out-of-range id seen, flags[1]: grouped-batch promise violated -> bits 0 and 1 of the output
+// ---- side stream (thread-local, per device): the id sorts of the train step do not depend on the tower, so they
+// run next to it (the tower's persistent CTAs leave room for small kernels).  Fork and join are events on the
+// caller's stream: the call stays asynchronous and capturable.
+struct SideStream {
+  int dev = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static thread_local SideStream g_side;
+
+static SideStream* side_stream() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  SideStream& s = g_side;
+  if (s.dev != dev) {
+    s = SideStream{};
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      s = SideStream{};
+      return nullptr;
+    }
+    s.dev = dev;
+  }
+  return &s;
+}
+
 __global__ void flag_to_float_kernel(const int32_t* flags, float* out) {
   *out = (float)((flags[0] ? 1 : 0) | (flags[1] ? 2 : 0));
 }
@@ -296,8 +328,10 @@ struct TrainWs {
   float* probs;
   float* stage_u;
   float* stage_i;
-  int32_t* sorted_keys;
+  int32_t* sorted_keys;    // users (or the users of the groups), sorted
   int32_t* sorted_index;
+  int32_t* sorted_keys_i;  // items, sorted
+  int32_t* sorted_index_i;
   void* sort_ws;
   size_t sort_ws_bytes;
   void* seg_ws;
@@ -325,6 +359,8 @@ static TrainWs carve_train(const MrModel& m, int64_t B, void* ws) {
   t.stage_i = cv.take<float>((size_t)B * (d_i + m.mf_dim));
   t.sorted_keys = cv.take<int32_t>(B);
   t.sorted_index = cv.take<int32_t>(B);
+  t.sorted_keys_i = cv.take<int32_t>(B);
+  t.sorted_index_i = cv.take<int32_t>(B);
   t.sort_ws_bytes = sort_workspace_bytes(B);
   t.sort_ws = cv.take<char>(t.sort_ws_bytes);
   t.seg_ws_bytes = segreduce_workspace_bytes(B, (d_u > d_i ? d_u : d_i) + m.mf_dim);
@@ -503,10 +539,41 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   // grouped batch (MR_TRAIN_USERS_GROUPED): user-only work once per group; the promise is checked on the device
   const bool grouped = (flags & MR_TRAIN_USERS_GROUPED) && use_tc(m) && tc_grouped_ok(m, B, group);
   const int gdiv = grouped ? group : 0;
-  if (grouped) {
-    rc = launch_check_grouped(users, B, group, t.flags + 1, st);
-    if (rc == MR_OK) rc = launch_group_heads(users, B / group, group, t.group_users, st);
+  const int64_t n_user_rows = grouped ? B / group : B;  // staged user-gradient rows: one per group or one per row
+  // stable sorts of the ids (keys of the segmented reductions below) on the side stream, under the tower
+  // (phase timing then sees only the launch cost of this block on the main stream; MR_NO_SIDE_STREAM=1 keeps
+  // everything on the caller's stream, for diagnostics)
+  static const bool no_side = getenv("MR_NO_SIDE_STREAM") != nullptr;
+  SideStream* side = no_side ? nullptr : side_stream();
+  {
+    cudaStream_t ss = st;
+    if (side != nullptr) {
+      MR_CUDA(cudaEventRecord(side->fork, st));
+      MR_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      ss = side->stream;
+    }
+    prof_mark(MR_PHASE_SORT, st);
+    if (opt->table_mode == MR_TABLES_DENSE) {  // the gradient tables the segmented reductions write into
+      MR_CUDA(cudaMemsetAsync(grads->user_mlp, 0, (size_t)m.num_users * d_u * sizeof(float), ss));
+      MR_CUDA(cudaMemsetAsync(grads->item_mlp, 0, (size_t)m.num_items * d_i * sizeof(float), ss));
+      if (m.mf_dim > 0) {
+        MR_CUDA(cudaMemsetAsync(grads->user_gmf, 0, (size_t)m.num_users * m.mf_dim * sizeof(float), ss));
+        MR_CUDA(cudaMemsetAsync(grads->item_gmf, 0, (size_t)m.num_items * m.mf_dim * sizeof(float), ss));
+      }
+    }
+    if (grouped) {
+      rc = launch_check_grouped(users, B, group, t.flags + 1, ss);
+      if (rc == MR_OK) rc = launch_group_heads(users, B / group, group, t.group_users, ss);
+      if (rc != MR_OK) return rc;
+    }
+    rc = launch_sort_pairs(grouped ? t.group_users : users, n_user_rows, bits_for(m.num_users), t.sorted_keys,
+                           t.sorted_index, t.sort_ws, t.sort_ws_bytes, ss);
+    if (rc == MR_OK)
+      rc = launch_sort_pairs(items, B, bits_for(m.num_items), t.sorted_keys_i, t.sorted_index_i, t.sort_ws,
+                             t.sort_ws_bytes, ss);
     if (rc != MR_OK) return rc;
+    if (side != nullptr) MR_CUDA(cudaEventRecord(side->join, ss));
+    prof_mark(MR_PHASE_MISC, st);
   }
   if (use_tc(m)) {
     // ---- tensor-core path: per sub-batch, forward layers -> head -> per layer weight gradient + backward
@@ -714,6 +781,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   rc = launch_sum_partials(t.loss_partial, grid, step_out + MR_OUT_LOSS_SUM, st);
   if (rc != MR_OK) return rc;
   }
+  if (side != nullptr) MR_CUDA(cudaStreamWaitEvent(st, side->join, 0));  // sorts and the group check are done
   flag_to_float_kernel<<<1, 1, 0, st>>>(t.flags, step_out + MR_OUT_BAD_IDS);
   MR_LAUNCH_CHECK("flag_to_float_kernel");
 
@@ -742,7 +810,6 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   prof_mark(MR_PHASE_MISC, st);
 
   // ---- embedding rows: stable sort by row id, segmented reduce in batch order, row update -------
-  const bool dense_mode = opt->table_mode == MR_TABLES_DENSE;
   RowUpdate u{};
   u.mode = opt->table_mode;
   u.optimizer = opt->optimizer;
@@ -751,20 +818,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   u.beta_1 = opt->beta_1;
   u.beta_2 = opt->beta_2;
   u.epsilon = opt->epsilon;
-  if (dense_mode) {
-    MR_CUDA(cudaMemsetAsync(grads->user_mlp, 0, (size_t)m.num_users * d_u * sizeof(float), st));
-    MR_CUDA(cudaMemsetAsync(grads->item_mlp, 0, (size_t)m.num_items * d_i * sizeof(float), st));
-    if (m.mf_dim > 0) {
-      MR_CUDA(cudaMemsetAsync(grads->user_gmf, 0, (size_t)m.num_users * m.mf_dim * sizeof(float), st));
-      MR_CUDA(cudaMemsetAsync(grads->item_gmf, 0, (size_t)m.num_items * m.mf_dim * sizeof(float), st));
-    }
-  }
   // users
-  prof_mark(MR_PHASE_SORT, st);
-  const int64_t n_user_rows = grouped ? B / group : B;  // staged user-gradient rows: one per group or one per row
-  rc = launch_sort_pairs(grouped ? t.group_users : users, n_user_rows, bits_for(m.num_users), t.sorted_keys, t.sorted_index,
-                         t.sort_ws, t.sort_ws_bytes, st);
-  if (rc != MR_OK) return rc;
   u.d0 = d_u;
   u.d1 = m.mf_dim;
   u.num_rows = m.num_users;
@@ -774,15 +828,12 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   rc = launch_segreduce(t.sorted_keys, t.sorted_index, n_user_rows, t.stage_u, u, t.seg_ws, t.seg_ws_bytes, st);
   if (rc != MR_OK) return rc;
   // items
-  prof_mark(MR_PHASE_SORT, st);
-  rc = launch_sort_pairs(items, B, bits_for(m.num_items), t.sorted_keys, t.sorted_index, t.sort_ws, t.sort_ws_bytes, st);
-  if (rc != MR_OK) return rc;
   u.d0 = d_i;
   u.num_rows = m.num_items;
   u.p0 = m.item_mlp; u.m0 = opt->m_item_mlp; u.v0 = opt->v_item_mlp; u.g0 = grads->item_mlp;
   u.p1 = m.item_gmf; u.m1 = opt->m_item_gmf; u.v1 = opt->v_item_gmf; u.g1 = grads->item_gmf;
   prof_mark(MR_PHASE_SEGREDUCE, st);
-  rc = launch_segreduce(t.sorted_keys, t.sorted_index, B, t.stage_i, u, t.seg_ws, t.seg_ws_bytes, st);
+  rc = launch_segreduce(t.sorted_keys_i, t.sorted_index_i, B, t.stage_i, u, t.seg_ws, t.seg_ws_bytes, st);
   prof_mark(-1, st);
   return rc;
 }
