@@ -392,11 +392,12 @@ def run_gpu(args, wl):
         ems = e0.elapsed_time(e1) / reps
         ab = algorithmic_bytes(wl, rows)
         peak, peak_kind = measured_peaks()
-        fwd_ms = sum(eph[k][0] for k in ("tile_forward", "tc_dense_fwd", "head")) / reps
+        fwd_ms = sum(eph[k][0] for k in ("tile_forward", "tc_dense_fwd", "head") if k in eph) / reps
         ach = ab["eval_per_user"] * n_eval / (max(fwd_ms, 1e-9) / 1e3) / 1e9
         eval_obj = {"metric": "hr10_eval_users_per_sec", "value": n_eval / (ems / 1e3), "unit": "users/s",
                     "users": n_eval, "candidates_per_user": egroup, "k": wl["k_eval"], "ms": ems,
                     "hr_at_k": float(sums[0].item()) / n_eval, "ndcg_at_k": float(sums[1].item()) / n_eval,
+                    "phase_ms": {k: v[0] / reps for k, v in eph.items() if v[1]},
                     "roofline": {"bound": "hbm", "kernel": "forward kernels (tcgen05 layers + head, or the SIMT tile kernel)",
                                  "forward_ms": fwd_ms, "achieved": ach, "peak": peak,
                                  "unit": "GB/s", "frac": ach / peak, "peak_kind": peak_kind, "traffic": None}}

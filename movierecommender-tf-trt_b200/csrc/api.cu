@@ -245,7 +245,7 @@ static TcWs carve_tc(const MrModel& m, bool train, int64_t B, void* ws) {
 
 // Forward of rows [r0, r1) on the tensor cores; leaves H[1..n-1] of the sub-batch in the workspace.
 static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users, const int32_t* items, int user_div,
-                           int64_t r0, int64_t r1, cudaStream_t st, int group = 0) {
+                           int64_t r0, int64_t r1, cudaStream_t st, int group = 0, bool users_per_group = false) {
   const int d_u = m.L[0] / 2;
   if (group > 0) {
     // grouped batch: Zu = E_user[user of the group] . W1[user rows] + b1 once per group, then
@@ -259,7 +259,7 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     a.num_items = m.num_items;
     a.d_u = d_u;
     a.user_div = 1;
-    a.user_mul = group;
+    a.user_mul = users_per_group ? 1 : group;  // `users` holds one id per group, or one per row
     a.b_packed = t.pack_fu;
     a.N = m.L[1];
     a.K = d_u;
@@ -396,6 +396,75 @@ static int check_opt(const MrModel& m, const MrOptState* o, const MrGrads* g) {
     MR_REQUIRE(m.l2[0] == 0.f, "layers_l2reg[0] != 0 makes embedding gradients dense; use MR_TABLES_DENSE");
   }
   return MR_OK;
+}
+
+// ---- fused ranking evaluation on the tensor-core path -----------------------------------------------------
+// Rows per launch: whole groups and whole 128-row tiles, at most 2^20 rows.
+static int64_t eval_sub_batch(int group) {
+  int64_t a = 128, b = group;
+  while (b) { const int64_t t = a % b; a = b; b = t; }
+  const int64_t l = (int64_t)128 / a * group;  // lcm(128, group)
+  const int64_t cap = (int64_t)1 << 20;
+  return l > cap ? 0 : cap / l * l;
+}
+
+static bool eval_fused_ok(const MrModel& m, int group) {
+  return use_tc(m) && head_rank_supported(m) && m.n_layers >= 2 && group <= 256 && eval_sub_batch(group) > 0;
+}
+
+static TcWs carve_eval(const MrModel& m, int group, int64_t rows, void* ws) {
+  TcWs t{};
+  Carver cv(ws);
+  int64_t sb = eval_sub_batch(group);
+  if (rows < sb) sb = (rows + 127) / 128 * 128;
+  const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
+  t.pack_fu = cv.take<float>((size_t)2 * d_u * m.L[1]);
+  t.pack_fi = cv.take<float>((size_t)2 * d_i * m.L[1]);
+  t.Zu = cv.take<float>((size_t)(sb / group + 1) * m.L[1]);
+  for (int l = 1; l < m.n_layers; ++l) {
+    if (l >= 2) t.pack_f[l] = cv.take<float>((size_t)2 * m.L[l - 1] * m.L[l]);
+    t.H[l] = cv.take<float>((size_t)sb * m.L[l]);
+  }
+  t.total = cv.off;
+  return t;
+}
+
+// users: one id per group; items: G * group, the positive last.  Forward with the user half of the first layer
+// once per user, then the fused score + position kernel.
+static int rank_eval_fused(const MrModel& m, const int32_t* users, const int32_t* items, int64_t G, int group, int k,
+                           int32_t* pos, float* probs, float* sums, int32_t* flags, float* partials, void* tc_ws,
+                           cudaStream_t st) {
+  const int64_t rows = G * group;
+  TcWs t = carve_eval(m, group, rows, tc_ws);
+  const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
+  prof_mark(MR_PHASE_MISC, st);
+  MR_CUDA(cudaMemsetAsync(flags, 0, 256, st));
+  int rc = launch_pack_weights(m.W[1], d_u, m.L[1], 0, t.pack_fu, st);
+  if (rc == MR_OK) rc = launch_pack_weights(m.W[1] + (size_t)d_u * m.L[1], d_i, m.L[1], 0, t.pack_fi, st);
+  for (int l = 2; rc == MR_OK && l < m.n_layers; ++l) rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 0, t.pack_f[l], st);
+  if (rc != MR_OK) return rc;
+  const int64_t sb = eval_sub_batch(group);
+  for (int64_t r0 = 0; r0 < rows; r0 += sb) {
+    const int64_t r1 = r0 + sb < rows ? r0 + sb : rows;
+    prof_mark(MR_PHASE_TC_DENSE_FWD, st);
+    rc = tc_forward_rows(m, t, users, items, 1, r0, r1, st, group, true);
+    if (rc != MR_OK) return rc;
+    prof_mark(MR_PHASE_HEAD, st);
+    HeadArgs h{};
+    h.model = &m;
+    h.h_last = t.H[m.n_layers - 1];
+    h.users = users;
+    h.items = items;
+    h.rows = r1 - r0;
+    h.row0 = r0;
+    h.flags = flags;
+    rc = launch_head_rank(h, group, pos, probs, st);
+    if (rc != MR_OK) return rc;
+  }
+  prof_mark(MR_PHASE_RANK, st);
+  rc = launch_rank_metrics(pos, G, k, sums, partials, st);
+  prof_mark(-1, st);
+  return rc;
 }
 
 }  // namespace mr
@@ -885,8 +954,12 @@ int mr_neumf_train_step(MrModel* model, MrOptState* opt, MrGrads* grads, const i
 
 size_t mr_rank_eval_workspace_bytes(const MrModel* model, int64_t G, int32_t group) {
   if (G < 0 || group < 1) return 0;
-  return mr_forward_workspace_bytes(model, G * group) + align_up((size_t)G * group * sizeof(float), 256) +
-         align_up(rank_partials_count(G) * sizeof(float), 256) + 256;
+  size_t fused = 0;
+  if (model != nullptr && model->n_layers >= 1 && model->n_layers <= MR_MAX_LAYERS && tc_eligible(*model) && group >= 2 &&
+      eval_sub_batch(group) > 0 && model->n_layers >= 2)
+    fused = carve_eval(*model, group, G * group, nullptr).total + 512;
+  const size_t plain = mr_forward_workspace_bytes(model, G * group) + align_up((size_t)G * group * sizeof(float), 256);
+  return (plain > fused ? plain : fused) + align_up(rank_partials_count(G) * sizeof(float), 256) + 512;
 }
 
 int mr_rank_eval(const MrModel* model, const int32_t* users, const int32_t* items, int64_t G, int32_t group, int32_t k,
@@ -896,6 +969,23 @@ int mr_rank_eval(const MrModel* model, const int32_t* users, const int32_t* item
   if (ws_bytes < mr_rank_eval_workspace_bytes(model, G, group)) {
     set_error("rank_eval workspace too small: %zu < %zu", ws_bytes, mr_rank_eval_workspace_bytes(model, G, group));
     return MR_ERR_WORKSPACE;
+  }
+  if (G == 0) {
+    if (sums != nullptr) MR_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(float), (cudaStream_t)stream));
+    return MR_OK;
+  }
+  {
+    int rc0 = check_model(model);
+    if (rc0 != MR_OK) return rc0;
+  }
+  MR_REQUIRE(users && items, "rank_eval: NULL ids");
+  if (rank == nullptr && eval_fused_ok(*model, group)) {
+    // fused path: [flags 256 B][partials][tensor-core workspace]
+    Carver cvf(ws);
+    int32_t* flags = cvf.take<int32_t>(64);
+    float* partials_f = cvf.take<float>(rank_partials_count(G));
+    return rank_eval_fused(*model, users, items, G, group, k, pos, probs, sums, flags, partials_f,
+                           static_cast<char*>(ws) + cvf.off, (cudaStream_t)stream);
   }
   const size_t fwd_bytes = mr_forward_workspace_bytes(model, G * group);
   Carver cv(static_cast<char*>(ws) + fwd_bytes);

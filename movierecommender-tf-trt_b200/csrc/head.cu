@@ -173,6 +173,95 @@ __global__ void __launch_bounds__(kHeadThreads, MAXQ <= 4 ? 2 : 1) head_kernel(c
   }
 }
 
+// Ranking evaluation, fused: GMF product + output unit + sigmoid of the `group` candidates of one user AND the
+// position of the positive (the LAST candidate, data_pipeline.py:113,148) under the RankLayer order
+// (model.py:344-352: descending probability, lower index first among ties), in one kernel -- the scores never
+// leave the SM unless the caller asks for them.  One CTA per group: its 8 warps score interleaved slices of
+// the candidates (8 rows per warp in flight), the probabilities meet in shared memory and the whole CTA counts
+//   pos = #{j : p_j > p_pos  or  (p_j == p_pos and j < group - 1)}.
+template <int MAXQ>
+__global__ void __launch_bounds__(kHeadThreads, 2) head_rank_kernel(const HeadParams p, int group,
+                                                                    int32_t* __restrict__ pos,
+                                                                    float* __restrict__ probs) {
+  __shared__ float sc[kHeadThreads];  // probabilities of the group's candidates (group <= 256)
+  const MrModel& m = p.m;
+  const int f = m.mf_dim, Ln = m.L[m.n_layers - 1], ncols = f + Ln;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kHeadThreads / 32;
+  constexpr int kRows = 8;  // rows scored per warp iteration: their loads are all in flight together
+  float wv[MAXQ];
+#pragma unroll
+  for (int q = 0; q < MAXQ; ++q) wv[q] = (lane + 32 * q < ncols) ? __ldg(m.w_out + lane + 32 * q) : 0.f;
+  const float b_out = __ldg(m.b_out);
+  const int64_t ngroups = p.rows / group;
+  const int per_warp = (group + kWarps - 1) / kWarps;  // <= 32: candidate j = warp + kWarps * i, i < per_warp
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t gg = p.row0 / group + g;  // global group index: users holds one id per group
+    const int64_t lr_first = g * group;
+    int u = __ldg(p.users + gg);
+    // this warp's item ids, lane-distributed: lane i holds the id of candidate warp + kWarps * i
+    const int jmine = warp + kWarps * lane;
+    const int idreg = (lane < per_warp && jmine < group) ? __ldg(p.items + p.row0 + lr_first + jmine) : 0;
+    const bool bad_u = (unsigned)u >= (unsigned)m.num_users;
+    if (bad_u) u = 0;
+    float gu[MAXQ];
+#pragma unroll
+    for (int q = 0; q < MAXQ; ++q) gu[q] = (lane + 32 * q < f) ? __ldg(m.user_gmf + (size_t)u * f + lane + 32 * q) : 0.f;
+    for (int i0 = 0; i0 < per_warp; i0 += kRows) {
+      int it[kRows];
+      bool live[kRows];
+      float hv[kRows][MAXQ];
+#pragma unroll
+      for (int rr = 0; rr < kRows; ++rr) {
+        const int j = warp + kWarps * (i0 + rr);
+        live[rr] = (i0 + rr) < per_warp && j < group;
+        it[rr] = __shfl_sync(0xffffffffu, idreg, (i0 + rr) & 31);
+      }
+      // loads first, unconditional (dead rows re-read the positive's row) and with no arithmetic on the loaded
+      // values: a branch or a multiply per row here makes the in-order issue wait for each row's data before
+      // the next row's loads go out (ncu: the first version spent 8 serial memory latencies per iteration)
+#pragma unroll
+      for (int rr = 0; rr < kRows; ++rr) {
+        const int j = live[rr] ? warp + kWarps * (i0 + rr) : group - 1;
+        const int iv = ((unsigned)it[rr] >= (unsigned)m.num_items) ? 0 : it[rr];
+        const float* hrow = p.h_last + (size_t)(lr_first + j) * Ln;
+        const float* grow = m.item_gmf + (size_t)iv * f;
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q) {
+          const int c = lane + 32 * q;
+          const float* src = c < f ? grow + c : hrow + (c < ncols ? c - f : 0);
+          hv[rr][q] = (c < ncols) ? __ldg(src) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < kRows; ++rr) {
+        if (!live[rr]) continue;  // warp-uniform
+        const int j = warp + kWarps * (i0 + rr);
+        float sacc = 0.f;
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q) {
+          const float x = (lane + 32 * q < f) ? gu[q] * hv[rr][q] : hv[rr][q];
+          sacc = fmaf(wv[q], x, sacc);
+        }
+        sacc = warp_sum(sacc);
+        const bool bad = bad_u || (unsigned)it[rr] >= (unsigned)m.num_items;
+        const float pr = bad ? nanf("") : sigmoidf_stable(sacc + b_out);
+        if (lane == 0) {
+          sc[j] = pr;
+          if (probs != nullptr) probs[p.row0 + lr_first + j] = pr;
+          if (bad) atomicOr(p.flags, 1);
+        }
+      }
+    }
+    __syncthreads();
+    const float key_pos = rank_key(sc[group - 1]);
+    const int j = threadIdx.x;
+    const int above = (j < group - 1) && (rank_key(sc[j]) >= key_pos);  // a negative that ties ranks first (lower index)
+    const int cnt = __syncthreads_count(above);
+    if (threadIdx.x == 0) pos[gg] = cnt;
+  }
+}
+
 // d w_out / d b_out / loss: sum of the CTA partial rows, one warp per column, lanes stride over the rows
 // and fold with the fixed shuffle tree (deterministic).  Runs once per step.
 __global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restrict__ head_partial, int grid_ctas,
@@ -244,6 +333,33 @@ int launch_head(const HeadArgs& a, cudaStream_t st) {
   else if (ncols <= 256) head_kernel<8, 2, false><<<grid, kHeadThreads, 0, st>>>(p);
   else head_kernel<16, 2, false><<<grid, kHeadThreads, 0, st>>>(p);
   MR_LAUNCH_CHECK("head_kernel");
+  return MR_OK;
+}
+
+bool head_rank_supported(const MrModel& m) { return m.mf_dim + m.L[m.n_layers - 1] <= 128; }
+
+// Fused score + rank of whole groups (forward only): a.users holds ONE id per group (global group index),
+// a.rows / a.row0 are rows (multiples of `group`); pos is indexed by the global group, probs by the global row.
+int launch_head_rank(const HeadArgs& a, int group, int32_t* pos, float* probs, cudaStream_t st) {
+  const MrModel& m = *a.model;
+  if (!head_rank_supported(m) || group < 2 || group > 256 || a.rows % group || a.row0 % group) {
+    set_error("head_rank kernel: needs mf_dim + last width <= 128 and whole groups of at most 256 rows");
+    return MR_ERR_INVALID;
+  }
+  if (a.rows == 0) return MR_OK;
+  HeadParams p{};
+  p.m = m;
+  p.h_last = a.h_last;
+  p.users = a.users;
+  p.items = a.items;
+  p.rows = a.rows;
+  p.row0 = a.row0;
+  p.user_div = 1;
+  p.flags = a.flags;
+  const int64_t ngroups = a.rows / group;
+  const int64_t cap = (int64_t)sm_count() * 2;  // persistent: two resident CTAs per SM, groups taken round-robin
+  head_rank_kernel<4><<<(unsigned)(ngroups < cap ? ngroups : cap), kHeadThreads, 0, st>>>(p, group, pos, probs);
+  MR_LAUNCH_CHECK("head_rank_kernel");
   return MR_OK;
 }
 

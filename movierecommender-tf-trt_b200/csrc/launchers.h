@@ -148,6 +148,10 @@ int head_grid();
 bool head_supports_group(const MrModel& m, int group);
 size_t head_partial_floats(const MrModel& m);
 int launch_head(const HeadArgs& a, cudaStream_t st);
+bool head_rank_supported(const MrModel& m);
+int launch_head_rank(const HeadArgs& a, int group, int32_t* pos, float* probs, cudaStream_t st);
+// metric sums from positions (rank.cu): sums = {hit_sum, dcg_sum}
+int launch_rank_metrics(const int32_t* pos, int64_t G, int k, float* sums, float* partials, cudaStream_t st);
 
 // ---- grouped batches (gather.cu): one positive and its negatives share the user ----------------------------
 // out[g] = sum_{j < group} in[g * group + j]  (rows of `width` floats, width % 4 == 0), fixed order

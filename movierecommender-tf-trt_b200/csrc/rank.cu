@@ -110,6 +110,20 @@ size_t rank_partials_count(int64_t G) {
   return (size_t)(nb < 1 ? 1 : nb) * 2;
 }
 
+int launch_rank_metrics(const int32_t* pos, int64_t G, int k, float* sums, float* partials, cudaStream_t st) {
+  if (sums == nullptr) return MR_OK;
+  if (G == 0) {
+    MR_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(float), st));
+    return MR_OK;
+  }
+  const int64_t nb = (G + kRankGroupsPerCta - 1) / kRankGroupsPerCta;
+  rank_metric_partial_kernel<<<(unsigned)nb, kRankThreads, 0, st>>>(pos, G, k, partials);
+  MR_LAUNCH_CHECK("rank_metric_partial_kernel");
+  rank_metric_final_kernel<<<1, 1024, 0, st>>>(partials, nb, sums);
+  MR_LAUNCH_CHECK("rank_metric_final_kernel");
+  return MR_OK;
+}
+
 int launch_rank_scores(const float* scores, int64_t G, int group, int k, const int32_t* label_col, int32_t* rank,
                        int32_t* pos, float* sums, float* partials, cudaStream_t st) {
   if (G == 0) {
