@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the NeuMF train step (BASELINE.json metric: NCF train samples/sec) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ml-20m|ml-1m] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ml-20m|ml-1m|large-sharded] [--impl reference]
 
 One "step" = one optimisation step (forward + BCE + backward + deterministic embedding-gradient
 reduction + legacy-Keras dense Adam + train-batch HR/DCG) on one synthetic batch.  N > 1 runs under
@@ -36,9 +36,32 @@ WORKLOADS = {
     # BASELINE.json configs[1]: ML-1M shape, reference default tower + GMF 8
     "ml-1m": dict(num_users=6040, num_items=3706, layers=[64, 32, 16, 8], mf_dim=8, negs=4,
                   batch=5 * 2 ** 16, eval_negs=99, k_eval=10, cpu_batch=5 * 2 ** 14, cpu_eval_users=6040),
+    # BASELINE.json configs[4]: synthetic large NeuMF, embed dim 128, tables ROW-SHARDED over the GPUs (owner =
+    # row % world), all-to-all of gathered rows and of their gradients; needs --gpus >= 2 (torchrun)
+    "large-sharded": dict(num_users=10_000_000, num_items=1_000_000, layers=[256, 128, 64], mf_dim=128, negs=4,
+                          batch=5 * 2 ** 18, eval_negs=99, k_eval=10, cpu_batch=5 * 2 ** 12, cpu_eval_users=256,
+                          sharded=True),
 }
 METRIC = "ncf_train_samples_per_sec"
 UNIT = "samples/s"
+
+# stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's "NCCL version ..." banner under torchrun),
+# so file descriptor 1 is pointed at stderr for the whole run and the line goes out through the saved descriptor.
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def synth_batches(wl, n_batches, seed, rows=None):
@@ -111,15 +134,34 @@ PHASE_KERNELS = {
 }
 
 
-def phase_interface_bytes(wl, rows):
+def phase_interface_bytes(wl, rows, grouped=False):
     """Bytes each phase must move per step GIVEN its interface (inputs read once, outputs written once) --
     the per-kernel roofline numerator.  The SURVEY 8(d) whole-step algorithmic figure (which charges no
-    intermediate) is reported separately as step_roofline."""
+    intermediate) is reported separately as step_roofline.  grouped: the launch sequence for grouped batches
+    (user half of the first layer once per group of negs+1 rows)."""
     L, f, n = wl["layers"], wl["mf_dim"], len(wl["layers"])
     d_u = L[0] // 2
-    dU, dI = d_u + f, L[0] - d_u + f
+    d_i = L[0] - d_u
+    dU, dI = d_u + f, d_i + f
     pairs = [(L[l - 1], L[l]) for l in range(1, n)]
     tables = wl["num_users"] * dU + wl["num_items"] * dI
+    if grouped:
+        G = rows // (wl["negs"] + 1)
+        L1 = L[1]
+        later = [(L[l - 1], L[l]) for l in range(2, n)]
+        return {
+            # Zu (G rows: user row in, L1 out) + first layer on the item row (+ one Zu row per group) + later layers
+            "tc_dense_fwd": G * 4 * (d_u + L1) + rows * (8 + 4 * (d_i + L1)) + G * 4 * L1 + rows * sum(4 * (a + b) for a, b in later),
+            # GMF user row once per group, its gradient once per group
+            "head": rows * (8 * L[-1] + 8 * f + 16) + G * (8 * f + 4),
+            "tc_wgrad": rows * (4 + 4 * (d_i + L1)) + G * (4 + 4 * (d_u + L1)) + rows * sum(4 * (a + b) for a, b in later),
+            # later layers as before; first layer: item half per row, user half per group on the group sums
+            "tc_dense_bwd": rows * sum(4 * (a + b) + 4 * a for a, b in later) + rows * 4 * (L1 + d_i) + G * 4 * (L1 + d_u),
+            "misc": rows * 4 * L1 + G * 4 * L1,  # group sums of dZ1
+            "segreduce": G * 2 * (4 * dU + 8) + rows * 2 * (4 * dI + 8),
+            "sort": (G + rows) * 2 * 16,
+            "optimizer": 28 * tables,
+        }
     return {
         "tile_train": rows * (4 * (dU + dI) + 12),
         "tc_dense_fwd": rows * (8 + sum(4 * (a + b) for a, b in pairs)),
@@ -254,14 +296,14 @@ def run_reference(args, wl):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def config_dict(args, wl, rows_override=None):
     return {"workload": "{} shape: {} users x {} items, NeuMF layers {} mf_dim {}, {} negatives/positive, "
                         "Adam (legacy Keras, dense over tables)".format(args.workload, wl["num_users"], wl["num_items"],
                                                                        wl["layers"], wl["mf_dim"], wl["negs"]),
-            "baseline_config": "BASELINE.json configs[{}]".format(2 if args.workload == "ml-20m" else 1),
+            "baseline_config": "BASELINE.json configs[{}]".format({"ml-20m": 2, "ml-1m": 1}.get(args.workload, 4)),
             "rows_per_step_per_gpu": wl["batch"] if rows_override is None else rows_override,
             "global_rows_per_step": (wl["batch"] if rows_override is None else rows_override) * args.gpus,
             "parallelism": "dp{} replicated tables, one all-reduce of dense+table gradients".format(args.gpus),
@@ -412,7 +454,7 @@ def run_gpu(args, wl):
     ab = algorithmic_bytes(wl, rows)
     peak, peak_kind = measured_peaks()
     step_ms = ms_total / args.steps
-    pbytes = phase_interface_bytes(wl, rows)
+    pbytes = phase_interface_bytes(wl, rows, grouped=bool(eng.uses_tensor_cores()) and wl["mf_dim"] + wl["layers"][-1] <= 128)
     phase_table = {}
     for name, (ms, cnt) in phases.items():
         if not cnt:
@@ -472,9 +514,147 @@ def run_gpu(args, wl):
     }
     if args.lean:
         line["lean"] = True
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_sharded(args, wl):
+    """BASELINE.json configs[4]: tables row-sharded over the ranks (owner = row % world), every rank trains on its
+    own batch of `batch` rows (weak scaling): all-to-all of ids, gathered rows and gradient rows (NCCL over
+    NVLink), owner-side deterministic sparse-row Adam, all-reduce of the replicated dense tower."""
+    import torch
+    import torch.distributed as dist
+    from movierec import _native as nat
+    from movierec._distributed import ShardedNeuMF
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world < 2:
+        raise SystemExit("--workload large-sharded shards the tables over the ranks: run it under torchrun with "
+                         "--gpus >= 2 (python -m torch.distributed.run --nproc-per-node N bench.py --gpus N --workload large-sharded)")
+    args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    rows, group = wl["batch"], wl["negs"] + 1
+    groups = rows // group
+    global_rows = rows * world
+    sh = ShardedNeuMF(wl["num_users"], wl["num_items"], wl["layers"], mf_dim=wl["mf_dim"], optimizer="adam", lr=1e-3,
+                      max_local_rows=1 << 21, seed=None)
+    n_batches = 4
+    rng = np.random.default_rng(1000 + rank)  # SURVEY 8(d): ids drawn uniformly per step (no CSR at this size)
+    host = []
+    for _ in range(n_batches):
+        u = np.repeat(rng.integers(0, wl["num_users"], groups, dtype=np.int32), group)
+        it = rng.integers(0, wl["num_items"], rows, dtype=np.int32)
+        y = np.tile(np.array([0] * wl["negs"] + [1], np.float32), groups)
+        host.append((u, it, y))
+    pinned = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in host]
+    resident = [tuple(t.to(dev) for t in b) for b in pinned]
+
+    def step(bufs, i):
+        u, it, y = bufs[i % n_batches]
+        return sh.train_step(u, it, y, global_rows, group=group, k=group, grouped=True)
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(resident, i)
+    sync_all()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nat.profile_begin()
+    sync_all()
+    ev0.record()
+    last = None
+    for i in range(args.steps):
+        last = step(resident, args.warmup + i)
+    ev1.record()
+    sync_all()
+    phases, launches = nat.profile_end()
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    final = last.cpu().numpy()
+    if int(final[4]) != 0 or not np.isfinite(final[0]):
+        raise SystemExit("bench produced invalid step outputs: {}".format(final))
+    # end to end: pinned host arrays in, step outputs back, every step
+    e2e_steps = max(3, min(args.steps, 10))
+    step(pinned, 0).cpu()
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        step(pinned, i + 1).cpu()
+    sync_all()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = global_rows * e2e_steps / float(t.item())
+    dist.barrier()
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    step_ms = ms_total / args.steps
+    peak, peak_kind = measured_peaks()
+    pbytes = phase_interface_bytes(wl, rows)
+    phase_table = {}
+    for name, (ms, cnt) in phases.items():
+        if not cnt:
+            continue
+        per_step = ms / args.steps
+        row = {"ms_per_step": per_step, "launch_groups_per_step": cnt / args.steps, "share_of_step": per_step / step_ms}
+        if name in pbytes and name not in ("segreduce", "sort", "optimizer"):  # those run on other sizes here
+            row["interface_bytes_per_step"] = pbytes[name]
+            row["gbs"] = pbytes[name] / (per_step / 1e3) / 1e9
+            row["frac_of_hbm_peak"] = row["gbs"] / peak
+        phase_table[name] = row
+    cand = [k for k in phase_table if "gbs" in phase_table[k]]
+    dom = max(cand, key=lambda k: phase_table[k]["ms_per_step"])
+    dom_groups = max(phases[dom][1], 1)
+    dom_avg_ms = phases[dom][0] / dom_groups
+    dom_bytes = pbytes[dom] * args.steps / dom_groups
+    achieved = dom_bytes / (dom_avg_ms / 1e3) / 1e9
+    L, f = wl["layers"], wl["mf_dim"]
+    row_bytes = 4 * (L[0] + 2 * f)  # one user row + one item row (MLP + GMF parts)
+    kernel_ms = sum(v["ms_per_step"] for v in phase_table.values())
+    line = {
+        "metric": METRIC, "value": global_rows * args.steps / (ms_total / 1e3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "large-sharded: {} users x {} items, NeuMF layers {} mf_dim {}, {} negatives/positive, "
+                               "sparse-row Adam at the owners".format(wl["num_users"], wl["num_items"], L, f, wl["negs"]),
+                   "baseline_config": "BASELINE.json configs[4]", "rows_per_step_per_gpu": rows,
+                   "global_rows_per_step": global_rows,
+                   "parallelism": "tables row-sharded over {} ranks (owner = row % world); per step and side: all-to-all of "
+                                  "ids, of gathered rows and of gradient rows, all-reduce of the dense tower".format(world),
+                   "table_bytes_total": 4 * (wl["num_users"] + wl["num_items"]) * (L[0] // 2 + f) * 3,
+                   "l2_policy": "working set larger than L2: 4 rotating batches of uniformly drawn ids over 11 GB of tables"},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rows * 12, "d2h_bytes_per_step": 32,
+                "steps": e2e_steps, "api": "ShardedNeuMF.train_step on pinned host arrays"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": PHASE_KERNELS.get(dom, dom), "phase": dom, "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                     "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_avg_ms, "launches_timed": dom_groups,
+                     "share_of_step": phase_table[dom]["share_of_step"]},
+        "exchange": {"bytes_per_step_per_rank_upper_bound": 2 * 2 * rows * row_bytes // 2,
+                     "note": "rows + gradient rows of the distinct ids of the batch, both directions, (world-1)/world of them "
+                             "remote; routing (unique / owner grouping) runs in torch ops between the library's kernels",
+                     "library_kernel_ms_per_step": kernel_ms, "routing_and_collectives_ms_per_step": step_ms - kernel_ms},
+        "phases": phase_table,
+        "cpu_baseline": {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                         "sample": "not timed: the CPU baseline leg runs at N=1 only and this workload needs N >= 2"},
+        "final_loss": float(final[0]) / rows,
+    }
+    emit(line)
+    dist.destroy_process_group()
 
 
 def main():
@@ -490,8 +670,11 @@ def main():
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     wl = WORKLOADS[args.workload]
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args, wl)
+    elif wl.get("sharded"):
+        run_sharded(args, wl)
     else:
         run_gpu(args, wl)
 
