@@ -47,6 +47,48 @@ __device__ __forceinline__ void apply_row_value(const RowUpdate& u, int row, int
   }
 }
 
+// Four consecutive columns c..c+3 of one table (the vector path guarantees d0 % 4 == 0 and c % 4 == 0, so the
+// four never straddle the two tables): 128-bit accesses instead of four scalar read-modify-writes per lane.
+__device__ __forceinline__ void apply_row_value4(const RowUpdate& u, int row, int c, float4 g) {
+  float *p, *m, *v, *gt;
+  int d, col;
+  if (c < u.d0) {
+    p = u.p0; m = u.m0; v = u.v0; gt = u.g0; d = u.d0; col = c;
+  } else {
+    p = u.p1; m = u.m1; v = u.v1; gt = u.g1; d = u.d1; col = c - u.d0;
+  }
+  const size_t at = (size_t)row * d + col;
+  if ((d & 3) != 0) {  // rows of this table are not 16-byte aligned: scalar path
+    apply_row_value(u, row, c, g.x);
+    apply_row_value(u, row, c + 1, g.y);
+    apply_row_value(u, row, c + 2, g.z);
+    apply_row_value(u, row, c + 3, g.w);
+    return;
+  }
+  if (u.mode == MR_TABLES_DENSE) {
+    *reinterpret_cast<float4*>(gt + at) = g;
+  } else if (u.optimizer == MR_OPT_ADAM) {
+    const float4 m0 = *reinterpret_cast<const float4*>(m + at), v0 = *reinterpret_cast<const float4*>(v + at);
+    float4 pw = *reinterpret_cast<const float4*>(p + at);
+    float4 mn, vn;
+    mn.x = u.beta_1 * m0.x + (1.f - u.beta_1) * g.x; vn.x = u.beta_2 * v0.x + (1.f - u.beta_2) * g.x * g.x;
+    mn.y = u.beta_1 * m0.y + (1.f - u.beta_1) * g.y; vn.y = u.beta_2 * v0.y + (1.f - u.beta_2) * g.y * g.y;
+    mn.z = u.beta_1 * m0.z + (1.f - u.beta_1) * g.z; vn.z = u.beta_2 * v0.z + (1.f - u.beta_2) * g.z * g.z;
+    mn.w = u.beta_1 * m0.w + (1.f - u.beta_1) * g.w; vn.w = u.beta_2 * v0.w + (1.f - u.beta_2) * g.w * g.w;
+    pw.x = pw.x - u.lr_t * mn.x / (sqrtf(vn.x) + u.epsilon);
+    pw.y = pw.y - u.lr_t * mn.y / (sqrtf(vn.y) + u.epsilon);
+    pw.z = pw.z - u.lr_t * mn.z / (sqrtf(vn.z) + u.epsilon);
+    pw.w = pw.w - u.lr_t * mn.w / (sqrtf(vn.w) + u.epsilon);
+    *reinterpret_cast<float4*>(m + at) = mn;
+    *reinterpret_cast<float4*>(v + at) = vn;
+    *reinterpret_cast<float4*>(p + at) = pw;
+  } else {
+    float4 pw = *reinterpret_cast<const float4*>(p + at);
+    pw.x -= u.lr * g.x; pw.y -= u.lr * g.y; pw.z -= u.lr * g.z; pw.w -= u.lr * g.w;
+    *reinterpret_cast<float4*>(p + at) = pw;
+  }
+}
+
 struct ChunkInfo {
   int nvalid;       // entries of the chunk that exist
   bool first_inc;   // run starting at entry 0 continues from the previous chunk
@@ -64,12 +106,8 @@ __device__ __forceinline__ void flush_run(const RowUpdate& u, const ChunkInfo& c
   const bool inc_first = (s == 0) && ci.first_inc;
   const bool inc_last = (t == ci.nvalid) && ci.last_inc;
   if (!inc_first && !inc_last) {
-    apply_row_value(u, key, c, acc.x);
-    if (VEC) {
-      apply_row_value(u, key, c + 1, acc.y);
-      apply_row_value(u, key, c + 2, acc.z);
-      apply_row_value(u, key, c + 3, acc.w);
-    }
+    if (VEC) apply_row_value4(u, key, c, acc);
+    else apply_row_value(u, key, c, acc.x);
     return;
   }
   float* slot0 = ci.out_rows + (size_t)(2 * ci.chunk) * ci.ld + c;
@@ -188,7 +226,9 @@ int launch_segreduce(const int32_t* sorted_keys, const int32_t* sorted_index, in
   Carver cv(ws);
   int32_t* kbuf[2] = {cv.take<int32_t>(n1), cv.take<int32_t>(n2)};
   float* rbuf[2] = {cv.take<float>((size_t)n1 * ld), cv.take<float>((size_t)n2 * ld)};
-  const bool vec = (ld & 3) == 0 && (u.d0 & 3) == 0 && (reinterpret_cast<uintptr_t>(staged) & 15) == 0;
+  uintptr_t align = reinterpret_cast<uintptr_t>(staged);
+  for (const float* q : {u.p0, u.m0, u.v0, u.g0, u.p1, u.m1, u.v1, u.g1}) align |= reinterpret_cast<uintptr_t>(q);
+  const bool vec = (ld & 3) == 0 && (u.d0 & 3) == 0 && (align & 15) == 0;
 
   const int32_t* keys = sorted_keys;
   const float* rows = staged;
