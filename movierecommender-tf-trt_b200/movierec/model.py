@@ -130,6 +130,22 @@ class NeuMFModel(object):
         rank, _, _ = _engine_module().rank_scores(probs, group, o._k, want_rank=True, device=self.engine.device)
         return [probs.cpu().numpy().reshape(-1, 1), rank.cpu().numpy()]
 
+    def recommend(self, user_id, candidate_items, top_k=10):
+        """Serving-shaped scoring (reference client, trt_client.py:47-57: one user, N candidate items, the K best):
+        returns (items (K,), scores (K,)) ordered as the RankLayer orders them (descending score, the earlier
+        candidate first among ties).  One forward of N rows that share the user (the user row is read once per
+        launch tile) and one rank pass, both on the device."""
+        items = np.asarray(candidate_items, dtype=np.int32).reshape(-1)
+        n = int(items.size)
+        if n == 0:
+            return items, np.zeros(0, np.float32)
+        eng = self.engine
+        _, probs, _ = eng.forward(np.asarray([user_id], dtype=np.int32), items, user_div=n, want_logits=False)
+        rank, _, _ = _engine_module().rank_scores(probs, n, min(int(top_k), n), want_rank=True, device=eng.device)
+        order = rank.cpu().numpy().reshape(-1)[:min(int(top_k), n)]
+        p = probs.cpu().numpy()
+        return items[order], p[order]
+
     def _step_logs(self, out, rows, group):
         loss = out[0] / rows + out[3]
         return {"loss": loss, OUTPUT_PRED + "_loss": out[0] / rows,

@@ -300,6 +300,28 @@ def test_grouped_and_ungrouped_steps_agree(eng_mod):
             rel_close(weights[True][0][k], weights[False][0][k], rtol=1e-4, what="{} grouped vs ungrouped {}".format(mode, k))
 
 
+def test_wgrad_ts_variant_matches_default(eng_mod, monkeypatch):
+    """MR_WGRAD_TS=1 selects the weight-gradient kernel whose A operand lives in tensor memory (tcgen05.st +
+    A-from-TMEM MMAs); it must produce the same dense gradients as the default shared-memory-operand kernel."""
+    nu, ni, L, f, negs = 900, 700, [256, 128, 64], 64, 4
+    rng = np.random.default_rng(23)
+    users, items, y = make_batch(rng, nu, ni, 777, negs)  # 3885 rows: ragged last chunk and tile
+    grads = {}
+    for ts in (False, True):
+        if ts:
+            monkeypatch.setenv("MR_WGRAD_TS", "1")
+        else:
+            monkeypatch.delenv("MR_WGRAD_TS", raising=False)
+        for grouped in (False, True):
+            eng = eng_mod.NeuMFEngine(nu, ni, L, [0, 0, 0], mf_dim=f, seed=8)
+            eng.train_grads(users, items, y, group=negs + 1, k=3, grouped=grouped)
+            grads[(ts, grouped)] = eng.g_dense.cpu().numpy().copy()
+    monkeypatch.delenv("MR_WGRAD_TS", raising=False)
+    w64 = None
+    for grouped in (False, True):
+        rel_close(grads[(True, grouped)], grads[(False, grouped)], rtol=4e-6, what="TS vs SS dense gradients, grouped={}".format(grouped))
+
+
 def test_out_of_range_ids_are_flagged(eng_mod):
     eng = eng_mod.NeuMFEngine(5, 10, [6, 4], [0, 0], seed=1)
     out = eng.train_step([0, 9], [1, 2], [0.0, 1.0], group=2, k=1).cpu().numpy()

@@ -227,3 +227,27 @@ def test_fit_generator_history_and_learning(mods, tmp_path):
     hr_o, dcg_o, _, _ = o.evaluate_groups(w, users, items, 100, 10)
     assert abs(hr - hr_o) <= 1e-3 and abs(dcg - dcg_o) <= 1e-3
     assert hr > 0.5  # chance level is 0.1: the model has learned the two taste clusters
+
+
+# ---- serving-shaped scoring (reference client: one user x N candidates -> top K, trt_client.py:47-57) -------------
+
+@pytest.mark.parametrize("layers,mf_dim,n", [([64, 32, 16, 8], 8, 1000), ([256, 128, 64], 64, 1000), ([6, 4], 0, 7)])
+def test_recommend_top_k_matches_oracle(mods, tmp_path, layers, mf_dim, n):
+    model = mods[0]
+    params = copy.deepcopy(TEST_PARAMS)
+    params.update(num_users=50, num_items=1200, layers_sizes=layers, layers_l2reg=[0.0] * len(layers), mf_dim=mf_dim, seed=3)
+    m = model.MovierecModel(params, output_dir=str(tmp_path))
+    w = dict(zip(m.model.weight_names, m.model.get_weights()))
+    rng = np.random.default_rng(5)
+    cand = rng.permutation(1200)[:n].astype(np.int32)
+    items, scores = m.model.recommend(17, cand, top_k=10)
+    k = min(10, n)
+    assert items.shape == (k,) and scores.shape == (k,)
+    p = o.forward(w, np.full(n, 17), cand)["p"].reshape(-1)
+    order = np.argsort(-p, kind="stable")[:k]
+    np.testing.assert_allclose(scores, p[order], rtol=1e-5, atol=1e-7)
+    # the same items wherever the oracle's scores are separated by more than the tolerance
+    sep = np.abs(np.diff(np.sort(p)[::-1][:k + 1])) > 1e-6
+    if np.all(sep):
+        assert np.array_equal(items, cand[order])
+    assert np.all(np.diff(scores) <= 0)
