@@ -423,15 +423,15 @@ def run_gpu(args, wl):
             eng.rank_eval(eu_d, ei_d, egroup, wl["k_eval"])
         torch.cuda.synchronize(dev)
         nat.profile_begin()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        e0.record()
-        for _ in range(reps):
+        reps = 7
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in evs:  # one event pair per sweep; the median is reported (a sweep is ~12 ms, host hiccups show)
+            a.record()
             pos, sums, _, _ = eng.rank_eval(eu_d, ei_d, egroup, wl["k_eval"])
-        e1.record()
+            b.record()
         torch.cuda.synchronize(dev)
         eph, _ = nat.profile_end()
-        ems = e0.elapsed_time(e1) / reps
+        ems = float(np.median([a.elapsed_time(b) for a, b in evs]))
         ab = algorithmic_bytes(wl, rows)
         peak, peak_kind = measured_peaks()
         fwd_ms = sum(eph[k][0] for k in ("tile_forward", "tc_dense_fwd", "head") if k in eph) / reps

@@ -7,6 +7,8 @@
 // One warp per row, lanes across columns (every row is read with coalesced 128-byte requests).
 // Algorithmic bytes per row: 4*L_last (h) + 8*f (GMF rows) + 12 (ids, label) read,
 // 4*L_last + 8*f + 8 written.
+#include <stdlib.h>
+
 #include "launchers.h"
 
 namespace mr {
@@ -173,6 +175,156 @@ __global__ void __launch_bounds__(kHeadThreads, MAXQ <= 4 ? 2 : 1) head_kernel(c
   }
 }
 
+// Grouped train head, specialised and software-pipelined: mf_dim = 32 * FQ and the last layer width = 32 * HQ are
+// compile-time, so a row's values take FQ + HQ registers per lane instead of MAXQ for each of three arrays, and
+// the freed registers hold the NEXT group: its row loads are issued before the current group is reduced and its
+// ids one group earlier still (the generic kernel above has no load in flight while it waits for ids or while
+// it reduces and stores: ncu showed it at ~2 TB/s of its ~1.5 GB per step).  Same arithmetic per row, same
+// outputs, same per-warp accumulation order as head_kernel<.., GROUPED = true>.
+template <int FQ, int HQ, int KR>
+__global__ void __launch_bounds__(kHeadThreads, 2) head_group_kernel(const HeadParams p) {
+  constexpr int f = 32 * FQ, Ln = 32 * HQ, ncols = f + Ln;
+  __shared__ float red[kHeadThreads / 32][ncols + 2];
+  const MrModel& m = p.m;
+  const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
+  const int su = d_u + f, si = d_i + f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float wg[FQ], wh[HQ];
+#pragma unroll
+  for (int q = 0; q < FQ; ++q) wg[q] = __ldg(m.w_out + lane + 32 * q);
+#pragma unroll
+  for (int q = 0; q < HQ; ++q) wh[q] = __ldg(m.w_out + f + lane + 32 * q);
+  const float b_out = __ldg(m.b_out);
+  float accg[FQ], acch[HQ], accb = 0.f, accl = 0.f;
+#pragma unroll
+  for (int q = 0; q < FQ; ++q) accg[q] = 0.f;
+#pragma unroll
+  for (int q = 0; q < HQ; ++q) acch[q] = 0.f;
+
+  struct Ids {
+    int u, it[KR];
+    float y[KR];
+  };
+  struct Rows {
+    float gu[FQ], gi[KR][FQ], h[KR][HQ], y[KR];
+    unsigned bad;  // bit rr: row rr has an out-of-range id
+  };
+  const int64_t ngroups = p.rows / KR;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  auto load_ids = [&](int64_t g, Ids& d) {
+    const int64_t gr0 = p.row0 + g * KR;
+    d.u = __ldg(p.users + gr0);
+#pragma unroll
+    for (int rr = 0; rr < KR; ++rr) {
+      d.it[rr] = __ldg(p.items + gr0 + rr);
+      d.y[rr] = __ldg(p.labels + gr0 + rr);
+    }
+  };
+  auto load_rows = [&](int64_t g, const Ids& d, Rows& r) {
+    const bool bad_u = (unsigned)d.u >= (unsigned)m.num_users;
+    const int u = bad_u ? 0 : d.u;
+    r.bad = 0;
+#pragma unroll
+    for (int q = 0; q < FQ; ++q) r.gu[q] = __ldg(m.user_gmf + (size_t)u * f + lane + 32 * q);
+#pragma unroll
+    for (int rr = 0; rr < KR; ++rr) {
+      const bool bad_i = (unsigned)d.it[rr] >= (unsigned)m.num_items;
+      const int it = bad_i ? 0 : d.it[rr];
+      if (bad_u || bad_i) r.bad |= 1u << rr;
+      r.y[rr] = d.y[rr];
+#pragma unroll
+      for (int q = 0; q < FQ; ++q) r.gi[rr][q] = __ldg(m.item_gmf + (size_t)it * f + lane + 32 * q);
+#pragma unroll
+      for (int q = 0; q < HQ; ++q) r.h[rr][q] = __ldg(p.h_last + (size_t)(g * KR + rr) * Ln + lane + 32 * q);
+    }
+  };
+  auto compute = [&](int64_t g, const Rows& r) {
+    if (r.bad && lane == 0) atomicOr(p.flags, 1);
+    float gu_acc[FQ];
+#pragma unroll
+    for (int q = 0; q < FQ; ++q) gu_acc[q] = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < KR; ++rr) {
+      const int64_t lr = g * KR + rr, gr = p.row0 + lr;
+      float x[FQ];
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < FQ; ++q) {
+        x[q] = r.gu[q] * r.gi[rr][q];
+        s = fmaf(wg[q], x[q], s);
+      }
+#pragma unroll
+      for (int q = 0; q < HQ; ++q) s = fmaf(wh[q], r.h[rr][q], s);
+      s = warp_sum(s);
+      const float z = s + b_out;
+      const float pr = sigmoidf_stable(z);
+      const bool bad = (r.bad >> rr) & 1u;
+      if (lane == 0 && p.probs != nullptr) p.probs[gr] = bad ? nanf("") : pr;
+      const float y = r.y[rr];
+      const float dz = bad ? 0.f : (pr - y) * p.inv_batch;
+      if (!bad) accl += bce_logits(z, y);
+      accb += dz;
+#pragma unroll
+      for (int q = 0; q < FQ; ++q) {
+        accg[q] = fmaf(dz, x[q], accg[q]);
+        const float gv = dz * wg[q];
+        gu_acc[q] = fmaf(gv, r.gi[rr][q], gu_acc[q]);
+        p.stage_i[(size_t)gr * si + d_i + lane + 32 * q] = gv * r.gu[q];
+      }
+#pragma unroll
+      for (int q = 0; q < HQ; ++q) {
+        acch[q] = fmaf(dz, r.h[rr][q], acch[q]);
+        p.dz_last[(size_t)lr * Ln + lane + 32 * q] = r.h[rr][q] > 0.f ? dz * wh[q] : 0.f;
+      }
+    }
+    const int64_t grp = (p.row0 + g * KR) / KR;
+#pragma unroll
+    for (int q = 0; q < FQ; ++q) p.stage_u[(size_t)grp * su + d_u + lane + 32 * q] = gu_acc[q];
+  };
+
+  Ids ids;
+  Rows ra, rb;
+  int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g < ngroups) {
+    load_ids(g, ids);
+    load_rows(g, ids, ra);
+    if (g + warps < ngroups) load_ids(g + warps, ids);
+  }
+  while (g < ngroups) {
+    // ra holds group g; ids hold group g + warps
+    if (g + warps < ngroups) {
+      load_rows(g + warps, ids, rb);
+      if (g + 2 * warps < ngroups) load_ids(g + 2 * warps, ids);
+    }
+    compute(g, ra);
+    g += warps;
+    if (g >= ngroups) break;
+    if (g + warps < ngroups) {
+      load_rows(g + warps, ids, ra);
+      if (g + 2 * warps < ngroups) load_ids(g + 2 * warps, ids);
+    }
+    compute(g, rb);
+    g += warps;
+  }
+
+  // per-warp sums -> shared -> this CTA's partial row, warps added in index order
+#pragma unroll
+  for (int q = 0; q < FQ; ++q) red[warp][lane + 32 * q] = accg[q];
+#pragma unroll
+  for (int q = 0; q < HQ; ++q) red[warp][f + lane + 32 * q] = acch[q];
+  if (lane == 0) {
+    red[warp][ncols] = accb;
+    red[warp][ncols + 1] = accl;
+  }
+  __syncthreads();
+  float* dst = p.head_partial + (size_t)blockIdx.x * (ncols + 2);
+  for (int j = threadIdx.x; j < ncols + 2; j += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < kHeadThreads / 32; ++w) t += red[w][j];
+    dst[j] += t;
+  }
+}
+
 // Ranking evaluation, fused: GMF product + output unit + sigmoid of the `group` candidates of one user AND the
 // position of the positive (the LAST candidate, data_pipeline.py:113,148) under the RankLayer order
 // (model.py:344-352: descending probability, lower index first among ties), in one kernel -- the scores never
@@ -319,6 +471,20 @@ int launch_head(const HeadArgs& a, cudaStream_t st) {
     if (!head_supports_group(m, a.group) || a.rows % a.group || a.row0 % a.group || p.user_div != 1) {
       set_error("head kernel: grouped mode needs group <= 8, mf_dim + last width <= 128 and whole groups");
       return MR_ERR_INVALID;
+    }
+    const bool special = a.labels != nullptr && m.mf_dim == 64 && m.L[m.n_layers - 1] == 64 && getenv("MR_HEAD_GENERIC") == nullptr;
+    if (special) {  // mf_dim = 64, last layer 64 (BASELINE configs[2]): the pipelined specialisation
+      switch (a.group) {
+        case 2: head_group_kernel<2, 2, 2><<<grid, kHeadThreads, 0, st>>>(p); break;
+        case 3: head_group_kernel<2, 2, 3><<<grid, kHeadThreads, 0, st>>>(p); break;
+        case 4: head_group_kernel<2, 2, 4><<<grid, kHeadThreads, 0, st>>>(p); break;
+        case 5: head_group_kernel<2, 2, 5><<<grid, kHeadThreads, 0, st>>>(p); break;
+        case 6: head_group_kernel<2, 2, 6><<<grid, kHeadThreads, 0, st>>>(p); break;
+        case 7: head_group_kernel<2, 2, 7><<<grid, kHeadThreads, 0, st>>>(p); break;
+        default: head_group_kernel<2, 2, 8><<<grid, kHeadThreads, 0, st>>>(p); break;
+      }
+      MR_LAUNCH_CHECK("head_group_kernel");
+      return MR_OK;
     }
     switch (a.group) {
       case 2: head_kernel<4, 2, true><<<grid, kHeadThreads, 0, st>>>(p); break;
