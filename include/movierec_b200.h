@@ -182,6 +182,14 @@ int mr_sample_negatives(const int64_t* csr_rowptr, const int32_t* csr_items, int
                         int64_t first_index, int32_t negs, uint64_t seed, uint64_t epoch,
                         int32_t* out_users, int32_t* out_items, float* out_labels, void* stream);
 
+/* Gather from a ROW-SHARDED table over peer pointers: row id lives on rank id % world at local index id / world;
+ * shards is a DEVICE array of `world` pointers to the ranks' slices (each (ceil(total_rows/world), dim) fp32 in the
+ * owning GPU's memory, mapped into this process through NVLink peer access -- e.g. torch symmetric memory).
+ * out[i,:] = row ids[i] (NaN for an out-of-range id).  This one kernel is the gather AND the exchange of the
+ * gathered rows of a row-sharded step.  The caller orders it against the owners' updates (a cross-rank barrier). */
+int mr_gather_rows_sharded(const float* const* shards, int32_t world, int64_t total_rows, int32_t dim,
+                           const int32_t* ids, int64_t n, float* out, void* stream);
+
 /* Owner-side update of ROW-SHARDED tables (data-parallel runs whose tables do not fit one GPU): n pairs
  * (local row id, gradient row [g0 | g1]) received from all ranks, duplicates allowed.  The pairs are
  * stably sorted by row id, summed per id in arrival order (deterministic, no atomics) and the sparse-row

@@ -494,6 +494,14 @@ int mr_gather_rows(const float* table, int64_t rows, int32_t dim, const int32_t*
   return launch_gather_rows(table, rows, dim, idx, n, out, (cudaStream_t)stream);
 }
 
+int mr_gather_rows_sharded(const float* const* shards, int32_t world, int64_t total_rows, int32_t dim,
+                           const int32_t* ids, int64_t n, float* out, void* stream) {
+  if (n == 0) return MR_OK;
+  MR_REQUIRE(shards && ids && out, "gather_rows_sharded: NULL pointer");
+  MR_REQUIRE(world >= 1 && total_rows > 0 && dim > 0 && n >= 0, "gather_rows_sharded: bad sizes");
+  return launch_gather_rows_sharded(shards, world, total_rows, dim, ids, n, out, (cudaStream_t)stream);
+}
+
 size_t mr_forward_workspace_bytes(const MrModel* model, int64_t B) {
   (void)B;
   size_t n = 256 + align_up((size_t)max_tile_ctas() * sizeof(float), 256);

@@ -39,6 +39,49 @@ int launch_gather_rows(const float* table, int64_t rows, int dim, const int32_t*
   return MR_OK;
 }
 
+// ---- row-sharded tables read over NVLink peer pointers ----------------------------------------------------------
+// out[i,:] = shard[owner(id)][id / world,:] with owner(id) = id % world, where shard[r] is rank r's slice of the
+// table in ITS memory (pointers exchanged through torch's symmetric memory, NVLink 5 / NVSwitch peer access).
+// The gather and the "all-to-all of gathered rows" of a row-sharded step are this one kernel: no id exchange, no
+// owner-side gather, no staging copies.  One warp per row, 128-bit loads; remote rows cross NVLink once.
+template <bool VEC>
+__global__ void __launch_bounds__(256) gather_rows_sharded_kernel(const float* const* __restrict__ shards, int world,
+                                                                  int64_t total_rows, int dim,
+                                                                  const int32_t* __restrict__ ids, int64_t n,
+                                                                  float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const int r = __ldg(ids + i);
+    const bool ok = (unsigned)r < (uint64_t)total_rows;
+    const unsigned id = ok ? (unsigned)r : 0u;
+    const unsigned local = id / (unsigned)world, owner = id - local * (unsigned)world;
+    const float* src = shards[owner] + (size_t)local * dim;
+    float* dst = out + (size_t)i * dim;
+    if (VEC) {
+      for (int c = lane * 4; c < dim; c += 128) {
+        float4 v = ok ? *reinterpret_cast<const float4*>(src + c) : make_float4(nanf(""), nanf(""), nanf(""), nanf(""));
+        *reinterpret_cast<float4*>(dst + c) = v;
+      }
+    } else {
+      for (int c = lane; c < dim; c += 32) dst[c] = ok ? src[c] : nanf("");
+    }
+  }
+}
+
+int launch_gather_rows_sharded(const float* const* shards, int world, int64_t total_rows, int dim, const int32_t* ids,
+                               int64_t n, float* out, cudaStream_t st) {
+  if (n == 0) return MR_OK;
+  const bool vec = (dim & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;  // shard bases are allocation starts
+  int64_t blocks = (n + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (vec) gather_rows_sharded_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(shards, world, total_rows, dim, ids, n, out);
+  else gather_rows_sharded_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(shards, world, total_rows, dim, ids, n, out);
+  MR_LAUNCH_CHECK("gather_rows_sharded_kernel");
+  return MR_OK;
+}
+
 // ---- grouped batches --------------------------------------------------------------------------------------
 // The reference's generator lays a batch out as groups of one positive and its negatives, all of one user
 // (data_pipeline.py:99-150).  Everything the tower computes from the user row alone is therefore shared by

@@ -153,6 +153,10 @@ int launch_head_rank(const HeadArgs& a, int group, int32_t* pos, float* probs, c
 // metric sums from positions (rank.cu): sums = {hit_sum, dcg_sum}
 int launch_rank_metrics(const int32_t* pos, int64_t G, int k, float* sums, float* partials, cudaStream_t st);
 
+// row-sharded tables over peer pointers (gather.cu): shards = device array of `world` table-slice pointers
+int launch_gather_rows_sharded(const float* const* shards, int world, int64_t total_rows, int dim, const int32_t* ids,
+                               int64_t n, float* out, cudaStream_t st);
+
 // ---- grouped batches (gather.cu): one positive and its negatives share the user ----------------------------
 // out[g] = sum_{j < group} in[g * group + j]  (rows of `width` floats, width % 4 == 0), fixed order
 int launch_group_sum_rows(const float* in, int64_t groups, int group, int width, float* out, cudaStream_t st);

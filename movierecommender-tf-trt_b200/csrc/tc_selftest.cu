@@ -192,7 +192,7 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 __global__ void __launch_bounds__(32 * 9, 1) tc_rate_kernel(int N, int iters, int nbuf, int flags, int writers,
                                                             int write_iters, long long* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ uint64_t done_bar;
+  __shared__ uint64_t done_bar, side_bar;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(32 * 9, 1) tc_rate_kernel(int N, int iters, in
   if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     tc::mbar_init(&done_bar, 1);
+    tc::mbar_init(&side_bar, 1);
     tc::mbar_init_fence();
   }
   tc::fence_proxy_async();
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(32 * 9, 1) tc_rate_kernel(int N, int iters, in
   const uint32_t tmem_base = tmem_slot;
   const bool ts = flags & 1, mn = flags & 2;
   if (tid == 0) {
-    const uint32_t idesc = tc::idesc_tf32(128, N, mn ? 1 : 0, mn ? 1 : 0);
+    const uint32_t idesc = tc::idesc_tf32(128, N, (mn && !ts) ? 1 : 0, mn ? 1 : 0);  // A in TMEM has no major-ness
     const uint32_t lbo = mn ? 8 * 512 : 128, sbo = mn ? 512 : 1024, lt = mn ? tc::kLayoutSw128Base32 : tc::kLayoutNone;
     const uint32_t kstep = mn ? 1024 : 256;
     const long long t0 = clock64();
@@ -225,7 +226,9 @@ __global__ void __launch_bounds__(32 * 9, 1) tc_rate_kernel(int N, int iters, in
         const uint64_t bh = tc::smem_desc(sb + kk * kstep, lbo, sbo, lt);
         const uint64_t bl = tc::smem_desc(sb + b_bytes + kk * kstep, lbo, sbo, lt);
         if (ts) {
-          const uint32_t ah = tmem_base + 256 + 8 * kk, al = tmem_base + 256 + 32 + 8 * kk;
+          // flags bit 3: A right behind the accumulator (column 128) instead of column 256; bit 4: A ring of 4 stages
+          const uint32_t abase = tmem_base + ((flags & 8) ? 128 : 256) + ((flags & 16) ? (uint32_t)(it & 3) * 64 : 0);
+          const uint32_t ah = abase + 8 * kk, al = abase + 32 + 8 * kk;
           mma_tf32_ts(tmem_base, ah, bh, idesc, 1);
           mma_tf32_ts(tmem_base, al, bh, idesc, 1);
           mma_tf32_ts(tmem_base, ah, bl, idesc, 1);
@@ -237,6 +240,7 @@ __global__ void __launch_bounds__(32 * 9, 1) tc_rate_kernel(int N, int iters, in
           tc::mma_tf32(tmem_base, ah, bl, idesc, 1);
         }
       }
+      if (flags & 4) tc::mma_commit(&side_bar);  // a commit per stage, as the pipelined kernels issue them
     }
     tc::mma_commit(&done_bar);
     tc::mbar_wait(&done_bar, 0);

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
 // 64 instead of 105.6 cycles.  Z stays a shared-memory MN-major operand exactly as in the SS kernel.
 //   warps 0-7  producers, two groups of four on alternate chunks (thread = TMEM lane for A, a float4 column for Z)
 //   warp 8  MMA issuer, warp 9  L2 prefetch
-template <bool GATHER, int NA, int NZ>
+template <bool GATHER, int NA, int NZ, int KC>
 __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_ts_kernel(const TcWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[8], empty_bar[8], done_bar;
@@ -318,13 +318,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_ts_kernel(const TcWgra
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int Fa = 32 * NA, Fb = 32 * NZ, halves = Fa / 128, zq = Fb >> 2;
-  constexpr int kACols = halves * 32;       // TMEM columns of one A stage: per half 16 hi + 16 lo
+  constexpr int kACols = halves * 2 * KC;   // TMEM columns of one A stage: per half KC hi + KC lo
   constexpr uint32_t kAccCols = halves * Fb;  // accumulators first, the A ring behind them
   const int S = p.stages;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr uint32_t z_bytes = (uint32_t)kWgKC * Fb * 4, stage_bytes = 2 * z_bytes;
+  constexpr uint32_t z_bytes = (uint32_t)KC * Fb * 4, stage_bytes = 2 * z_bytes;
 
-  const int64_t total_chunks = (p.rows + kWgKC - 1) / kWgKC;
+  const int64_t total_chunks = (p.rows + KC - 1) / KC;
   const int64_t per_cta = (total_chunks + gridDim.x - 1) / gridDim.x;
   const int64_t chunk_lo = min(total_chunks, per_cta * blockIdx.x);
   const int64_t chunk_hi = min(total_chunks, chunk_lo + per_cta);
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_ts_kernel(const TcWgra
     // (TMEM lane 32 * (warp % 4) + lane) and a fixed float4 column of Z; global loads run one group iteration
     // ahead in registers, the row ids one more (lane r of every warp keeps the ids of row r of the chunk).
     const int group = warp >> 2, f = tid & 127, t = tid & 127;
-    constexpr int PZ = NZ;  // float4 of Z per thread and chunk: 16 rows x Fb/4 over 128 threads
+    constexpr int PZ = NZ * KC / 16;  // float4 of Z per thread and chunk: KC rows x Fb/4 over 128 threads
     int64_t ld_chunk = chunk_lo + group;   // chunk whose VALUES are loaded next
     int64_t id_chunk = chunk_lo + group;   // chunk whose IDS are loaded next
     int st_stage = group % S;
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_ts_kernel(const TcWgra
     int uid = 0, iid = 0;  // ids of row `lane` (< 16) of the chunk the next issue_loads will read
     auto load_ids = [&]() {
       if (GATHER) {
-        const int64_t lr = id_chunk * kWgKC + (lane & (kWgKC - 1));
+        const int64_t lr = id_chunk * KC + (lane & (KC - 1));  // KC <= 32: lane r keeps the ids of row r
         uid = 0;
         iid = 0;
         if (lr < p.rows) {
@@ -369,13 +369,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_ts_kernel(const TcWgra
       }
       id_chunk += 2;
     };
-    auto issue_loads = [&](float(&x)[halves * kWgKC], float4(&xz)[PZ]) {
-      const int64_t crow0 = ld_chunk * kWgKC;
+    auto issue_loads = [&](float(&x)[halves * KC], float4(&xz)[PZ]) {
+      const int64_t crow0 = ld_chunk * KC;
       ld_chunk += 2;
       const int my_u = uid, my_i = iid;
       load_ids();  // for the chunk after this one: their latency hides behind this chunk's loads
 #pragma unroll
-      for (int r = 0; r < kWgKC; ++r) {
+      for (int r = 0; r < KC; ++r) {
         const int64_t lr = crow0 + r;
         const bool ok = lr < p.rows && !(p.debug & 2);
         const int u = GATHER ? __shfl_sync(0xffffffffu, my_u, r) : 0;
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_ts_kernel(const TcWgra
               v = __ldg(p.a_dense + (size_t)lr * Fa + c);
             }
           }
-          x[h * kWgKC + r] = v;
+          x[h * KC + r] = v;
         }
       }
 #pragma unroll
@@ -406,23 +406,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_ts_kernel(const TcWgra
         xz[i] = (lr < p.rows && !(p.debug & 2)) ? ldg4(p.z + (size_t)lr * Fb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto store_chunk = [&](const float(&x)[halves * kWgKC], const float4(&xz)[PZ]) {
+    auto store_chunk = [&](const float(&x)[halves * KC], const float4(&xz)[PZ]) {
       const int stage = st_stage;
       const uint32_t phase = st_phase;
       st_stage += 2;
       while (st_stage >= S) { st_stage -= S; st_phase ^= 1; }
       tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-      tc::fence_after_sync();
+      if (!(p.debug & 256)) tc::fence_after_sync();
       uint8_t* st = smem + (size_t)stage * stage_bytes;
       if (!(p.debug & 4)) {
 #pragma unroll
         for (int h = 0; h < halves; ++h) {
-          float hi[kWgKC], lo[kWgKC];
+          float hi[KC], lo[KC];
 #pragma unroll
-          for (int r = 0; r < kWgKC; ++r) tc::split_tf32_fast(x[h * kWgKC + r], hi[r], lo[r]);
-          const uint32_t taddr = tmem_base + kAccCols + (uint32_t)stage * kACols + (uint32_t)h * 32 + ((uint32_t)(32 * (warp & 3)) << 16);
-          tc::tmem_st16(taddr, hi);
-          tc::tmem_st16(taddr + 16, lo);
+          for (int r = 0; r < KC; ++r) tc::split_tf32_fast(x[h * KC + r], hi[r], lo[r]);
+          const uint32_t taddr = tmem_base + kAccCols + (uint32_t)stage * kACols + (uint32_t)h * 2 * KC + ((uint32_t)(32 * (warp & 3)) << 16);
+#pragma unroll
+          for (int q = 0; q < KC / 16; ++q) {
+            tc::tmem_st16(taddr + 16 * q, hi + 16 * q);
+            tc::tmem_st16(taddr + KC + 16 * q, lo + 16 * q);
+          }
         }
 #pragma unroll
         for (int i = 0; i < PZ; ++i) {
@@ -434,18 +437,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_ts_kernel(const TcWgra
           dbacc.w += xz[i].w;
           float4 hi, lo;
           tc::split_tf32x4(xz[i], hi, lo);
-          const uint32_t off = tc::mn_off(r, c, kWgKC / 4);
+          const uint32_t off = tc::mn_off(r, c, KC / 4);
           *reinterpret_cast<float4*>(st + off) = hi;
           *reinterpret_cast<float4*>(st + z_bytes + off) = lo;
         }
         tc::tmem_st_wait();
       }
       tc::fence_proxy_async();
-      tc::fence_before_sync();
+      if (!(p.debug & 256)) tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
     };
-    float xa[2][halves * kWgKC];
+    float xa[2][halves * KC];
     float4 bz[2][PZ];
     const int64_t mine = my_chunks > group ? (my_chunks - group + 1) / 2 : 0;  // chunks of this group
     if (mine > 0) {
@@ -457,16 +460,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_ts_kernel(const TcWgra
       for (int j = 0; j < 2; ++j) {
         const int64_t i = i0 + j;
         if (i < mine) {
-          if (i + 1 < mine) issue_loads(xa[(j + 1) & 1], bz[(j + 1) & 1]);
+          if (i + 1 < mine && !(p.debug & 512)) issue_loads(xa[(j + 1) & 1], bz[(j + 1) & 1]);
           store_chunk(xa[j], bz[j]);
         }
       }
     }
   } else if (warp == kWgPrefetchWarp) {
     if (!(p.debug & 128)) {
-      const int64_t row_lo = chunk_lo * kWgKC, row_hi = min(p.rows, chunk_hi * kWgKC);
+      const int64_t row_lo = chunk_lo * KC, row_hi = min(p.rows, chunk_hi * KC);
       for (int64_t r0 = row_lo; r0 < row_hi; r0 += 32) {
-        const int64_t n = (r0 - row_lo) / kWgKC;
+        const int64_t n = (r0 - row_lo) / KC;
         while (n >= (int64_t)*reinterpret_cast<volatile int*>(&chunks_issued) + kWgPrefetchAhead) __nanosleep(256);
         const int64_t lr = r0 + lane;
         if (lr >= row_hi) continue;
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_ts_kernel(const TcWgra
     // ---- MMA issuer
     if (tc::elect_one()) {
       const uint32_t idesc = tc::idesc_tf32(128, Fb, 0, 1);  // A from TMEM (K-major by construction), Z MN-major
-      const uint32_t lbo = (kWgKC / 4) * 512, sbo = 512;
+      const uint32_t lbo = (KC / 4) * 512, sbo = 512;
       const uint64_t dbase = tc::smem_desc(0, lbo, sbo, tc::kLayoutSw128Base32);
       const uint32_t s0 = tc::smem_u32(smem);
       int stage = 0;
@@ -503,12 +506,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_ts_kernel(const TcWgra
         const uint32_t sz = s0 + (uint32_t)stage * stage_bytes;
         const uint32_t a0 = tmem_base + kAccCols + (uint32_t)stage * kACols;
 #pragma unroll
-        for (int kk = 0; kk < kWgKC / 8; ++kk) {
+        for (int kk = 0; kk < KC / 8; ++kk) {
           const uint64_t zh = dbase + ((sz + kk * 1024) >> 4);
           const uint64_t zl = dbase + ((sz + z_bytes + kk * 1024) >> 4);
 #pragma unroll
           for (int h = 0; h < halves; ++h) {
-            const uint32_t ah = a0 + (uint32_t)h * 32 + 8 * kk, al = ah + 16;
+            const uint32_t ah = a0 + (uint32_t)h * 2 * KC + 8 * kk, al = ah + KC;
             const uint32_t d = tmem_base + (uint32_t)h * Fb;
             tc::mma_tf32_ts(d, ah, zh, idesc, (n | kk) != 0);
             tc::mma_tf32_ts(d, al, zh, idesc, 1);
@@ -595,10 +598,13 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
   // stage hand-off, not the data path, is what costs) -- kept for the next round, see DESIGN.md.
   const bool ts = getenv("MR_WGRAD_TS") != nullptr && halves_h * a.Fb + 2 * halves_h * 32 <= 512 &&
                   (!a.gather || a.d_u % 128 == 0);
-  const size_t sb = ts ? (size_t)2 * kWgKC * a.Fb * 4 : (size_t)2 * kWgKC * (a.Fa + a.Fb) * 4;
+  // TS chunks are 32 rows (12 MMAs per half and hand-off instead of 6: the issuing thread's per-chunk overhead is
+  // what bounds that kernel) when the TMEM columns allow at least 3 stages, else 16
+  const int ts_kc = ts && (512 - halves_h * a.Fb) / (halves_h * 64) >= 3 && getenv("MR_WGRAD_TS16") == nullptr ? 32 : 16;
+  const size_t sb = ts ? (size_t)2 * ts_kc * a.Fb * 4 : (size_t)2 * kWgKC * (a.Fa + a.Fb) * 4;
   int stages = (int)((190 * 1024) / sb);
   if (ts) {
-    const int tmem_stages = (512 - halves_h * a.Fb) / (halves_h * 32);
+    const int tmem_stages = (512 - halves_h * a.Fb) / (halves_h * 2 * ts_kc);
     if (stages > tmem_stages) stages = tmem_stages;
   }
   if (stages > 8) stages = 8;
@@ -617,7 +623,8 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
   int rc = MR_ERR_INVALID;
 #define MR_WG_CASE(G, NA_, NZ_)                                                                          \
   if (a.gather == G && na == NA_ && nz == NZ_) {                                                         \
-    auto kern = ts ? tc_wgrad_ts_kernel<G, NA_, NZ_> : tc_wgrad_kernel<G, NA_, NZ_>;                     \
+    auto kern = ts ? (ts_kc == 32 ? tc_wgrad_ts_kernel<G, NA_, NZ_, 32> : tc_wgrad_ts_kernel<G, NA_, NZ_, 16>)  \
+                   : tc_wgrad_kernel<G, NA_, NZ_>;                                                       \
     MR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
     kern<<<grid, kWgThreads, smem, st>>>(p);                                                             \
     rc = MR_OK;                                                                                          \

@@ -84,11 +84,17 @@ class ShardedNeuMF(object):
          gradients and the identical dense update everywhere.
 
     The result equals the single-GPU step in sparse-row ("lazy") Adam mode on the global batch up to
-    summation order.  torch.distributed moves bytes (NCCL over NVLink on GPUs); all arithmetic is in the
-    CUDA library."""
+    summation order.  All arithmetic is in the CUDA library.
+
+    peer_gather (default on GPUs of one box): the shards live in torch symmetric memory, every rank holds the
+    peer pointers of all slices, and step 2 is ONE kernel (`mr_gather_rows_sharded`) that reads each needed row
+    from its owner's memory over NVLink straight into the cache -- no exchange of gathered rows, no owner-side
+    gather, no staging copies; the ids still go to the owners (4 bytes a row) because the gradient rows of
+    step 4 follow them.  A symmetric-memory barrier at the start of the step orders the gathers after the
+    owners' updates of the previous step.  With peer_gather off, step 2 is the NCCL all-to-all pair."""
 
     def __init__(self, num_users, num_items, layers_sizes, mf_dim=0, optimizer="adam", lr=1e-3, beta_1=0.9,
-                 beta_2=0.999, max_local_rows=1 << 20, seed=None, process_group=None):
+                 beta_2=0.999, max_local_rows=1 << 20, seed=None, process_group=None, peer_gather=None):
         import numpy as np
         from . import _engine
         if not dist.is_initialized():
@@ -109,19 +115,40 @@ class ShardedNeuMF(object):
         self.f = e.mf_dim
         rng = np.random.default_rng(None if seed is None else seed + 7919 * (self.rank + 1))
         self.shard = {}
+        symm = None
+        if peer_gather is None:
+            peer_gather = dev.type == "cuda" and dist.get_backend(process_group) == "nccl"
+        if peer_gather:
+            import torch.distributed._symmetric_memory as symm  # peer pointers over NVLink (one box)
+        self.peer_gather = bool(peer_gather)
+        self._barrier_handle = None
+        pg_name = (process_group if process_group is not None else dist.group.WORLD).group_name if peer_gather else None
         for side, total, d in (("user", self.num_users, e.d_u), ("item", self.num_items, e.d_i)):
             rows = (total - self.rank + self.world - 1) // self.world if total > self.rank else 0
+            rows_max = (total + self.world - 1) // self.world  # symmetric allocations have one size on all ranks
             tabs = {}
             for kind, width, fan_in in (("mlp", d, total), ("gmf", self.f, total)):
                 if width == 0:
                     tabs[kind] = None
                     continue
                 lim = (6.0 / (fan_in + width)) ** 0.5  # glorot-uniform of the FULL table (model.py:163)
-                t = torch.empty((max(rows, 1), width), dtype=torch.float32, device=dev)
-                t.uniform_(-lim, lim, generator=None) if seed is None else t.copy_(
-                    torch.from_numpy(rng.uniform(-lim, lim, size=(max(rows, 1), width)).astype("float32")))
-                tabs[kind] = {"p": t, "m": torch.zeros_like(t), "v": torch.zeros_like(t)}
-            self.shard[side] = {"rows": rows, "tabs": tabs, "d": d}
+                if peer_gather:
+                    t = symm.empty((max(rows_max, 1), width), dtype=torch.float32, device=dev)
+                else:
+                    t = torch.empty((max(rows_max, 1), width), dtype=torch.float32, device=dev)
+                if seed is None:
+                    t.uniform_(-lim, lim)
+                else:
+                    t.copy_(torch.from_numpy(rng.uniform(-lim, lim, size=tuple(t.shape)).astype("float32")))
+                tabs[kind] = {"p": t, "m": torch.zeros(t.shape, dtype=torch.float32, device=dev),
+                              "v": torch.zeros(t.shape, dtype=torch.float32, device=dev)}
+                if peer_gather:
+                    hdl = symm.rendezvous(t, pg_name)
+                    tabs[kind]["handle"] = hdl
+                    tabs[kind]["peers"] = torch.tensor(list(hdl.buffer_ptrs), dtype=torch.int64, device=dev)
+                    if self._barrier_handle is None:
+                        self._barrier_handle = hdl
+            self.shard[side] = {"rows": rows, "tabs": tabs, "d": d, "total": total}
         self._ws = None
 
     # ---- helpers --------------------------------------------------------------------------------------
@@ -158,14 +185,28 @@ class ShardedNeuMF(object):
             raise ValueError("batch touches {} distinct {} rows, more than max_local_rows={}".format(n_u, side, self.capacity))
         local = torch.div(wanted, self.world, rounding_mode="floor").to(torch.int32)
         tabs = self.shard[side]["tabs"]
-        parts = [self._engine_mod.gather_rows(tabs[k]["p"], local) for k in ("mlp", "gmf") if tabs[k] is not None]
-        rows = self._a2a(torch.cat(parts, dim=1) if len(parts) > 1 else parts[0], rc, sc, width=sum(p.shape[1] for p in parts))
         d = self.shard[side]["d"]
         mlp_name = self._engine_mod.K_USER if side == "user" else self._engine_mod.K_ITEM
-        e._tables[mlp_name][:n_u].copy_(rows[:, :d])
-        if self.f:
-            gmf_name = self._engine_mod.K_GMF_USER if side == "user" else self._engine_mod.K_GMF_ITEM
-            e._tables[gmf_name][:n_u].copy_(rows[:, d:])
+        gmf_name = self._engine_mod.K_GMF_USER if side == "user" else self._engine_mod.K_GMF_ITEM
+        if self.peer_gather:
+            # one kernel per table: every needed row straight from its owner's memory into the cache
+            import ctypes as C
+            nat = self._engine_mod.nat
+            ids32 = uniq_s.to(torch.int32)
+            for kind, name in (("mlp", mlp_name), ("gmf", gmf_name)):
+                if tabs[kind] is None:
+                    continue
+                t = tabs[kind]
+                nat.check(nat.lib.mr_gather_rows_sharded(C.c_void_p(t["peers"].data_ptr()), self.world, self.shard[side]["total"],
+                                                         int(t["p"].shape[1]), C.c_void_p(ids32.data_ptr()), n_u,
+                                                         C.c_void_p(e._tables[name].data_ptr()), e._stream()),
+                          "mr_gather_rows_sharded")
+        else:
+            parts = [self._engine_mod.gather_rows(tabs[k]["p"], local) for k in ("mlp", "gmf") if tabs[k] is not None]
+            rows = self._a2a(torch.cat(parts, dim=1) if len(parts) > 1 else parts[0], rc, sc, width=sum(p.shape[1] for p in parts))
+            e._tables[mlp_name][:n_u].copy_(rows[:, :d])
+            if self.f:
+                e._tables[gmf_name][:n_u].copy_(rows[:, d:])
         return {"slots": slots, "n": n_u, "send_counts": sc, "recv_counts": rc, "local": local}
 
     def _push_grads(self, side, route):
@@ -204,6 +245,8 @@ class ShardedNeuMF(object):
         dev = e.device
         users = self._engine_mod.as_device_i32(users, dev).long()
         items = self._engine_mod.as_device_i32(items, dev).long()
+        if self.peer_gather:
+            self._barrier_handle.barrier()  # every owner has applied the previous step before anyone reads its rows
         ru = self._fetch("user", users)
         ri = self._fetch("item", items)
         out = e.train_grads(ru["slots"], ri["slots"], labels, group=group, k=k, inv_global_batch=1.0 / float(global_rows),

@@ -88,6 +88,7 @@ SIGNATURES = {
     "mr_tc_probe": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mr_tc_gemm_selftest": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "mr_tc_rate": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "mr_gather_rows_sharded": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _i64, _vp, _vp]),
     "mr_sparse_rows_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "mr_sparse_rows_update": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i32, _f, _f, _f, _f,
                                         _f, _vp, _sz, _vp]),

@@ -39,5 +39,12 @@ if __name__ == "__main__":
                 wi = 2000 * 64 // (4 * writers)
                 m, mx = rate(N, nbuf=3, flags=flags, writers=writers, write_iters=wi)
                 print("N={} {} + {} writer warps storing 32 KB per stage: {:6.1f} {:6.1f}".format(N, name, writers, m, mx))
+    # a tcgen05.commit after every stage of 12 MMAs (flags bit 2), as the pipelined kernels issue them
+    for flags, name in ((4, "SS + commit per stage"), (5, "TS + commit per stage"), (6, "SS MN-major + commit"), (7, "TS, MN-major B + commit")):
+        m, mx = rate(128, nbuf=3, flags=flags)
+        print("N=128 {:28s}: {:6.1f} {:6.1f}".format(name, m, mx))
+    for flags, name in ((7 | 8, "TS MN-B commit, A at column 128"), (7 | 16, "TS MN-B commit, A ring of 4 stages"), (7 | 8 | 16, "TS MN-B commit, col 128 + ring")):
+        m, mx = rate(128, nbuf=3, flags=flags)
+        print("N=128 {:36s}: {:6.1f} {:6.1f}".format(name, m, mx))
     m, mx = rate(128, nbuf=3, flags=0, grid=1)
     print("single CTA, N=128 SS: {:.1f}".format(m))
