@@ -434,8 +434,14 @@ __global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restric
 
 int head_grid() { return sm_count() * 8; }
 
+// widths the pipelined specialisation is instantiated for: (mf_dim, last layer)
+static bool head_special_widths(const MrModel& m) {
+  const int f = m.mf_dim, Ln = m.L[m.n_layers - 1];
+  return (f == 64 && Ln == 64) || (f == 128 && Ln == 64);
+}
+
 bool head_supports_group(const MrModel& m, int group) {
-  return group >= 2 && group <= 8 && m.mf_dim + m.L[m.n_layers - 1] <= 128;
+  return group >= 2 && group <= 8 && (m.mf_dim + m.L[m.n_layers - 1] <= 128 || head_special_widths(m));
 }
 
 size_t head_partial_floats(const MrModel& m) { return (size_t)head_grid() * (m.mf_dim + m.L[m.n_layers - 1] + 2); }
@@ -469,22 +475,30 @@ int launch_head(const HeadArgs& a, cudaStream_t st) {
   const int grid = head_grid();
   if (a.group > 0) {
     if (!head_supports_group(m, a.group) || a.rows % a.group || a.row0 % a.group || p.user_div != 1) {
-      set_error("head kernel: grouped mode needs group <= 8, mf_dim + last width <= 128 and whole groups");
+      set_error("head kernel: grouped mode needs group <= 8, supported head widths and whole groups");
       return MR_ERR_INVALID;
     }
-    const bool special = a.labels != nullptr && m.mf_dim == 64 && m.L[m.n_layers - 1] == 64 && getenv("MR_HEAD_GENERIC") == nullptr;
-    if (special) {  // mf_dim = 64, last layer 64 (BASELINE configs[2]): the pipelined specialisation
-      switch (a.group) {
-        case 2: head_group_kernel<2, 2, 2><<<grid, kHeadThreads, 0, st>>>(p); break;
-        case 3: head_group_kernel<2, 2, 3><<<grid, kHeadThreads, 0, st>>>(p); break;
-        case 4: head_group_kernel<2, 2, 4><<<grid, kHeadThreads, 0, st>>>(p); break;
-        case 5: head_group_kernel<2, 2, 5><<<grid, kHeadThreads, 0, st>>>(p); break;
-        case 6: head_group_kernel<2, 2, 6><<<grid, kHeadThreads, 0, st>>>(p); break;
-        case 7: head_group_kernel<2, 2, 7><<<grid, kHeadThreads, 0, st>>>(p); break;
-        default: head_group_kernel<2, 2, 8><<<grid, kHeadThreads, 0, st>>>(p); break;
-      }
+    const bool wide = ncols > 128;  // only the specialisation covers these
+    const bool special = a.labels != nullptr && head_special_widths(m) && (wide || getenv("MR_HEAD_GENERIC") == nullptr);
+    if (special) {  // the pipelined specialisation: BASELINE configs[2] (f = 64) and configs[4] (f = 128), last layer 64
+#define MR_HEAD_GROUP(FQ_)                                                                                   \
+  switch (a.group) {                                                                                       \
+    case 2: head_group_kernel<FQ_, 2, 2><<<grid, kHeadThreads, 0, st>>>(p); break;                          \
+    case 3: head_group_kernel<FQ_, 2, 3><<<grid, kHeadThreads, 0, st>>>(p); break;                          \
+    case 4: head_group_kernel<FQ_, 2, 4><<<grid, kHeadThreads, 0, st>>>(p); break;                          \
+    case 5: head_group_kernel<FQ_, 2, 5><<<grid, kHeadThreads, 0, st>>>(p); break;                          \
+    case 6: head_group_kernel<FQ_, 2, 6><<<grid, kHeadThreads, 0, st>>>(p); break;                          \
+    case 7: head_group_kernel<FQ_, 2, 7><<<grid, kHeadThreads, 0, st>>>(p); break;                          \
+    default: head_group_kernel<FQ_, 2, 8><<<grid, kHeadThreads, 0, st>>>(p); break;                         \
+  }
+      if (m.mf_dim == 64) { MR_HEAD_GROUP(2) } else { MR_HEAD_GROUP(4) }
+#undef MR_HEAD_GROUP
       MR_LAUNCH_CHECK("head_group_kernel");
       return MR_OK;
+    }
+    if (wide) {
+      set_error("head kernel: grouped training with mf_dim + last width = %d needs labels", ncols);
+      return MR_ERR_INVALID;
     }
     switch (a.group) {
       case 2: head_kernel<4, 2, true><<<grid, kHeadThreads, 0, st>>>(p); break;

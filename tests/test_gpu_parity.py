@@ -55,6 +55,7 @@ CONFIGS = [
     (300, 200, [256, 128, 64], 64, 4, 41),   # ML-20M tower (tensor-core path)
     (300, 200, [128, 128, 32], 0, 4, 301),   # tensor-core path, no GMF, several tiles + a ragged tail
     (100, 100, [256, 256], 16, 2, 90),       # tensor-core path, one hidden layer, N = 256
+    (300, 200, [256, 128, 64], 128, 4, 37),  # BASELINE config 5 widths (embed dim 128): wide head
 ]
 
 
@@ -133,6 +134,8 @@ TRAIN_CASES = [
     (6, "adam", "sparse", [0, 0, 0]),
     (7, "adam", "dense", [0, 0.01, 0]),
     (8, "sgd", "dense", [0, 0]),
+    (9, "adam", "sparse", [0, 0, 0]),
+    (9, "sgd", "dense", [0, 0, 0]),
 ]
 
 
@@ -143,7 +146,7 @@ def test_train_steps_match_oracle(eng_mod, case):
 
 # the grouped-batch path (user-only work once per group) on the tensor-core configs, plus configs that are not
 # eligible for it (the flag must then be harmless): same oracle, same tolerances
-GROUPED_CASES = [c for c in TRAIN_CASES if c[0] in (4, 6, 7, 8)]
+GROUPED_CASES = [c for c in TRAIN_CASES if c[0] in (4, 6, 7, 8, 9)]
 
 
 @pytest.mark.parametrize("case", GROUPED_CASES, ids=lambda c: "cfg{}-{}-{}".format(c[0], c[1], c[2]))
