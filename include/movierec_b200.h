@@ -229,6 +229,16 @@ int mr_profile_end(float* phase_ms, int64_t* phase_count, int64_t* kernel_launch
 int mr_set_compute_path(int32_t path);
 int mr_uses_tensor_cores(const MrModel* model);
 
+/* Item-projected first layer (tensor-core path; replaces, like the rest of the tower, the Embedding + Dense of
+ * model.py:154-181).  The first Dense layer is linear before its ReLU, so its item half E_item . W1[item rows] is
+ * computed once per ITEM when a call has at least twice as many rows as there are items, and gathered per row; the
+ * backward pass sums dZ1 per item before the item half of its GEMMs.  Used by the grouped train step with dense
+ * gradient tables and by the fused ranking eval when layers_sizes[1] == layers_sizes[0] / 2 and there are at least
+ * three layers.  Thread-local selector: 0 = automatic (default), 1 = off, 2 = on wherever eligible.  Set it before
+ * the workspace-size queries: the per-item buffers are part of the workspace. */
+int mr_set_item_projection(int32_t mode);
+int mr_uses_item_projection(const MrModel* model, int64_t rows);
+
 /* Building blocks exposed for tests and for data-parallel callers. */
 /* Single-tile tcgen05 GEMM self-test: D[128 x N] = A . B^T on the tensor cores (TF32 or 3xTF32), A given
  * as [128 x K] (a_mn = 0) or [K x 128] (a_mn = 1), B as [N x K] (b_mn = 0) or [K x N] (b_mn = 1).

@@ -177,10 +177,35 @@ static bool tc_eligible(const MrModel& m) {
 
 static bool use_tc(const MrModel& m) { return g_path != 1 && tc_eligible(m); }
 
+// Item-projected first layer (grouped train step, fused ranking eval).  The first Dense layer is linear before its
+// ReLU, so E_item . W1[item rows] is a function of the item alone: with `rows` rows per step and num_items << rows
+// it is computed once per ITEM (Pi, one GEMM over the item table) and the per-row part of the layer becomes a
+// gather + add + ReLU.  Backward by the same linearity: dZ1 rows are segment-summed by item FIRST (the sorted
+// segmented reduction that already exists, fed dZ1 instead of dZ1 . W1i^T), then the item half of the backward
+// GEMM and of the weight gradient run on num_items rows instead of `rows`.  Same values up to summation order.
+// Needs L1 == d_i so that the staged item rows keep their width d_i + f, and dense gradient tables.
+static thread_local int g_item_proj = 0;  // 0 auto, 1 never, 2 whenever eligible
+
+static bool item_proj_ok(const MrModel& m, int64_t rows) {
+  static const bool off = getenv("MR_NO_ITEM_PROJECTION") != nullptr;
+  if (off || g_item_proj == 1 || g_path == 1 || !tc_eligible(m) || m.n_layers < 3) return false;
+  const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
+  if (d_i % 128 || d_i > 256 || m.L[1] != d_i) return false;
+  if (g_item_proj == 2) return true;
+  return 2 * (int64_t)m.num_items <= rows;  // three GEMMs over num_items rows replace three over `rows` rows
+}
+
 // Rows per launch of the tensor-core kernels: the whole batch up to 2^20 rows (persistent CTAs need many
 // tiles each to reach steady state; intermediates of 1M rows are ~1.5 GB of workspace), split evenly above.
+static int64_t sub_batch_cap(const char* env, int64_t dflt) {  // diagnostics: MR_*_SUB_BATCH_ROWS = 2^14 .. 2^20
+  const char* v = getenv(env);
+  if (v == nullptr) return dflt;
+  const long long r = atoll(v);
+  return r >= (1 << 14) && r <= (1 << 20) ? (int64_t)r : dflt;
+}
+
 static int64_t tc_sub_batch(int64_t B) {
-  const int64_t cap = (int64_t)1 << 20;
+  static const int64_t cap = sub_batch_cap("MR_TC_SUB_BATCH_ROWS", (int64_t)1 << 20);
   const int64_t parts = B <= cap ? 1 : (B + cap - 1) / cap;
   const int64_t sb = ((B < 1 ? 1 : B) + parts - 1) / parts;
   return (sb + 127) / 128 * 128;
@@ -200,6 +225,9 @@ struct TcWs {
   float* pack_bi;  // backward, item rows
   float* Zu;       // (sub-batch groups x L1): user half of the first layer + bias, one row per group
   float* S1;       // (sub-batch groups x L1): dZ[1] summed over the rows of each group
+  // item-projected first layer (item_proj_ok)
+  float* Pi;       // (num_items x L1): E_item . W1[item rows]
+  float* Si;       // (num_items x L1): dZ[1] summed over the rows of each item (train)
   size_t total;
 };
 
@@ -210,7 +238,7 @@ static bool tc_grouped_ok(const MrModel& m, int64_t B, int group) {
   const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
   if (d_u % 128 || d_i % 128 || d_u > 256 || d_i > 256) return false;
   if (B % group) return false;
-  const int64_t cap = (int64_t)1 << 20;
+  const int64_t cap = sub_batch_cap("MR_TC_SUB_BATCH_ROWS", (int64_t)1 << 20);
   const int64_t parts = B <= cap ? 1 : (B + cap - 1) / cap;
   if (parts > 1 && (tc_sub_batch(B) % group)) return false;  // sub-batch boundaries must not split a group
   return true;
@@ -238,6 +266,10 @@ static TcWs carve_tc(const MrModel& m, bool train, int64_t B, void* ws) {
     const int64_t sg = sb / 2 + 1;  // groups per sub-batch (group >= 2)
     t.Zu = cv.take<float>((size_t)sg * m.L[1]);
     t.S1 = cv.take<float>((size_t)sg * m.L[1]);
+    if (item_proj_ok(m, B)) {
+      t.Pi = cv.take<float>((size_t)m.num_items * m.L[1]);
+      t.Si = cv.take<float>((size_t)m.num_items * m.L[1]);
+    }
   }
   t.total = cv.off;
   return t;
@@ -271,6 +303,10 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     a.out = t.Zu;
     int rc = launch_tc_dense(a, st);
     if (rc != MR_OK) return rc;
+    if (t.Pi != nullptr) {  // item-projected first layer: H1 = relu(Pi[item] + Zu[group])
+      rc = launch_h1_from_projection(t.Pi, m.num_items, items, r0, r1 - r0, t.Zu, group, m.L[1], t.H[1], t.bits[1], st);
+      if (rc != MR_OK) return rc;
+    } else {
     TcDenseArgs b{};
     b.gather = true;
     b.item_tab = m.item_mlp;
@@ -291,6 +327,7 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     b.bits_out = t.bits[1];
     rc = launch_tc_dense(b, st);
     if (rc != MR_OK) return rc;
+    }
   }
   for (int l = group > 0 ? 2 : 1; l < m.n_layers; ++l) {
     TcDenseArgs a{};
@@ -317,6 +354,22 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     if (rc != MR_OK) return rc;
   }
   return MR_OK;
+}
+
+// Pi = E_item . W1[item rows] over the whole item table (pack_fi must hold the packed item rows of W[1]).
+static int tc_project_items(const MrModel& m, const TcWs& t, cudaStream_t st) {
+  const int d_u = m.L[0] / 2;
+  TcDenseArgs a{};
+  a.a_dense = m.item_mlp;
+  a.b_packed = t.pack_fi;
+  a.N = m.L[1];
+  a.K = m.L[0] - d_u;
+  a.rows = m.num_items;
+  a.row0 = 0;
+  a.epilogue = TC_EPI_BIAS_RELU;
+  a.linear = true;
+  a.out = t.Pi;
+  return launch_tc_dense(a, st);
 }
 
 struct TrainWs {
@@ -404,7 +457,7 @@ static int64_t eval_sub_batch(int group) {
   int64_t a = 128, b = group;
   while (b) { const int64_t t = a % b; a = b; b = t; }
   const int64_t l = (int64_t)128 / a * group;  // lcm(128, group)
-  const int64_t cap = (int64_t)1 << 20;
+  static const int64_t cap = sub_batch_cap("MR_EVAL_SUB_BATCH_ROWS", (int64_t)1 << 20);
   return l > cap ? 0 : cap / l * l;
 }
 
@@ -421,6 +474,7 @@ static TcWs carve_eval(const MrModel& m, int group, int64_t rows, void* ws) {
   t.pack_fu = cv.take<float>((size_t)2 * d_u * m.L[1]);
   t.pack_fi = cv.take<float>((size_t)2 * d_i * m.L[1]);
   t.Zu = cv.take<float>((size_t)(sb / group + 1) * m.L[1]);
+  if (item_proj_ok(m, rows)) t.Pi = cv.take<float>((size_t)m.num_items * m.L[1]);
   for (int l = 1; l < m.n_layers; ++l) {
     if (l >= 2) t.pack_f[l] = cv.take<float>((size_t)2 * m.L[l - 1] * m.L[l]);
     t.H[l] = cv.take<float>((size_t)sb * m.L[l]);
@@ -443,6 +497,11 @@ static int rank_eval_fused(const MrModel& m, const int32_t* users, const int32_t
   if (rc == MR_OK) rc = launch_pack_weights(m.W[1] + (size_t)d_u * m.L[1], d_i, m.L[1], 0, t.pack_fi, st);
   for (int l = 2; rc == MR_OK && l < m.n_layers; ++l) rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 0, t.pack_f[l], st);
   if (rc != MR_OK) return rc;
+  if (t.Pi != nullptr) {
+    prof_mark(MR_PHASE_TC_DENSE_FWD, st);
+    rc = tc_project_items(m, t, st);
+    if (rc != MR_OK) return rc;
+  }
   const int64_t sb = eval_sub_batch(group);
   for (int64_t r0 = 0; r0 < rows; r0 += sb) {
     const int64_t r1 = r0 + sb < rows ? r0 + sb : rows;
@@ -616,6 +675,8 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   // grouped batch (MR_TRAIN_USERS_GROUPED): user-only work once per group; the promise is checked on the device
   const bool grouped = (flags & MR_TRAIN_USERS_GROUPED) && use_tc(m) && tc_grouped_ok(m, B, group);
   const int gdiv = grouped ? group : 0;
+  // item-projected first layer: item half of the first layer once per item (see item_proj_ok)
+  const bool proj = grouped && opt->table_mode == MR_TABLES_DENSE && item_proj_ok(m, B);
   const int64_t n_user_rows = grouped ? B / group : B;  // staged user-gradient rows: one per group or one per row
   // stable sorts of the ids (keys of the segmented reductions below) on the side stream, under the tower
   // (phase timing then sees only the launch cost of this block on the main stream; MR_NO_SIDE_STREAM=1 keeps
@@ -632,7 +693,10 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     prof_mark(MR_PHASE_SORT, st);
     if (opt->table_mode == MR_TABLES_DENSE) {  // the gradient tables the segmented reductions write into
       MR_CUDA(cudaMemsetAsync(grads->user_mlp, 0, (size_t)m.num_users * d_u * sizeof(float), ss));
-      MR_CUDA(cudaMemsetAsync(grads->item_mlp, 0, (size_t)m.num_items * d_i * sizeof(float), ss));
+      if (proj)  // the per-item sums of dZ[1]; grads->item_mlp is then written whole by a GEMM on them
+        MR_CUDA(cudaMemsetAsync(carve_tc(m, true, B, t.tc_ws).Si, 0, (size_t)m.num_items * m.L[1] * sizeof(float), ss));
+      else
+        MR_CUDA(cudaMemsetAsync(grads->item_mlp, 0, (size_t)m.num_items * d_i * sizeof(float), ss));
       if (m.mf_dim > 0) {
         MR_CUDA(cudaMemsetAsync(grads->user_gmf, 0, (size_t)m.num_users * m.mf_dim * sizeof(float), ss));
         MR_CUDA(cudaMemsetAsync(grads->item_gmf, 0, (size_t)m.num_items * m.mf_dim * sizeof(float), ss));
@@ -657,6 +721,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     const int P = sm_count();  // rows of the partial buffer = CTAs of the weight-gradient kernel
     const int n = m.n_layers, f = m.mf_dim;
     TcWs tw = carve_tc(m, true, B, t.tc_ws);
+    if (!proj) tw.Pi = tw.Si = nullptr;
     MR_CUDA(cudaMemsetAsync(t.dense_partial, 0, (size_t)P * t.dense_stride * sizeof(float), st));
     MR_CUDA(cudaMemsetAsync(tw.head_partial, 0, head_partial_floats(m) * sizeof(float), st));
     for (int l = grouped ? 2 : 1; l < n; ++l) {
@@ -671,6 +736,11 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       if (rc == MR_OK) rc = launch_pack_weights(Wi, d_i, m.L[1], 0, tw.pack_fi, st);
       if (rc == MR_OK) rc = launch_pack_weights(Wu, d_u, m.L[1], 1, tw.pack_bu, st);
       if (rc == MR_OK) rc = launch_pack_weights(Wi, d_i, m.L[1], 1, tw.pack_bi, st);
+      if (rc != MR_OK) return rc;
+    }
+    if (proj) {
+      prof_mark(MR_PHASE_TC_DENSE_FWD, st);
+      rc = tc_project_items(m, tw, st);
       if (rc != MR_OK) return rc;
     }
     const int64_t sb = tc_sub_batch(B);
@@ -704,9 +774,13 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
           // first layer of a grouped batch: item half per row, user half per group on S1 = group sums of dZ[1]
           const int64_t ng = (r1 - r0) / group, g0 = r0 / group;
           prof_mark(MR_PHASE_MISC, st);
-          rc = launch_group_sum_rows(tw.dZ[1], ng, group, m.L[1], tw.S1, st);
+          if (proj)  // dZ[1] of these rows sits in the item staging rows (columns [0, L1), stride d_i + f)
+            rc = launch_group_sum_rows(t.stage_i + (size_t)r0 * (d_i + f), ng, group, m.L[1], tw.S1, st, d_i + f);
+          else
+            rc = launch_group_sum_rows(tw.dZ[1], ng, group, m.L[1], tw.S1, st);
           if (rc != MR_OK) return rc;
           prof_mark(MR_PHASE_TC_WGRAD, st);
+          if (!proj) {
           TcWgradArgs wi{};
           wi.gather = true;
           wi.item_tab = m.item_mlp;
@@ -724,6 +798,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
           wi.partial_stride = t.dense_stride;
           rc = launch_tc_wgrad(wi, st);
           if (rc != MR_OK) return rc;
+          }
           TcWgradArgs wu{};
           wu.gather = true;
           wu.user_tab = m.user_mlp;
@@ -738,11 +813,14 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
           wu.rows = ng;
           wu.row0 = g0;
           wu.dw_partial = t.dense_partial + (m.W[1] - m.dense);
-          wu.db_partial = nullptr;  // the bias gradient came with the item half (column sums of dZ[1])
+          // the bias gradient (column sums of dZ[1]) comes with the item half, or from the group sums when the
+          // item half runs per item
+          wu.db_partial = proj ? t.dense_partial + (m.b[1] - m.dense) : nullptr;
           wu.partial_stride = t.dense_stride;
           rc = launch_tc_wgrad(wu, st);
           if (rc != MR_OK) return rc;
           prof_mark(MR_PHASE_TC_DENSE_BWD, st);
+          if (!proj) {
           TcDenseArgs bi{};
           bi.a_dense = tw.dZ[1];
           bi.d_u = 0;  // every output column belongs to the item row
@@ -758,6 +836,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
           bi.si = d_i + f;
           rc = launch_tc_dense(bi, st);
           if (rc != MR_OK) return rc;
+          }
           TcDenseArgs bu{};
           bu.a_dense = tw.S1;
           bu.d_u = d_u;  // every output column belongs to the user row of the group
@@ -810,6 +889,10 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
           a.epilogue = TC_EPI_MASK;
           a.mask_bits = tw.bits[l - 1];
           a.out = tw.dZ[l - 1];
+          if (proj && l - 1 == 1) {  // dZ[1] goes straight into the item staging rows: the keys of its per-item sums
+            a.out = t.stage_i + (size_t)r0 * (d_i + f);
+            a.out_ld = d_i + f;
+          }
         } else {
           a.epilogue = TC_EPI_STAGE;
           a.stage_u = t.stage_u;
@@ -820,6 +903,48 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
         rc = launch_tc_dense(a, st);
         if (rc != MR_OK) return rc;
       }
+    }
+    if (proj) {
+      // item half of the first layer's backward on per-item sums: Si = segment sums of [dZ1 | GMF row gradient] by
+      // item (GMF part straight into its gradient table), then d E_item = Si . W1i^T and d W1i = E_item^T . Si
+      if (side != nullptr) MR_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+      RowUpdate ui{};
+      ui.mode = MR_TABLES_DENSE;
+      ui.optimizer = opt->optimizer;
+      ui.d0 = m.L[1];
+      ui.d1 = f;
+      ui.num_rows = m.num_items;
+      ui.g0 = tw.Si;
+      ui.g1 = grads->item_gmf;
+      prof_mark(MR_PHASE_SEGREDUCE, st);
+      rc = launch_segreduce(t.sorted_keys_i, t.sorted_index_i, B, t.stage_i, ui, t.seg_ws, t.seg_ws_bytes, st);
+      if (rc != MR_OK) return rc;
+      prof_mark(MR_PHASE_TC_DENSE_BWD, st);
+      TcDenseArgs bi{};
+      bi.a_dense = tw.Si;
+      bi.b_packed = tw.pack_bi;
+      bi.N = d_i;
+      bi.K = m.L[1];
+      bi.rows = m.num_items;
+      bi.row0 = 0;
+      bi.epilogue = TC_EPI_BIAS_RELU;
+      bi.linear = true;
+      bi.out = grads->item_mlp;
+      rc = launch_tc_dense(bi, st);
+      if (rc != MR_OK) return rc;
+      prof_mark(MR_PHASE_TC_WGRAD, st);
+      TcWgradArgs wi{};
+      wi.a_dense = m.item_mlp;
+      wi.z = tw.Si;
+      wi.Fa = d_i;
+      wi.Fb = m.L[1];
+      wi.rows = m.num_items;
+      wi.row0 = 0;
+      wi.dw_partial = t.dense_partial + (m.W[1] - m.dense) + (size_t)d_u * m.L[1];
+      wi.db_partial = nullptr;
+      wi.partial_stride = t.dense_stride;
+      rc = launch_tc_wgrad(wi, st);
+      if (rc != MR_OK) return rc;
     }
     prof_mark(MR_PHASE_MISC, st);
     rc = launch_head_reduce(m, tw.head_partial, t.dense_partial + (m.w_out - m.dense),
@@ -909,8 +1034,10 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   u.num_rows = m.num_items;
   u.p0 = m.item_mlp; u.m0 = opt->m_item_mlp; u.v0 = opt->v_item_mlp; u.g0 = grads->item_mlp;
   u.p1 = m.item_gmf; u.m1 = opt->m_item_gmf; u.v1 = opt->v_item_gmf; u.g1 = grads->item_gmf;
-  prof_mark(MR_PHASE_SEGREDUCE, st);
-  rc = launch_segreduce(t.sorted_keys_i, t.sorted_index_i, B, t.stage_i, u, t.seg_ws, t.seg_ws_bytes, st);
+  if (!proj) {  // (the item-projected step reduced the item rows before its per-item GEMMs)
+    prof_mark(MR_PHASE_SEGREDUCE, st);
+    rc = launch_segreduce(t.sorted_keys_i, t.sorted_index_i, B, t.stage_i, u, t.seg_ws, t.seg_ws_bytes, st);
+  }
   prof_mark(-1, st);
   return rc;
 }
@@ -1114,6 +1241,17 @@ int mr_set_compute_path(int32_t path) {
   MR_REQUIRE(path >= 0 && path <= 2, "compute path must be 0 (auto), 1 (SIMT) or 2 (tensor cores)");
   g_path = path;
   return MR_OK;
+}
+
+int mr_set_item_projection(int32_t mode) {
+  MR_REQUIRE(mode >= 0 && mode <= 2, "item projection mode must be 0 (auto), 1 (off) or 2 (on where eligible)");
+  g_item_proj = mode;
+  return MR_OK;
+}
+
+int mr_uses_item_projection(const MrModel* model, int64_t rows) {
+  if (model == nullptr || model->n_layers < 1 || model->n_layers > MR_MAX_LAYERS) return 0;
+  return item_proj_ok(*model, rows) ? 1 : 0;
 }
 
 int mr_uses_tensor_cores(const MrModel* model) {

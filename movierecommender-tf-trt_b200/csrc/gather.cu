@@ -91,15 +91,15 @@ int launch_gather_rows_sharded(const float* const* shards, int world, int64_t to
 // out[g] = sum_{j < group} in[g * group + j], rows of `width` floats, added in order j = 0, 1, ...
 // HBM-bound: (group + 1) * width * 4 bytes per group.
 __global__ void __launch_bounds__(256) group_sum_rows_kernel(const float* __restrict__ in, int64_t groups, int group,
-                                                             int width4, float* __restrict__ out) {
+                                                             int width4, int ld4, float* __restrict__ out) {
   const int64_t total = groups * width4;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t g = e / width4;
     const int c = (int)(e - g * width4);
-    const float4* src = reinterpret_cast<const float4*>(in) + g * group * width4 + c;
+    const float4* src = reinterpret_cast<const float4*>(in) + g * group * ld4 + c;
     float4 s = ld_stream4(reinterpret_cast<const float*>(src));
     for (int j = 1; j < group; ++j) {
-      const float4 v = ld_stream4(reinterpret_cast<const float*>(src + (int64_t)j * width4));
+      const float4 v = ld_stream4(reinterpret_cast<const float*>(src + (int64_t)j * ld4));
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     reinterpret_cast<float4*>(out)[e] = s;
@@ -127,14 +127,90 @@ static unsigned grid_for(int64_t work_items) {
   return (unsigned)(blocks < 1 ? 1 : blocks);
 }
 
-int launch_group_sum_rows(const float* in, int64_t groups, int group, int width, float* out, cudaStream_t st) {
+int launch_group_sum_rows(const float* in, int64_t groups, int group, int width, float* out, cudaStream_t st,
+                          int in_ld) {
   if (groups == 0) return MR_OK;
-  if (width % 4 || group < 1 || ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)) {
-    set_error("group_sum_rows: width=%d must be a multiple of 4 and the buffers 16-byte aligned", width);
+  if (in_ld <= 0) in_ld = width;
+  if (width % 4 || in_ld % 4 || in_ld < width || group < 1 ||
+      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)) {
+    set_error("group_sum_rows: width=%d / stride=%d must be multiples of 4 and the buffers 16-byte aligned", width, in_ld);
     return MR_ERR_INVALID;
   }
-  group_sum_rows_kernel<<<grid_for(groups * (width / 4)), 256, 0, st>>>(in, groups, group, width / 4, out);
+  group_sum_rows_kernel<<<grid_for(groups * (width / 4)), 256, 0, st>>>(in, groups, group, width / 4, in_ld / 4, out);
   MR_LAUNCH_CHECK("group_sum_rows_kernel");
+  return MR_OK;
+}
+
+// ---- item-projected first layer ------------------------------------------------------------------------------
+// The first Dense layer is linear before its ReLU, so its item half depends on the item alone:
+//   z1[r] = E_item[i_r] . W1[item rows] + (E_user[u_r] . W1[user rows] + b1) = Pi[i_r] + Zu[group of r].
+// When a step has many more rows than there are items (ML-20M shape: 1.3 M rows, 26,744 items) Pi is one small GEMM
+// over the item table and the per-row part of the layer is this gather: one warp per row, 128-bit loads of the
+// L2-resident Pi row and of the group's Zu row, ReLU, a coalesced store of H1 and the ReLU bits of the backward pass.
+// HBM-bound: 4 * width + width / 8 + 4 bytes written / read per row (Pi and Zu rows hit L2).
+template <int ROWS>
+__global__ void __launch_bounds__(256) h1_from_projection_kernel(const float* __restrict__ Pi, int32_t num_items,
+                                                                 const int32_t* __restrict__ items, int64_t row0,
+                                                                 int64_t rows, const float* __restrict__ Zu, int group,
+                                                                 int width, float* __restrict__ H1,
+                                                                 uint32_t* __restrict__ bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int words = width >> 5;
+  for (int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ROWS; base < rows; base += warps * ROWS) {
+    for (int c0 = 0; c0 < width; c0 += 128) {
+      const int col = c0 + 4 * lane;
+      const bool active = col < width;
+      float4 a[ROWS], z[ROWS];
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j) {
+        const int64_t r = base + j;
+        a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        z[j] = a[j];
+        if (r < rows && active) {
+          const int it = __ldg(items + row0 + r);
+          if ((unsigned)it < (unsigned)num_items) a[j] = ldg4(Pi + (size_t)it * width + col);  // bad ids: a zero row
+          z[j] = ldg4(Zu + (size_t)((uint32_t)r / (uint32_t)group) * width + col);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j) {
+        const int64_t r = base + j;
+        float4 v;
+        v.x = fmaxf(a[j].x + z[j].x, 0.f);
+        v.y = fmaxf(a[j].y + z[j].y, 0.f);
+        v.z = fmaxf(a[j].z + z[j].z, 0.f);
+        v.w = fmaxf(a[j].w + z[j].w, 0.f);
+        if (r < rows && active) *reinterpret_cast<float4*>(H1 + (size_t)r * width + col) = v;
+        if (bits != nullptr) {  // word q of a row = columns [32 q, 32 q + 32): the 4-bit pieces of lanes 8 q .. 8 q + 7
+          uint32_t w = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
+          w = active ? w << (4 * (lane & 7)) : 0u;
+          w |= __shfl_xor_sync(0xffffffffu, w, 1);
+          w |= __shfl_xor_sync(0xffffffffu, w, 2);
+          w |= __shfl_xor_sync(0xffffffffu, w, 4);
+          const int q = (c0 >> 5) + (lane >> 3);
+          if (r < rows && (lane & 7) == 0 && q < words) bits[(size_t)r * words + q] = w;
+        }
+      }
+    }
+  }
+}
+
+int launch_h1_from_projection(const float* Pi, int32_t num_items, const int32_t* items, int64_t row0, int64_t rows,
+                              const float* Zu, int group, int width, float* H1, uint32_t* bits, cudaStream_t st) {
+  if (rows == 0) return MR_OK;
+  if (width % 32 || width < 32 || group < 1 ||
+      ((reinterpret_cast<uintptr_t>(Pi) | reinterpret_cast<uintptr_t>(Zu) | reinterpret_cast<uintptr_t>(H1)) & 15)) {
+    set_error("h1_from_projection: width=%d must be a multiple of 32 and the buffers 16-byte aligned", width);
+    return MR_ERR_INVALID;
+  }
+  constexpr int kRows = 4;  // rows per warp in flight
+  int64_t blocks = (rows + 8 * kRows - 1) / (8 * kRows);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  h1_from_projection_kernel<kRows><<<(unsigned)blocks, 256, 0, st>>>(Pi, num_items, items, row0, rows, Zu, group, width,
+                                                                     H1, bits);
+  MR_LAUNCH_CHECK("h1_from_projection_kernel");
   return MR_OK;
 }
 

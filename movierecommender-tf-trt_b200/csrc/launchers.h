@@ -96,6 +96,7 @@ struct TcDenseArgs {
   const uint32_t* mask_bits;  // TC_EPI_MASK: ReLU bits written by the forward layer
   uint32_t* bits_out;         // TC_EPI_BIAS_RELU, optional
   float* out;
+  int32_t out_ld;             // row stride of `out` in floats (0 = N, a multiple of 4 otherwise)
   float* stage_u;
   float* stage_i;
   int32_t su, si;
@@ -158,8 +159,14 @@ int launch_gather_rows_sharded(const float* const* shards, int world, int64_t to
                                int64_t n, float* out, cudaStream_t st);
 
 // ---- grouped batches (gather.cu): one positive and its negatives share the user ----------------------------
-// out[g] = sum_{j < group} in[g * group + j]  (rows of `width` floats, width % 4 == 0), fixed order
-int launch_group_sum_rows(const float* in, int64_t groups, int group, int width, float* out, cudaStream_t st);
+// out[g] = sum_{j < group} in[g * group + j]  (rows of `width` floats, width % 4 == 0, input row stride in_ld
+// floats, 0 = width), fixed order
+int launch_group_sum_rows(const float* in, int64_t groups, int group, int width, float* out, cudaStream_t st,
+                          int in_ld = 0);
+// Item-projected first layer: H1[r] = relu(Pi[items[row0 + r]] + Zu[r / group]) and its ReLU bits; Pi holds
+// E_item . W1[item rows] for every item (width floats per row), Zu the user half + bias of each group.
+int launch_h1_from_projection(const float* Pi, int32_t num_items, const int32_t* items, int64_t row0, int64_t rows,
+                              const float* Zu, int group, int width, float* H1, uint32_t* bits, cudaStream_t st);
 // out[g] = ids[g * group]
 int launch_group_heads(const int32_t* ids, int64_t groups, int group, int32_t* out, cudaStream_t st);
 // *flag = 1 when some ids[r] != ids[r - r % group]

@@ -67,7 +67,8 @@ struct TcDenseParams {
   int32_t relu;          // EPI_BIAS_RELU: apply the ReLU (0 = linear output)
   const uint32_t* mask_bits;  // EPI_MASK: [rows x N/32] ReLU bits of the previous layer's output, launch-local rows
   uint32_t* bits_out;    // EPI_BIAS_RELU, optional: [rows x N/32] bits (h > 0) for the backward pass
-  float* out;            // EPI_BIAS_RELU / EPI_MASK: [rows x N], launch-local rows
+  float* out;            // EPI_BIAS_RELU / EPI_MASK: [rows x N], launch-local rows, row stride out_ld floats
+  int32_t out_ld;
   float* stage_u;        // EPI_STAGE: global rows, widths su / si, split at d_u
   float* stage_i;
   int32_t su, si;
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
               dst = (c < p.d_u) ? p.stage_u + (size_t)(p.row0 + lr) * p.su + c
                                 : p.stage_i + (size_t)(p.row0 + lr) * p.si + (c - p.d_u);
             } else {
-              dst = p.out + (size_t)lr * N + c;
+              dst = p.out + (size_t)lr * p.out_ld + c;
             }
             *reinterpret_cast<float4*>(dst) = x;
           }
@@ -475,6 +476,7 @@ int launch_tc_dense(const TcDenseArgs& a, cudaStream_t st) {
   p.mask_bits = a.mask_bits;
   p.bits_out = a.bits_out;
   p.out = a.out;
+  p.out_ld = a.out_ld > 0 ? a.out_ld : a.N;
   p.stage_u = a.stage_u;
   p.stage_i = a.stage_i;
   p.su = a.su;

@@ -257,6 +257,10 @@ class NeuMFEngine(object):
     def uses_tensor_cores(self):
         return bool(nat.lib.mr_uses_tensor_cores(C.byref(self._model)))
 
+    def uses_item_projection(self, rows):
+        """True when a call over `rows` rows computes the item half of the first layer once per item."""
+        return bool(nat.lib.mr_uses_item_projection(C.byref(self._model), int(rows)))
+
     def _workspace(self, nbytes):
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
@@ -381,6 +385,13 @@ def set_compute_path(path):
     """'auto' (tensor cores where the layer widths allow, else the SIMT kernel), 'simt' or 'tc'."""
     code = {"auto": 0, "simt": 1, "tc": 2}[path]
     nat.check(nat.lib.mr_set_compute_path(code), "mr_set_compute_path")
+
+
+def set_item_projection(mode):
+    """Item half of the first layer once per item instead of once per row: 'auto' (when a call has at least twice
+    as many rows as there are items), 'off' or 'on' (wherever the model is eligible)."""
+    code = {"auto": 0, "off": 1, "on": 2}[mode]
+    nat.check(nat.lib.mr_set_item_projection(code), "mr_set_item_projection")
 
 
 def rank_scores(scores, group, k, label_col=None, want_rank=True, device=None):

@@ -331,6 +331,128 @@ def test_out_of_range_ids_are_flagged(eng_mod):
     assert out[4] != 0
 
 
+# ---- item-projected first layer: E_item . W1[item rows] once per item, per-item sums of dZ1 in the backward pass ----
+
+PROJECTED_CASES = [
+    # (num_users, num_items, layers, mf_dim, negs, groups), optimizer, l2, selector
+    ((300, 200, [256, 128, 64], 64, 4, 41), "adam", [0, 0, 0], "on"),        # fewer rows than 2 x items: forced
+    ((300, 60, [256, 128, 64], 64, 4, 301), "adam", [0, 0.01, 0], "auto"),   # several tiles + ragged tail, Pi < 1 tile
+    ((300, 200, [256, 128, 64], 128, 4, 37), "sgd", [0.001, 0, 0], "on"),    # BASELINE config 5 widths, table l2
+    ((500, 130, [256, 128, 128, 32], 0, 1, 700), "adam", [0, 0, 0, 0], "auto"),  # no GMF, 4 layers, groups of 2
+]
+
+
+@pytest.mark.parametrize("case", PROJECTED_CASES, ids=lambda c: "ni{}-f{}-{}-{}".format(c[0][1], c[0][3], c[1], c[3]))
+def test_item_projected_train_steps_match_oracle(eng_mod, case):
+    (nu, ni, L, f, negs, groups), opt, l2, selector = case
+    rng = np.random.default_rng(300 + ni)
+    params = {"layers_sizes": L, "layers_l2reg": l2, "optimizer": opt, "lr": 0.001, "beta_1": 0.9, "beta_2": 0.999,
+              "num_negs_per_pos": negs, "k": 2}
+    eng_mod.set_item_projection(selector)
+    try:
+        eng = eng_mod.NeuMFEngine(nu, ni, L, l2, mf_dim=f, optimizer=opt, lr=0.001, table_mode="dense", seed=11)
+        assert eng.uses_tensor_cores() and eng.uses_item_projection(groups * (negs + 1))
+        w = eng.get_weights()
+        st = o.new_opt_state(w)
+        for step in range(3):
+            users, items, y = make_batch(rng, nu, ni, groups, negs)
+            if step == 1:
+                items[: len(items) // 2] = items[0]  # one hot item: a segment spanning many chunks of the reduction
+            B = len(y)
+            g = o.backward(w, o.forward(w, users, items), y, None, l2)
+            out = eng.train_step(users, items, y, group=negs + 1, k=2, grouped=True).cpu().numpy().astype(np.float64)
+            assert out[4] == 0
+            for name, (off, shape) in eng._dense_slices.items():
+                got = eng.g_dense[off:off + int(np.prod(shape))].cpu().numpy().reshape(shape)
+                rel_close(got, g[name].reshape(shape), rtol=2e-5, what="grad {} step {}".format(name, step))
+            for name, t in eng.g_tables.items():
+                want = g[name] - (2.0 * l2[0]) * w[name] if l2[0] else g[name]
+                rel_close(t.cpu().numpy(), want, rtol=2e-5, what="table grad {} step {}".format(name, step))
+            loss, hr, dcg = o.train_step(w, st, users, items, y, params, adam_mode="dense")
+            got_loss = out[0] / B + out[3]
+            assert abs(got_loss - loss) <= 2e-5 * max(abs(loss), 1e-3), (got_loss, loss)
+            G = B // (negs + 1)
+            assert abs(out[1] / G - hr) <= 1e-3 and abs(out[2] / G - dcg) <= 1e-3
+            got = eng.get_weights()
+            # tolerances as in _train_steps_vs_oracle, except for Adam's amplification term: here the bias gradient of
+            # the first layer is summed per group first, then over groups (the oracle sums rows), and a near-cancelling
+            # entry (|g| ~ 1e-6, both sums within 5e-9 of each other, i.e. 5e-6 of the tensor's scale -- checked above)
+            # moves Adam's normalised update g / (|g| + eps) by up to ~1e-3 of lr
+            for k in w:
+                rel_close(got[k], w[k], rtol=RTOL * (step + 1), atol=(1e-3 if opt == "adam" else 1e-4) * 0.001 * (step + 1),
+                          what="weight {} after step {}".format(k, step + 1))
+    finally:
+        eng_mod.set_item_projection("auto")
+
+
+def test_item_projection_on_and_off_agree_and_are_deterministic(eng_mod):
+    """Zipf-hot users and items, 30,000 rows over 3,000 items (the automatic choice projects): the per-item launch
+    sequence against the per-row one, and against itself."""
+    nu, ni, L, f, negs, groups = 5000, 3000, [256, 128, 64], 64, 4, 6000
+    runs = {}
+    try:
+        for tag, selector in (("off", "off"), ("on", "auto"), ("again", "auto")):
+            eng_mod.set_item_projection(selector)
+            rng = np.random.default_rng(23)
+            eng = eng_mod.NeuMFEngine(nu, ni, L, [0, 0, 0], mf_dim=f, table_mode="dense", optimizer="sgd", lr=0.5, seed=6)
+            assert eng.uses_item_projection(groups * (negs + 1)) == (selector != "off")
+            outs = []
+            for _ in range(3):
+                users = np.repeat(np.minimum(rng.zipf(1.3, groups) - 1, nu - 1), negs + 1)
+                items = np.minimum(rng.zipf(1.2, groups * (negs + 1)) - 1, ni - 1)
+                y = np.tile([0] * negs + [1], groups).astype(np.float32)
+                outs.append(eng.train_step(users, items, y, group=negs + 1, k=3, grouped=True).cpu().numpy())
+            runs[tag] = (eng.get_weights(), outs)
+    finally:
+        eng_mod.set_item_projection("auto")
+    for a, b in zip(runs["off"][1], runs["on"][1]):
+        assert abs(a[0] - b[0]) <= 1e-5 * abs(a[0]) and a[1] == b[1] and a[4] == 0 and b[4] == 0
+    for k in runs["off"][0]:  # SGD at lr 0.5 over three steps: see test_grouped_and_ungrouped_steps_agree
+        rel_close(runs["on"][0][k], runs["off"][0][k], rtol=1e-4, what="projected vs per-row " + k)
+        assert np.array_equal(runs["on"][0][k], runs["again"][0][k]), k
+    for a, b in zip(runs["on"][1], runs["again"][1]):
+        assert np.array_equal(a, b)
+
+
+def test_item_projected_rank_eval_matches_oracle(eng_mod):
+    nu, ni, L, f = 300, 500, [256, 128, 64], 64
+    rng = np.random.default_rng(14)
+    eng = eng_mod.NeuMFEngine(nu, ni, L, [0] * 3, mf_dim=f, seed=5)
+    w = eng.get_weights()
+    G, group, k = 257, 100, 10
+    users = rng.integers(0, nu, G)
+    items = rng.integers(0, ni, G * group)
+    items[5 * group:6 * group] = items[5 * group]
+    assert eng.uses_item_projection(G * group)
+    hr_o, dcg_o, pos_o, p_o = o.evaluate_groups(w, users, items, group, k)
+    got = {}
+    try:
+        for selector in ("auto", "off"):
+            eng_mod.set_item_projection(selector)
+            pos, sums, rank, probs = eng.rank_eval(users, items, group, k, want_rank=True, want_probs=True)
+            p = probs.cpu().numpy()
+            rel_close(p, p_o, what="eval probs, item projection " + selector)
+            np.testing.assert_array_equal(pos.cpu().numpy(), o.positive_positions(p, group))
+            np.testing.assert_array_equal(rank.cpu().numpy(), o.rank_groups(p, group))
+            assert pos.cpu().numpy()[5] == group - 1
+            s = sums.cpu().numpy()
+            assert abs(s[0] / G - hr_o) <= 1e-3 and abs(s[1] / G - dcg_o) <= 1e-3
+            got[selector] = p
+    finally:
+        eng_mod.set_item_projection("auto")
+    rel_close(got["auto"], got["off"], what="eval probs projected vs per-row")
+
+
+def test_item_projection_treats_bad_item_ids_like_the_per_row_path(eng_mod):
+    nu, ni, L, f, negs = 300, 40, [256, 128, 64], 64, 4
+    rng = np.random.default_rng(3)
+    users, items, y = make_batch(rng, nu, ni, 64, negs)
+    items[17] = ni + 5
+    eng = eng_mod.NeuMFEngine(nu, ni, L, [0, 0, 0], mf_dim=f, seed=2)
+    assert eng.uses_item_projection(len(y))
+    assert int(eng.train_step(users, items, y, group=negs + 1, k=3, grouped=True).cpu().numpy()[4]) & 1
+
+
 # ---- ranking ------------------------------------------------------------------------------------
 
 def test_rank_scores_reference_vectors(eng_mod, golden_dir):
