@@ -134,7 +134,7 @@ PHASE_KERNELS = {
 }
 
 
-def phase_interface_bytes(wl, rows, grouped=False, projected=False):
+def phase_interface_bytes(wl, rows, grouped=False, projected=False, user_projected=False):
     """Bytes each phase must move per step GIVEN its interface (inputs read once, outputs written once) --
     the per-kernel roofline numerator.  The SURVEY 8(d) whole-step algorithmic figure (which charges no
     intermediate) is reported separately as step_roofline.  grouped: the launch sequence for grouped batches
@@ -153,12 +153,13 @@ def phase_interface_bytes(wl, rows, grouped=False, projected=False):
             # item half of the first layer once per ITEM: Pi = E_item . W1i over the item table, per row a gather of
             # the (L2-resident) Pi row + the group's Zu row -> H1 and its ReLU bits; backward on per-item sums of dZ1
             ni = wl["num_items"]
+            nu = wl["num_users"] if user_projected else G  # rows of the user-half GEMMs: users, or groups
             return {
-                "tc_dense_fwd": ni * 4 * (d_i + L1) + G * 4 * (d_u + L1) + rows * (4 + 4 * L1 + L1 // 8) + G * 4 * L1
+                "tc_dense_fwd": ni * 4 * (d_i + L1) + nu * 4 * (d_u + L1) + rows * (4 + 4 * L1 + L1 // 8) + G * 4 * L1
                                 + rows * sum(4 * (a + b) for a, b in later),
                 "head": rows * (8 * L[-1] + 8 * f + 16) + G * (8 * f + 4),
-                "tc_wgrad": ni * 4 * (d_i + L1) + G * (4 + 4 * (d_u + L1)) + rows * sum(4 * (a + b) for a, b in later),
-                "tc_dense_bwd": rows * sum(4 * (a + b) + 4 * a for a, b in later) + ni * 4 * (L1 + d_i) + G * 4 * (L1 + d_u),
+                "tc_wgrad": ni * 4 * (d_i + L1) + nu * (4 + 4 * (d_u + L1)) + rows * sum(4 * (a + b) for a, b in later),
+                "tc_dense_bwd": rows * sum(4 * (a + b) + 4 * a for a, b in later) + ni * 4 * (L1 + d_i) + nu * 4 * (L1 + d_u),
                 "misc": rows * 4 * L1 + G * 4 * L1,
                 "segreduce": G * 2 * (4 * dU + 8) + rows * 2 * (4 * dI + 8),
                 "sort": (G + rows) * 2 * 16,
@@ -471,7 +472,8 @@ def run_gpu(args, wl):
     step_ms = ms_total / args.steps
     grouped_seq = bool(eng.uses_tensor_cores()) and wl["mf_dim"] + wl["layers"][-1] <= 128
     projected_seq = grouped_seq and bool(eng.uses_item_projection(rows))
-    pbytes = phase_interface_bytes(wl, rows, grouped=grouped_seq, projected=projected_seq)
+    uprojected_seq = projected_seq and bool(eng.uses_user_projection(rows, wl["negs"] + 1))
+    pbytes = phase_interface_bytes(wl, rows, grouped=grouped_seq, projected=projected_seq, user_projected=uprojected_seq)
     phase_table = {}
     for name, (ms, cnt) in phases.items():
         if not cnt:
@@ -508,7 +510,7 @@ def run_gpu(args, wl):
                 "steps": e2e_steps, "api": "MovierecModel.model.train_on_batch([x_users, x_items], y) on pinned host arrays"
                 if dp is None else "DataParallelNeuMF.train_step on pinned host arrays"},
         "gpu_launches": launches,
-        "launch_sequence": {"grouped": grouped_seq, "item_projection": projected_seq},
+        "launch_sequence": {"grouped": grouped_seq, "item_projection": projected_seq, "user_projection": uprojected_seq},
         "roofline": {"bound": "hbm", "kernel": PHASE_KERNELS.get(dom, dom), "phase": dom,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_kind": peak_kind, "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_avg_ms,

@@ -238,6 +238,9 @@ int mr_uses_tensor_cores(const MrModel* model);
  * the workspace-size queries: the per-item buffers are part of the workspace. */
 int mr_set_item_projection(int32_t mode);
 int mr_uses_item_projection(const MrModel* model, int64_t rows);
+/* The train step does the same for the user half (E_user . W1[user rows] + b1 once per user, per-user sums of the
+ * group sums of dZ1) when, in addition, there are no more users than the step has groups. */
+int mr_uses_user_projection(const MrModel* model, int64_t rows, int32_t group);
 
 /* Building blocks exposed for tests and for data-parallel callers. */
 /* Single-tile tcgen05 GEMM self-test: D[128 x N] = A . B^T on the tensor cores (TF32 or 3xTF32), A given

@@ -195,6 +195,16 @@ static bool item_proj_ok(const MrModel& m, int64_t rows) {
   return 2 * (int64_t)m.num_items <= rows;  // three GEMMs over num_items rows replace three over `rows` rows
 }
 
+// The same for the user half (train step): with no more users than a step has groups, E_user . W1[user rows] + b1 is
+// computed once per USER (Pu), and the group sums of dZ1 are segment-summed by user before the user half of the
+// backward GEMM and of the weight gradient.  Needs the item projection and L1 == d_u.
+static bool user_proj_ok(const MrModel& m, int64_t rows, int group) {
+  if (!item_proj_ok(m, rows) || group < 2) return false;
+  static const bool off = getenv("MR_NO_USER_PROJECTION") != nullptr;
+  if (off || m.L[1] != m.L[0] / 2) return false;
+  return g_item_proj == 2 || (int64_t)m.num_users <= rows / group;
+}
+
 // Rows per launch of the tensor-core kernels: the whole batch up to 2^20 rows (persistent CTAs need many
 // tiles each to reach steady state; intermediates of 1M rows are ~1.5 GB of workspace), split evenly above.
 static int64_t sub_batch_cap(const char* env, int64_t dflt) {  // diagnostics: MR_*_SUB_BATCH_ROWS = 2^14 .. 2^20
@@ -228,6 +238,8 @@ struct TcWs {
   // item-projected first layer (item_proj_ok)
   float* Pi;       // (num_items x L1): E_item . W1[item rows]
   float* Si;       // (num_items x L1): dZ[1] summed over the rows of each item (train)
+  float* Pu;       // (num_users x L1): E_user . W1[user rows] + b1 (train, user_proj_ok)
+  float* Su;       // (num_users x L1): dZ[1] summed over the rows of each user (train)
   size_t total;
 };
 
@@ -269,6 +281,10 @@ static TcWs carve_tc(const MrModel& m, bool train, int64_t B, void* ws) {
     if (item_proj_ok(m, B)) {
       t.Pi = cv.take<float>((size_t)m.num_items * m.L[1]);
       t.Si = cv.take<float>((size_t)m.num_items * m.L[1]);
+      if (m.L[1] == d_u) {  // user projection: decided per call (it depends on the group size)
+        t.Pu = cv.take<float>((size_t)m.num_users * m.L[1]);
+        t.Su = cv.take<float>((size_t)m.num_users * m.L[1]);
+      }
     }
   }
   t.total = cv.off;
@@ -283,6 +299,11 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     // grouped batch: Zu = E_user[user of the group] . W1[user rows] + b1 once per group, then
     // H1 = relu(E_item[item] . W1[item rows] + Zu[row / group]) per row
     const int d_i = m.L[0] - d_u;
+    if (t.Pu != nullptr) {  // user- and item-projected first layer: H1 = relu(Pi[item] + Pu[user])
+      const int rc = launch_h1_from_projection(t.Pi, m.num_items, items, r0, r1 - r0, t.Pu, group, users, m.num_users, m.L[1],
+                                               t.H[1], t.bits[1], st);
+      if (rc != MR_OK) return rc;
+    } else {
     TcDenseArgs a{};
     a.gather = true;
     a.user_tab = m.user_mlp;
@@ -304,7 +325,8 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     int rc = launch_tc_dense(a, st);
     if (rc != MR_OK) return rc;
     if (t.Pi != nullptr) {  // item-projected first layer: H1 = relu(Pi[item] + Zu[group])
-      rc = launch_h1_from_projection(t.Pi, m.num_items, items, r0, r1 - r0, t.Zu, group, m.L[1], t.H[1], t.bits[1], st);
+      rc = launch_h1_from_projection(t.Pi, m.num_items, items, r0, r1 - r0, t.Zu, group, nullptr, 0, m.L[1], t.H[1],
+                                     t.bits[1], st);
       if (rc != MR_OK) return rc;
     } else {
     TcDenseArgs b{};
@@ -327,6 +349,7 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     b.bits_out = t.bits[1];
     rc = launch_tc_dense(b, st);
     if (rc != MR_OK) return rc;
+    }
     }
   }
   for (int l = group > 0 ? 2 : 1; l < m.n_layers; ++l) {
@@ -369,6 +392,22 @@ static int tc_project_items(const MrModel& m, const TcWs& t, cudaStream_t st) {
   a.epilogue = TC_EPI_BIAS_RELU;
   a.linear = true;
   a.out = t.Pi;
+  return launch_tc_dense(a, st);
+}
+
+// Pu = E_user . W1[user rows] + b1 over the whole user table (pack_fu must hold the packed user rows of W[1]).
+static int tc_project_users(const MrModel& m, const TcWs& t, cudaStream_t st) {
+  TcDenseArgs a{};
+  a.a_dense = m.user_mlp;
+  a.b_packed = t.pack_fu;
+  a.N = m.L[1];
+  a.K = m.L[0] / 2;
+  a.rows = m.num_users;
+  a.row0 = 0;
+  a.epilogue = TC_EPI_BIAS_RELU;
+  a.bias = m.b[1];
+  a.linear = true;
+  a.out = t.Pu;
   return launch_tc_dense(a, st);
 }
 
@@ -677,6 +716,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   const int gdiv = grouped ? group : 0;
   // item-projected first layer: item half of the first layer once per item (see item_proj_ok)
   const bool proj = grouped && opt->table_mode == MR_TABLES_DENSE && item_proj_ok(m, B);
+  const bool uproj = proj && user_proj_ok(m, B, group);
   const int64_t n_user_rows = grouped ? B / group : B;  // staged user-gradient rows: one per group or one per row
   // stable sorts of the ids (keys of the segmented reductions below) on the side stream, under the tower
   // (phase timing then sees only the launch cost of this block on the main stream; MR_NO_SIDE_STREAM=1 keeps
@@ -692,7 +732,10 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     }
     prof_mark(MR_PHASE_SORT, st);
     if (opt->table_mode == MR_TABLES_DENSE) {  // the gradient tables the segmented reductions write into
-      MR_CUDA(cudaMemsetAsync(grads->user_mlp, 0, (size_t)m.num_users * d_u * sizeof(float), ss));
+      if (uproj)
+        MR_CUDA(cudaMemsetAsync(carve_tc(m, true, B, t.tc_ws).Su, 0, (size_t)m.num_users * m.L[1] * sizeof(float), ss));
+      else
+        MR_CUDA(cudaMemsetAsync(grads->user_mlp, 0, (size_t)m.num_users * d_u * sizeof(float), ss));
       if (proj)  // the per-item sums of dZ[1]; grads->item_mlp is then written whole by a GEMM on them
         MR_CUDA(cudaMemsetAsync(carve_tc(m, true, B, t.tc_ws).Si, 0, (size_t)m.num_items * m.L[1] * sizeof(float), ss));
       else
@@ -722,6 +765,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     const int n = m.n_layers, f = m.mf_dim;
     TcWs tw = carve_tc(m, true, B, t.tc_ws);
     if (!proj) tw.Pi = tw.Si = nullptr;
+    if (!uproj) tw.Pu = tw.Su = nullptr;
     MR_CUDA(cudaMemsetAsync(t.dense_partial, 0, (size_t)P * t.dense_stride * sizeof(float), st));
     MR_CUDA(cudaMemsetAsync(tw.head_partial, 0, head_partial_floats(m) * sizeof(float), st));
     for (int l = grouped ? 2 : 1; l < n; ++l) {
@@ -741,6 +785,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     if (proj) {
       prof_mark(MR_PHASE_TC_DENSE_FWD, st);
       rc = tc_project_items(m, tw, st);
+      if (rc == MR_OK && uproj) rc = tc_project_users(m, tw, st);
       if (rc != MR_OK) return rc;
     }
     const int64_t sb = tc_sub_batch(B);
@@ -774,7 +819,10 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
           // first layer of a grouped batch: item half per row, user half per group on S1 = group sums of dZ[1]
           const int64_t ng = (r1 - r0) / group, g0 = r0 / group;
           prof_mark(MR_PHASE_MISC, st);
-          if (proj)  // dZ[1] of these rows sits in the item staging rows (columns [0, L1), stride d_i + f)
+          if (uproj)  // ... and their group sums go to the user staging rows: the user half runs on per-user sums
+            rc = launch_group_sum_rows(t.stage_i + (size_t)r0 * (d_i + f), ng, group, m.L[1],
+                                       t.stage_u + (size_t)g0 * (d_u + f), st, d_i + f, d_u + f);
+          else if (proj)  // dZ[1] of these rows sits in the item staging rows (columns [0, L1), stride d_i + f)
             rc = launch_group_sum_rows(t.stage_i + (size_t)r0 * (d_i + f), ng, group, m.L[1], tw.S1, st, d_i + f);
           else
             rc = launch_group_sum_rows(tw.dZ[1], ng, group, m.L[1], tw.S1, st);
@@ -799,6 +847,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
           rc = launch_tc_wgrad(wi, st);
           if (rc != MR_OK) return rc;
           }
+          if (uproj) continue;
           TcWgradArgs wu{};
           wu.gather = true;
           wu.user_tab = m.user_mlp;
@@ -919,6 +968,19 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       prof_mark(MR_PHASE_SEGREDUCE, st);
       rc = launch_segreduce(t.sorted_keys_i, t.sorted_index_i, B, t.stage_i, ui, t.seg_ws, t.seg_ws_bytes, st);
       if (rc != MR_OK) return rc;
+      if (uproj) {  // per-user sums of [group sums of dZ1 | GMF row gradient]
+        RowUpdate uu{};
+        uu.mode = MR_TABLES_DENSE;
+        uu.optimizer = opt->optimizer;
+        uu.d0 = m.L[1];
+        uu.d1 = f;
+        uu.num_rows = m.num_users;
+        uu.g0 = tw.Su;
+        uu.g1 = grads->user_gmf;
+        prof_mark(MR_PHASE_SEGREDUCE, st);
+        rc = launch_segreduce(t.sorted_keys, t.sorted_index, n_user_rows, t.stage_u, uu, t.seg_ws, t.seg_ws_bytes, st);
+        if (rc != MR_OK) return rc;
+      }
       prof_mark(MR_PHASE_TC_DENSE_BWD, st);
       TcDenseArgs bi{};
       bi.a_dense = tw.Si;
@@ -945,6 +1007,34 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       wi.partial_stride = t.dense_stride;
       rc = launch_tc_wgrad(wi, st);
       if (rc != MR_OK) return rc;
+      if (uproj) {  // d E_user = Su . W1u^T, d W1u = E_user^T . Su, d b1 = column sums of Su
+        prof_mark(MR_PHASE_TC_DENSE_BWD, st);
+        TcDenseArgs bu{};
+        bu.a_dense = tw.Su;
+        bu.b_packed = tw.pack_bu;
+        bu.N = d_u;
+        bu.K = m.L[1];
+        bu.rows = m.num_users;
+        bu.row0 = 0;
+        bu.epilogue = TC_EPI_BIAS_RELU;
+        bu.linear = true;
+        bu.out = grads->user_mlp;
+        rc = launch_tc_dense(bu, st);
+        if (rc != MR_OK) return rc;
+        prof_mark(MR_PHASE_TC_WGRAD, st);
+        TcWgradArgs wu{};
+        wu.a_dense = m.user_mlp;
+        wu.z = tw.Su;
+        wu.Fa = d_u;
+        wu.Fb = m.L[1];
+        wu.rows = m.num_users;
+        wu.row0 = 0;
+        wu.dw_partial = t.dense_partial + (m.W[1] - m.dense);
+        wu.db_partial = t.dense_partial + (m.b[1] - m.dense);
+        wu.partial_stride = t.dense_stride;
+        rc = launch_tc_wgrad(wu, st);
+        if (rc != MR_OK) return rc;
+      }
     }
     prof_mark(MR_PHASE_MISC, st);
     rc = launch_head_reduce(m, tw.head_partial, t.dense_partial + (m.w_out - m.dense),
@@ -1026,9 +1116,11 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   u.num_rows = m.num_users;
   u.p0 = m.user_mlp; u.m0 = opt->m_user_mlp; u.v0 = opt->v_user_mlp; u.g0 = grads->user_mlp;
   u.p1 = m.user_gmf; u.m1 = opt->m_user_gmf; u.v1 = opt->v_user_gmf; u.g1 = grads->user_gmf;
-  prof_mark(MR_PHASE_SEGREDUCE, st);
-  rc = launch_segreduce(t.sorted_keys, t.sorted_index, n_user_rows, t.stage_u, u, t.seg_ws, t.seg_ws_bytes, st);
-  if (rc != MR_OK) return rc;
+  if (!uproj) {
+    prof_mark(MR_PHASE_SEGREDUCE, st);
+    rc = launch_segreduce(t.sorted_keys, t.sorted_index, n_user_rows, t.stage_u, u, t.seg_ws, t.seg_ws_bytes, st);
+    if (rc != MR_OK) return rc;
+  }
   // items
   u.d0 = d_i;
   u.num_rows = m.num_items;
@@ -1252,6 +1344,11 @@ int mr_set_item_projection(int32_t mode) {
 int mr_uses_item_projection(const MrModel* model, int64_t rows) {
   if (model == nullptr || model->n_layers < 1 || model->n_layers > MR_MAX_LAYERS) return 0;
   return item_proj_ok(*model, rows) ? 1 : 0;
+}
+
+int mr_uses_user_projection(const MrModel* model, int64_t rows, int32_t group) {
+  if (model == nullptr || model->n_layers < 1 || model->n_layers > MR_MAX_LAYERS) return 0;
+  return user_proj_ok(*model, rows, group) ? 1 : 0;
 }
 
 int mr_uses_tensor_cores(const MrModel* model) {

@@ -91,7 +91,7 @@ int launch_gather_rows_sharded(const float* const* shards, int world, int64_t to
 // out[g] = sum_{j < group} in[g * group + j], rows of `width` floats, added in order j = 0, 1, ...
 // HBM-bound: (group + 1) * width * 4 bytes per group.
 __global__ void __launch_bounds__(256) group_sum_rows_kernel(const float* __restrict__ in, int64_t groups, int group,
-                                                             int width4, int ld4, float* __restrict__ out) {
+                                                             int width4, int ld4, float* __restrict__ out, int out_ld4) {
   const int64_t total = groups * width4;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t g = e / width4;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) group_sum_rows_kernel(const float* __rest
       const float4 v = ld_stream4(reinterpret_cast<const float*>(src + (int64_t)j * ld4));
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    reinterpret_cast<float4*>(out)[e] = s;
+    reinterpret_cast<float4*>(out)[g * out_ld4 + c] = s;
   }
 }
 
@@ -128,15 +128,17 @@ static unsigned grid_for(int64_t work_items) {
 }
 
 int launch_group_sum_rows(const float* in, int64_t groups, int group, int width, float* out, cudaStream_t st,
-                          int in_ld) {
+                          int in_ld, int out_ld) {
   if (groups == 0) return MR_OK;
   if (in_ld <= 0) in_ld = width;
-  if (width % 4 || in_ld % 4 || in_ld < width || group < 1 ||
+  if (out_ld <= 0) out_ld = width;
+  if (width % 4 || in_ld % 4 || in_ld < width || out_ld % 4 || out_ld < width || group < 1 ||
       ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)) {
     set_error("group_sum_rows: width=%d / stride=%d must be multiples of 4 and the buffers 16-byte aligned", width, in_ld);
     return MR_ERR_INVALID;
   }
-  group_sum_rows_kernel<<<grid_for(groups * (width / 4)), 256, 0, st>>>(in, groups, group, width / 4, in_ld / 4, out);
+  group_sum_rows_kernel<<<grid_for(groups * (width / 4)), 256, 0, st>>>(in, groups, group, width / 4, in_ld / 4, out,
+                                                                        out_ld / 4);
   MR_LAUNCH_CHECK("group_sum_rows_kernel");
   return MR_OK;
 }
@@ -152,6 +154,7 @@ template <int ROWS>
 __global__ void __launch_bounds__(256) h1_from_projection_kernel(const float* __restrict__ Pi, int32_t num_items,
                                                                  const int32_t* __restrict__ items, int64_t row0,
                                                                  int64_t rows, const float* __restrict__ Zu, int group,
+                                                                 const int32_t* __restrict__ users, int32_t num_users,
                                                                  int width, float* __restrict__ H1,
                                                                  uint32_t* __restrict__ bits) {
   const int lane = threadIdx.x & 31;
@@ -170,7 +173,12 @@ __global__ void __launch_bounds__(256) h1_from_projection_kernel(const float* __
         if (r < rows && active) {
           const int it = __ldg(items + row0 + r);
           if ((unsigned)it < (unsigned)num_items) a[j] = ldg4(Pi + (size_t)it * width + col);  // bad ids: a zero row
-          z[j] = ldg4(Zu + (size_t)((uint32_t)r / (uint32_t)group) * width + col);
+          if (users == nullptr) {
+            z[j] = ldg4(Zu + (size_t)((uint32_t)r / (uint32_t)group) * width + col);
+          } else {  // Zu holds one row per USER (user-projected first layer)
+            const int u = __ldg(users + row0 + r);
+            if ((unsigned)u < (unsigned)num_users) z[j] = ldg4(Zu + (size_t)u * width + col);
+          }
         }
       }
 #pragma unroll
@@ -197,7 +205,8 @@ __global__ void __launch_bounds__(256) h1_from_projection_kernel(const float* __
 }
 
 int launch_h1_from_projection(const float* Pi, int32_t num_items, const int32_t* items, int64_t row0, int64_t rows,
-                              const float* Zu, int group, int width, float* H1, uint32_t* bits, cudaStream_t st) {
+                              const float* Zu, int group, const int32_t* users, int32_t num_users, int width, float* H1,
+                              uint32_t* bits, cudaStream_t st) {
   if (rows == 0) return MR_OK;
   if (width % 32 || width < 32 || group < 1 ||
       ((reinterpret_cast<uintptr_t>(Pi) | reinterpret_cast<uintptr_t>(Zu) | reinterpret_cast<uintptr_t>(H1)) & 15)) {
@@ -208,8 +217,8 @@ int launch_h1_from_projection(const float* Pi, int32_t num_items, const int32_t*
   int64_t blocks = (rows + 8 * kRows - 1) / (8 * kRows);
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  h1_from_projection_kernel<kRows><<<(unsigned)blocks, 256, 0, st>>>(Pi, num_items, items, row0, rows, Zu, group, width,
-                                                                     H1, bits);
+  h1_from_projection_kernel<kRows><<<(unsigned)blocks, 256, 0, st>>>(Pi, num_items, items, row0, rows, Zu, group, users,
+                                                                     num_users, width, H1, bits);
   MR_LAUNCH_CHECK("h1_from_projection_kernel");
   return MR_OK;
 }

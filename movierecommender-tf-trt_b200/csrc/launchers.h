@@ -159,14 +159,16 @@ int launch_gather_rows_sharded(const float* const* shards, int world, int64_t to
                                int64_t n, float* out, cudaStream_t st);
 
 // ---- grouped batches (gather.cu): one positive and its negatives share the user ----------------------------
-// out[g] = sum_{j < group} in[g * group + j]  (rows of `width` floats, width % 4 == 0, input row stride in_ld
+// out[g] = sum_{j < group} in[g * group + j]  (rows of `width` floats, width % 4 == 0, row strides in_ld / out_ld
 // floats, 0 = width), fixed order
 int launch_group_sum_rows(const float* in, int64_t groups, int group, int width, float* out, cudaStream_t st,
-                          int in_ld = 0);
+                          int in_ld = 0, int out_ld = 0);
 // Item-projected first layer: H1[r] = relu(Pi[items[row0 + r]] + Zu[r / group]) and its ReLU bits; Pi holds
-// E_item . W1[item rows] for every item (width floats per row), Zu the user half + bias of each group.
+// E_item . W1[item rows] for every item (width floats per row), Zu the user half + bias of each group -- or, with
+// `users` (one id per row, global rows), of each USER: row r then adds Zu[users[row0 + r]].
 int launch_h1_from_projection(const float* Pi, int32_t num_items, const int32_t* items, int64_t row0, int64_t rows,
-                              const float* Zu, int group, int width, float* H1, uint32_t* bits, cudaStream_t st);
+                              const float* Zu, int group, const int32_t* users, int32_t num_users, int width, float* H1,
+                              uint32_t* bits, cudaStream_t st);
 // out[g] = ids[g * group]
 int launch_group_heads(const int32_t* ids, int64_t groups, int group, int32_t* out, cudaStream_t st);
 // *flag = 1 when some ids[r] != ids[r - r % group]

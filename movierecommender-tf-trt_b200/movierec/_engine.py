@@ -261,6 +261,10 @@ class NeuMFEngine(object):
         """True when a call over `rows` rows computes the item half of the first layer once per item."""
         return bool(nat.lib.mr_uses_item_projection(C.byref(self._model), int(rows)))
 
+    def uses_user_projection(self, rows, group):
+        """True when a grouped train step over `rows` rows also computes the user half once per user."""
+        return bool(nat.lib.mr_uses_user_projection(C.byref(self._model), int(rows), int(group)))
+
     def _workspace(self, nbytes):
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)

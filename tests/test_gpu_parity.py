@@ -339,6 +339,7 @@ PROJECTED_CASES = [
     ((300, 60, [256, 128, 64], 64, 4, 301), "adam", [0, 0.01, 0], "auto"),   # several tiles + ragged tail, Pi < 1 tile
     ((300, 200, [256, 128, 64], 128, 4, 37), "sgd", [0.001, 0, 0], "on"),    # BASELINE config 5 widths, table l2
     ((500, 130, [256, 128, 128, 32], 0, 1, 700), "adam", [0, 0, 0, 0], "auto"),  # no GMF, 4 layers, groups of 2
+    ((2000, 90, [256, 128, 64], 64, 4, 301), "adam", [0, 0, 0], "auto"),     # more users than groups: items only
 ]
 
 
@@ -352,6 +353,7 @@ def test_item_projected_train_steps_match_oracle(eng_mod, case):
     try:
         eng = eng_mod.NeuMFEngine(nu, ni, L, l2, mf_dim=f, optimizer=opt, lr=0.001, table_mode="dense", seed=11)
         assert eng.uses_tensor_cores() and eng.uses_item_projection(groups * (negs + 1))
+        assert eng.uses_user_projection(groups * (negs + 1), negs + 1) == (selector == "on" or nu <= groups)
         w = eng.get_weights()
         st = o.new_opt_state(w)
         for step in range(3):
