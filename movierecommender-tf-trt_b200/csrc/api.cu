@@ -293,7 +293,8 @@ static TcWs carve_tc(const MrModel& m, bool train, int64_t B, void* ws) {
 
 // Forward of rows [r0, r1) on the tensor cores; leaves H[1..n-1] of the sub-batch in the workspace.
 static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users, const int32_t* items, int user_div,
-                           int64_t r0, int64_t r1, cudaStream_t st, int group = 0, bool users_per_group = false) {
+                           int64_t r0, int64_t r1, cudaStream_t st, int group = 0, bool users_per_group = false,
+                           bool head_dot = false) {
   const int d_u = m.L[0] / 2;
   if (group > 0) {
     // grouped batch: Zu = E_user[user of the group] . W1[user rows] + b1 once per group, then
@@ -373,6 +374,10 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     a.bias = m.b[l];
     a.out = t.H[l];
     a.bits_out = t.bits[l];  // NULL in forward-only runs
+    if (head_dot && l == m.n_layers - 1) {  // H[l] then holds one float per row: relu(.) . w_out[MLP columns]
+      a.epilogue = TC_EPI_HEAD_DOT;
+      a.head_w = m.w_out + m.mf_dim;
+    }
     int rc = launch_tc_dense(a, st);
     if (rc != MR_OK) return rc;
   }
@@ -501,7 +506,8 @@ static int64_t eval_sub_batch(int group) {
 }
 
 static bool eval_fused_ok(const MrModel& m, int group) {
-  return use_tc(m) && head_rank_supported(m) && m.n_layers >= 2 && group <= 256 && eval_sub_batch(group) > 0;
+  return use_tc(m) && (head_rank_supported(m) || (m.n_layers >= 3 && head_rank_takes_dot(m, group))) && m.n_layers >= 2 &&
+         group <= 256 && eval_sub_batch(group) > 0;
 }
 
 static TcWs carve_eval(const MrModel& m, int group, int64_t rows, void* ws) {
@@ -545,11 +551,15 @@ static int rank_eval_fused(const MrModel& m, const int32_t* users, const int32_t
   for (int64_t r0 = 0; r0 < rows; r0 += sb) {
     const int64_t r1 = r0 + sb < rows ? r0 + sb : rows;
     prof_mark(MR_PHASE_TC_DENSE_FWD, st);
-    rc = tc_forward_rows(m, t, users, items, 1, r0, r1, st, group, true);
+    // the last hidden layer's epilogue dots its output with the output unit's weights when the score kernel has
+    // the matching variant (a plain layer must precede it: l >= 2 of the grouped sequence)
+    const bool head_dot = m.n_layers >= 3 && head_rank_takes_dot(m, group);
+    rc = tc_forward_rows(m, t, users, items, 1, r0, r1, st, group, true, head_dot);
     if (rc != MR_OK) return rc;
     prof_mark(MR_PHASE_HEAD, st);
     HeadArgs h{};
     h.model = &m;
+    h.h_is_dot = head_dot;
     h.h_last = t.H[m.n_layers - 1];
     h.users = users;
     h.items = items;

@@ -418,16 +418,19 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_rank_kernel(const HeadPa
 // software-pipelined like head_group_kernel: a warp scores its candidates of a group in two halves of up to KH
 // rows; while one half is reduced the other half's rows -- and, across the group boundary, the next group's first
 // half, ids and user row -- are already in flight.  Requires ceil(group / 8) <= 2 * KH.
+// HQ == 0: p.h_last holds one float per row, the last hidden layer already dotted with its output-unit weights by
+// the layer's own epilogue (tc_dense EPI_HEAD_DOT); only the GMF rows are read here.
 template <int FQ, int HQ, int KH>
 __global__ void __launch_bounds__(kHeadThreads, 2) head_rank_pipe_kernel(const HeadParams p, int group,
                                                                          int32_t* __restrict__ pos,
                                                                          float* __restrict__ probs) {
   constexpr int f = 32 * FQ, Ln = 32 * HQ;
+  constexpr int HA = HQ > 0 ? HQ : 1;  // array extent (HQ == 0: slot 0 carries the row's partial logit)
   constexpr int kWarps = kHeadThreads / 32;
   __shared__ float sc[kHeadThreads];
   const MrModel& m = p.m;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float wg[FQ], wh[HQ];
+  float wg[FQ], wh[HA];
 #pragma unroll
   for (int q = 0; q < FQ; ++q) wg[q] = __ldg(m.w_out + lane + 32 * q);
 #pragma unroll
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_rank_pipe_kernel(const H
   const int per_warp = (group + kWarps - 1) / kWarps;  // candidate j = warp + kWarps * i, i < per_warp
 
   struct Half {
-    float gi[KH][FQ], h[KH][HQ];
+    float gi[KH][FQ], h[KH][HA];
     unsigned bad;  // bit rr: out-of-range item id
   };
   // ids of this warp's candidates of group g, lane-distributed (lane i: candidate warp + kWarps * i), and the user
@@ -461,11 +464,12 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_rank_pipe_kernel(const H
         it = 0;
       }
       const float* grow = m.item_gmf + (size_t)it * f;
-      const float* hrow = p.h_last + (size_t)(g * group + j) * Ln;
+      const float* hrow = p.h_last + (size_t)(g * group + j) * (HQ > 0 ? Ln : 1);
 #pragma unroll
       for (int q = 0; q < FQ; ++q) r.gi[rr][q] = __ldg(grow + lane + 32 * q);
 #pragma unroll
       for (int q = 0; q < HQ; ++q) r.h[rr][q] = __ldg(hrow + lane + 32 * q);
+      if (HQ == 0) r.h[rr][0] = __ldg(hrow);
     }
   };
   auto score_half = [&](int64_t g, int half, const Half& r, const float (&gu)[FQ], bool bad_u) {
@@ -480,6 +484,7 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_rank_pipe_kernel(const H
 #pragma unroll
       for (int q = 0; q < HQ; ++q) s = fmaf(wh[q], r.h[rr][q], s);
       s = warp_sum(s);
+      if (HQ == 0) s += r.h[rr][0];
       const bool bad = bad_u || ((r.bad >> rr) & 1u);
       const float pr = bad ? nanf("") : sigmoidf_stable(s + b_out);
       if (lane == 0) {
@@ -528,6 +533,93 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_rank_pipe_kernel(const H
     badu_cur = badu_nxt;
 #pragma unroll
     for (int q = 0; q < FQ; ++q) gu_cur[q] = gu_nxt[q];
+  }
+}
+
+// Score + position with ONE WARP PER GROUP, for the partial-logit form (p.h_last = one float per row: the last
+// hidden layer already dotted with its output-unit weights by tc_dense EPI_HEAD_DOT).  What is left per candidate
+// is the GMF term, a dot product of f = 32 * NV floats: eight lanes take one row (NV 128-bit loads each, 128
+// contiguous bytes per eight lanes), so a load instruction covers four rows and the reduction is three shuffles;
+// the group's scores meet in the warp's slice of shared memory and the position is a ballot-free count.  No CTA
+// barrier: the CTA-per-group kernels above spend ~6 us per group on two serial half-group round trips with 16 warps
+// per SM (ncu: issue-active 60 %, 3 TB/s); here every warp is independent and KS steps (4 * KS rows) are in flight.
+template <int NV>
+__global__ void __launch_bounds__(kHeadThreads) head_rank_warp_kernel(const HeadParams p, int group,
+                                                                      int32_t* __restrict__ pos,
+                                                                      float* __restrict__ probs) {
+  constexpr int f = 32 * NV, KS = 5;
+  constexpr int kWarps = kHeadThreads / 32;
+  __shared__ float sc[kWarps][256];
+  const MrModel& m = p.m;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & 7, quad = lane >> 3;
+  float4 wg[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) wg[v] = ldg4(m.w_out + 32 * v + 4 * sub);
+  const float b_out = __ldg(m.b_out);
+  const int64_t ngroups = p.rows / group;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+  const int nsteps = (group + 3) >> 2;
+  float* my_sc = sc[warp];
+  for (int64_t g = (int64_t)blockIdx.x * kWarps + warp; g < ngroups; g += nwarps) {
+    const int64_t gg = p.row0 / group + g;
+    int u = __ldg(p.users + gg);
+    const bool bad_u = (unsigned)u >= (unsigned)m.num_users;
+    if (bad_u) u = 0;
+    float4 gu[NV];  // w_out[:f] * user GMF row, this lane's columns
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const float4 x = ldg4(m.user_gmf + (size_t)u * f + 32 * v + 4 * sub);
+      gu[v] = make_float4(x.x * wg[v].x, x.y * wg[v].y, x.z * wg[v].z, x.w * wg[v].w);
+    }
+    const int64_t lr0 = g * group;  // launch-local first row of the group
+    for (int s0 = 0; s0 < nsteps; s0 += KS) {
+      int it[KS];
+      float4 gi[KS][NV];
+      float z[KS];
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const int row = (s0 + k) * 4 + quad;
+        const int rr = row < group ? row : group - 1;  // dead slots re-read the positive's row
+        it[k] = __ldg(p.items + p.row0 + lr0 + rr);
+        z[k] = __ldg(p.h_last + lr0 + rr);
+      }
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const int iv = (unsigned)it[k] >= (unsigned)m.num_items ? 0 : it[k];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) gi[k][v] = ldg4(m.item_gmf + (size_t)iv * f + 32 * v + 4 * sub);
+      }
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const int row = (s0 + k) * 4 + quad;
+        float s = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          s = fmaf(gu[v].x, gi[k][v].x, s);
+          s = fmaf(gu[v].y, gi[k][v].y, s);
+          s = fmaf(gu[v].z, gi[k][v].z, s);
+          s = fmaf(gu[v].w, gi[k][v].w, s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        const bool bad = bad_u || (unsigned)it[k] >= (unsigned)m.num_items;
+        const float pr = bad ? nanf("") : sigmoidf_stable(s + z[k] + b_out);
+        if (sub == 0 && row < group) {
+          my_sc[row] = pr;
+          if (probs != nullptr) probs[p.row0 + lr0 + row] = pr;
+          if (bad) atomicOr(p.flags, 1);
+        }
+      }
+    }
+    __syncwarp();
+    const float key_pos = rank_key(my_sc[group - 1]);
+    int cnt = 0;
+    for (int j = lane; j < group - 1; j += 32) cnt += rank_key(my_sc[j]) >= key_pos ? 1 : 0;  // ties rank first
+    cnt = warp_sum_int(cnt);
+    if (lane == 0) pos[gg] = cnt;
+    __syncwarp();
   }
 }
 
@@ -635,12 +727,25 @@ int launch_head(const HeadArgs& a, cudaStream_t st) {
 
 bool head_rank_supported(const MrModel& m) { return m.mf_dim + m.L[m.n_layers - 1] <= 128; }
 
+static bool head_rank_pipe_ok(const MrModel& m, int group) {
+  return m.mf_dim == 64 && m.L[m.n_layers - 1] == 64 && (group + 7) / 8 <= 14 && getenv("MR_HEAD_GENERIC") == nullptr;
+}
+
+bool head_rank_takes_dot(const MrModel& m, int group) {
+  const bool widths = m.mf_dim == 32 || m.mf_dim == 64 || m.mf_dim == 128;  // head_rank_warp_kernel<1 | 2 | 4>
+  return widths && group >= 2 && group <= 256 && getenv("MR_NO_HEAD_DOT") == nullptr &&
+         (reinterpret_cast<uintptr_t>(m.user_gmf) | reinterpret_cast<uintptr_t>(m.item_gmf) |
+          reinterpret_cast<uintptr_t>(m.w_out)) % 16 == 0;
+}
+
 // Fused score + rank of whole groups (forward only): a.users holds ONE id per group (global group index),
 // a.rows / a.row0 are rows (multiples of `group`); pos is indexed by the global group, probs by the global row.
 int launch_head_rank(const HeadArgs& a, int group, int32_t* pos, float* probs, cudaStream_t st) {
   const MrModel& m = *a.model;
-  if (!head_rank_supported(m) || group < 2 || group > 256 || a.rows % group || a.row0 % group) {
-    set_error("head_rank kernel: needs mf_dim + last width <= 128 and whole groups of at most 256 rows");
+  if (!(a.h_is_dot ? head_rank_takes_dot(m, group) : head_rank_supported(m)) || group < 2 || group > 256 ||
+      a.rows % group || a.row0 % group) {
+    set_error("head_rank kernel: needs mf_dim + last width <= 128 (or the partial-logit form with mf_dim 32, 64 or "
+              "128) and whole groups of at most 256 rows");
     return MR_ERR_INVALID;
   }
   if (a.rows == 0) return MR_OK;
@@ -656,7 +761,20 @@ int launch_head_rank(const HeadArgs& a, int group, int32_t* pos, float* probs, c
   const int64_t ngroups = a.rows / group;
   const int64_t cap = (int64_t)sm_count() * 2;  // persistent: two resident CTAs per SM, groups taken round-robin
   const unsigned grid = (unsigned)(ngroups < cap ? ngroups : cap);
-  if (m.mf_dim == 64 && m.L[m.n_layers - 1] == 64 && (group + 7) / 8 <= 14 && getenv("MR_HEAD_GENERIC") == nullptr)
+  if (a.h_is_dot) {
+    // one warp per group: enough CTAs for full occupancy, groups taken round-robin by the warps
+    const int64_t wcap = (int64_t)sm_count() * 8;
+    const int64_t want = (ngroups + kHeadThreads / 32 - 1) / (kHeadThreads / 32);
+    const unsigned wgrid = (unsigned)(want < wcap ? want : wcap);
+    if (m.mf_dim == 64 && head_rank_pipe_ok(m, group) && getenv("MR_HEAD_RANK_PIPE") != nullptr)  // diagnostics (A/B)
+      head_rank_pipe_kernel<2, 0, 7><<<grid, kHeadThreads, 0, st>>>(p, group, pos, probs);
+    else if (m.mf_dim == 32)
+      head_rank_warp_kernel<1><<<wgrid, kHeadThreads, 0, st>>>(p, group, pos, probs);
+    else if (m.mf_dim == 64)
+      head_rank_warp_kernel<2><<<wgrid, kHeadThreads, 0, st>>>(p, group, pos, probs);
+    else
+      head_rank_warp_kernel<4><<<wgrid, kHeadThreads, 0, st>>>(p, group, pos, probs);
+  } else if (head_rank_pipe_ok(m, group))
     head_rank_pipe_kernel<2, 2, 7><<<grid, kHeadThreads, 0, st>>>(p, group, pos, probs);
   else
     head_rank_kernel<4><<<grid, kHeadThreads, 0, st>>>(p, group, pos, probs);

@@ -74,7 +74,7 @@ int launch_sample_negatives(const int64_t* rowptr, const int32_t* csr_items, int
                             float* out_labels, cudaStream_t st);
 
 // ---- tc_dense.cu / tc_wgrad.cu / head.cu: tensor-core path of the train step ------------------------
-enum { TC_EPI_BIAS_RELU = 0, TC_EPI_MASK = 1, TC_EPI_STAGE = 2 };
+enum { TC_EPI_BIAS_RELU = 0, TC_EPI_MASK = 1, TC_EPI_STAGE = 2, TC_EPI_HEAD_DOT = 3 };
 struct TcDenseArgs {
   bool gather;            // A = [user row | item row] gathered by id, else a_dense
   const float* a_dense;
@@ -89,7 +89,8 @@ struct TcDenseArgs {
   int32_t N, K;
   int64_t rows, row0;
   int epilogue;
-  const float* bias;          // TC_EPI_BIAS_RELU, optional
+  const float* bias;          // TC_EPI_BIAS_RELU, optional; TC_EPI_HEAD_DOT, required
+  const float* head_w;        // TC_EPI_HEAD_DOT: out[r] = relu(acc[r] + bias) . head_w  (out: one float per row)
   const float* addend;        // TC_EPI_BIAS_RELU, optional: row r adds addend[r / addend_div] (launch-local rows x N)
   int32_t addend_div;
   bool linear;                // TC_EPI_BIAS_RELU without the ReLU
@@ -127,6 +128,8 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t st);
 struct HeadArgs {
   const MrModel* model;
   const float* h_last;    // [rows x L_last] launch-local rows
+  bool h_is_dot;          // launch_head_rank: h_last holds [rows] floats, the last layer already dotted with its
+                          // output-unit weights (tc_dense TC_EPI_HEAD_DOT)
   const int32_t* users;
   const int32_t* items;
   const float* labels;    // NULL = forward only
@@ -150,6 +153,7 @@ bool head_supports_group(const MrModel& m, int group);
 size_t head_partial_floats(const MrModel& m);
 int launch_head(const HeadArgs& a, cudaStream_t st);
 bool head_rank_supported(const MrModel& m);
+bool head_rank_takes_dot(const MrModel& m, int group);  // launch_head_rank accepts h_is_dot for this model
 int launch_head_rank(const HeadArgs& a, int group, int32_t* pos, float* probs, cudaStream_t st);
 // metric sums from positions (rank.cu): sums = {hit_sum, dcg_sum}
 int launch_rank_metrics(const int32_t* pos, int64_t G, int k, float* sums, float* partials, cudaStream_t st);

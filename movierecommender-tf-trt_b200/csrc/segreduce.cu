@@ -23,7 +23,10 @@ namespace mr {
 constexpr int kSkip = -1;     // empty slot
 constexpr int kPastEnd = -2;  // lane beyond n
 constexpr int kNoNeighbour = -3;
-constexpr int kBatch = 8;     // rows loaded per lane before they are added
+constexpr int kBatch = 8;     // rows loaded per lane before they are added (level 0: thousands of chunks in flight)
+constexpr int kBatchUpper = 16;  // upper levels: few chunks, so a chunk's own latency is the launch's duration --
+                                 // deeper batches and one warp per 128-column slab (gridDim.y) cut its serial
+                                 // load rounds from 8 to 2 (ncu: every upper-level launch took 20-25 us)
 
 __device__ __forceinline__ void apply_row_value(const RowUpdate& u, int row, int c, float g) {
   float *p, *m, *v, *gt;
@@ -131,7 +134,7 @@ __device__ __forceinline__ void flush_run(const RowUpdate& u, const ChunkInfo& c
 
 // keys[n]; INDIRECT: row of entry e is rows[index[e]], else rows[e].  out_keys/out_rows hold two slots
 // per chunk (may be NULL when there is a single chunk: then nothing can be incomplete).
-template <bool INDIRECT, bool VEC>
+template <bool INDIRECT, bool VEC, int KB>
 __global__ void __launch_bounds__(256) segreduce_level_kernel(const int32_t* __restrict__ keys,
                                                               const int32_t* __restrict__ index, int64_t n,
                                                               const float* __restrict__ rows, int32_t* __restrict__ out_keys,
@@ -159,22 +162,22 @@ __global__ void __launch_bounds__(256) segreduce_level_kernel(const int32_t* __r
   ci.chunk = chunk;
   ci.ld = ld;
   ci.out_rows = out_rows;
-  if (out_keys != nullptr && lane == 0) {
+  if (out_keys != nullptr && lane == 0 && blockIdx.y == 0) {
     out_keys[2 * chunk] = ci.first_inc ? key0 : kSkip;
     out_keys[2 * chunk + 1] = ci.last_inc ? keyl : kSkip;
   }
 
   constexpr int W = VEC ? 4 : 1;
-  for (int cb = 0; cb < ld; cb += 32 * W) {
+  for (int cb = blockIdx.y * 32 * W; cb < ld; cb += gridDim.y * 32 * W) {
     const int c = cb + lane * W;
     const bool on = c < ld;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int run_key = key0, run_start = 0;
-    for (int j0 = 0; j0 < ci.nvalid; j0 += kBatch) {
-      float4 v[kBatch];
+    for (int j0 = 0; j0 < ci.nvalid; j0 += KB) {
+      float4 v[KB];
 #pragma unroll
-      for (int q = 0; q < kBatch; ++q) {
-        const int j = j0 + q;  // j < 32 always (nvalid <= 32, kBatch divides 32)
+      for (int q = 0; q < KB; ++q) {
+        const int j = j0 + q;  // j < 32 always (nvalid <= 32, KB divides 32)
         const int64_t sj = __shfl_sync(0xffffffffu, src, j);
         const bool okj = __shfl_sync(0xffffffffu, (int)ok, j) != 0;
         v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(256) segreduce_level_kernel(const int32_t* __r
         }
       }
 #pragma unroll
-      for (int q = 0; q < kBatch; ++q) {
+      for (int q = 0; q < KB; ++q) {
         const int j = j0 + q;
         if (j < ci.nvalid) {
           if (j > 0 && ((starts >> j) & 1u)) {  // a new run starts: close the previous one
@@ -240,11 +243,13 @@ int launch_segreduce(const int32_t* sorted_keys, const int32_t* sorted_index, in
     float* orows = last ? nullptr : rbuf[level & 1];
     const unsigned blocks = (unsigned)((nchunks + 7) / 8);
     if (level == 0) {
-      if (vec) segreduce_level_kernel<true, true><<<blocks, 256, 0, st>>>(keys, sorted_index, cur, rows, ok, orows, u);
-      else segreduce_level_kernel<true, false><<<blocks, 256, 0, st>>>(keys, sorted_index, cur, rows, ok, orows, u);
+      if (vec) segreduce_level_kernel<true, true, kBatch><<<blocks, 256, 0, st>>>(keys, sorted_index, cur, rows, ok, orows, u);
+      else segreduce_level_kernel<true, false, kBatch><<<blocks, 256, 0, st>>>(keys, sorted_index, cur, rows, ok, orows, u);
     } else {
-      if (vec) segreduce_level_kernel<false, true><<<blocks, 256, 0, st>>>(keys, nullptr, cur, rows, ok, orows, u);
-      else segreduce_level_kernel<false, false><<<blocks, 256, 0, st>>>(keys, nullptr, cur, rows, ok, orows, u);
+      const int per = vec ? 128 : 32;  // columns a warp covers per pass
+      const dim3 grid(blocks, (unsigned)((ld + per - 1) / per));
+      if (vec) segreduce_level_kernel<false, true, kBatchUpper><<<grid, 256, 0, st>>>(keys, nullptr, cur, rows, ok, orows, u);
+      else segreduce_level_kernel<false, false, kBatchUpper><<<grid, 256, 0, st>>>(keys, nullptr, cur, rows, ok, orows, u);
     }
     MR_LAUNCH_CHECK("segreduce_level_kernel");
     if (last) break;

@@ -9,6 +9,9 @@
 //   epilogue: EPI_BIAS_RELU  h = relu(acc + b)          forward Dense/ReLU (model.py:175-181)
 //             EPI_MASK       dz = acc * (h_prev > 0)    backward through the previous ReLU
 //             EPI_STAGE      rows of dL/dx0 split into the user / item staging buffers
+//             EPI_HEAD_DOT   z[r] = relu(acc + b) . w     the last hidden layer folded into the output unit's dot
+//                                                         product (ranking eval: thread = row, so the dot needs no
+//                                                         shuffles and the layer's output never reaches HBM)
 //
 // Persistent, warp-specialised CTA (416 threads), 128 batch rows per tile, K streamed in chunks of 32:
 //   warps 0-7  producers: every warp fills a slice of every K-chunk; the global loads of a chunk are issued
@@ -45,7 +48,7 @@ constexpr int kTcKC = 32;  // K elements per pipeline stage
 constexpr int kEpiLd = 36;  // floats per row of an epilogue warp's 32x32 staging tile (16-byte aligned, conflict-free)
 
 enum { A_GATHER = 0, A_DENSE = 1 };
-enum { EPI_BIAS_RELU = 0, EPI_MASK = 1, EPI_STAGE = 2 };
+enum { EPI_BIAS_RELU = 0, EPI_MASK = 1, EPI_STAGE = 2, EPI_HEAD_DOT = 3 };
 
 struct TcDenseParams {
   // A operand
@@ -65,6 +68,7 @@ struct TcDenseParams {
   const float* addend;   // EPI_BIAS_RELU, optional: [rows / addend_div x N] added before the activation (launch-local rows)
   int32_t addend_div;
   int32_t relu;          // EPI_BIAS_RELU: apply the ReLU (0 = linear output)
+  const float* head_w;   // EPI_HEAD_DOT: [N] output-unit weights of this layer's columns; out = [rows] partial logits
   const uint32_t* mask_bits;  // EPI_MASK: [rows x N/32] ReLU bits of the previous layer's output, launch-local rows
   uint32_t* bits_out;    // EPI_BIAS_RELU, optional: [rows x N/32] bits (h > 0) for the backward pass
   float* out;            // EPI_BIAS_RELU / EPI_MASK: [rows x N], launch-local rows, row stride out_ld floats
@@ -330,10 +334,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       // optional per-group addend row of this thread's row (the rows of a group read the same line)
       const float* arow = (EPI == EPI_BIAS_RELU && p.addend != nullptr && my_ok)
                               ? p.addend + (size_t)((uint32_t)my_lr / (uint32_t)p.addend_div) * N : nullptr;
+      float zdot = 0.f;  // EPI_HEAD_DOT
       for (int c0 = 0; c0 < ((p.debug & 32) ? 0 : N); c0 += 32) {
         float v[32];
         tc::tmem_ld16(taddr + c0, v);
         tc::tmem_ld16(taddr + c0 + 16, v + 16);
+        if (EPI == EPI_HEAD_DOT) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bv = ldg4(p.bias + c0 + 4 * q), wv = ldg4(p.head_w + c0 + 4 * q);
+            zdot = fmaf(fmaxf(v[4 * q + 0] + bv.x, 0.f), wv.x, zdot);
+            zdot = fmaf(fmaxf(v[4 * q + 1] + bv.y, 0.f), wv.y, zdot);
+            zdot = fmaf(fmaxf(v[4 * q + 2] + bv.z, 0.f), wv.z, zdot);
+            zdot = fmaf(fmaxf(v[4 * q + 3] + bv.w, 0.f), wv.w, zdot);
+          }
+          continue;  // nothing to stage: one float per row leaves after the last column block
+        }
         if (EPI == EPI_BIAS_RELU) {
           uint32_t bits = 0;
           if (p.bias != nullptr) {
@@ -389,6 +405,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
         }
         __syncwarp();
       }
+      if (EPI == EPI_HEAD_DOT && my_ok) p.out[my_lr] = zdot;
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[b]);
@@ -473,6 +490,7 @@ int launch_tc_dense(const TcDenseArgs& a, cudaStream_t st) {
   p.rows = a.rows;
   p.row0 = a.row0;
   p.bias = a.bias;
+  p.head_w = a.head_w;
   p.mask_bits = a.mask_bits;
   p.bits_out = a.bits_out;
   p.out = a.out;
@@ -493,6 +511,9 @@ int launch_tc_dense(const TcDenseArgs& a, cudaStream_t st) {
     case TC_EPI_BIAS_RELU: return launch_dense_t<A_DENSE, EPI_BIAS_RELU>(p, st);
     case TC_EPI_MASK: return launch_dense_t<A_DENSE, EPI_MASK>(p, st);
     case TC_EPI_STAGE: return launch_dense_t<A_DENSE, EPI_STAGE>(p, st);
+    case TC_EPI_HEAD_DOT:
+      if (a.bias == nullptr || a.head_w == nullptr || a.out == nullptr) return MR_ERR_INVALID;
+      return launch_dense_t<A_DENSE, EPI_HEAD_DOT>(p, st);
   }
   return MR_ERR_INVALID;
 }

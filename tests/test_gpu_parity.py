@@ -416,7 +416,7 @@ def test_item_projection_on_and_off_agree_and_are_deterministic(eng_mod):
         assert np.array_equal(a, b)
 
 
-def test_item_projected_rank_eval_matches_oracle(eng_mod):
+def test_item_projected_rank_eval_matches_oracle(eng_mod, monkeypatch):
     nu, ni, L, f = 300, 500, [256, 128, 64], 64
     rng = np.random.default_rng(14)
     eng = eng_mod.NeuMFEngine(nu, ni, L, [0] * 3, mf_dim=f, seed=5)
@@ -429,13 +429,17 @@ def test_item_projected_rank_eval_matches_oracle(eng_mod):
     hr_o, dcg_o, pos_o, p_o = o.evaluate_groups(w, users, items, group, k)
     got = {}
     try:
-        for selector in ("auto", "off"):
-            eng_mod.set_item_projection(selector)
-            pos, sums, rank, probs = eng.rank_eval(users, items, group, k, want_rank=True, want_probs=True)
+        # third pass: the last hidden layer written out and dotted by the score kernel (MR_NO_HEAD_DOT) instead of
+        # folded into the output unit's dot product by the layer's own epilogue
+        for selector in ("auto", "off", "auto-nodot"):
+            eng_mod.set_item_projection(selector.split("-")[0])
+            if selector.endswith("nodot"):
+                monkeypatch.setenv("MR_NO_HEAD_DOT", "1")
+            # positions only: the fused sequence (a full permutation request takes the forward + rank kernels)
+            pos, sums, _, probs = eng.rank_eval(users, items, group, k, want_probs=True)
             p = probs.cpu().numpy()
             rel_close(p, p_o, what="eval probs, item projection " + selector)
             np.testing.assert_array_equal(pos.cpu().numpy(), o.positive_positions(p, group))
-            np.testing.assert_array_equal(rank.cpu().numpy(), o.rank_groups(p, group))
             assert pos.cpu().numpy()[5] == group - 1
             s = sums.cpu().numpy()
             assert abs(s[0] / G - hr_o) <= 1e-3 and abs(s[1] / G - dcg_o) <= 1e-3
@@ -443,6 +447,36 @@ def test_item_projected_rank_eval_matches_oracle(eng_mod):
     finally:
         eng_mod.set_item_projection("auto")
     rel_close(got["auto"], got["off"], what="eval probs projected vs per-row")
+    rel_close(got["auto"], got["auto-nodot"], what="eval probs, last layer folded into the dot vs written out")
+
+
+@pytest.mark.parametrize("f,group,L", [(32, 7, [256, 128, 32]), (128, 100, [256, 128, 64]), (64, 256, [256, 128, 128, 64]),
+                                       (64, 2, [256, 128, 64])])
+def test_fused_rank_eval_widths_and_group_sizes(eng_mod, f, group, L):
+    """The warp-per-group score + position kernel (last layer folded into the dot): GMF widths 32 / 64 / 128, groups
+    that are not multiples of four, the largest group, bad ids, a fully tied group."""
+    nu, ni = 400, 90
+    rng = np.random.default_rng(f + group)
+    eng = eng_mod.NeuMFEngine(nu, ni, L, [0] * len(L), mf_dim=f, seed=8)
+    w = eng.get_weights()
+    G, k = 301, min(10, group)
+    users = rng.integers(0, nu, G)
+    items = rng.integers(0, ni, G * group)
+    items[3 * group:4 * group] = items[3 * group]
+    pos, sums, _, probs = eng.rank_eval(users, items, group, k, want_probs=True)
+    p = probs.cpu().numpy()
+    hr_o, dcg_o, pos_o, p_o = o.evaluate_groups(w, users, items, group, k)
+    rel_close(p, p_o, what="eval probs f={} group={}".format(f, group))
+    np.testing.assert_array_equal(pos.cpu().numpy(), o.positive_positions(p, group))
+    assert pos.cpu().numpy()[3] == group - 1
+    s = sums.cpu().numpy()
+    assert abs(s[0] / G - hr_o) <= 1e-3 and abs(s[1] / G - dcg_o) <= 1e-3
+    bad = items.copy()
+    bad[5 * group + 1] = ni + 3
+    pos_b, _, _, probs_b = eng.rank_eval(users, bad, group, k, want_probs=True)
+    assert np.isnan(probs_b.cpu().numpy()[5 * group + 1])
+    keep = np.arange(G) != 5
+    np.testing.assert_array_equal(pos_b.cpu().numpy()[keep], pos.cpu().numpy()[keep])
 
 
 def test_item_projection_treats_bad_item_ids_like_the_per_row_path(eng_mod):
