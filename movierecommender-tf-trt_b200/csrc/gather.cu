@@ -152,58 +152,74 @@ int launch_group_sum_rows(const float* in, int64_t groups, int group, int width,
 // over the item table and the per-row part of the layer is this gather: one warp per row, 128-bit loads of the
 // L2-resident Pi row and of the group's Zu row, ReLU, a coalesced store of H1 and the ReLU bits of the backward pass.
 // HBM-bound: 4 * width + width / 8 + 4 bytes written / read per row (Pi and Zu rows hit L2).
-template <int ROWS, bool STREAM>
-__global__ void __launch_bounds__(256) h1_from_projection_kernel(const float* __restrict__ Pi, int32_t num_items,
-                                                                 const int32_t* __restrict__ items, int64_t row0,
-                                                                 int64_t rows, const float* __restrict__ Zu, int group,
-                                                                 const int32_t* __restrict__ users, int32_t num_users,
-                                                                 int width, float* __restrict__ H1,
-                                                                 uint32_t* __restrict__ bits) {
+template <int ROWS>
+__global__ void __launch_bounds__(256, 4) h1_from_projection_kernel(const float* __restrict__ Pi, int32_t num_items,
+                                                                    const int32_t* __restrict__ items, int64_t row0,
+                                                                    int64_t rows, const float* __restrict__ Zu, int group,
+                                                                    const int32_t* __restrict__ users, int32_t num_users,
+                                                                    int width, float* __restrict__ H1,
+                                                                    uint32_t* __restrict__ bits) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int words = width >> 5;
+  const int c0 = blockIdx.y * 128;  // a warp covers 128 columns of its rows; wider layers take gridDim.y slabs
+  const int col = c0 + 4 * lane;
+  const bool active = col < width;
+  items += row0;
+  if (users != nullptr) users += row0;
   for (int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * ROWS; base < rows; base += warps * ROWS) {
-    for (int c0 = 0; c0 < width; c0 += 128) {
-      const int col = c0 + 4 * lane;
-      const bool active = col < width;
-      float4 a[ROWS], z[ROWS];
+    // ids first (every row's loads in flight together), then the rows.  The rows of a group share the user, so the
+    // user-side row is loaded once per run of equal source rows (warp-uniform test): with groups of 5 that takes the
+    // L2 reads of this kernel -- its bound, ~8 TB/s of L2 traffic in the first version -- from 2 to ~1.4 rows per
+    // output row, with the 100-candidate groups of the ranking eval to 1.25.
+    int it[ROWS], zi[ROWS];  // zi: source row of the user-side addend, -1: none (row past the end / id out of range)
 #pragma unroll
-      for (int j = 0; j < ROWS; ++j) {
-        const int64_t r = base + j;
-        a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        z[j] = a[j];
-        if (r < rows && active) {
-          const int it = __ldg(items + row0 + r);
-          if ((unsigned)it < (unsigned)num_items) a[j] = ldg4(Pi + (size_t)it * width + col);  // bad ids: a zero row
-          if (users == nullptr) {
-            z[j] = ldg4(Zu + (size_t)((uint32_t)r / (uint32_t)group) * width + col);
-          } else {  // Zu holds one row per USER (user-projected first layer)
-            const int u = __ldg(users + row0 + r);
-            if ((unsigned)u < (unsigned)num_users) z[j] = ldg4(Zu + (size_t)u * width + col);
-          }
+    for (int j = 0; j < ROWS; ++j) {
+      const int64_t r = base + j;
+      it[j] = -1;
+      zi[j] = -1;
+      if (r < rows) {
+        it[j] = __ldg(items + r);
+        if (users == nullptr) {
+          zi[j] = (int)((uint32_t)r / (uint32_t)group);
+        } else {  // Zu holds one row per USER (user-projected first layer)
+          const int u = __ldg(users + r);
+          if ((unsigned)u < (unsigned)num_users) zi[j] = u;
         }
       }
+    }
+    float4 a[ROWS], z[ROWS];
 #pragma unroll
-      for (int j = 0; j < ROWS; ++j) {
-        const int64_t r = base + j;
-        float4 v;
-        v.x = fmaxf(a[j].x + z[j].x, 0.f);
-        v.y = fmaxf(a[j].y + z[j].y, 0.f);
-        v.z = fmaxf(a[j].z + z[j].z, 0.f);
-        v.w = fmaxf(a[j].w + z[j].w, 0.f);
-        if (r < rows && active) {  // STREAM: evict-first stores, the 0.3 GB of H1 must not push Pi / Pu out of L2
-          if (STREAM) __stcs(reinterpret_cast<float4*>(H1 + (size_t)r * width + col), v);
-          else *reinterpret_cast<float4*>(H1 + (size_t)r * width + col) = v;
-        }
-        if (bits != nullptr) {  // word q of a row = columns [32 q, 32 q + 32): the 4-bit pieces of lanes 8 q .. 8 q + 7
-          uint32_t w = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
-          w = active ? w << (4 * (lane & 7)) : 0u;
-          w |= __shfl_xor_sync(0xffffffffu, w, 1);
-          w |= __shfl_xor_sync(0xffffffffu, w, 2);
-          w |= __shfl_xor_sync(0xffffffffu, w, 4);
-          const int q = (c0 >> 5) + (lane >> 3);
-          if (r < rows && (lane & 7) == 0 && q < words) bits[(size_t)r * words + q] = w;
-        }
+    for (int j = 0; j < ROWS; ++j) {
+      a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      z[j] = a[j];
+      if (active) {
+        if ((unsigned)it[j] < (unsigned)num_items) a[j] = ldg4(Pi + (size_t)it[j] * width + col);  // bad ids: a zero row
+        if (zi[j] >= 0 && (j == 0 || zi[j] != zi[j - 1])) z[j] = ldg4(Zu + (size_t)zi[j] * width + col);
+      }
+    }
+    // copies only after every load has been issued (a copy waits for its source row: placed in the loop above it
+    // exposed one memory latency per repeated row and made the kernel 40 % slower)
+#pragma unroll
+    for (int j = 1; j < ROWS; ++j)
+      if (zi[j] >= 0 && zi[j] == zi[j - 1]) z[j] = z[j - 1];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+      const int64_t r = base + j;
+      float4 v;
+      v.x = fmaxf(a[j].x + z[j].x, 0.f);
+      v.y = fmaxf(a[j].y + z[j].y, 0.f);
+      v.z = fmaxf(a[j].z + z[j].z, 0.f);
+      v.w = fmaxf(a[j].w + z[j].w, 0.f);
+      if (r < rows && active) *reinterpret_cast<float4*>(H1 + (size_t)r * width + col) = v;
+      if (bits != nullptr) {  // word q of a row = columns [32 q, 32 q + 32): the 4-bit pieces of lanes 8 q .. 8 q + 7
+        uint32_t w = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
+        w = active ? w << (4 * (lane & 7)) : 0u;
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        const int q = (c0 >> 5) + (lane >> 3);
+        if (r < rows && (lane & 7) == 0 && q < words) bits[(size_t)r * words + q] = w;
       }
     }
   }
@@ -222,15 +238,10 @@ int launch_h1_from_projection(const float* Pi, int32_t num_items, const int32_t*
   int64_t blocks = (rows + 8 * kRows - 1) / (8 * kRows);
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  // evict-first stores of H1 (to keep Pi / Pu in L2) measured 2 % slower than plain stores on the ML-20M step:
-  // opt-in for diagnostics only
-  static const bool plain = getenv("MR_H1_STREAM_STORES") == nullptr;
-  if (plain)
-    h1_from_projection_kernel<kRows, false><<<(unsigned)blocks, 256, 0, st>>>(Pi, num_items, items, row0, rows, Zu, group,
-                                                                              users, num_users, width, H1, bits);
-  else
-    h1_from_projection_kernel<kRows, true><<<(unsigned)blocks, 256, 0, st>>>(Pi, num_items, items, row0, rows, Zu, group,
-                                                                             users, num_users, width, H1, bits);
+  const dim3 grid((unsigned)blocks, (unsigned)((width + 127) / 128));
+  // (evict-first stores of H1, to keep Pi / Pu in L2, measured 2 % slower than plain stores on the ML-20M step)
+  h1_from_projection_kernel<kRows><<<grid, 256, 0, st>>>(Pi, num_items, items, row0, rows, Zu, group, users, num_users,
+                                                         width, H1, bits);
   MR_LAUNCH_CHECK("h1_from_projection_kernel");
   return MR_OK;
 }

@@ -335,7 +335,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       const float* arow = (EPI == EPI_BIAS_RELU && p.addend != nullptr && my_ok)
                               ? p.addend + (size_t)((uint32_t)my_lr / (uint32_t)p.addend_div) * N : nullptr;
       float zdot = 0.f;  // EPI_HEAD_DOT
-      for (int c0 = 0; c0 < ((p.debug & 32) ? 0 : N); c0 += 32) {
+      // fully unrolled over the (at most 8) 32-column blocks so that mbits[] is indexed at compile time: with a
+      // run-time index the array lived in local memory and ncu showed the epilogue warps of the backward layers,
+      // which bound that kernel, waiting on those loads for a third of their time
+      const int ncols_epi = (p.debug & 32) ? 0 : N;
+#pragma unroll
+      for (int cb = 0; cb < 8; ++cb) {
+        const int c0 = 32 * cb;
+        if (c0 >= ncols_epi) break;
         float v[32];
         tc::tmem_ld16(taddr + c0, v);
         tc::tmem_ld16(taddr + c0 + 16, v + 16);
@@ -376,7 +383,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
             if (my_ok) p.bits_out[(size_t)my_lr * (N >> 5) + (c0 >> 5)] = bits;
           }
         } else if (EPI == EPI_MASK) {
-          const uint32_t bits = mbits[c0 >> 5];
+          const uint32_t bits = mbits[cb];
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (!((bits >> i) & 1u)) v[i] = 0.f;
