@@ -296,10 +296,15 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
                            int64_t r0, int64_t r1, cudaStream_t st, int group = 0, bool users_per_group = false,
                            bool head_dot = false) {
   const int d_u = m.L[0] / 2;
+  bool proj_in_producer = false;
   if (group > 0) {
     // grouped batch: Zu = E_user[user of the group] . W1[user rows] + b1 once per group, then
     // H1 = relu(E_item[item] . W1[item rows] + Zu[row / group]) per row
     const int d_i = m.L[0] - d_u;
+    // ranking eval (no backward pass wants H1): the producers of the second layer compute the projected first layer
+    const bool fuse_h1 = t.Pi != nullptr && t.Pu == nullptr && t.bits[1] == nullptr && m.n_layers >= 3 &&
+                         getenv("MR_NO_PROJ_PRODUCER") == nullptr;
+    proj_in_producer = fuse_h1;
     if (t.Pu != nullptr) {  // user- and item-projected first layer: H1 = relu(Pi[item] + Pu[user])
       const int rc = launch_h1_from_projection(t.Pi, m.num_items, items, r0, r1 - r0, t.Pu, group, users, m.num_users, m.L[1],
                                                t.H[1], t.bits[1], st);
@@ -325,7 +330,8 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     a.out = t.Zu;
     int rc = launch_tc_dense(a, st);
     if (rc != MR_OK) return rc;
-    if (t.Pi != nullptr) {  // item-projected first layer: H1 = relu(Pi[item] + Zu[group])
+    if (fuse_h1) {
+    } else if (t.Pi != nullptr) {  // item-projected first layer: H1 = relu(Pi[item] + Zu[group])
       rc = launch_h1_from_projection(t.Pi, m.num_items, items, r0, r1 - r0, t.Zu, group, nullptr, 0, m.L[1], t.H[1],
                                      t.bits[1], st);
       if (rc != MR_OK) return rc;
@@ -374,6 +380,12 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     a.bias = m.b[l];
     a.out = t.H[l];
     a.bits_out = t.bits[l];  // NULL in forward-only runs
+    if (proj_in_producer && l == 2) {
+      a.a_dense = nullptr;
+      a.proj_i = t.Pi;
+      a.proj_u = t.Zu;
+      a.proj_div = group;
+    }
     if (head_dot && l == m.n_layers - 1) {  // H[l] then holds one float per row: relu(.) . w_out[MLP columns]
       a.epilogue = TC_EPI_HEAD_DOT;
       a.head_w = m.w_out + m.mf_dim;

@@ -78,6 +78,9 @@ enum { TC_EPI_BIAS_RELU = 0, TC_EPI_MASK = 1, TC_EPI_STAGE = 2, TC_EPI_HEAD_DOT 
 struct TcDenseArgs {
   bool gather;            // A = [user row | item row] gathered by id, else a_dense
   const float* a_dense;
+  const float* proj_i;    // A = relu(proj_i[items[row0 + r]] + proj_u[r / proj_div]) (rows of K floats): the item-projected
+  const float* proj_u;    // first layer computed by this layer's producers; needs items / num_items
+  int32_t proj_div;
   const float* user_tab;
   const float* item_tab;
   const int32_t* users;

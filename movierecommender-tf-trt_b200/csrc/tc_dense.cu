@@ -3,7 +3,9 @@
 //     OUT[rows x N] = epilogue( A[rows x K] . Bw[N x K]^T )        3xTF32 on the tensor cores, fp32 accumulate
 //
 //   A    : batch rows.  A_GATHER: row r = [user_mlp[u[r]] | item_mlp[i[r]]] (the embedding gather of
-//          model.py:161-172 fused into the first layer); A_DENSE: a row-major fp32 activation matrix.
+//          model.py:161-172 fused into the first layer); A_DENSE: a row-major fp32 activation matrix;
+//          A_PROJ: row r = relu(Pi[i[r]] + Zu[r / group]), the item-projected first layer (api.cu) computed by the
+//          producers of the SECOND layer, so that H1 never exists in memory (ranking eval).
 //   Bw   : a dense kernel (or its transpose), pre-split into TF32 hi/lo and pre-arranged in core-matrix
 //          order by pack_weights_kernel, so one cp.async.bulk per K-chunk drops it into shared memory.
 //   epilogue: EPI_BIAS_RELU  h = relu(acc + b)          forward Dense/ReLU (model.py:175-181)
@@ -47,12 +49,15 @@ constexpr int kTcTileRows = 128;
 constexpr int kTcKC = 32;  // K elements per pipeline stage
 constexpr int kEpiLd = 36;  // floats per row of an epilogue warp's 32x32 staging tile (16-byte aligned, conflict-free)
 
-enum { A_GATHER = 0, A_DENSE = 1 };
+enum { A_GATHER = 0, A_DENSE = 1, A_PROJ = 2 };
 enum { EPI_BIAS_RELU = 0, EPI_MASK = 1, EPI_STAGE = 2, EPI_HEAD_DOT = 3 };
 
 struct TcDenseParams {
   // A operand
   const float* a_dense;  // [rows x K] (A_DENSE)
+  const float* proj_i;   // (A_PROJ) [num_items x K] item half of the first layer, indexed by items[]
+  const float* proj_u;   // (A_PROJ) [rows / proj_div x K] user half + bias, launch-local row r reads row r / proj_div
+  int32_t proj_div;
   const float* user_tab; // (A_GATHER) user rows of width d_u, item rows of width K - d_u
   const float* item_tab;
   const int32_t* users;
@@ -154,7 +159,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
           ok[g] = lr < p.rows;
           src_u[g] = nullptr;
           src_i[g] = nullptr;
-          if (AMODE == A_GATHER) {
+          if (AMODE == A_PROJ) {
+            if (ok[g]) {
+              const int it = __ldg(p.items + p.row0 + lr);
+              src_u[g] = p.proj_u + (size_t)((uint32_t)lr / (uint32_t)p.proj_div) * K;
+              src_i[g] = (unsigned)it < (unsigned)p.num_items ? p.proj_i + (size_t)it * K : nullptr;  // bad id: zero row
+            }
+          } else if (AMODE == A_GATHER) {
             if (ok[g]) {
               const uint32_t grow = (uint32_t)(p.row0 + lr);  // B < 2^31
               const bool has_u = p.d_u > 0, has_i = p.d_u < K;
@@ -181,9 +192,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ok[g] && !(p.debug & 2)) {
             if (AMODE == A_GATHER) v = (col < p.d_u) ? ldg4(src_u[g] + col) : ldg4(src_i[g] + (col - p.d_u));
-            else v = ldg4(src_u[g] + col);
+            else v = ldg4(src_u[g] + col);  // A_PROJ: the user-side row; the item-side row comes with issue_loads_item
           }
           x[2 * g + h] = v;
+        }
+      }
+    };
+    // A_PROJ: the item-side rows of the chunk issue_loads just took (same tile cache, same columns)
+    auto issue_loads_item = [&](int c, float4(&y)[2 * RG]) {
+      const int col0 = c * kTcKC;
+#pragma unroll
+      for (int g = 0; g < RG; ++g) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = col0 + 4 * (4 * h + csub);
+          y[2 * g + h] = (ok[g] && src_i[g] != nullptr) ? ldg4(src_i[g] + col) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     };
@@ -227,6 +250,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
     constexpr int D = kTcLoadAhead, NB = kTcLoadAhead + 1;
     float4 buf[NB][2 * RG];
     const int64_t mine = total > group ? (total - group + G - 1) / G : 0;  // chunks of this group
+    if (AMODE == A_PROJ) {
+      // two source rows per element: both register buffers hold ONE chunk (no load-ahead; Pi and Zu are L2- and
+      // L1-resident, and the other producer group's chunk overlaps this one's latency)
+      for (int64_t i = 0; i < mine; ++i) {
+        const int c = ld_c;
+        issue_loads(buf[0]);
+        issue_loads_item(c, buf[NB - 1]);
+#pragma unroll
+        for (int e = 0; e < 2 * RG; ++e) {
+          buf[0][e].x = fmaxf(buf[0][e].x + buf[NB - 1][e].x, 0.f);
+          buf[0][e].y = fmaxf(buf[0][e].y + buf[NB - 1][e].y, 0.f);
+          buf[0][e].z = fmaxf(buf[0][e].z + buf[NB - 1][e].z, 0.f);
+          buf[0][e].w = fmaxf(buf[0][e].w + buf[NB - 1][e].w, 0.f);
+        }
+        store_chunk(i * G < S, buf[0]);
+      }
+    } else {
 #pragma unroll
     for (int j = 0; j < D; ++j)
       if (j < mine) issue_loads(buf[j]);
@@ -239,6 +279,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
           store_chunk(i * G < S, buf[j]);
         }
       }
+    }
     }
   } else if (warp == kTcMmaWarp) {
     // ================================ MMA issuer ================================================
@@ -283,7 +324,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
     // The producers keep one chunk per group in flight in registers (32 KB per SM), which covers L2 latency
     // but not DRAM latency at full bandwidth.  This warp pulls the A rows of the tile kTcPrefetchAhead tiles
     // ahead of the MMA issuer into L2 (prefetch.global.L2 holds no registers), so the producers' loads hit L2.
-    if (!(p.debug & 128)) {
+    if (!(p.debug & 128) && AMODE != A_PROJ) {  // (A_PROJ reads L2-resident projections)
       int64_t it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         while (it >= (int64_t)*reinterpret_cast<volatile int*>(&tiles_started) + kTcPrefetchAhead) __nanosleep(256);
@@ -488,6 +529,9 @@ int launch_tc_dense(const TcDenseArgs& a, cudaStream_t st) {
   p.d_u = a.d_u;
   p.user_div = a.user_div < 1 ? 1 : a.user_div;
   p.user_mul = a.user_mul < 1 ? 1 : a.user_mul;
+  p.proj_i = a.proj_i;
+  p.proj_u = a.proj_u;
+  p.proj_div = a.proj_div < 1 ? 1 : a.proj_div;
   p.addend = a.addend;
   p.addend_div = a.addend_div < 1 ? 1 : a.addend_div;
   p.relu = a.linear ? 0 : 1;
@@ -513,6 +557,12 @@ int launch_tc_dense(const TcDenseArgs& a, cudaStream_t st) {
   if (a.gather) {
     if (a.epilogue != TC_EPI_BIAS_RELU) return MR_ERR_INVALID;
     return launch_dense_t<A_GATHER, EPI_BIAS_RELU>(p, st);
+  }
+  if (a.proj_i != nullptr) {  // A = relu(Pi[item] + Zu[row / proj_div])
+    if (a.proj_u == nullptr || a.items == nullptr) return MR_ERR_INVALID;
+    if (a.epilogue == TC_EPI_BIAS_RELU) return launch_dense_t<A_PROJ, EPI_BIAS_RELU>(p, st);
+    if (a.epilogue == TC_EPI_HEAD_DOT && a.bias && a.head_w && a.out) return launch_dense_t<A_PROJ, EPI_HEAD_DOT>(p, st);
+    return MR_ERR_INVALID;
   }
   switch (a.epilogue) {
     case TC_EPI_BIAS_RELU: return launch_dense_t<A_DENSE, EPI_BIAS_RELU>(p, st);

@@ -431,10 +431,15 @@ def test_item_projected_rank_eval_matches_oracle(eng_mod, monkeypatch):
     try:
         # third pass: the last hidden layer written out and dotted by the score kernel (MR_NO_HEAD_DOT) instead of
         # folded into the output unit's dot product by the layer's own epilogue
-        for selector in ("auto", "off", "auto-nodot"):
+        # fourth pass: H1 written by the gather kernel (MR_NO_PROJ_PRODUCER) instead of computed by the second layer's
+        # producers
+        for selector in ("auto", "off", "auto-nodot", "auto-noprod"):
             eng_mod.set_item_projection(selector.split("-")[0])
             if selector.endswith("nodot"):
                 monkeypatch.setenv("MR_NO_HEAD_DOT", "1")
+            if selector.endswith("noprod"):
+                monkeypatch.delenv("MR_NO_HEAD_DOT")
+                monkeypatch.setenv("MR_NO_PROJ_PRODUCER", "1")
             # positions only: the fused sequence (a full permutation request takes the forward + rank kernels)
             pos, sums, _, probs = eng.rank_eval(users, items, group, k, want_probs=True)
             p = probs.cpu().numpy()
@@ -448,6 +453,7 @@ def test_item_projected_rank_eval_matches_oracle(eng_mod, monkeypatch):
         eng_mod.set_item_projection("auto")
     rel_close(got["auto"], got["off"], what="eval probs projected vs per-row")
     rel_close(got["auto"], got["auto-nodot"], what="eval probs, last layer folded into the dot vs written out")
+    rel_close(got["auto"], got["auto-noprod"], what="eval probs, H1 in the producers vs written out")
 
 
 @pytest.mark.parametrize("f,group,L", [(32, 7, [256, 128, 32]), (128, 100, [256, 128, 64]), (64, 256, [256, 128, 128, 64]),
