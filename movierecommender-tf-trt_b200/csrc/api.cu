@@ -301,11 +301,16 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     // grouped batch: Zu = E_user[user of the group] . W1[user rows] + b1 once per group, then
     // H1 = relu(E_item[item] . W1[item rows] + Zu[row / group]) per row
     const int d_i = m.L[0] - d_u;
-    // ranking eval (no backward pass wants H1): the producers of the second layer compute the projected first layer
-    const bool fuse_h1 = t.Pi != nullptr && t.Pu == nullptr && t.bits[1] == nullptr && m.n_layers >= 3 &&
-                         getenv("MR_NO_PROJ_PRODUCER") == nullptr;
+    // the producers of the second layer compute the projected first layer; in the ranking eval H1 then never exists
+    // in memory, in the train step they also write it (and its ReLU bits) for the backward pass
+    const bool train_rows = t.bits[1] != nullptr;
+    // (train step: measured 0.08 ms SLOWER than the separate gather kernel -- the extra 64-byte stores land on the
+    // pipe that bounds the layer kernel -- so there it is opt-in, MR_PROJ_PRODUCER_TRAIN=1, and covered by a test)
+    const bool fuse_h1 = t.Pi != nullptr && m.n_layers >= 3 && getenv("MR_NO_PROJ_PRODUCER") == nullptr &&
+                         (!train_rows || getenv("MR_PROJ_PRODUCER_TRAIN") != nullptr);
     proj_in_producer = fuse_h1;
-    if (t.Pu != nullptr) {  // user- and item-projected first layer: H1 = relu(Pi[item] + Pu[user])
+    if (fuse_h1 && t.Pu != nullptr) {
+    } else if (t.Pu != nullptr) {  // user- and item-projected first layer: H1 = relu(Pi[item] + Pu[user])
       const int rc = launch_h1_from_projection(t.Pi, m.num_items, items, r0, r1 - r0, t.Pu, group, users, m.num_users, m.L[1],
                                                t.H[1], t.bits[1], st);
       if (rc != MR_OK) return rc;
@@ -385,6 +390,15 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
       a.proj_i = t.Pi;
       a.proj_u = t.Zu;
       a.proj_div = group;
+      if (t.Pu != nullptr) {  // one row per USER
+        a.proj_u = t.Pu;
+        a.proj_ids = users;
+        a.proj_u_rows = m.num_users;
+      }
+      if (t.bits[1] != nullptr) {
+        a.h1_out = t.H[1];
+        a.h1_bits = t.bits[1];
+      }
     }
     if (head_dot && l == m.n_layers - 1) {  // H[l] then holds one float per row: relu(.) . w_out[MLP columns]
       a.epilogue = TC_EPI_HEAD_DOT;

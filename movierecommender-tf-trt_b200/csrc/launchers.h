@@ -81,6 +81,10 @@ struct TcDenseArgs {
   const float* proj_i;    // A = relu(proj_i[items[row0 + r]] + proj_u[r / proj_div]) (rows of K floats): the item-projected
   const float* proj_u;    // first layer computed by this layer's producers; needs items / num_items
   int32_t proj_div;
+  const int32_t* proj_ids;  // optional: row r reads proj_u[proj_ids[row0 + r]] (proj_u_rows rows) instead of r / proj_div
+  int32_t proj_u_rows;
+  float* h1_out;            // optional (training): the A rows [rows x K] and their ReLU bits [rows x K/32]
+  uint32_t* h1_bits;
   const float* user_tab;
   const float* item_tab;
   const int32_t* users;

@@ -56,8 +56,12 @@ struct TcDenseParams {
   // A operand
   const float* a_dense;  // [rows x K] (A_DENSE)
   const float* proj_i;   // (A_PROJ) [num_items x K] item half of the first layer, indexed by items[]
-  const float* proj_u;   // (A_PROJ) [rows / proj_div x K] user half + bias, launch-local row r reads row r / proj_div
-  int32_t proj_div;
+  const float* proj_u;   // (A_PROJ) [rows / proj_div x K] user half + bias, launch-local row r reads row r / proj_div;
+  int32_t proj_div;      //          with proj_ids: [proj_u_rows x K], row r reads row proj_ids[row0 + r]
+  const int32_t* proj_ids;
+  int32_t proj_u_rows;
+  float* h1_out;         // (A_PROJ, optional) [rows x K] launch-local rows: the A rows, for the backward pass
+  uint32_t* h1_bits;     // (A_PROJ, optional) [rows x K/32] their ReLU bits
   const float* user_tab; // (A_GATHER) user rows of width d_u, item rows of width K - d_u
   const float* item_tab;
   const int32_t* users;
@@ -162,7 +166,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
           if (AMODE == A_PROJ) {
             if (ok[g]) {
               const int it = __ldg(p.items + p.row0 + lr);
-              src_u[g] = p.proj_u + (size_t)((uint32_t)lr / (uint32_t)p.proj_div) * K;
+              if (p.proj_ids == nullptr) {
+                src_u[g] = p.proj_u + (size_t)((uint32_t)lr / (uint32_t)p.proj_div) * K;
+              } else {
+                const int u = __ldg(p.proj_ids + p.row0 + lr);
+                src_u[g] = (unsigned)u < (unsigned)p.proj_u_rows ? p.proj_u + (size_t)u * K : nullptr;  // bad id: zero row
+              }
               src_i[g] = (unsigned)it < (unsigned)p.num_items ? p.proj_i + (size_t)it * K : nullptr;  // bad id: zero row
             }
           } else if (AMODE == A_GATHER) {
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ok[g] && !(p.debug & 2)) {
             if (AMODE == A_GATHER) v = (col < p.d_u) ? ldg4(src_u[g] + col) : ldg4(src_i[g] + (col - p.d_u));
-            else v = ldg4(src_u[g] + col);  // A_PROJ: the user-side row; the item-side row comes with issue_loads_item
+            else if (AMODE == A_DENSE || src_u[g] != nullptr) v = ldg4(src_u[g] + col);  // A_PROJ: the user-side row
           }
           x[2 * g + h] = v;
         }
@@ -263,6 +272,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
           buf[0][e].y = fmaxf(buf[0][e].y + buf[NB - 1][e].y, 0.f);
           buf[0][e].z = fmaxf(buf[0][e].z + buf[NB - 1][e].z, 0.f);
           buf[0][e].w = fmaxf(buf[0][e].w + buf[NB - 1][e].w, 0.f);
+        }
+        if (p.h1_out != nullptr) {
+          // training: the backward pass wants these rows (A of the weight gradient) and their ReLU bits.  A row's 32
+          // columns of the chunk sit in four lanes (csub) x two pieces (h): 64-byte stores, bits OR-ed over the lanes
+          const int64_t trow0 = (blockIdx.x + cached_tile * gridDim.x) * kTcTileRows;
+#pragma unroll
+          for (int g = 0; g < RG; ++g) {
+            const int64_t lr = trow0 + 8 * RG * pw + 8 * g + rsub;
+            uint32_t w = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4 v = buf[0][2 * g + h];
+              if (ok[g]) *reinterpret_cast<float4*>(p.h1_out + (size_t)lr * K + c * kTcKC + 4 * (4 * h + csub)) = v;
+              const uint32_t nib = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
+              w |= nib << (4 * (4 * h + csub));
+            }
+            w |= __shfl_xor_sync(0xffffffffu, w, 8);
+            w |= __shfl_xor_sync(0xffffffffu, w, 16);
+            if (csub == 0 && ok[g] && p.h1_bits != nullptr) p.h1_bits[(size_t)lr * (K >> 5) + c] = w;
+          }
         }
         store_chunk(i * G < S, buf[0]);
       }
@@ -532,6 +561,10 @@ int launch_tc_dense(const TcDenseArgs& a, cudaStream_t st) {
   p.proj_i = a.proj_i;
   p.proj_u = a.proj_u;
   p.proj_div = a.proj_div < 1 ? 1 : a.proj_div;
+  p.proj_ids = a.proj_ids;
+  p.proj_u_rows = a.proj_u_rows;
+  p.h1_out = a.h1_out;
+  p.h1_bits = a.h1_bits;
   p.addend = a.addend;
   p.addend_div = a.addend_div < 1 ? 1 : a.addend_div;
   p.relu = a.linear ? 0 : 1;

@@ -387,14 +387,17 @@ def test_item_projected_train_steps_match_oracle(eng_mod, case):
         eng_mod.set_item_projection("auto")
 
 
-def test_item_projection_on_and_off_agree_and_are_deterministic(eng_mod):
+def test_item_projection_on_and_off_agree_and_are_deterministic(eng_mod, monkeypatch):
     """Zipf-hot users and items, 30,000 rows over 3,000 items (the automatic choice projects): the per-item launch
     sequence against the per-row one, and against itself."""
     nu, ni, L, f, negs, groups = 5000, 3000, [256, 128, 64], 64, 4, 6000
     runs = {}
     try:
-        for tag, selector in (("off", "off"), ("on", "auto"), ("again", "auto")):
+        # "producers": H1 and its ReLU bits written by the second layer's producers (opt-in variant of the train step)
+        for tag, selector in (("off", "off"), ("on", "auto"), ("again", "auto"), ("producers", "auto")):
             eng_mod.set_item_projection(selector)
+            if tag == "producers":
+                monkeypatch.setenv("MR_PROJ_PRODUCER_TRAIN", "1")
             rng = np.random.default_rng(23)
             eng = eng_mod.NeuMFEngine(nu, ni, L, [0, 0, 0], mf_dim=f, table_mode="dense", optimizer="sgd", lr=0.5, seed=6)
             assert eng.uses_item_projection(groups * (negs + 1)) == (selector != "off")
@@ -411,6 +414,7 @@ def test_item_projection_on_and_off_agree_and_are_deterministic(eng_mod):
         assert abs(a[0] - b[0]) <= 1e-5 * abs(a[0]) and a[1] == b[1] and a[4] == 0 and b[4] == 0
     for k in runs["off"][0]:  # SGD at lr 0.5 over three steps: see test_grouped_and_ungrouped_steps_agree
         rel_close(runs["on"][0][k], runs["off"][0][k], rtol=1e-4, what="projected vs per-row " + k)
+        rel_close(runs["producers"][0][k], runs["on"][0][k], rtol=1e-5, what="H1 from the producers vs the gather kernel " + k)
         assert np.array_equal(runs["on"][0][k], runs["again"][0][k]), k
     for a, b in zip(runs["on"][1], runs["again"][1]):
         assert np.array_equal(a, b)
