@@ -218,7 +218,8 @@ enum { MR_PHASE_TILE_TRAIN = 0, /* fused gather+tower+head+BCE+backward kernel *
        MR_PHASE_TC_DENSE_BWD = 9,  /* tcgen05 backward-activation layers */
        MR_PHASE_TC_WGRAD = 10,     /* tcgen05 weight-gradient layers */
        MR_PHASE_HEAD = 11,         /* GMF + output unit + BCE (+ their gradients) */
-       MR_NUM_PHASES = 12 };
+       MR_PHASE_H1_GATHER = 12,    /* item-projected first layer: gather + add + ReLU of the projected rows */
+       MR_NUM_PHASES = 13 };
 int mr_profile_begin(void);
 int mr_profile_end(float* phase_ms, int64_t* phase_count, int64_t* kernel_launches);
 

@@ -311,9 +311,11 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     proj_in_producer = fuse_h1;
     if (fuse_h1 && t.Pu != nullptr) {
     } else if (t.Pu != nullptr) {  // user- and item-projected first layer: H1 = relu(Pi[item] + Pu[user])
+      prof_mark(MR_PHASE_H1_GATHER, st);
       const int rc = launch_h1_from_projection(t.Pi, m.num_items, items, r0, r1 - r0, t.Pu, group, users, m.num_users, m.L[1],
                                                t.H[1], t.bits[1], st);
       if (rc != MR_OK) return rc;
+      prof_mark(MR_PHASE_TC_DENSE_FWD, st);
     } else {
     TcDenseArgs a{};
     a.gather = true;
@@ -337,9 +339,11 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     if (rc != MR_OK) return rc;
     if (fuse_h1) {
     } else if (t.Pi != nullptr) {  // item-projected first layer: H1 = relu(Pi[item] + Zu[group])
+      prof_mark(MR_PHASE_H1_GATHER, st);
       rc = launch_h1_from_projection(t.Pi, m.num_items, items, r0, r1 - r0, t.Zu, group, nullptr, 0, m.L[1], t.H[1],
                                      t.bits[1], st);
       if (rc != MR_OK) return rc;
+      prof_mark(MR_PHASE_TC_DENSE_FWD, st);
     } else {
     TcDenseArgs b{};
     b.gather = true;

@@ -325,6 +325,172 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_group_kernel(const HeadP
   }
 }
 
+// Grouped train head, third form (mf_dim = 64, last width = 64, groups of at most 5 rows): EIGHT LANES PER ROW.  A
+// quad of eight lanes owns a whole group -- its user GMF row, the KR rows of H_last and of item GMF rows, the group's
+// user-gradient row -- so a warp instruction moves four rows with 128-bit accesses (128 contiguous bytes per quad),
+// a row's dot product folds with three shuffles instead of five, and all 4 * KR rows of a warp iteration are in
+// flight together while the next iteration's ids are already on their way.  ncu on the warp-per-row kernels above:
+// 60 % issue-active at 3 TB/s -- instruction-bound, not HBM-bound; this layout issues a quarter of the memory
+// instructions per row.  Same arithmetic per row; the sums over rows (d w_out, d b_out, loss) fold per quad in row
+// order, then quads and warps in index order (deterministic).
+constexpr int kQuadThreads = 128;
+template <int KR>
+__global__ void __launch_bounds__(kQuadThreads) head_quad_kernel(const HeadParams p) {
+  constexpr int f = 64, Ln = 64, ncols = f + Ln, NV = 2;
+  constexpr int kWarps = kQuadThreads / 32;
+  __shared__ __align__(16) float red[kWarps * 4][ncols + 4];  // rows of 16-byte multiples: the lanes store float4
+  const MrModel& m = p.m;
+  const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
+  const int su = d_u + f, si = d_i + f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & 7, quad = lane >> 3;
+  float4 wg[NV], wh[NV], accg[NV], acch[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    wg[v] = ldg4(m.w_out + 32 * v + 4 * sub);
+    wh[v] = ldg4(m.w_out + f + 32 * v + 4 * sub);
+    accg[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acch[v] = accg[v];
+  }
+  const float b_out = __ldg(m.b_out);
+  float accb = 0.f, accl = 0.f;
+  const int64_t ngroups = p.rows / KR;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+
+  // ids of a warp iteration (groups g0 .. g0 + 3 = rows g0 * KR .. + 4 * KR - 1), lane-distributed; the quad's user
+  auto load_ids = [&](int64_t g0, int& item, float& y, int& u) {
+    const int64_t r0 = g0 * KR, left = p.rows - r0;
+    item = 0;
+    y = 0.f;
+    if (lane < 4 * KR && lane < left) {
+      item = __ldg(p.items + p.row0 + r0 + lane);
+      y = __ldg(p.labels + p.row0 + r0 + lane);
+    }
+    const int64_t g = g0 + quad;
+    u = g < ngroups ? __ldg(p.users + p.row0 + g * KR) : 0;
+  };
+  int64_t itn = (int64_t)blockIdx.x * kWarps + warp;
+  int item_c = 0, u_c = 0, item_n = 0, u_n = 0;
+  float y_c = 0.f, y_n = 0.f;
+  if (4 * itn < ngroups) load_ids(4 * itn, item_c, y_c, u_c);
+  for (; 4 * itn < ngroups; itn += nwarps) {
+    const int64_t g = 4 * itn + quad;
+    const bool live = g < ngroups;
+    if (4 * (itn + nwarps) < ngroups) load_ids(4 * (itn + nwarps), item_n, y_n, u_n);
+    const bool bad_u = live && (unsigned)u_c >= (unsigned)m.num_users;
+    const int uu = (bad_u || !live) ? 0 : u_c;
+    const int64_t lr0 = (live ? g : 0) * KR;  // launch-local first row of the quad's group (dead quads re-read group 0)
+    float4 gu[NV], gi[KR][NV], h[KR][NV];
+    int itv[KR];
+    float yv[KR];
+#pragma unroll
+    for (int rr = 0; rr < KR; ++rr) {
+      itv[rr] = __shfl_sync(0xffffffffu, item_c, quad * KR + rr);
+      yv[rr] = __shfl_sync(0xffffffffu, y_c, quad * KR + rr);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) gu[v] = ldg4(m.user_gmf + (size_t)uu * f + 32 * v + 4 * sub);
+#pragma unroll
+    for (int rr = 0; rr < KR; ++rr) {
+      const int iv = (unsigned)itv[rr] >= (unsigned)m.num_items ? 0 : itv[rr];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        gi[rr][v] = ldg4(m.item_gmf + (size_t)iv * f + 32 * v + 4 * sub);
+        h[rr][v] = ldg4(p.h_last + (size_t)(lr0 + rr) * Ln + 32 * v + 4 * sub);
+      }
+    }
+    float4 gu_acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) gu_acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool any_bad = false;
+#pragma unroll
+    for (int rr = 0; rr < KR; ++rr) {
+      const int64_t lr = lr0 + rr, gr = p.row0 + lr;
+      float4 x[NV];
+      float s = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        x[v] = make_float4(gu[v].x * gi[rr][v].x, gu[v].y * gi[rr][v].y, gu[v].z * gi[rr][v].z, gu[v].w * gi[rr][v].w);
+        s = fmaf(wg[v].x, x[v].x, s);
+        s = fmaf(wg[v].y, x[v].y, s);
+        s = fmaf(wg[v].z, x[v].z, s);
+        s = fmaf(wg[v].w, x[v].w, s);
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        s = fmaf(wh[v].x, h[rr][v].x, s);
+        s = fmaf(wh[v].y, h[rr][v].y, s);
+        s = fmaf(wh[v].z, h[rr][v].z, s);
+        s = fmaf(wh[v].w, h[rr][v].w, s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      const float z = s + b_out;
+      const float pr = sigmoidf_stable(z);
+      const bool bad = bad_u || (unsigned)itv[rr] >= (unsigned)m.num_items;
+      any_bad |= bad && live;
+      if (live && sub == 0 && p.probs != nullptr) p.probs[gr] = bad ? nanf("") : pr;
+      const float y = yv[rr];
+      const float dz = (bad || !live) ? 0.f : (pr - y) * p.inv_batch;
+      if (live && !bad) accl += bce_logits(z, y);
+      accb += dz;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        accg[v].x = fmaf(dz, x[v].x, accg[v].x);
+        accg[v].y = fmaf(dz, x[v].y, accg[v].y);
+        accg[v].z = fmaf(dz, x[v].z, accg[v].z);
+        accg[v].w = fmaf(dz, x[v].w, accg[v].w);
+        const float4 gv = make_float4(dz * wg[v].x, dz * wg[v].y, dz * wg[v].z, dz * wg[v].w);
+        gu_acc[v].x = fmaf(gv.x, gi[rr][v].x, gu_acc[v].x);
+        gu_acc[v].y = fmaf(gv.y, gi[rr][v].y, gu_acc[v].y);
+        gu_acc[v].z = fmaf(gv.z, gi[rr][v].z, gu_acc[v].z);
+        gu_acc[v].w = fmaf(gv.w, gi[rr][v].w, gu_acc[v].w);
+        acch[v].x = fmaf(dz, h[rr][v].x, acch[v].x);
+        acch[v].y = fmaf(dz, h[rr][v].y, acch[v].y);
+        acch[v].z = fmaf(dz, h[rr][v].z, acch[v].z);
+        acch[v].w = fmaf(dz, h[rr][v].w, acch[v].w);
+        if (live) {
+          *reinterpret_cast<float4*>(p.stage_i + (size_t)gr * si + d_i + 32 * v + 4 * sub) =
+              make_float4(gv.x * gu[v].x, gv.y * gu[v].y, gv.z * gu[v].z, gv.w * gu[v].w);
+          *reinterpret_cast<float4*>(p.dz_last + (size_t)lr * Ln + 32 * v + 4 * sub) =
+              make_float4(h[rr][v].x > 0.f ? dz * wh[v].x : 0.f, h[rr][v].y > 0.f ? dz * wh[v].y : 0.f,
+                          h[rr][v].z > 0.f ? dz * wh[v].z : 0.f, h[rr][v].w > 0.f ? dz * wh[v].w : 0.f);
+        }
+      }
+    }
+    if (live) {
+      const int64_t grp = (p.row0 + g * KR) / KR;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        *reinterpret_cast<float4*>(p.stage_u + (size_t)grp * su + d_u + 32 * v + 4 * sub) = gu_acc[v];
+      if (any_bad && sub == 0) atomicOr(p.flags, 1);
+    }
+    item_c = item_n;
+    y_c = y_n;
+    u_c = u_n;
+  }
+
+  // per-quad sums -> shared -> this CTA's partial row, quads and warps added in index order
+  float* my = red[warp * 4 + quad];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    *reinterpret_cast<float4*>(my + 32 * v + 4 * sub) = accg[v];
+    *reinterpret_cast<float4*>(my + f + 32 * v + 4 * sub) = acch[v];
+  }
+  if (sub == 0) {
+    my[ncols] = accb;  // every lane of a quad holds the same accb / accl
+    my[ncols + 1] = accl;
+  }
+  __syncthreads();
+  float* dst = p.head_partial + (size_t)blockIdx.x * (ncols + 2);
+  for (int j = threadIdx.x; j < ncols + 2; j += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < kWarps * 4; ++w) t += red[w][j];
+    dst[j] += t;
+  }
+}
+
 // Ranking evaluation, fused: GMF product + output unit + sigmoid of the `group` candidates of one user AND the
 // position of the positive (the LAST candidate, data_pipeline.py:113,148) under the RankLayer order
 // (model.py:344-352: descending probability, lower index first among ties), in one kernel -- the scores never
@@ -689,6 +855,23 @@ int launch_head(const HeadArgs& a, cudaStream_t st) {
     }
     const bool wide = ncols > 128;  // only the specialisation covers these
     const bool special = a.labels != nullptr && head_special_widths(m) && (wide || getenv("MR_HEAD_GENERIC") == nullptr);
+    const uintptr_t al = reinterpret_cast<uintptr_t>(m.user_gmf) | reinterpret_cast<uintptr_t>(m.item_gmf) |
+                         reinterpret_cast<uintptr_t>(m.w_out) | reinterpret_cast<uintptr_t>(a.h_last) |
+                         reinterpret_cast<uintptr_t>(a.dz_last) | reinterpret_cast<uintptr_t>(a.stage_u) |
+                         reinterpret_cast<uintptr_t>(a.stage_i);
+    if (special && m.mf_dim == 64 && a.group <= 5 && (al & 15) == 0 && (m.L[0] / 2) % 4 == 0 &&
+        getenv("MR_HEAD_PIPE") == nullptr) {  // eight lanes per row (BASELINE configs[2])
+      const int64_t want = (a.rows / a.group + 15) / 16;  // 16 groups per CTA iteration
+      const unsigned qgrid = (unsigned)(want < grid ? want : grid);
+      switch (a.group) {
+        case 2: head_quad_kernel<2><<<qgrid, kQuadThreads, 0, st>>>(p); break;
+        case 3: head_quad_kernel<3><<<qgrid, kQuadThreads, 0, st>>>(p); break;
+        case 4: head_quad_kernel<4><<<qgrid, kQuadThreads, 0, st>>>(p); break;
+        default: head_quad_kernel<5><<<qgrid, kQuadThreads, 0, st>>>(p); break;
+      }
+      MR_LAUNCH_CHECK("head_quad_kernel");
+      return MR_OK;
+    }
     if (special) {  // the pipelined specialisation: BASELINE configs[2] (f = 64) and configs[4] (f = 128), last layer 64
 #define MR_HEAD_GROUP(FQ_)                                                                                   \
   switch (a.group) {                                                                                       \

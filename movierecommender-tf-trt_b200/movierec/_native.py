@@ -129,9 +129,9 @@ def check(rc, what):
         raise MovierecNativeError("{} failed (status {}): {}".format(what, rc, last_error()))
 
 
-NUM_PHASES = 12
+NUM_PHASES = 13
 PHASE_NAMES = ["tile_train", "misc", "sort", "segreduce", "optimizer", "tile_forward", "rank", "sampler",
-               "tc_dense_fwd", "tc_dense_bwd", "tc_wgrad", "head"]
+               "tc_dense_fwd", "tc_dense_bwd", "tc_wgrad", "head", "h1_gather"]
 
 
 def profile_begin():
