@@ -90,6 +90,7 @@ struct SideStream {
   int dev = -1;
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork2 = nullptr, join2 = nullptr;  // second excursion of a step: the user-side segmented reduction
 };
 static thread_local SideStream g_side;
 
@@ -104,7 +105,9 @@ static SideStream* side_stream() {
     s = SideStream{};
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join2, cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
       s = SideStream{};
       return nullptr;
@@ -463,6 +466,8 @@ struct TrainWs {
   size_t sort_ws_bytes;
   void* seg_ws;
   size_t seg_ws_bytes;
+  void* seg_ws_u;  // user-side reduction when it runs next to the item-side one
+  size_t seg_ws_u_bytes;
   void* tc_ws;
   size_t tc_ws_bytes;
   int32_t* pos;
@@ -492,6 +497,8 @@ static TrainWs carve_train(const MrModel& m, int64_t B, void* ws) {
   t.sort_ws = cv.take<char>(t.sort_ws_bytes);
   t.seg_ws_bytes = segreduce_workspace_bytes(B, (d_u > d_i ? d_u : d_i) + m.mf_dim);
   t.seg_ws = cv.take<char>(t.seg_ws_bytes);
+  t.seg_ws_u_bytes = segreduce_workspace_bytes(B / 2 + 1, d_u + m.mf_dim);
+  t.seg_ws_u = cv.take<char>(t.seg_ws_u_bytes);
   t.pos = cv.take<int32_t>(B);
   t.rank_partials = cv.take<float>(rank_partials_count(B));
   t.group_users = cv.take<int32_t>(B / 2 + 1);
@@ -1005,10 +1012,31 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       ui.num_rows = m.num_items;
       ui.g0 = tw.Si;
       ui.g1 = grads->item_gmf;
+      // the two reductions are independent: the user side runs on the side stream, so the latency-bound upper
+      // levels of one chain (20 us launches of a few CTAs) run under the other chain
+      cudaStream_t su_st = st;
+      if (uproj && side != nullptr) {
+        MR_CUDA(cudaEventRecord(side->fork2, st));
+        MR_CUDA(cudaStreamWaitEvent(side->stream, side->fork2, 0));
+        su_st = side->stream;
+      }
+      if (uproj && su_st != st) {
+        RowUpdate uu{};
+        uu.mode = MR_TABLES_DENSE;
+        uu.optimizer = opt->optimizer;
+        uu.d0 = m.L[1];
+        uu.d1 = f;
+        uu.num_rows = m.num_users;
+        uu.g0 = tw.Su;
+        uu.g1 = grads->user_gmf;
+        rc = launch_segreduce(t.sorted_keys, t.sorted_index, n_user_rows, t.stage_u, uu, t.seg_ws_u, t.seg_ws_u_bytes, su_st);
+        if (rc != MR_OK) return rc;
+        MR_CUDA(cudaEventRecord(side->join2, su_st));
+      }
       prof_mark(MR_PHASE_SEGREDUCE, st);
       rc = launch_segreduce(t.sorted_keys_i, t.sorted_index_i, B, t.stage_i, ui, t.seg_ws, t.seg_ws_bytes, st);
       if (rc != MR_OK) return rc;
-      if (uproj) {  // per-user sums of [group sums of dZ1 | GMF row gradient]
+      if (uproj && su_st == st) {  // per-user sums of [group sums of dZ1 | GMF row gradient]
         RowUpdate uu{};
         uu.mode = MR_TABLES_DENSE;
         uu.optimizer = opt->optimizer;
@@ -1047,6 +1075,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       wi.partial_stride = t.dense_stride;
       rc = launch_tc_wgrad(wi, st);
       if (rc != MR_OK) return rc;
+      if (uproj && su_st != st) MR_CUDA(cudaStreamWaitEvent(st, side->join2, 0));
       if (uproj) {  // d E_user = Su . W1u^T, d W1u = E_user^T . Su, d b1 = column sums of Su
         prof_mark(MR_PHASE_TC_DENSE_BWD, st);
         TcDenseArgs bu{};
