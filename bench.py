@@ -163,8 +163,8 @@ def phase_interface_bytes(wl, rows, grouped=False, projected=False, user_project
                 "tc_wgrad": ni * 4 * (d_i + L1) + nu * (4 + 4 * (d_u + L1)) + rows * sum(4 * (a + b) for a, b in later),
                 "tc_dense_bwd": rows * sum(4 * (a + b) + 4 * a for a, b in later) + ni * 4 * (L1 + d_i) + nu * 4 * (L1 + d_u),
                 "misc": rows * 4 * L1 + G * 4 * L1,
-                "segreduce": G * 2 * (4 * dU + 8) + rows * 2 * (4 * dI + 8),
-                "sort": (G + rows) * 2 * 16,
+                # (user-projected steps reduce the user side on the side stream, under the item side: not counted here)
+                "segreduce": (0 if user_projected else G * 2 * (4 * dU + 8)) + rows * 2 * (4 * dI + 8),
                 "optimizer": 28 * tables,
             }
         return {
@@ -496,7 +496,9 @@ def run_gpu(args, wl):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dom + "_dram_bytes_per_launch")
+            per_step = json.load(f).get(args.workload, {}).get(dom + "_dram_bytes_per_step")
+            # ncu measured one step; a "launch" here is one launch group of the phase, like `achieved`
+            traffic = per_step * args.steps / dom_groups if per_step else None
     tc_flops = 3.0 * ab["flops_step"]  # 3xTF32: every fp32 product is three tensor-core products
     if args.lean:
         cpu_value, cpu_ms, cpu_rows, cpu_eval = None, None, 0, None
