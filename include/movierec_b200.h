@@ -256,6 +256,21 @@ int mr_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int
 /* Diagnostics: sustained tcgen05 issue rate of the 3xTF32 stage pattern on static operands (tools/tc_rate.py). */
 int mr_tc_rate(int32_t N, int32_t iters, int32_t nbuf, int32_t flags, int32_t writers, int32_t write_iters,
                int64_t* out_cycles, int32_t grid, void* stream);
+/* Dataset preparation on the device.
+ * mr_split_last_two replaces the pandas groupby of load_ratings_train_test_sets (movierec/data_pipeline.py:190-198):
+ * order[e] = row number of the e-th rating when the ratings are ordered by user, file order kept inside a user (a
+ * stable sort); part[e] = 2 for the last rating of its user (test), 1 for the one before it (validation), 0
+ * otherwise (train).  mr_build_user_csr builds what the sampler searches (the per-positive pandas filter of
+ * data_pipeline.py:103-112 restated as a table): rowptr [num_users + 1] int64 and, per user, the ascending list of
+ * the DISTINCT items of its (user, item) pairs; rowptr[num_users] = number of distinct pairs <= n (csr_items has room
+ * for n).  *flag |= 1 when an id lies outside [0, num_users) / [0, num_items): such pairs are left out of the lists,
+ * and the split of such input is undefined.  All arrays [device]; flag must be zeroed by the caller. */
+size_t mr_split_workspace_bytes(int64_t n);
+int mr_split_last_two(const int32_t* users, int64_t n, int32_t num_users, int32_t* order, int32_t* part, int32_t* flag,
+                      void* ws, size_t ws_bytes, void* stream);
+size_t mr_user_csr_workspace_bytes(int64_t n);
+int mr_build_user_csr(const int32_t* users, const int32_t* items, int64_t n, int32_t num_users, int32_t num_items,
+                      int64_t* rowptr, int32_t* csr_items, int32_t* flag, void* ws, size_t ws_bytes, void* stream);
 /* Stable LSD radix sort of (key, original index) pairs on the low `key_bits` bits. */
 size_t mr_sort_workspace_bytes(int64_t n);
 int mr_sort_pairs(const int32_t* keys, int64_t n, int32_t key_bits, int32_t* sorted_keys,

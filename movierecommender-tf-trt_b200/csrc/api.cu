@@ -1456,6 +1456,26 @@ int mr_profile_end(float* phase_ms, int64_t* phase_count, int64_t* kernel_launch
   return MR_OK;
 }
 
+size_t mr_split_workspace_bytes(int64_t n) { return split_workspace_bytes(n < 0 ? 0 : n); }
+
+int mr_split_last_two(const int32_t* users, int64_t n, int32_t num_users, int32_t* order, int32_t* part, int32_t* flag,
+                      void* ws, size_t ws_bytes, void* stream) {
+  MR_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && num_users > 0, "split: bad n / num_users");
+  if (n == 0) return MR_OK;
+  MR_REQUIRE(users && order && part && flag && ws, "split: NULL pointer");
+  return launch_split_last_two(users, n, num_users, order, part, flag, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+size_t mr_user_csr_workspace_bytes(int64_t n) { return user_csr_workspace_bytes(n < 0 ? 0 : n); }
+
+int mr_build_user_csr(const int32_t* users, const int32_t* items, int64_t n, int32_t num_users, int32_t num_items,
+                      int64_t* rowptr, int32_t* csr_items, int32_t* flag, void* ws, size_t ws_bytes, void* stream) {
+  MR_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && num_users > 0 && num_items > 0, "user csr: bad sizes");
+  MR_REQUIRE(rowptr && flag && ws && (n == 0 || (users && items && csr_items)), "user csr: NULL pointer");
+  return launch_build_user_csr(users, items, n, num_users, num_items, rowptr, csr_items, flag, ws, ws_bytes,
+                               (cudaStream_t)stream);
+}
+
 size_t mr_sort_workspace_bytes(int64_t n) { return sort_workspace_bytes(n < 0 ? 0 : n); }
 
 int mr_sort_pairs(const int32_t* keys, int64_t n, int32_t key_bits, int32_t* sorted_keys, int32_t* sorted_index,

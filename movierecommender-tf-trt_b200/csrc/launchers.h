@@ -185,6 +185,15 @@ int launch_group_heads(const int32_t* ids, int64_t groups, int group, int32_t* o
 // *flag = 1 when some ids[r] != ids[r - r % group]
 int launch_check_grouped(const int32_t* ids, int64_t n, int group, int32_t* flag, cudaStream_t st);
 
+// ---- dataset.cu: split and per-user item lists on the device ------------------------------------------------------
+size_t split_workspace_bytes(int64_t n);
+int launch_split_last_two(const int32_t* users, int64_t n, int32_t num_users, int32_t* order, int32_t* part,
+                          int32_t* flag, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t user_csr_workspace_bytes(int64_t n);
+int launch_build_user_csr(const int32_t* users, const int32_t* items, int64_t n, int32_t num_users, int32_t num_items,
+                          int64_t* rowptr, int32_t* csr_items, int32_t* flag, void* ws, size_t ws_bytes,
+                          cudaStream_t st);
+
 // ---- tc_selftest.cu ---------------------------------------------------------------------------
 int launch_tc_rate(int N, int iters, int nbuf, int flags, int writers, int write_iters, long long* out, int grid,
                    cudaStream_t st);

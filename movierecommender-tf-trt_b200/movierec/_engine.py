@@ -443,6 +443,48 @@ def sort_pairs(keys, key_bits):
     return out_k, out_i
 
 
+def split_last_two(users, num_users):
+    """Leave-last-two-out split on the device (reference data_pipeline.py:190-198).  users: the user id of every
+    rating in file order.  Returns (order, part) device int32 tensors: order = row numbers sorted by user (stable),
+    part[e] = 2 / 1 / 0 for the test / validation / train rating at position e of that order."""
+    require_cuda()
+    device = torch.device("cuda:{}".format(torch.cuda.current_device()))
+    users = as_device_i32(users, device)
+    n = users.numel()
+    order, part = torch.empty_like(users), torch.empty_like(users)
+    flag = torch.zeros(1, dtype=torch.int32, device=device)
+    nbytes = max(int(nat.lib.mr_split_workspace_bytes(n)), 256)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    nat.check(nat.lib.mr_split_last_two(_ptr(users), n, int(num_users), _ptr(order), _ptr(part), _ptr(flag), _ptr(ws),
+                                        nbytes, st), "mr_split_last_two")
+    if int(flag.item()):
+        raise IndexError("split_last_two: a user id lies outside [0, {})".format(num_users))
+    return order, part
+
+
+def build_user_csr(users, items, num_users, num_items):
+    """Per-user ascending lists of the distinct items of the (user, item) pairs, built on the device: what the
+    negative sampler searches.  Returns (rowptr int64 (num_users + 1,), csr_items int32 (pairs,)) device tensors."""
+    require_cuda()
+    device = torch.device("cuda:{}".format(torch.cuda.current_device()))
+    users, items = as_device_i32(users, device), as_device_i32(items, device)
+    n = users.numel()
+    if items.numel() != n:
+        raise ValueError("users ({}) and items ({}) differ in length".format(n, items.numel()))
+    rowptr = torch.empty(int(num_users) + 1, dtype=torch.int64, device=device)
+    csr = torch.empty(max(n, 1), dtype=torch.int32, device=device)
+    flag = torch.zeros(1, dtype=torch.int32, device=device)
+    nbytes = max(int(nat.lib.mr_user_csr_workspace_bytes(n)), 256)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    nat.check(nat.lib.mr_build_user_csr(_ptr(users), _ptr(items), n, int(num_users), int(num_items), _ptr(rowptr),
+                                        _ptr(csr), _ptr(flag), _ptr(ws), nbytes, st), "mr_build_user_csr")
+    if int(flag.item()):
+        raise IndexError("build_user_csr: an id lies outside [0, {}) x [0, {})".format(num_users, num_items))
+    return rowptr, csr[:int(rowptr[-1].item())]
+
+
 def sample_negatives(rowptr, csr_items, num_items, pos_users, pos_items, first_index, negs, seed, epoch):
     """Device sampler (data_pipeline.py:99-113, 136-150).  Returns (users, items, labels) device
     tensors of length P*(negs+1) laid out as the reference batches (negatives, then the positive)."""

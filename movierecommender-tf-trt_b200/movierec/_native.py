@@ -92,6 +92,10 @@ SIGNATURES = {
     "mr_sparse_rows_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "mr_sparse_rows_update": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i32, _f, _f, _f, _f,
                                         _f, _vp, _sz, _vp]),
+    "mr_split_workspace_bytes": (C.c_size_t, [_i64]),
+    "mr_split_last_two": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mr_user_csr_workspace_bytes": (C.c_size_t, [_i64]),
+    "mr_build_user_csr": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mr_set_compute_path": (C.c_int, [_i32]),
     "mr_uses_tensor_cores": (C.c_int, [_PM]),
     "mr_set_item_projection": (C.c_int, [_i32]),

@@ -95,15 +95,21 @@ class MovieLensDataGenerator(object):
         if self.extra_data is not None:
             all_u = np.concatenate([users, np.asarray(self.extra_data[COL_USER_ID].values, dtype=np.int64)])
             all_i = np.concatenate([items, np.asarray(self.extra_data[COL_ITEM_ID].values, dtype=np.int64)])
-        rowptr, csr = build_user_csr(all_u, all_i)
+        # per-user sorted item lists built on the device (mr_build_user_csr: two stable radix sorts + compaction);
+        # build_user_csr below is the same table in NumPy, kept for host-side use and as the tests' cross-check
+        if len(all_u) and (all_u.min() < 0 or all_i.min() < 0):
+            raise ValueError("negative user / item ids")
+        n_u = int(all_u.max()) + 1 if len(all_u) else 1
+        n_i = int(all_i.max()) + 1 if len(all_i) else 1
+        rowptr, csr = _engine.build_user_csr(all_u.astype(np.int32), all_i.astype(np.int32), n_u, n_i)
         self._device = {
             "dev": dev,
-            "rowptr": torch.from_numpy(rowptr).to(dev),
-            "csr": torch.from_numpy(csr).to(dev),
+            "rowptr": rowptr,
+            "csr": csr,
             "users": torch.from_numpy(users.astype(np.int32)).to(dev),
             "items": torch.from_numpy(items.astype(np.int32)).to(dev),
             "min_candidates_checked": False,
-            "degree_max": int(np.max(np.diff(rowptr))) if len(rowptr) > 1 else 0,
+            "degree_max": int((rowptr[1:] - rowptr[:-1]).max().item()) if rowptr.numel() > 1 else 0,
         }
 
     def device_batch(self, idx):
@@ -150,17 +156,36 @@ def build_user_csr(users, items):
     return rowptr, (key & 0xFFFFFFFF).astype(np.int32)
 
 
-def split_leave_last_two_out(ratings_df, col_user=COL_USER_ID):
+def _cuda_available():
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except ImportError:  # pragma: no cover
+        return False
+
+
+def split_leave_last_two_out(ratings_df, col_user=COL_USER_ID, on_device=None):
     """Per user, in file order: last rating -> test, second last -> validation, the rest -> train
-    (reference data_pipeline.py:190-198); each part ordered by user then file order, index reset."""
+    (reference data_pipeline.py:190-198); each part ordered by user then file order, index reset.
+    on_device: None = on the GPU when there is one (20 M ratings: milliseconds instead of seconds of pandas /
+    NumPy), False = the NumPy statement of the same rule (host-only environments), True = require the GPU."""
     users = np.asarray(ratings_df[col_user].values)
-    order = np.argsort(users, kind="stable")
-    su = users[order]
-    n = len(su)
-    is_last = np.ones(n, bool)
-    is_last[:-1] = su[1:] != su[:-1]
-    is_second_last = np.zeros(n, bool)
-    is_second_last[:-1] = is_last[1:] & (su[:-1] == su[1:])
+    order = is_last = is_second_last = None
+    if on_device is None:
+        on_device = _cuda_available() and len(users) > 0 and users.min() >= 0 and users.max() < 2 ** 31 - 1
+    if on_device:  # mr_split_last_two: stable radix sort by user + one pass over the sorted users
+        from . import _engine
+        d_order, d_part = _engine.split_last_two(users.astype(np.int32), int(users.max()) + 1)
+        order, part = d_order.cpu().numpy().astype(np.int64), d_part.cpu().numpy()
+        is_last, is_second_last = part == 2, part == 1
+    else:
+        order = np.argsort(users, kind="stable")
+        su = users[order]
+        n = len(su)
+        is_last = np.ones(n, bool)
+        is_last[:-1] = su[1:] != su[:-1]
+        is_second_last = np.zeros(n, bool)
+        is_second_last[:-1] = is_last[1:] & (su[:-1] == su[1:])
     test = ratings_df.iloc[order[is_last]].reset_index(drop=True)
     validation = ratings_df.iloc[order[is_second_last]].reset_index(drop=True)
     train = ratings_df.iloc[order[~(is_last | is_second_last)]].reset_index(drop=True)

@@ -593,6 +593,78 @@ def test_sampler_bit_exact_vs_oracle(eng_mod):
                 assert len(set(got[p, :negs].tolist())) == negs
 
 
+# ---- dataset preparation on the device: split and per-user item lists ---------------------------
+
+def _ratings(rng, nu, ni, n, min_per_user=2):
+    users = np.concatenate([np.repeat(np.arange(nu), min_per_user), rng.integers(0, nu, n - nu * min_per_user)])
+    rng.shuffle(users)
+    return users.astype(np.int32), rng.integers(0, ni, len(users)).astype(np.int32)
+
+
+@pytest.mark.parametrize("nu,ni,n", [(3, 5, 9), (40, 60, 1000), (943, 1682, 100000), (6040, 3706, 1000209)])
+def test_device_split_matches_oracle(eng_mod, nu, ni, n):
+    rng = np.random.default_rng(n)
+    users, _ = _ratings(rng, nu, ni, n)
+    order, part = eng_mod.split_last_two(users, nu)
+    order, part = order.cpu().numpy(), part.cpu().numpy()
+    np.testing.assert_array_equal(order, np.argsort(users, kind="stable"))  # bit-exact: a stable sort by user
+    tr, va, te = o.leave_last_two_out(users)  # pinned by the reference's own known-answer test (test_oracle.py)
+    np.testing.assert_array_equal(order[part == 0], tr)
+    np.testing.assert_array_equal(order[part == 1], va)
+    np.testing.assert_array_equal(order[part == 2], te)
+
+
+def test_device_split_edge_cases(eng_mod):
+    # a user with one rating has a test row only; empty input; out-of-range ids are refused
+    order, part = eng_mod.split_last_two(np.array([2, 0, 2, 2, 1, 0], np.int32), 3)
+    assert order.cpu().numpy().tolist() == [1, 5, 4, 0, 2, 3] and part.cpu().numpy().tolist() == [1, 2, 2, 0, 1, 2]
+    order, part = eng_mod.split_last_two(np.zeros(0, np.int32), 3)
+    assert order.numel() == 0 and part.numel() == 0
+    with pytest.raises(IndexError):
+        eng_mod.split_last_two(np.array([0, 3], np.int32), 3)
+
+
+@pytest.mark.parametrize("nu,ni,n", [(3, 5, 9), (40, 60, 5000), (943, 1682, 100000), (6040, 3706, 1000209)])
+def test_device_user_csr_matches_oracle(eng_mod, nu, ni, n):
+    rng = np.random.default_rng(n + 1)
+    users, items = _ratings(rng, nu, ni, n)  # dense enough for many duplicate pairs at the small sizes
+    rowptr, csr = eng_mod.build_user_csr(users, items, nu, ni)
+    want_rowptr, want_csr = o.build_csr(nu, users, items)
+    np.testing.assert_array_equal(rowptr.cpu().numpy(), want_rowptr)
+    np.testing.assert_array_equal(csr.cpu().numpy(), want_csr)
+
+
+def test_device_user_csr_edge_cases(eng_mod):
+    # users without ratings (empty rows at both ends and in the middle), duplicates, empty input, bad ids
+    users = np.array([5, 2, 5, 5, 2, 7], np.int32)
+    items = np.array([9, 1, 3, 9, 1, 0], np.int32)
+    rowptr, csr = eng_mod.build_user_csr(users, items, 10, 10)
+    assert rowptr.cpu().numpy().tolist() == [0, 0, 0, 1, 1, 1, 3, 3, 4, 4, 4]
+    assert csr.cpu().numpy().tolist() == [1, 3, 9, 0]
+    rowptr, csr = eng_mod.build_user_csr(np.zeros(0, np.int32), np.zeros(0, np.int32), 4, 4)
+    assert rowptr.cpu().numpy().tolist() == [0] * 5 and csr.numel() == 0
+    with pytest.raises(IndexError):
+        eng_mod.build_user_csr(np.array([0, 1], np.int32), np.array([0, 4], np.int32), 2, 4)
+
+
+def test_generator_uses_the_device_csr(eng_mod):
+    """The generator's table is the device-built one and equals the NumPy statement of the same table."""
+    import pandas as pd
+    from movierec import data_pipeline
+    rng = np.random.default_rng(5)
+    users, items = _ratings(rng, 50, 80, 2000, min_per_user=3)
+    df = pd.DataFrame({"userId": users, "itemId": items, "rating": np.ones(len(users), np.float32)})
+    gen = data_pipeline.MovieLensDataGenerator("ml-100k", df, batch_size=50, negatives_per_positive=4, shuffle=False)
+    gen.device_batch(0)
+    rowptr, csr = data_pipeline.build_user_csr(users, items)
+    np.testing.assert_array_equal(gen._device["rowptr"].cpu().numpy(), rowptr)
+    np.testing.assert_array_equal(gen._device["csr"].cpu().numpy(), csr)
+    train, validation, test = data_pipeline.split_leave_last_two_out(df)             # on the device
+    train_h, validation_h, test_h = data_pipeline.split_leave_last_two_out(df, on_device=False)
+    for a, b in ((train, train_h), (validation, validation_h), (test, test_h)):
+        pd.testing.assert_frame_equal(a, b)
+
+
 # ---- BASELINE sizes: size-independent properties --------------------------------------------------
 
 def test_full_size_ml20m_properties(eng_mod):
