@@ -294,6 +294,13 @@ static TcWs carve_tc(const MrModel& m, bool train, int64_t B, void* ws) {
   return t;
 }
 
+// Train step without H1 in memory (experiment, MR_TRAIN_NO_H1=1): the second layer's forward producers AND the
+// producers of its weight gradient recompute relu(Pi[item] + Pu[user]) from the L2-resident projections.
+static bool train_without_h1() {
+  static const bool on = getenv("MR_TRAIN_NO_H1") != nullptr;
+  return on;
+}
+
 // Forward of rows [r0, r1) on the tensor cores; leaves H[1..n-1] of the sub-batch in the workspace.
 static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users, const int32_t* items, int user_div,
                            int64_t r0, int64_t r1, cudaStream_t st, int group = 0, bool users_per_group = false,
@@ -310,7 +317,7 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     // (train step: measured 0.08 ms SLOWER than the separate gather kernel -- the extra 64-byte stores land on the
     // pipe that bounds the layer kernel -- so there it is opt-in, MR_PROJ_PRODUCER_TRAIN=1, and covered by a test)
     const bool fuse_h1 = t.Pi != nullptr && m.n_layers >= 3 && getenv("MR_NO_PROJ_PRODUCER") == nullptr &&
-                         (!train_rows || getenv("MR_PROJ_PRODUCER_TRAIN") != nullptr);
+                         (!train_rows || getenv("MR_PROJ_PRODUCER_TRAIN") != nullptr || train_without_h1());
     proj_in_producer = fuse_h1;
     if (fuse_h1 && t.Pu != nullptr) {
     } else if (t.Pu != nullptr) {  // user- and item-projected first layer: H1 = relu(Pi[item] + Pu[user])
@@ -402,8 +409,8 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
         a.proj_ids = users;
         a.proj_u_rows = m.num_users;
       }
-      if (t.bits[1] != nullptr) {
-        a.h1_out = t.H[1];
+      if (t.bits[1] != nullptr) {  // training: the ReLU bits for the backward layer; H1 itself only if someone reads it
+        a.h1_out = train_without_h1() ? nullptr : t.H[1];
         a.h1_bits = t.bits[1];
       }
     }
@@ -969,6 +976,17 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
         w.dw_partial = t.dense_partial + (m.W[l] - m.dense);
         w.db_partial = t.dense_partial + (m.b[l] - m.dense);
         w.partial_stride = t.dense_stride;
+        if (proj && l == 2 && train_without_h1() && getenv("MR_NO_PROJ_PRODUCER") == nullptr) {
+          w.a_dense = nullptr;  // H1 was never stored: recomputed from the projections
+          w.proj_i = tw.Pi;
+          w.proj_u = tw.Zu;
+          w.proj_div = group;
+          if (tw.Pu != nullptr) {
+            w.proj_u = tw.Pu;
+            w.proj_ids = users;
+            w.proj_u_rows = m.num_users;
+          }
+        }
         rc = launch_tc_wgrad(w, st);
         if (rc != MR_OK) return rc;
         prof_mark(MR_PHASE_TC_DENSE_BWD, st);

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
           buf[0][e].z = fmaxf(buf[0][e].z + buf[NB - 1][e].z, 0.f);
           buf[0][e].w = fmaxf(buf[0][e].w + buf[NB - 1][e].w, 0.f);
         }
-        if (p.h1_out != nullptr) {
+        if (p.h1_out != nullptr || p.h1_bits != nullptr) {
           // training: the backward pass wants these rows (A of the weight gradient) and their ReLU bits.  A row's 32
           // columns of the chunk sit in four lanes (csub) x two pieces (h): 64-byte stores, bits OR-ed over the lanes
           const int64_t trow0 = (blockIdx.x + cached_tile * gridDim.x) * kTcTileRows;
@@ -284,7 +284,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const float4 v = buf[0][2 * g + h];
-              if (ok[g]) *reinterpret_cast<float4*>(p.h1_out + (size_t)lr * K + c * kTcKC + 4 * (4 * h + csub)) = v;
+              if (ok[g] && p.h1_out != nullptr)
+                *reinterpret_cast<float4*>(p.h1_out + (size_t)lr * K + c * kTcKC + 4 * (4 * h + csub)) = v;
               const uint32_t nib = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
               w |= nib << (4 * (4 * h + csub));
             }

@@ -41,6 +41,11 @@ struct TcWgradParams {
   const int32_t* users;
   const int32_t* items;
   int32_t num_users, num_items, d_u, user_mul;  // d_u = 0 or Fa: one table only; user rows read users[r * user_mul]
+  // AM = 2 (projected first layer): A row r = relu(proj_i[items[row0 + r]] + proj_u[proj_ids ? proj_ids[row0 + r] : r / proj_div])
+  const float* proj_i;
+  const float* proj_u;
+  const int32_t* proj_ids;
+  int32_t proj_u_rows, proj_div;
   const float* z;
   int32_t Fa, Fb;
   int64_t rows, row0;
@@ -52,8 +57,12 @@ struct TcWgradParams {
 };
 
 // NA / NZ: float4 loads per producer thread and chunk for A / Z (Fa / 32 and Fb / 32).
-template <bool GATHER, int NA, int NZ>
+// AM: 0 = A is a dense matrix, 1 = gathered embedding rows, 2 = the projected first layer recomputed from its two
+// L2-resident projections (the train step then never stores H1: api.cu).
+template <int AM, int NA, int NZ>
 __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradParams p) {
+  constexpr bool GATHER = AM == 1;
+  constexpr bool PROJ = AM == 2;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[8], empty_bar[8], done_bar;
   __shared__ uint32_t tmem_slot;
@@ -106,7 +115,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
     constexpr int PA = NA * G / 2;                      // float4 of A per thread and chunk (16 rows x Fa/4 over TG threads)
     constexpr int PZ = NZ * G >= 2 ? NZ * G / 2 : 1;    // float4 of Z per thread and chunk (Fb = 32, G = 1: half of the threads idle)
 
-    auto issue_loads = [&](float4(&xa)[PA], float4(&xz)[PZ]) {
+    constexpr int PB = PROJ ? PA : 1;  // PROJ: the user-side pieces ride in a second buffer until the conversion
+    auto issue_loads = [&](float4(&xa)[PA], float4(&xz)[PZ], float4(&xb)[PB]) {
       const int64_t crow0 = ld_chunk * kWgKC;  // launch-local first row of the chunk
       ld_chunk += G;
 #pragma unroll
@@ -115,7 +125,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
         const int r = idx / aq, c = (idx - r * aq) << 2;
         const int64_t lr = crow0 + r;
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lr < p.rows && !(p.debug & 2)) {
+        if (PROJ) {
+          float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (lr < p.rows) {
+            const int it = __ldg(p.items + p.row0 + lr);
+            if ((unsigned)it < (unsigned)p.num_items) x = ldg4(p.proj_i + (size_t)it * Fa + c);  // bad ids: zero rows
+            if (p.proj_ids != nullptr) {
+              const int u = __ldg(p.proj_ids + p.row0 + lr);
+              if ((unsigned)u < (unsigned)p.proj_u_rows) y = ldg4(p.proj_u + (size_t)u * Fa + c);
+            } else {
+              y = ldg4(p.proj_u + (size_t)((uint32_t)lr / (uint32_t)p.proj_div) * Fa + c);
+            }
+          }
+          xb[i] = y;
+        } else if (lr < p.rows && !(p.debug & 2)) {
           if (GATHER) {
             if (c < p.d_u) {
               const int u = __ldg(p.users + (p.row0 + lr) * p.user_mul);
@@ -138,7 +161,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
         xz[i] = (r < kWgKC && lr < p.rows && !(p.debug & 2)) ? ldg4(p.z + (size_t)lr * Fb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto store_chunk = [&](const float4(&xa)[PA], const float4(&xz)[PZ]) {
+    auto store_chunk = [&](float4(&xa)[PA], const float4(&xz)[PZ], const float4(&xb)[PB]) {
       const int stage = st_stage;
       const uint32_t phase = st_phase;
       st_stage += G;
@@ -150,6 +173,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
         for (int i = 0; i < PA; ++i) {
           const int idx = t + TG * i;
           const int r = idx / aq, c = (idx - r * aq) << 2;
+          if (PROJ) {
+            xa[i].x = fmaxf(xa[i].x + xb[i].x, 0.f);
+            xa[i].y = fmaxf(xa[i].y + xb[i].y, 0.f);
+            xa[i].z = fmaxf(xa[i].z + xb[i].z, 0.f);
+            xa[i].w = fmaxf(xa[i].w + xb[i].w, 0.f);
+          }
           float4 hi, lo;
           tc::split_tf32x4(xa[i], hi, lo);
           const uint32_t off = tc::mn_off(r, c, kWgKC / 4);
@@ -179,18 +208,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
     };
 
     constexpr int D = kWgLoadAhead, NB = kWgLoadAhead + 1;
-    float4 ba[NB][PA], bz[NB][PZ];
+    float4 ba[NB][PA], bz[NB][PZ], bb[NB][PB];
     const int64_t mine = my_chunks > group ? (my_chunks - group + G - 1) / G : 0;  // chunks of this group
 #pragma unroll
     for (int j = 0; j < D; ++j)
-      if (j < mine) issue_loads(ba[j], bz[j]);
+      if (j < mine) issue_loads(ba[j], bz[j], bb[j]);
     for (int64_t i0 = 0; i0 < mine; i0 += NB) {
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         const int64_t i = i0 + j;
         if (i < mine) {
-          if (i + D < mine) issue_loads(ba[(j + D) % NB], bz[(j + D) % NB]);
-          store_chunk(ba[j], bz[j]);
+          if (i + D < mine) issue_loads(ba[(j + D) % NB], bz[(j + D) % NB], bb[(j + D) % NB]);
+          store_chunk(ba[j], bz[j], bb[j]);
         }
       }
     }
@@ -203,7 +232,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const TcWgradPa
         while (n >= (int64_t)*reinterpret_cast<volatile int*>(&chunks_issued) + kWgPrefetchAhead) __nanosleep(256);
         const int64_t lr = r0 + lane;
         if (lr >= row_hi) continue;
-        if (GATHER) {
+        if (PROJ) {  // the projections are L2-resident: only Z is prefetched
+        } else if (GATHER) {
           const int u = p.d_u > 0 ? __ldg(p.users + (p.row0 + lr) * p.user_mul) : 0;
           const int it = p.d_u < Fa ? __ldg(p.items + p.row0 + lr) : 0;
           if ((unsigned)u < (unsigned)p.num_users && (unsigned)it < (unsigned)p.num_items) {
@@ -582,6 +612,11 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
   p.num_items = a.num_items;
   p.d_u = a.d_u;
   p.user_mul = a.user_mul < 1 ? 1 : a.user_mul;
+  p.proj_i = a.proj_i;
+  p.proj_u = a.proj_u;
+  p.proj_ids = a.proj_ids;
+  p.proj_u_rows = a.proj_u_rows;
+  p.proj_div = a.proj_div < 1 ? 1 : a.proj_div;
   p.z = a.z;
   p.Fa = a.Fa;
   p.Fb = a.Fb;
@@ -596,7 +631,12 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
   // Opt-in (MR_WGRAD_TS=1): parity-green on B200 but slower than the SS kernel in its first form (ML-20M weight
   // gradients 1.21 ms against 1.00 ms; with every producer action switched off 0.74 ms against 0.57 ms, i.e. the
   // stage hand-off, not the data path, is what costs) -- kept for the next round, see DESIGN.md.
-  const bool ts = getenv("MR_WGRAD_TS") != nullptr && halves_h * a.Fb + 2 * halves_h * 32 <= 512 &&
+  const bool proj = a.proj_i != nullptr;
+  if (proj && (a.Fa != 128 || a.gather || a.proj_u == nullptr || a.items == nullptr)) {
+    set_error("tc wgrad: the projected A operand needs Fa = 128, item ids and both projections");
+    return MR_ERR_INVALID;
+  }
+  const bool ts = !proj && getenv("MR_WGRAD_TS") != nullptr && halves_h * a.Fb + 2 * halves_h * 32 <= 512 &&
                   (!a.gather || a.d_u % 128 == 0);
   // TS chunks are 32 rows (12 MMAs per half and hand-off instead of 6: the issuing thread's per-chunk overhead is
   // what bounds that kernel) when the TMEM columns allow at least 3 stages, else 16
@@ -630,7 +670,19 @@ int launch_tc_wgrad(const TcWgradArgs& a, cudaStream_t st) {
     rc = MR_OK;                                                                                          \
   }
 #define MR_WG_NZ(G, NA_) MR_WG_CASE(G, NA_, 1) MR_WG_CASE(G, NA_, 2) MR_WG_CASE(G, NA_, 4) MR_WG_CASE(G, NA_, 8)
-  MR_WG_NZ(true, 4) MR_WG_NZ(true, 8) MR_WG_NZ(false, 4) MR_WG_NZ(false, 8)
+#define MR_WG_PROJ(NZ_)                                                                                  \
+  if (proj && nz == NZ_) {                                                                               \
+    auto kern = tc_wgrad_kernel<2, 4, NZ_>;                                                              \
+    MR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    kern<<<grid, kWgThreads, smem, st>>>(p);                                                             \
+    rc = MR_OK;                                                                                          \
+  }
+  if (proj) {
+    MR_WG_PROJ(1) MR_WG_PROJ(2) MR_WG_PROJ(4) MR_WG_PROJ(8)
+  } else {
+    MR_WG_NZ(true, 4) MR_WG_NZ(true, 8) MR_WG_NZ(false, 4) MR_WG_NZ(false, 8)
+  }
+#undef MR_WG_PROJ
 #undef MR_WG_NZ
 #undef MR_WG_CASE
   if (rc != MR_OK) {
