@@ -349,6 +349,36 @@ class NeuMFEngine(object):
                   "mr_neumf_apply")
         self.iterations = int(self._opt.iterations)
 
+    # ---- region-wise apply: lets a data-parallel caller overlap the all-reduce of one region with the update of
+    # the previous one (the all-reduce is NVLink-bound, the Adam sweep HBM-bound)
+    def gradient_regions(self):
+        """[(name, gradient tensor)]: the dense block and every gradient table, largest first."""
+        regs = [("dense", self.g_dense)] + [(k, self.g_tables[k]) for k in self.g_tables]
+        return sorted(regs, key=lambda r: -r[1].numel())
+
+    def apply_region(self, name):
+        """The optimizer sweep of mr_neumf_apply for one region (same kernel, same step size); finish_apply()
+        advances the step counter once every region is done."""
+        if not self.table_state:
+            raise RuntimeError("this engine caches rows owned by other ranks; use apply_dense_only()")
+        t = self.iterations + 1
+        adam = self.optimizer == "adam"
+        f32 = lambda x: float(np.float32(x))  # the C side holds lr and the betas as floats
+        lr_t = f32(self.lr)
+        if adam:  # adam_lr_t of api.cu: double arithmetic on the float-valued hyper-parameters
+            lr_t = f32(self.lr) * math.sqrt(1.0 - f32(self.beta_2) ** t) / (1.0 - f32(self.beta_1) ** t)
+        if name == "dense":
+            p, g, m, v, l2 = self.dense, self.g_dense, self.m_dense, self.v_dense, 0.0
+        else:
+            p, g, l2 = self._tables[name], self.g_tables[name], self.l2[0]
+            m, v = (self.m[name], self.v[name]) if adam else (None, None)
+        nat.check(nat.lib.mr_optimizer_flat(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(),
+                                            nat.OPT_ADAM if adam else nat.OPT_SGD, lr_t, self.beta_1, self.beta_2,
+                                            ADAM_EPSILON, l2, self._stream()), "mr_optimizer_flat")
+
+    def finish_apply(self):
+        self.iterations += 1
+
     def adam_lr_t(self, t):
         """Legacy-Keras Adam step size for step t (1-based): lr*sqrt(1-b2^t)/(1-b1^t)."""
         return self.lr * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
