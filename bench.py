@@ -684,8 +684,8 @@ def run_sharded(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)   # ~0.3 s timed at N=1: several nvidia-smi clock samples
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ml-20m", choices=sorted(WORKLOADS))
     ap.add_argument("--lean", action="store_true",
