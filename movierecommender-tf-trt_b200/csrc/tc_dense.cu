@@ -33,7 +33,11 @@
 
 namespace mr {
 
-constexpr int kTcMmaWarp = 8;                     // warps 0-7 are producers
+// Warp roles: [0, NPROD) producers, NPROD the MMA issuer, NPROD + 1 the L2 prefetch warp, then NEPI epilogue warps.
+// Two shapes, 14 warps each: 8 producers + 4 epilogue warps (layers bound by their producers / the MMA operand
+// fetches), or 4 producers + 8 epilogue warps for the layers ncu showed EPILOGUE-bound (the backward layer: K = 64,
+// N = 128 -- producers idle 64 % of their samples, the four epilogue warps busy 85 %): a TMEM lane quarter is then
+// served by two warps that take alternate 32-column blocks.
 #ifndef MR_TC_LOAD_AHEAD
 #define MR_TC_LOAD_AHEAD 1
 #endif
@@ -42,8 +46,7 @@ constexpr int kTcLoadAhead = MR_TC_LOAD_AHEAD;    // group iterations the produc
 #define MR_TC_GROUPS 2
 #endif
 constexpr int kTcGroups = MR_TC_GROUPS;           // producer groups (8 / kTcGroups warps each) taking chunks round-robin
-constexpr int kTcPrefetchWarp = kTcMmaWarp + 5;
-constexpr int kTcThreads = 32 * (kTcMmaWarp + 6);  // producers + MMA warp + 4 epilogue warps + L2 prefetch warp
+constexpr int kTcThreads = 32 * 14;
 constexpr int kTcPrefetchAhead = 2;                // tiles the prefetch warp runs ahead of the MMA issuer
 constexpr int kTcTileRows = 128;
 constexpr int kTcKC = 32;  // K elements per pipeline stage
@@ -89,8 +92,10 @@ struct TcDenseParams {
   int32_t debug;         // MR_TC_DEBUG (diagnostics only): 1 = skip weight copies after the first pass, 2 = skip A loads
 };
 
-template <int AMODE, int EPI>
+template <int AMODE, int EPI, int NPROD = 8, int NEPI = 4>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDenseParams p) {
+  static_assert(NPROD + NEPI + 2 == kTcThreads / 32, "14 warps");
+  constexpr int kTcMmaWarp = NPROD, kTcPrefetchWarp = NPROD + 1, kTcEpiWarp0 = NPROD + 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[8], empty_bar[8], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
@@ -109,12 +114,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      tc::mbar_init(&full_bar[s], 8 / kTcGroups + 1);  // the group's producer warps + the weight copy's expect_tx arrive
+      tc::mbar_init(&full_bar[s], NPROD / (NPROD == 8 ? kTcGroups : 1) + 1);  // the group's producer warps + the weight copy's expect_tx
       tc::mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(&acc_full[b], 1);
-      tc::mbar_init(&acc_empty[b], 4);
+      tc::mbar_init(&acc_empty[b], NEPI);
     }
     tc::mbar_init_fence();
     tiles_started = 0;
@@ -131,8 +136,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
     // run kTcLoadAhead chunks ahead of the conversion in a rotating set of register buffers, so 3 x 16 KB per
     // SM are in flight and a load has three chunk periods to arrive (ncu: the producers of the first version,
     // one chunk ahead, sat in long-scoreboard stalls for more than half of their samples).
-    constexpr int G = kTcGroups, WPG = 8 / G;     // warps per group
-    constexpr int RG = 2 * G;                     // 8-row groups per thread and chunk (a warp covers 16*G rows)
+    constexpr int G = NPROD == 8 ? kTcGroups : 1, WPG = NPROD / G;  // producer groups, warps per group
+    constexpr int RG = 16 / WPG;                  // 8-row groups per thread and chunk (a warp covers 128 / WPG rows)
     const int group = warp / WPG, pw = warp % WPG;
     const int rsub = lane & 7, csub = lane >> 3;  // 8 rows x 4 sixteen-byte chunks per warp instruction
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -399,7 +404,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       // 32 columns per pass: TMEM -> registers (thread = row) -> shared tile -> coalesced global stores
       // (thread-per-row stores wrote 16-byte pieces of 32 different rows per instruction and made the
       // epilogue the bottleneck of the backward layers).
-      float* tile_s = epi_smem + (size_t)quarter * (32 * kEpiLd);
+      float* tile_s = epi_smem + (size_t)(warp - kTcEpiWarp0) * (32 * kEpiLd);
       const int64_t my_lr = wrow0 + lane;  // the row this thread owns while the data is thread-per-row
       const bool my_ok = my_lr < p.rows;
       // optional per-group addend row of this thread's row (the rows of a group read the same line)
@@ -414,6 +419,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       for (int cb = 0; cb < 8; ++cb) {
         const int c0 = 32 * cb;
         if (c0 >= ncols_epi) break;
+        if (NEPI == 8 && (cb & 1) != ((warp - kTcEpiWarp0) >> 2)) continue;  // the quarter's other warp takes this block
         float v[32];
         tc::tmem_ld16(taddr + c0, v);
         tc::tmem_ld16(taddr + c0 + 16, v + 16);
@@ -520,10 +526,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, int K_in, int N
 
 static size_t dense_stage_bytes(int N) { return (size_t)2 * kTcTileRows * kTcKC * 4 + (size_t)2 * N * kTcKC * 4; }
 
-template <int AMODE, int EPI>
+template <int AMODE, int EPI, int NPROD = 8, int NEPI = 4>
 static int launch_dense_t(TcDenseParams p, cudaStream_t st) {
   const size_t sb = dense_stage_bytes(p.N);
-  const size_t epi_bytes = (size_t)4 * 32 * kEpiLd * sizeof(float);
+  const size_t epi_bytes = (size_t)NEPI * 32 * kEpiLd * sizeof(float);
   int stages = (int)((226 * 1024 - epi_bytes - 2048) / sb);
   if (stages > 8) stages = 8;
   if (stages < 2) {
@@ -536,7 +542,7 @@ static int launch_dense_t(TcDenseParams p, cudaStream_t st) {
     p.debug = dbg ? atoi(dbg) : 0;
   }
   const size_t smem = sb * stages + epi_bytes;
-  auto kern = tc_dense_kernel<AMODE, EPI>;
+  auto kern = tc_dense_kernel<AMODE, EPI, NPROD, NEPI>;
   MR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = (p.rows + kTcTileRows - 1) / kTcTileRows;
   if (ntiles == 0) return MR_OK;
@@ -599,8 +605,16 @@ int launch_tc_dense(const TcDenseArgs& a, cudaStream_t st) {
     return MR_ERR_INVALID;
   }
   switch (a.epilogue) {
-    case TC_EPI_BIAS_RELU: return launch_dense_t<A_DENSE, EPI_BIAS_RELU>(p, st);
-    case TC_EPI_MASK: return launch_dense_t<A_DENSE, EPI_MASK>(p, st);
+    case TC_EPI_BIAS_RELU: {
+      static const bool eight = getenv("MR_TC_EPI8_FWD") != nullptr;  // experiment: N = 128 plain layers (Pi, Pu, dE = S . W^T)
+      if (eight && a.N >= 128) return launch_dense_t<A_DENSE, EPI_BIAS_RELU, 4, 8>(p, st);
+      return launch_dense_t<A_DENSE, EPI_BIAS_RELU>(p, st);
+    }
+    case TC_EPI_MASK: {
+      static const bool four = getenv("MR_TC_EPI4") != nullptr;  // diagnostics: the 8 + 4 warp shape everywhere
+      if (four || a.N < 64) return launch_dense_t<A_DENSE, EPI_MASK>(p, st);
+      return launch_dense_t<A_DENSE, EPI_MASK, 4, 8>(p, st);
+    }
     case TC_EPI_STAGE: return launch_dense_t<A_DENSE, EPI_STAGE>(p, st);
     case TC_EPI_HEAD_DOT:
       if (a.bias == nullptr || a.head_w == nullptr || a.out == nullptr) return MR_ERR_INVALID;
