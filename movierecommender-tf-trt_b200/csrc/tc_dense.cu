@@ -47,7 +47,10 @@ constexpr int kTcLoadAhead = MR_TC_LOAD_AHEAD;    // group iterations the produc
 #endif
 constexpr int kTcGroups = MR_TC_GROUPS;           // producer groups (8 / kTcGroups warps each) taking chunks round-robin
 constexpr int kTcThreads = 32 * 14;
-constexpr int kTcPrefetchAhead = 2;                // tiles the prefetch warp runs ahead of the MMA issuer
+#ifndef MR_TC_PREFETCH_AHEAD
+#define MR_TC_PREFETCH_AHEAD 2
+#endif
+constexpr int kTcPrefetchAhead = MR_TC_PREFETCH_AHEAD;  // tiles the prefetch warp runs ahead of the MMA issuer
 constexpr int kTcTileRows = 128;
 constexpr int kTcKC = 32;  // K elements per pipeline stage
 constexpr int kEpiLd = 36;  // floats per row of an epilogue warp's 32x32 staging tile (16-byte aligned, conflict-free)

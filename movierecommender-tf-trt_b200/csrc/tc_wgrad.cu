@@ -22,7 +22,13 @@ namespace mr {
 
 constexpr int kWgThreads = 320;  // 8 producer warps + MMA warp + L2 prefetch warp
 constexpr int kWgPrefetchWarp = 9;
-constexpr int kWgPrefetchAhead = 24;  // chunks (of 16 rows) the prefetch warp runs ahead of the MMA issuer
+// Chunks the L2 prefetch warp runs ahead of the MMA issuer.  Swept on the ML-20M step (weight-gradient phase, ms):
+// 4: 0.470, 8: 0.436, 10: 0.435, 12: 0.442, 16: 0.447, 24: 0.478, 48: 0.545 -- at 24 chunks the 148 CTAs keep 87 MB
+// of prefetched lines in the 126 MB L2 and lines are evicted before their load arrives (L2 hit rate 33 %, ncu).
+#ifndef MR_WG_PREFETCH_AHEAD
+#define MR_WG_PREFETCH_AHEAD 8
+#endif
+constexpr int kWgPrefetchAhead = MR_WG_PREFETCH_AHEAD;
 constexpr int kWgMmaWarp = 8;
 constexpr int kWgKC = 16;  // batch rows per pipeline stage
 #ifndef MR_WG_LOAD_AHEAD
