@@ -208,17 +208,19 @@ static bool user_proj_ok(const MrModel& m, int64_t rows, int group) {
   return g_item_proj == 2 || (int64_t)m.num_users <= rows / group;
 }
 
-// Rows per launch of the tensor-core kernels: the whole batch up to 2^20 rows (persistent CTAs need many
-// tiles each to reach steady state; intermediates of 1M rows are ~1.5 GB of workspace), split evenly above.
+// Rows per launch of the tensor-core kernels: the whole batch up to 2^21 rows (persistent CTAs need many
+// tiles each to reach steady state: one launch of 1,310,720 rows instead of two of 655,360 takes the ML-20M step
+// from 2.48 to 2.45 ms, and four of 327,680 cost +0.25 ms; intermediates are ~2.3 KB of workspace per row), split
+// evenly above.
 static int64_t sub_batch_cap(const char* env, int64_t dflt) {  // diagnostics: MR_*_SUB_BATCH_ROWS = 2^14 .. 2^20
   const char* v = getenv(env);
   if (v == nullptr) return dflt;
   const long long r = atoll(v);
-  return r >= (1 << 14) && r <= (1 << 20) ? (int64_t)r : dflt;
+  return r >= (1 << 14) && r <= (1 << 22) ? (int64_t)r : dflt;
 }
 
 static int64_t tc_sub_batch(int64_t B) {
-  static const int64_t cap = sub_batch_cap("MR_TC_SUB_BATCH_ROWS", (int64_t)1 << 20);
+  static const int64_t cap = sub_batch_cap("MR_TC_SUB_BATCH_ROWS", (int64_t)1 << 21);
   const int64_t parts = B <= cap ? 1 : (B + cap - 1) / cap;
   const int64_t sb = ((B < 1 ? 1 : B) + parts - 1) / parts;
   return (sb + 127) / 128 * 128;
@@ -253,7 +255,7 @@ static bool tc_grouped_ok(const MrModel& m, int64_t B, int group) {
   const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
   if (d_u % 128 || d_i % 128 || d_u > 256 || d_i > 256) return false;
   if (B % group) return false;
-  const int64_t cap = sub_batch_cap("MR_TC_SUB_BATCH_ROWS", (int64_t)1 << 20);
+  const int64_t cap = sub_batch_cap("MR_TC_SUB_BATCH_ROWS", (int64_t)1 << 21);
   const int64_t parts = B <= cap ? 1 : (B + cap - 1) / cap;
   if (parts > 1 && (tc_sub_batch(B) % group)) return false;  // sub-batch boundaries must not split a group
   return true;
@@ -545,7 +547,7 @@ static int64_t eval_sub_batch(int group) {
   int64_t a = 128, b = group;
   while (b) { const int64_t t = a % b; a = b; b = t; }
   const int64_t l = (int64_t)128 / a * group;  // lcm(128, group)
-  static const int64_t cap = sub_batch_cap("MR_EVAL_SUB_BATCH_ROWS", (int64_t)1 << 20);
+  static const int64_t cap = sub_batch_cap("MR_EVAL_SUB_BATCH_ROWS", (int64_t)1 << 21);
   return l > cap ? 0 : cap / l * l;
 }
 
