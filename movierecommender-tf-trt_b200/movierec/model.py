@@ -94,12 +94,29 @@ class NeuMFModel(object):
         self.engine.set_weights(weights)
 
     def save_weights(self, path):
+        """Keras-layout HDF5 when h5py is installed (the reference's format, model.py:245), else an .npz payload
+        under the same file name."""
+        from .util import keras_h5
+        if keras_h5.have_h5py():
+            keras_h5.write(path, self.engine.get_weights(), self.engine.weight_names(),
+                           self.engine.get_optimizer_state())
+            return
         arrays = dict(self.engine.get_weights())
         arrays.update({"optimizer/" + k: np.asarray(v) for k, v in self.engine.get_optimizer_state().items()})
         with open(path, "wb") as f:  # keep the caller's file name (np.savez would append .npz)
             np.savez(f, **arrays)
 
     def load_weights(self, path):
+        from .util import keras_h5
+        if keras_h5.is_hdf5(path):  # written by Keras (the reference) or by save_weights above
+            weights, opt = keras_h5.read(path)
+            missing = [k for k in self.engine.weight_names() if k not in weights]
+            if missing:
+                raise ValueError("weight file {} lacks {}".format(path, ", ".join(missing)))
+            self.engine.set_weights({k: weights[k] for k in self.engine.weight_names()})
+            if opt:
+                self.engine.set_optimizer_state(opt)
+            return
         with np.load(path) as z:
             self.engine.set_weights({k: z[k] for k in self.engine.weight_names()})
             opt = {k[len("optimizer/"):]: z[k] for k in z.files if k.startswith("optimizer/")}

@@ -228,3 +228,32 @@ def test_load_ratings_data_zero_based(tmp_path):
     assert df.userId.tolist() == [0, 1] and df.itemId.tolist() == [0, 2] and df.rating.tolist() == [5.0, 3.0]
     with pytest.raises(FileNotFoundError):
         ml.load_ratings_data(str(tmp_path), "ml-1m", download=False)
+
+
+def test_keras_h5_round_trip(tmp_path):
+    """Keras-layout HDF5 weight files; needs h5py, which this image does not ship."""
+    pytest.importorskip("h5py")
+    from movierec.util import keras_h5
+    from oracle import movierec_oracle as o
+    w = o.init_weights(7, 9, [6, 4], mf_dim=2)
+    order = o.weight_names([6, 4], 2)
+    path = str(tmp_path / "m_weights.h5")
+    keras_h5.write(path, w, order, {"iterations": np.array(3), "m/dense": np.arange(5.0)})
+    assert keras_h5.is_hdf5(path)
+    got, opt = keras_h5.read(path)
+    assert set(got) == set(order)
+    for k in order:
+        np.testing.assert_array_equal(got[k], w[k])
+    assert int(opt["iterations"]) == 3 and opt["m/dense"].tolist() == list(np.arange(5.0))
+
+
+def test_keras_h5_detection_and_missing_h5py(tmp_path):
+    from movierec.util import keras_h5
+    p = tmp_path / "x.h5"
+    p.write_bytes(b"PK\x03\x04 not hdf5")
+    assert not keras_h5.is_hdf5(str(p))
+    p.write_bytes(keras_h5.HDF5_MAGIC + b"\0" * 64)
+    assert keras_h5.is_hdf5(str(p))
+    if not keras_h5.have_h5py():
+        with pytest.raises(ImportError, match="h5py is not installed"):
+            keras_h5.read(str(p))
