@@ -51,6 +51,30 @@ class OracleEngine(object):
         o.adam_step(self.w, self.state, g, p["lr"], p["beta_1"], p["beta_2"])
 
 
+class RegionOracleEngine(OracleEngine):
+    """Adds the region-wise surface (gradient_regions / apply_region / finish_apply) the wrapper uses with
+    MR_DP_OVERLAP=1: one region per parameter tensor, largest first."""
+
+    def __init__(self, weights, params):
+        OracleEngine.__init__(self, weights, params)
+        self.applied = []
+
+    def gradient_regions(self):
+        regs, off = [], 0
+        for k_, n in zip(self.names, self.sizes):
+            regs.append((k_, self.g_flat[off:off + n]))
+            off += n
+        return sorted(regs, key=lambda r: -r[1].numel())
+
+    def apply_region(self, name):
+        self.applied.append(name)
+
+    def finish_apply(self):
+        assert sorted(self.applied) == sorted(self.names), self.applied  # every region exactly once
+        self.applied = []
+        self.apply()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -72,12 +96,15 @@ def _global_batch(step):
     return users, items, y
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, overlap=False):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    if overlap:
+        os.environ["MR_DP_OVERLAP"] = "1"
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from movierec._distributed import DataParallelNeuMF, shard_batch
     w0 = o.init_weights(9, 13, PARAMS["layers_sizes"], 2, np.random.default_rng(1))
-    dp = DataParallelNeuMF(OracleEngine(w0, PARAMS))
+    dp = DataParallelNeuMF((RegionOracleEngine if overlap else OracleEngine)(w0, PARAMS))
+    assert dp.overlap == overlap
     loss_local = []
     for step in range(3):
         users, items, y = _global_batch(step)
@@ -91,9 +118,10 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_data_parallel_matches_single_process(tmp_path):
+@pytest.mark.parametrize("overlap", [False, True], ids=["one-all-reduce", "region-wise"])
+def test_two_rank_data_parallel_matches_single_process(tmp_path, overlap):
     out = str(tmp_path / "rank0.npz")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, overlap), nprocs=2, join=True)
     got = np.load(out)
     w = o.init_weights(9, 13, PARAMS["layers_sizes"], 2, np.random.default_rng(1))
     st = o.new_opt_state(w)
