@@ -265,6 +265,13 @@ int mr_tc_rate(int32_t N, int32_t iters, int32_t nbuf, int32_t flags, int32_t wr
  * the DISTINCT items of its (user, item) pairs; rowptr[num_users] = number of distinct pairs <= n (csr_items has room
  * for n).  *flag |= 1 when an id lies outside [0, num_users) / [0, num_items): such pairs are left out of the lists,
  * and the split of such input is undefined.  All arrays [device]; flag must be zeroed by the caller. */
+/* mr_remap_ids: dense ids for datasets whose ids are sparse or 1-based (the reference keeps the raw MovieLens ids and
+ * sizes its tables by constants, movielens_utils.py:51-55).  dense_ids[i] = rank of ids[i] among
+ * the DISTINCT ids in ascending order, unique_ids[r] = the id of rank r (room for n), *num_unique = their number
+ * [device].  Ids outside [0, id_limit) get dense id -1 and raise bit 0 of *flag. */
+size_t mr_remap_workspace_bytes(int64_t n);
+int mr_remap_ids(const int32_t* ids, int64_t n, int32_t id_limit, int32_t* dense_ids, int32_t* unique_ids,
+                 int64_t* num_unique, int32_t* flag, void* ws, size_t ws_bytes, void* stream);
 size_t mr_split_workspace_bytes(int64_t n);
 int mr_split_last_two(const int32_t* users, int64_t n, int32_t num_users, int32_t* order, int32_t* part, int32_t* flag,
                       void* ws, size_t ws_bytes, void* stream);

@@ -1487,6 +1487,15 @@ int mr_split_last_two(const int32_t* users, int64_t n, int32_t num_users, int32_
   return launch_split_last_two(users, n, num_users, order, part, flag, ws, ws_bytes, (cudaStream_t)stream);
 }
 
+size_t mr_remap_workspace_bytes(int64_t n) { return remap_workspace_bytes(n < 0 ? 0 : n); }
+
+int mr_remap_ids(const int32_t* ids, int64_t n, int32_t id_limit, int32_t* dense_ids, int32_t* unique_ids,
+                 int64_t* num_unique, int32_t* flag, void* ws, size_t ws_bytes, void* stream) {
+  MR_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && id_limit > 0, "remap: bad n / id_limit");
+  MR_REQUIRE(num_unique && flag && ws && (n == 0 || (ids && dense_ids && unique_ids)), "remap: NULL pointer");
+  return launch_remap_ids(ids, n, id_limit, dense_ids, unique_ids, num_unique, flag, ws, ws_bytes, (cudaStream_t)stream);
+}
+
 size_t mr_user_csr_workspace_bytes(int64_t n) { return user_csr_workspace_bytes(n < 0 ? 0 : n); }
 
 int mr_build_user_csr(const int32_t* users, const int32_t* items, int64_t n, int32_t num_users, int32_t num_items,

@@ -157,6 +157,102 @@ __global__ void __launch_bounds__(kDsThreads) csr_rowptr_kernel(const int32_t* _
   }
 }
 
+// ---- dense id remapping: ids -> ranks among the distinct ids (the reference has none, SURVEY App. B-6: MovieLens
+// ids are 1-based and sparse, so its tables carry rows that are never used) -------------------------------------
+// first[e] = sorted entry e opens a run of equal ids (ids outside [0, limit) were clamped to `limit`: dropped)
+__device__ __forceinline__ bool run_first(const int32_t* sk, int64_t e) { return e == 0 || __ldg(sk + e - 1) != __ldg(sk + e); }
+
+__global__ void __launch_bounds__(kDsThreads) runs_count_kernel(const int32_t* __restrict__ sk, int64_t n, int32_t limit,
+                                                                unsigned* __restrict__ counts) {
+  __shared__ unsigned wsum[kDsThreads / 32];
+  const int64_t base = (int64_t)blockIdx.x * kDsTile;
+  unsigned c = 0;
+  for (int q = 0; q < kDsPerThread; ++q) {
+    const int64_t e = base + (int64_t)q * kDsThreads + threadIdx.x;
+    if (e < n && (unsigned)__ldg(sk + e) < (unsigned)limit && run_first(sk, e)) ++c;
+  }
+  c = (unsigned)warp_sum_int((int)c);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < kDsThreads / 32; ++w) t += wsum[w];
+    counts[blockIdx.x] = t;
+  }
+}
+
+// rank of every sorted entry = number of runs opened up to and including it, minus one; scattered back through
+// the sort's index (dense[idx[e]] = rank), and the id of every run written at its rank
+__global__ void __launch_bounds__(kDsThreads) runs_rank_kernel(const int32_t* __restrict__ sk, const int32_t* __restrict__ idx,
+                                                               int64_t n, int32_t limit, const int64_t* __restrict__ offsets,
+                                                               int32_t* __restrict__ dense, int32_t* __restrict__ unique) {
+  __shared__ unsigned wsum[kDsThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t base = (int64_t)blockIdx.x * kDsTile;
+  int64_t out = offsets[blockIdx.x];
+  for (int q = 0; q < kDsPerThread; ++q) {
+    const int64_t e = base + (int64_t)q * kDsThreads + threadIdx.x;
+    const bool ok = e < n && (unsigned)__ldg(sk + e) < (unsigned)limit;
+    const bool first = ok && run_first(sk, e);
+    const unsigned m = __ballot_sync(0xffffffffu, first);
+    if (lane == 0) wsum[w] = __popc(m);
+    __syncthreads();
+    unsigned before = 0, total = 0;
+    for (int k = 0; k < kDsThreads / 32; ++k) {
+      const unsigned c = wsum[k];
+      if (k < w) before += c;
+      total += c;
+    }
+    if (e < n) {
+      const int64_t rank = out + before + __popc(m & (0xffffffffu >> (31 - lane))) - 1;  // runs opened up to here - 1
+      dense[__ldg(idx + e)] = ok ? (int32_t)rank : -1;
+      if (first) unique[rank] = __ldg(sk + e);
+    }
+    out += total;
+    __syncthreads();
+  }
+}
+
+size_t remap_workspace_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  const int64_t nb = (n + kDsTile - 1) / kDsTile;
+  return sort_workspace_bytes(n) + align_up((size_t)n * 4, 256) * 3 + align_up((size_t)nb * 4, 256) +
+         align_up((size_t)nb * 8, 256) + 512;
+}
+
+int launch_remap_ids(const int32_t* ids, int64_t n, int32_t limit, int32_t* dense, int32_t* unique, int64_t* num_unique,
+                     int32_t* flag, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int64_t nb = (n + kDsTile - 1) / kDsTile;
+  Carver cv(ws);
+  int32_t* clamped = cv.take<int32_t>(n > 0 ? n : 1);
+  int32_t* sk = cv.take<int32_t>(n > 0 ? n : 1);
+  int32_t* idx = cv.take<int32_t>(n > 0 ? n : 1);
+  unsigned* counts = cv.take<unsigned>(nb > 0 ? nb : 1);
+  int64_t* offsets = cv.take<int64_t>(nb > 0 ? nb : 1);
+  void* sort_ws = cv.take<char>(sort_workspace_bytes(n > 0 ? n : 1));
+  if (ws_bytes < cv.off) {
+    set_error("remap workspace too small: %zu < %zu", ws_bytes, cv.off);
+    return MR_ERR_WORKSPACE;
+  }
+  if (n == 0) {
+    MR_CUDA(cudaMemsetAsync(num_unique, 0, sizeof(int64_t), st));
+    return MR_OK;
+  }
+  int bits = 1;
+  while (bits < 31 && ((int64_t)1 << bits) <= limit) ++bits;
+  clamp_ids_kernel<<<ds_grid(n), kDsThreads, 0, st>>>(ids, n, limit, clamped, flag);
+  MR_LAUNCH_CHECK("clamp_ids_kernel");
+  int rc = launch_sort_pairs(clamped, n, bits, sk, idx, sort_ws, sort_workspace_bytes(n), st);
+  if (rc != MR_OK) return rc;
+  runs_count_kernel<<<(unsigned)nb, kDsThreads, 0, st>>>(sk, n, limit, counts);
+  MR_LAUNCH_CHECK("runs_count_kernel");
+  scan_counts_kernel<<<1, 1024, 0, st>>>(counts, nb, offsets, num_unique);
+  MR_LAUNCH_CHECK("scan_counts_kernel");
+  runs_rank_kernel<<<(unsigned)nb, kDsThreads, 0, st>>>(sk, idx, n, limit, offsets, dense, unique);
+  MR_LAUNCH_CHECK("runs_rank_kernel");
+  return MR_OK;
+}
+
 size_t split_workspace_bytes(int64_t n) {
   if (n < 1) n = 1;
   return sort_workspace_bytes(n) + align_up((size_t)n * 4, 256) * 2 + 256;

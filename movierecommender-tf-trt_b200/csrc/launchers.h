@@ -193,6 +193,9 @@ int launch_check_grouped(const int32_t* ids, int64_t n, int group, int32_t* flag
 size_t split_workspace_bytes(int64_t n);
 int launch_split_last_two(const int32_t* users, int64_t n, int32_t num_users, int32_t* order, int32_t* part,
                           int32_t* flag, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t remap_workspace_bytes(int64_t n);
+int launch_remap_ids(const int32_t* ids, int64_t n, int32_t limit, int32_t* dense, int32_t* unique, int64_t* num_unique,
+                     int32_t* flag, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t user_csr_workspace_bytes(int64_t n);
 int launch_build_user_csr(const int32_t* users, const int32_t* items, int64_t n, int32_t num_users, int32_t num_items,
                           int64_t* rowptr, int32_t* csr_items, int32_t* flag, void* ws, size_t ws_bytes,

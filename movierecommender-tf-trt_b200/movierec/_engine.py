@@ -473,6 +473,28 @@ def sort_pairs(keys, key_bits):
     return out_k, out_i
 
 
+def remap_ids(ids, id_limit=None):
+    """Dense ids on the device: returns (dense_ids int32 (n,), unique_ids int32 (distinct,)) with
+    unique_ids ascending and unique_ids[dense_ids] == ids (np.unique(ids, return_inverse=True) of the oracle)."""
+    require_cuda()
+    device = torch.device("cuda:{}".format(torch.cuda.current_device()))
+    ids = as_device_i32(ids, device)
+    n = ids.numel()
+    if id_limit is None:
+        id_limit = int(ids.max().item()) + 1 if n else 1
+    dense, unique = torch.empty_like(ids), torch.empty(max(n, 1), dtype=torch.int32, device=device)
+    count = torch.zeros(1, dtype=torch.int64, device=device)
+    flag = torch.zeros(1, dtype=torch.int32, device=device)
+    nbytes = max(int(nat.lib.mr_remap_workspace_bytes(n)), 256)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    nat.check(nat.lib.mr_remap_ids(_ptr(ids), n, int(id_limit), _ptr(dense), _ptr(unique), _ptr(count), _ptr(flag),
+                                   _ptr(ws), nbytes, st), "mr_remap_ids")
+    if int(flag.item()):
+        raise IndexError("remap_ids: an id lies outside [0, {})".format(id_limit))
+    return dense, unique[:int(count.item())]
+
+
 def split_last_two(users, num_users):
     """Leave-last-two-out split on the device (reference data_pipeline.py:190-198).  users: the user id of every
     rating in file order.  Returns (order, part) device int32 tensors: order = row numbers sorted by user (stable),

@@ -92,6 +92,8 @@ SIGNATURES = {
     "mr_sparse_rows_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "mr_sparse_rows_update": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i32, _f, _f, _f, _f,
                                         _f, _vp, _sz, _vp]),
+    "mr_remap_workspace_bytes": (C.c_size_t, [_i64]),
+    "mr_remap_ids": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mr_split_workspace_bytes": (C.c_size_t, [_i64]),
     "mr_split_last_two": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mr_user_csr_workspace_bytes": (C.c_size_t, [_i64]),

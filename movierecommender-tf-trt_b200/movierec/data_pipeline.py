@@ -192,6 +192,29 @@ def split_leave_last_two_out(ratings_df, col_user=COL_USER_ID, on_device=None):
     return train, validation, test
 
 
+def remap_dense_ids(ratings_df, columns=(COL_USER_ID, COL_ITEM_ID), on_device=None):
+    """New in this package (the reference keeps the raw, 1-based, sparse MovieLens ids and sizes its tables by
+    constants, movielens_utils.py:51-55): replace the ids of each column by their rank among the distinct ids.
+    Returns (DataFrame with dense ids, {column: array of the original id of every dense id}).  On the GPU when there
+    is one (mr_remap_ids), else np.unique."""
+    out = ratings_df.copy()
+    maps = {}
+    if on_device is None:
+        on_device = _cuda_available()
+    for col in columns:
+        ids = np.asarray(ratings_df[col].values)
+        if on_device and len(ids) and ids.min() >= 0 and ids.max() < 2 ** 31 - 1:
+            from . import _engine
+            dense, unique = _engine.remap_ids(ids.astype(np.int32))
+            out[col] = dense.cpu().numpy().astype(ids.dtype)
+            maps[col] = unique.cpu().numpy().astype(ids.dtype)
+        else:
+            unique, dense = np.unique(ids, return_inverse=True)
+            out[col] = dense.reshape(-1).astype(ids.dtype)
+            maps[col] = unique
+    return out, maps
+
+
 def load_ratings_train_test_sets(dataset_name, data_dir, download=True):
     """
     Load a Movielens ratings file and split it into (train, validation, test) DataFrames with columns

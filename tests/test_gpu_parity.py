@@ -647,6 +647,23 @@ def test_device_user_csr_edge_cases(eng_mod):
         eng_mod.build_user_csr(np.array([0, 1], np.int32), np.array([0, 4], np.int32), 2, 4)
 
 
+@pytest.mark.parametrize("n,limit", [(1, 5), (9, 4), (5000, 70000), (1000209, 3953), (100000, 2 ** 30)])
+def test_device_remap_ids_matches_numpy_unique(eng_mod, n, limit):
+    rng = np.random.default_rng(n)
+    ids = (rng.integers(0, min(limit, 200000), n) * max(1, limit // 200000)).astype(np.int32)  # sparse, with repeats
+    ids = np.minimum(ids, limit - 1)
+    dense, unique = eng_mod.remap_ids(ids, limit)
+    want_unique, want_dense = np.unique(ids, return_inverse=True)
+    np.testing.assert_array_equal(unique.cpu().numpy(), want_unique)
+    np.testing.assert_array_equal(dense.cpu().numpy(), want_dense.reshape(-1))
+    d2, u2 = eng_mod.remap_ids(ids)  # limit from the data
+    assert torch.equal(d2, dense) and torch.equal(u2, unique)
+    with pytest.raises(IndexError):
+        eng_mod.remap_ids(np.array([0, limit], np.int64).astype(np.int32) if limit < 2 ** 30 else np.array([-1], np.int32), limit)
+    d0, u0 = eng_mod.remap_ids(np.zeros(0, np.int32), 7)
+    assert d0.numel() == 0 and u0.numel() == 0
+
+
 def test_generator_uses_the_device_csr(eng_mod):
     """The generator's table is the device-built one and equals the NumPy statement of the same table."""
     import pandas as pd

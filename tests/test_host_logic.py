@@ -230,6 +230,15 @@ def test_load_ratings_data_zero_based(tmp_path):
         ml.load_ratings_data(str(tmp_path), "ml-1m", download=False)
 
 
+def test_remap_dense_ids_host_path():
+    df = pd.DataFrame({"userId": [10, 3, 10, 7, 3], "itemId": [100, 5, 5, 42, 100], "rating": [1.0, 2.0, 3.0, 4.0, 5.0]})
+    out, maps = data_pipeline.remap_dense_ids(df, on_device=False)
+    assert out.userId.tolist() == [2, 0, 2, 1, 0] and out.itemId.tolist() == [2, 0, 0, 1, 2]
+    assert maps["userId"].tolist() == [3, 7, 10] and maps["itemId"].tolist() == [5, 42, 100]
+    assert out.rating.tolist() == df.rating.tolist() and df.userId.tolist() == [10, 3, 10, 7, 3]  # input untouched
+    assert (maps["userId"][out.userId.values] == df.userId.values).all()
+
+
 def test_keras_h5_round_trip(tmp_path):
     """Keras-layout HDF5 weight files; needs h5py, which this image does not ship."""
     pytest.importorskip("h5py")
