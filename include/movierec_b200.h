@@ -219,7 +219,8 @@ enum { MR_PHASE_TILE_TRAIN = 0, /* fused gather+tower+head+BCE+backward kernel *
        MR_PHASE_TC_WGRAD = 10,     /* tcgen05 weight-gradient layers */
        MR_PHASE_HEAD = 11,         /* GMF + output unit + BCE (+ their gradients) */
        MR_PHASE_H1_GATHER = 12,    /* item-projected first layer: gather + add + ReLU of the projected rows */
-       MR_NUM_PHASES = 13 };
+       MR_PHASE_FUSED_TILE = 13,   /* fused per-tile train kernel of the projected tower (tc_fused.cu) */
+       MR_NUM_PHASES = 14 };
 int mr_profile_begin(void);
 int mr_profile_end(float* phase_ms, int64_t* phase_count, int64_t* kernel_launches);
 
@@ -253,6 +254,10 @@ int mr_tc_probe(const float* raw_a, int32_t n_words, int32_t start_off, int32_t 
                 float* D, void* stream);
 int mr_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
                         int32_t three_x, void* stream);
+/* The same single-tile GEMM on the operand form of the fused train kernel: three bf16 parts per operand, six part
+ * products, SWIZZLE_128B tiles read K-major (x_mn = 0) or MN-major (x_mn = 1); K % 16 == 0, K <= 256. */
+int mr_bf16x3_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
+                            void* stream);
 /* Diagnostics: sustained tcgen05 issue rate of the 3xTF32 stage pattern on static operands (tools/tc_rate.py). */
 int mr_tc_rate(int32_t N, int32_t iters, int32_t nbuf, int32_t flags, int32_t writers, int32_t write_iters,
                int64_t* out_cycles, int32_t grid, void* stream);

@@ -245,6 +245,7 @@ struct TcWs {
   float* Si;       // (num_items x L1): dZ[1] summed over the rows of each item (train)
   float* Pu;       // (num_users x L1): E_user . W1[user rows] + b1 (train, user_proj_ok)
   float* Su;       // (num_users x L1): dZ[1] summed over the rows of each user (train)
+  uint16_t* w2_image;  // fused train kernel: W[2] as its shared-memory operand image (tc_fused.cu)
   size_t total;
 };
 
@@ -291,6 +292,7 @@ static TcWs carve_tc(const MrModel& m, bool train, int64_t B, void* ws) {
         t.Su = cv.take<float>((size_t)m.num_users * m.L[1]);
       }
     }
+    t.w2_image = cv.take<uint16_t>(fused_w2_image_bytes() / sizeof(uint16_t));
   }
   t.total = cv.off;
   return t;
@@ -845,8 +847,49 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       if (rc == MR_OK && uproj) rc = tc_project_users(m, tw, st);
       if (rc != MR_OK) return rc;
     }
+    // The per-row work of the projected step in ONE kernel (tc_fused.cu): H1, the second layer forward, the head,
+    // the second layer's weight gradient and backward, the staged rows and their group sums never leave the SM.
+    static const bool no_fused = getenv("MR_NO_FUSED_TRAIN") != nullptr;
+    const bool fused = uproj && !no_fused && fused_train_supported(m, group);
+    int fused_grid = 0;
+    if (fused) {
+      prof_mark(MR_PHASE_FUSED_TILE, st);
+      FusedTrainArgs fa{};
+      fa.Pi = tw.Pi;
+      fa.Pu = tw.Pu;
+      fa.user_gmf = m.user_gmf;
+      fa.item_gmf = m.item_gmf;
+      fa.users = users;
+      fa.items = items;
+      fa.labels = labels;
+      fa.num_users = m.num_users;
+      fa.num_items = m.num_items;
+      fa.rows = B;
+      fa.group = group;
+      fa.W2 = m.W[2];
+      fa.w2_image = tw.w2_image;
+      fa.b2 = m.b[2];
+      fa.w_out = m.w_out;
+      fa.b_out = m.b_out;
+      fa.inv_batch = inv_global_batch;
+      fa.probs = t.probs;
+      fa.stage_i = t.stage_i;
+      fa.stage_u = t.stage_u;
+      fa.si = d_i + f;
+      fa.su = d_u + f;
+      fa.partial = t.dense_partial;
+      fa.partial_stride = t.dense_stride;
+      fa.off_w2 = m.W[2] - m.dense;
+      fa.off_b2 = m.b[2] - m.dense;
+      fa.off_wout = m.w_out - m.dense;
+      fa.off_bout = m.b_out - m.dense;
+      fa.loss_partial = t.loss_partial;
+      fa.flags = t.flags;
+      rc = launch_fused_train(fa, st, &fused_grid);
+      if (rc != MR_OK) return rc;
+    }
     const int64_t sb = tc_sub_batch(B);
-    for (int64_t r0 = 0; r0 < B; r0 += sb) {
+    for (int64_t r0 = 0; r0 < B && !fused; r0 += sb) {
       const int64_t r1 = r0 + sb < B ? r0 + sb : B;
       prof_mark(MR_PHASE_TC_DENSE_FWD, st);
       rc = tc_forward_rows(m, tw, users, items, 1, r0, r1, st, gdiv);
@@ -1127,8 +1170,11 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       }
     }
     prof_mark(MR_PHASE_MISC, st);
-    rc = launch_head_reduce(m, tw.head_partial, t.dense_partial + (m.w_out - m.dense),
-                            t.dense_partial + (m.b_out - m.dense), step_out + MR_OUT_LOSS_SUM, st);
+    if (fused)  // (its d w_out / d b_out partials sit in the CTAs' rows of the dense partial buffer already)
+      rc = launch_sum_partials(t.loss_partial, fused_grid, step_out + MR_OUT_LOSS_SUM, st);
+    else
+      rc = launch_head_reduce(m, tw.head_partial, t.dense_partial + (m.w_out - m.dense),
+                              t.dense_partial + (m.b_out - m.dense), step_out + MR_OUT_LOSS_SUM, st);
     if (rc != MR_OK) return rc;
     rc = launch_dense_reduce(m, t.dense_partial, t.dense_stride, P, grads->dense, st);
     if (rc != MR_OK) return rc;
@@ -1350,6 +1396,12 @@ int mr_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int
                         int32_t three_x, void* stream) {
   MR_REQUIRE(A && B && D, "tc selftest: NULL pointer");
   return launch_tc_selftest(A, B, D, N, K, a_mn, b_mn, three_x, (cudaStream_t)stream);
+}
+
+int mr_bf16x3_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
+                            void* stream) {
+  MR_REQUIRE(A && B && D, "bf16x3 selftest: NULL pointer");
+  return launch_bf16x3_selftest(A, B, D, N, K, a_mn, b_mn, (cudaStream_t)stream);
 }
 
 int mr_tc_probe(const float* raw_a, int32_t n_words, int32_t start_off, int32_t lbo, int32_t sbo, int32_t a_mn, float* D,

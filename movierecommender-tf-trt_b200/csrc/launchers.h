@@ -201,6 +201,39 @@ int launch_build_user_csr(const int32_t* users, const int32_t* items, int64_t n,
                           int64_t* rowptr, int32_t* csr_items, int32_t* flag, void* ws, size_t ws_bytes,
                           cudaStream_t st);
 
+// ---- tc_fused.cu: the projected tower's per-row work of a grouped train step in ONE kernel ----------------------
+struct FusedTrainArgs {
+  const float* Pi;        // [num_items x L1] item half of the first layer
+  const float* Pu;        // [num_users x L1] user half + bias
+  const float* user_gmf;
+  const float* item_gmf;
+  const int32_t* users;
+  const int32_t* items;
+  const float* labels;
+  int32_t num_users, num_items;
+  int64_t rows;
+  int32_t group;
+  const float* W2;        // (L1, L2) Keras layout; packed into w2_image by the launcher
+  uint16_t* w2_image;     // fused_w2_image_bytes() of workspace
+  const float* b2;
+  const float* w_out;
+  const float* b_out;
+  float inv_batch;
+  float* probs;
+  float* stage_i;         // [rows x si]: dZ1 | d gmf_i
+  float* stage_u;         // [rows / group x su]: group sums of dZ1 | d gmf_u
+  int32_t si, su;
+  float* partial;         // dense-gradient partial rows (one per CTA, zeroed by the caller), stride partial_stride
+  int64_t partial_stride;
+  int64_t off_w2, off_b2, off_wout, off_bout;
+  float* loss_partial;    // one float per CTA (written, not accumulated)
+  int32_t* flags;
+};
+bool fused_train_supported(const MrModel& m, int group);
+size_t fused_w2_image_bytes();
+int launch_fused_train(const FusedTrainArgs& a, cudaStream_t st, int* grid_out);
+int launch_bf16x3_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn, int b_mn, cudaStream_t st);
+
 // ---- tc_selftest.cu ---------------------------------------------------------------------------
 int launch_tc_rate(int N, int iters, int nbuf, int flags, int writers, int write_iters, long long* out, int grid,
                    cudaStream_t st);

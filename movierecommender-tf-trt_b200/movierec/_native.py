@@ -87,6 +87,7 @@ SIGNATURES = {
     "mr_sort_pairs": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
     "mr_tc_probe": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "mr_tc_gemm_selftest": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mr_bf16x3_gemm_selftest": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "mr_tc_rate": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "mr_gather_rows_sharded": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _i64, _vp, _vp]),
     "mr_sparse_rows_workspace_bytes": (_sz, [_i64, _i32, _i32]),
@@ -135,9 +136,9 @@ def check(rc, what):
         raise MovierecNativeError("{} failed (status {}): {}".format(what, rc, last_error()))
 
 
-NUM_PHASES = 13
+NUM_PHASES = 14
 PHASE_NAMES = ["tile_train", "misc", "sort", "segreduce", "optimizer", "tile_forward", "rank", "sampler",
-               "tc_dense_fwd", "tc_dense_bwd", "tc_wgrad", "head", "h1_gather"]
+               "tc_dense_fwd", "tc_dense_bwd", "tc_wgrad", "head", "h1_gather", "fused_tile"]
 
 
 def profile_begin():
