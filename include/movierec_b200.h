@@ -98,8 +98,11 @@ typedef struct MrGrads {
  * negatives) share one user.  The tensor-core path then computes everything that depends on the user row alone
  * once per group (user half of the first layer forward, backward and weight gradient on group-summed
  * gradients, one staged user-gradient row per group).  The statement is verified on the device; a violation
- * sets bit 1 of step_out[MR_OUT_BAD_IDS].  Without the flag no layout is assumed. */
-enum { MR_TRAIN_USERS_GROUPED = 1 };
+ * sets bit 1 of step_out[MR_OUT_BAD_IDS].  Without the flag no layout is assumed.
+ * MR_TRAIN_NO_DENSE_L2: leave the hidden kernels' regulariser term 2*l2[l]*W[l] (model.py:178) out of grads.dense.
+ * Data-parallel callers that SUM the ranks' gradients pass it on every rank but one, so that the term is counted
+ * once (the tables' term is added by mr_neumf_apply, after the reduction). */
+enum { MR_TRAIN_USERS_GROUPED = 1, MR_TRAIN_NO_DENSE_L2 = 2 };
 
 /* Per-step scalars written by the train step (device floats, MR_STEP_OUT_FLOATS of them). */
 enum { MR_OUT_LOSS_SUM = 0, /* sum over rows of BCE (model.py:213-215), unscaled */
@@ -163,11 +166,14 @@ int mr_rank_eval(const MrModel* model, const int32_t* users, const int32_t* item
                  int32_t group, int32_t k, int32_t* rank, int32_t* pos, float* probs, float* sums,
                  void* ws, size_t ws_bytes, void* stream);
 
-/* RankLayer + metrics on caller-supplied scores (model.py:336-455); label_col (G) may be NULL
- * meaning "last column".  rank may be NULL. */
+/* RankLayer + metrics on caller-supplied scores (model.py:336-455).  The label column of group g is
+ * label_col[g] when label_col (G) is given, else the argmax of labels[g*group .. (g+1)*group) (first maximum:
+ * K.argmax(y_true), model.py:447-448) when labels (G*group) is given, else the last column (the generator's
+ * layout).  rank may be NULL. */
 size_t mr_rank_scores_workspace_bytes(int64_t G);
 int mr_rank_scores(const float* scores, int64_t G, int32_t group, int32_t k, const int32_t* label_col,
-                   int32_t* rank, int32_t* pos, float* sums, void* ws, size_t ws_bytes, void* stream);
+                   const float* labels, int32_t* rank, int32_t* pos, float* sums, void* ws, size_t ws_bytes,
+                   void* stream);
 
 /* On-device negative sampler -- replaces _get_random_negatives_and_positive
  * (data_pipeline.py:99-113): for positive p (global index first_index + p, user pos_users[p]) draw

@@ -1176,7 +1176,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       rc = launch_head_reduce(m, tw.head_partial, t.dense_partial + (m.w_out - m.dense),
                               t.dense_partial + (m.b_out - m.dense), step_out + MR_OUT_LOSS_SUM, st);
     if (rc != MR_OK) return rc;
-    rc = launch_dense_reduce(m, t.dense_partial, t.dense_stride, P, grads->dense, st);
+    rc = launch_dense_reduce(m, t.dense_partial, t.dense_stride, P, grads->dense, st, !(flags & MR_TRAIN_NO_DENSE_L2));
     if (rc != MR_OK) return rc;
   } else {
   rc = launch_transpose_kernels(m, t.wt, st);
@@ -1204,7 +1204,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   rc = launch_neumf_tiles(a, st, &grid);
   prof_mark(MR_PHASE_MISC, st);
   if (rc != MR_OK) return rc;
-  rc = launch_dense_reduce(m, t.dense_partial, t.dense_stride, grid, grads->dense, st);
+  rc = launch_dense_reduce(m, t.dense_partial, t.dense_stride, grid, grads->dense, st, !(flags & MR_TRAIN_NO_DENSE_L2));
   if (rc != MR_OK) return rc;
   rc = launch_sum_partials(t.loss_partial, grid, step_out + MR_OUT_LOSS_SUM, st);
   if (rc != MR_OK) return rc;
@@ -1231,8 +1231,9 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
 
   if (group > 0) {
     prof_mark(MR_PHASE_RANK, st);
+    // label column = argmax of the group's labels (model.py:447-448): any layout of the positive is ranked right
     rc = launch_rank_scores(t.probs, B / group, group, k, nullptr, nullptr, t.pos, step_out + MR_OUT_HIT_SUM,
-                            t.rank_partials, st);
+                            t.rank_partials, st, labels);
     if (rc != MR_OK) return rc;
   }
   prof_mark(MR_PHASE_MISC, st);
@@ -1365,8 +1366,9 @@ int mr_rank_eval(const MrModel* model, const int32_t* users, const int32_t* item
 
 size_t mr_rank_scores_workspace_bytes(int64_t G) { return align_up(rank_partials_count(G < 0 ? 0 : G) * sizeof(float), 256); }
 
-int mr_rank_scores(const float* scores, int64_t G, int32_t group, int32_t k, const int32_t* label_col, int32_t* rank,
-                   int32_t* pos, float* sums, void* ws, size_t ws_bytes, void* stream) {
+int mr_rank_scores(const float* scores, int64_t G, int32_t group, int32_t k, const int32_t* label_col,
+                   const float* labels, int32_t* rank, int32_t* pos, float* sums, void* ws, size_t ws_bytes,
+                   void* stream) {
   MR_REQUIRE(scores && pos, "rank_scores: NULL pointer");
   MR_REQUIRE(G >= 0 && group >= 1 && group <= MR_MAX_NEGS + 1, "rank_scores: bad G=%lld group=%d", (long long)G, group);
   if (sums != nullptr) {
@@ -1376,7 +1378,8 @@ int mr_rank_scores(const float* scores, int64_t G, int32_t group, int32_t k, con
       return MR_ERR_WORKSPACE;
     }
   }
-  return launch_rank_scores(scores, G, group, k, label_col, rank, pos, sums, static_cast<float*>(ws), (cudaStream_t)stream);
+  return launch_rank_scores(scores, G, group, k, label_col, rank, pos, sums, static_cast<float*>(ws), (cudaStream_t)stream,
+                            labels);
 }
 
 int mr_sample_negatives(const int64_t* csr_rowptr, const int32_t* csr_items, int32_t num_items, const int32_t* pos_users,

@@ -30,7 +30,7 @@ int choose_tile_rows(const MrModel& m, bool train);
 int launch_neumf_tiles(const TileLaunch& a, cudaStream_t st, int* grid_out);
 int launch_transpose_kernels(const MrModel& m, float* wt, cudaStream_t st);
 int launch_dense_reduce(const MrModel& m, const float* partial, int64_t stride, int grid_ctas, float* out,
-                        cudaStream_t st);
+                        cudaStream_t st, bool with_l2 = true);
 int launch_sum_partials(const float* partial, int n, float* out, cudaStream_t st);
 int launch_l2_penalty(const float* x, int64_t n, float coef, float* out, cudaStream_t st);
 
@@ -64,8 +64,9 @@ int launch_optimizer_flat(float* p, const float* g, float* m, float* v, int64_t 
 
 // ---- rank.cu ---------------------------------------------------------------------------------
 size_t rank_partials_count(int64_t G);
+// label column of group g: label_col[g], else argmax of labels[g * group ..] (labels != NULL), else the last column
 int launch_rank_scores(const float* scores, int64_t G, int group, int k, const int32_t* label_col, int32_t* rank,
-                       int32_t* pos, float* sums, float* partials, cudaStream_t st);
+                       int32_t* pos, float* sums, float* partials, cudaStream_t st, const float* labels = nullptr);
 
 // ---- sampler.cu ------------------------------------------------------------------------------
 int launch_sample_negatives(const int64_t* rowptr, const int32_t* csr_items, int32_t num_items,

@@ -11,8 +11,11 @@ namespace mr {
 constexpr int kRankThreads = 256;
 constexpr int kRankGroupsPerCta = 1024;  // groups folded into one partial sum
 
+// Label column of a group: label_col[g] when given, else argmax of the group's labels (first maximum, as
+// K.argmax(y_true) at model.py:447-448) when `labels` is given, else the last column (the generator's layout).
 __global__ void __launch_bounds__(kRankThreads) rank_positions_kernel(const float* __restrict__ scores, int64_t G,
                                                                       int group, const int32_t* __restrict__ label_col,
+                                                                      const float* __restrict__ labels,
                                                                       int32_t* __restrict__ rank,
                                                                       int32_t* __restrict__ pos) {
   const int lane = threadIdx.x & 31;
@@ -20,6 +23,22 @@ __global__ void __launch_bounds__(kRankThreads) rank_positions_kernel(const floa
   for (int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < G; g += warps) {
     const float* s = scores + g * group;
     int lc = label_col != nullptr ? __ldg(label_col + g) : group - 1;
+    if (label_col == nullptr && labels != nullptr) {
+      const float* y = labels + g * group;
+      float best = -INFINITY;
+      int bi = group;  // (a NaN label never wins; an all-NaN group falls back to column 0 below)
+      for (int j = lane; j < group; j += 32) {
+        const float v = __ldg(y + j);
+        if (v > best) { best = v; bi = j; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      lc = bi >= group ? 0 : bi;
+    }
     lc = min(max(lc, 0), group - 1);
     const float sp = rank_key(__ldg(s + lc));
     int cnt = 0;
@@ -125,7 +144,7 @@ int launch_rank_metrics(const int32_t* pos, int64_t G, int k, float* sums, float
 }
 
 int launch_rank_scores(const float* scores, int64_t G, int group, int k, const int32_t* label_col, int32_t* rank,
-                       int32_t* pos, float* sums, float* partials, cudaStream_t st) {
+                       int32_t* pos, float* sums, float* partials, cudaStream_t st, const float* labels) {
   if (G == 0) {
     if (sums != nullptr) MR_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(float), st));
     return MR_OK;
@@ -133,7 +152,7 @@ int launch_rank_scores(const float* scores, int64_t G, int group, int k, const i
   int64_t blocks = (G + 7) / 8;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  rank_positions_kernel<<<(unsigned)blocks, kRankThreads, 0, st>>>(scores, G, group, label_col, rank, pos);
+  rank_positions_kernel<<<(unsigned)blocks, kRankThreads, 0, st>>>(scores, G, group, label_col, labels, rank, pos);
   MR_LAUNCH_CHECK("rank_positions_kernel");
   if (sums != nullptr) {
     const int64_t nb = (G + kRankGroupsPerCta - 1) / kRankGroupsPerCta;

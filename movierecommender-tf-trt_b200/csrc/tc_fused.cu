@@ -139,6 +139,19 @@ __device__ __forceinline__ void bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Diagnostics build (-DMR_FUSED_TIMING, tools/fused_timing.py): one thread per role accumulates clock64 deltas per
+// segment of its tile loop; g_fused_timing[cta][role * 16 + segment].
+#ifdef MR_FUSED_TIMING
+__device__ long long g_fused_timing[256 * 48];
+#define FZ_T_DECL long long tz_[16] = {0}; long long tz_last_ = clock64();
+#define FZ_T(seg) { const long long n_ = clock64(); tz_[seg] += n_ - tz_last_; tz_last_ = n_; }
+#define FZ_T_FLUSH(role, cond) if (cond) { for (int q_ = 0; q_ < 16; ++q_) g_fused_timing[blockIdx.x * 48 + (role) * 16 + q_] = tz_[q_]; }
+#else
+#define FZ_T_DECL
+#define FZ_T(seg)
+#define FZ_T_FLUSH(role, cond)
+#endif
+
 struct FusedParams {
   const float* Pi;        // [num_items x 128]  E_item . W1[item rows]
   const float* Pu;        // [num_users x 128]  E_user . W1[user rows] + b1
@@ -250,10 +263,12 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
     bar_sync(1, kProdThreads);
     bool any_bad = false;
     int64_t it = 0;
+    FZ_T_DECL
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
       const int64_t row0 = tile * TR;
       const int32_t* ids = ids_s + buf * 160;
+      FZ_T(0)
       if (tile + gridDim.x < ntiles) load_ids(tile + gridDim.x, buf ^ 1, true);
 
       // ---- H1 = relu(Pi[item] + Pu[user]): all loads of the tile first
@@ -275,9 +290,11 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
           xi[s][j] = iok ? ldg4(p.Pi + (size_t)itm * kD1 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      FZ_T(1)
       if (it > 0) {  // the weight-gradient MMAs of the previous tile have read H1
         tc::mbar_wait(&h1_free, (uint32_t)((it - 1) & 1));
       }
+      FZ_T(2)
       uint8_t* bits_b = smem + oBits + buf * (128 * 16);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -315,6 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
         tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&h1_full[half]);
+        FZ_T(3 + half)
       }
 
       // ---- GMF branch, part 1: gmf_u * gmf_i . w_out[:f] per row (its rows are loaded once and kept for part 2)
@@ -363,9 +381,11 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&gmf_ready);
+      FZ_T(5)
 
       // ---- GMF branch, part 2 (after the epilogue has dz): row gradients, straight to the staged rows
       tc::mbar_wait(&dz2_full, (uint32_t)(it & 1));
+      FZ_T(6)
 #pragma unroll
       for (int s = 0; s < GSLOTS; ++s) {
         const int idx = tid + kProdThreads * s;
@@ -394,9 +414,12 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
         }
         if (gvalid) *reinterpret_cast<float4*>(p.stage_u + (size_t)(grow0 / GROUP) * p.su + kD1 + 4 * pc) = ga;
       }
+      FZ_T(7)
       cp_async_wait_all();
       bar_sync(1, kProdThreads);  // the next tile's ids are in place; gdot / flags / dz may be rewritten
+      FZ_T(8)
     }
+    FZ_T_FLUSH(0, tid == 0)
     if (any_bad) atomicOr(p.flags, 1);
     *reinterpret_cast<float4*>(smem + oRedG + 16 * tid) = accg;
   } else if (warp == kMmaWarp) {
@@ -412,6 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
       constexpr int PA[6] = {0, 0, 1, 0, 2, 1}, PB[6] = {0, 1, 0, 2, 0, 1};
       tc::mbar_wait(&w2_bar, 0);
       int64_t it = 0;
+      FZ_T_DECL
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const uint32_t ph = (uint32_t)(it & 1);
         // forward: acc_fwd[slot][j] = sum_i H1[slot][i] W2[i][j], one 64-feature half as soon as it has landed
@@ -419,6 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
         for (int half = 0; half < 2; ++half) {
           tc::mbar_wait(&h1_full[half], ph);
           tc::fence_after_sync();
+          FZ_T(2 * half)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
@@ -428,11 +453,13 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
               mma_bf16(tmem_base + cFwd, dk + (a >> 4), dmn + (b >> 4), id_fwd, (half | ks | q) != 0);
             }
           }
+          FZ_T(2 * half + 1)
         }
         tc::mma_commit(&fwd_done);
         // weight gradient first (it frees H1 for the producers), then backward
         tc::mbar_wait(&dz2_full, ph);
         tc::fence_after_sync();
+        FZ_T(4)
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
@@ -443,6 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
           }
         }
         tc::mma_commit(&h1_free);
+        FZ_T(5)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
@@ -453,7 +481,9 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
           }
         }
         tc::mma_commit(&bwd_done);
+        FZ_T(6)
       }
+      FZ_T_FLUSH(1, true)
     }
   } else {
     // ================================ epilogues (thread = row = TMEM lane) ===================================
@@ -465,6 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
     float cs_w[2] = {0.f, 0.f}, cs_b[2] = {0.f, 0.f};  // column sums (columns lane, lane + 32) of dz * H2 and of dZ2
     float accb = 0.f, accl = 0.f;
     int64_t it = 0;
+    FZ_T_DECL
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
       const int64_t row0 = tile * TR;
@@ -475,6 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
       // ---- epilogue 1
       tc::mbar_wait(&fwd_done, ph);
       tc::fence_after_sync();
+      FZ_T(0)
       float h[64];
       tmem_ld32(lane_addr + cFwd, h);
       tmem_ld32(lane_addr + cFwd + 32, h + 32);
@@ -492,7 +524,9 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
         zdot = fmaf(h[4 * q + 2], wv.z, zdot);
         zdot = fmaf(h[4 * q + 3], wv.w, zdot);
       }
+      FZ_T(1)
       tc::mbar_wait(&gmf_ready, ph);
+      FZ_T(2)
       const int flag = flag_s[slot];
       const float z = zdot + gdot_s[slot] + b_out;
       const float pr = sigmoidf_stable(z);
@@ -531,10 +565,12 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&dz2_full);
+      FZ_T(3)
 
       // ---- epilogue 2: dZ1 = acc_bwd * (H1 > 0) -> staged item rows; group sums -> staged user rows
       tc::mbar_wait(&bwd_done, ph);
       tc::fence_after_sync();
+      FZ_T(4)
       const uint4 bw = *reinterpret_cast<const uint4*>(smem + oBits + (it & 1) * (128 * 16) + slot * 16);
       const uint32_t bwv[4] = {bw.x, bw.y, bw.z, bw.w};
       const int64_t qrow0 = row0 + quarter * RQ;          // first row of this warp's quarter
@@ -569,7 +605,9 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
         __syncwarp();
       }
       tc::fence_before_sync();
+      FZ_T(5)
     }
+    FZ_T_FLUSH(2, warp == kEpiWarp0 && lane == 0)
     // ---- end of the CTA's tiles: dW2 (TMEM lane = input unit) and the column sums
     if (it > 0) {
       float* dst = p.partial + (size_t)blockIdx.x * p.partial_stride + p.off_w2 + (size_t)slot * kD2;
@@ -714,6 +752,12 @@ int launch_fused_train(const FusedTrainArgs& a, cudaStream_t st, int* grid_out) 
   MR_LAUNCH_CHECK("neumf_fused_train_kernel");
   return MR_OK;
 }
+
+#ifdef MR_FUSED_TIMING
+extern "C" int mr_fused_timing_read(long long* out_host) {
+  return cudaMemcpyFromSymbol(out_host, fz::g_fused_timing, sizeof(long long) * 256 * 48) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // ---- single-tile GEMM on the same operand layout, descriptors and split (tests/test_gpu_tc.py) ----------------------
 //   D[128 x N] = A . B^T,  A = [128 x K] (K-major) or given as [K x 128] (MN-major), B = [N x K] or given as [K x N].

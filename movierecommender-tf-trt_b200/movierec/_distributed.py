@@ -62,8 +62,10 @@ class DataParallelNeuMF(object):
         Returns the rank-local step outputs (loss/hit/dcg sums over the local rows).
         grouped: see NeuMFEngine.train_step (batches are split by whole groups, so the layout survives)."""
         e = self.engine
+        # the hidden kernels' l2 term 2*l2*W is part of the gradients this call returns; the all-reduce below SUMS the
+        # ranks' gradients, so only rank 0 adds it (the tables' l2 term is added by apply(), after the reduction)
         out = e.train_grads(users, items, labels, group=group, k=k, inv_global_batch=1.0 / float(global_rows),
-                            grouped=grouped)
+                            grouped=grouped, dense_l2=(self.rank == 0))
         if self.overlap and hasattr(e, "gradient_regions"):
             # region by region, largest first: the Adam sweep of one region runs (on the compute stream) under the
             # all-reduce of the next ones (on NCCL's stream); work.wait() orders the streams, the host never blocks

@@ -308,7 +308,7 @@ class NeuMFEngine(object):
                   "mr_users_grouped")
         return int(flag.item()) == 0
 
-    def _train_args(self, users, items, labels, group, k, inv_global_batch, grouped=False):
+    def _train_args(self, users, items, labels, group, k, inv_global_batch, grouped=False, dense_l2=True):
         users = as_device_i32(users, self.device)
         items = as_device_i32(items, self.device)
         labels = as_device_f32(labels, self.device)
@@ -321,6 +321,8 @@ class NeuMFEngine(object):
         self._opt.iterations = self.iterations
         keep = (users, items, labels, ws)
         flags = nat.TRAIN_USERS_GROUPED if (grouped and group > 1) else 0
+        if not dense_l2:
+            flags |= nat.TRAIN_NO_DENSE_L2
         args = (C.byref(self._model), C.byref(self._opt), C.byref(self._grads), _ptr(users), _ptr(items), _ptr(labels),
                 B, int(group), int(k), flags, inv, _ptr(self.step_out), _ptr(ws), ws.numel(), self._stream())
         return args, keep
@@ -336,8 +338,10 @@ class NeuMFEngine(object):
         self.iterations = int(self._opt.iterations)
         return self.step_out.clone()
 
-    def train_grads(self, users, items, labels, group=0, k=0, inv_global_batch=None, grouped=False):
-        args, keep = self._train_args(users, items, labels, group, k, inv_global_batch, grouped)
+    def train_grads(self, users, items, labels, group=0, k=0, inv_global_batch=None, grouped=False, dense_l2=True):
+        """Gradients only (no update).  dense_l2=False leaves the hidden kernels' 2*l2*W term out of g_dense: a
+        data-parallel caller that sums the ranks' gradients lets exactly one rank add it."""
+        args, keep = self._train_args(users, items, labels, group, k, inv_global_batch, grouped, dense_l2)
         nat.check(nat.lib.mr_neumf_train_grads(*args), "mr_neumf_train_grads")
         return self.step_out.clone()
 
@@ -428,8 +432,9 @@ def set_item_projection(mode):
     nat.check(nat.lib.mr_set_item_projection(code), "mr_set_item_projection")
 
 
-def rank_scores(scores, group, k, label_col=None, want_rank=True, device=None):
-    """RankLayer + metrics on caller-supplied scores (model.py:336-455), on device."""
+def rank_scores(scores, group, k, label_col=None, want_rank=True, device=None, labels=None):
+    """RankLayer + metrics on caller-supplied scores (model.py:336-455), on device.  The label column of a group is
+    label_col[g], else the argmax of the group's `labels` (model.py:447-448), else the last column."""
     require_cuda()
     device = torch.device(device if device is not None else "cuda:{}".format(torch.cuda.current_device()))
     s = as_device_f32(scores, device)
@@ -440,11 +445,14 @@ def rank_scores(scores, group, k, label_col=None, want_rank=True, device=None):
     sums = torch.zeros(2, dtype=torch.float32, device=device)
     rank = torch.empty((G, group), dtype=torch.int32, device=device) if want_rank else None
     lc = as_device_i32(label_col, device) if label_col is not None else None
+    lab = as_device_f32(labels, device) if labels is not None else None
+    if lab is not None and lab.numel() != s.numel():
+        raise ValueError("labels ({}) and scores ({}) differ in length".format(lab.numel(), s.numel()))
     nbytes = max(int(nat.lib.mr_rank_scores_workspace_bytes(G)), 256)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
     st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-    nat.check(nat.lib.mr_rank_scores(_ptr(s), G, int(group), int(k), _ptr(lc), _ptr(rank), _ptr(pos), _ptr(sums), _ptr(ws),
-                                     nbytes, st), "mr_rank_scores")
+    nat.check(nat.lib.mr_rank_scores(_ptr(s), G, int(group), int(k), _ptr(lc), _ptr(lab), _ptr(rank), _ptr(pos), _ptr(sums),
+                                     _ptr(ws), nbytes, st), "mr_rank_scores")
     return rank, pos, sums
 
 

@@ -15,6 +15,7 @@ MR_MAX_NEGS = 1023
 MR_STEP_OUT_FLOATS = 8
 OUT_LOSS_SUM, OUT_HIT_SUM, OUT_DCG_SUM, OUT_L2_PENALTY, OUT_BAD_IDS = 0, 1, 2, 3, 4
 TRAIN_USERS_GROUPED = 1  # MR_TRAIN_USERS_GROUPED
+TRAIN_NO_DENSE_L2 = 2    # MR_TRAIN_NO_DENSE_L2
 OPT_ADAM, OPT_SGD = 0, 1
 TABLES_DENSE, TABLES_SPARSE = 0, 1
 
@@ -81,7 +82,7 @@ SIGNATURES = {
     "mr_rank_eval_workspace_bytes": (_sz, [_PM, _i64, _i32]),
     "mr_rank_eval": (C.c_int, [_PM, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mr_rank_scores_workspace_bytes": (_sz, [_i64]),
-    "mr_rank_scores": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "mr_rank_scores": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mr_sample_negatives": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i64, _i64, _i32, _u64, _u64, _vp, _vp, _vp, _vp]),
     "mr_sort_workspace_bytes": (_sz, [_i64]),
     "mr_sort_pairs": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),

@@ -202,7 +202,8 @@ class NeuMFModel(object):
         group = o._num_negs_per_pos_eval + 1
         _, probs, loss = eng.forward(x_users, x_items, labels=y, want_logits=False)
         rows = probs.numel()
-        _, _, sums = _engine_module().rank_scores(probs, group, o._k, want_rank=False, device=eng.device)
+        # the label column is the argmax of y_true per group (model.py:447-448), wherever the batch puts its positive
+        _, _, sums = _engine_module().rank_scores(probs, group, o._k, want_rank=False, device=eng.device, labels=y)
         return torch.cat([loss, sums]), rows
 
     def evaluate_generator(self, generator, steps=None):

@@ -34,9 +34,12 @@ class OracleEngine(object):
     def gradient_tensors(self):
         return [self.g_flat]
 
-    def train_grads(self, users, items, labels, group=0, k=0, inv_global_batch=None, grouped=False):
+    def train_grads(self, users, items, labels, group=0, k=0, inv_global_batch=None, grouped=False, dense_l2=True):
+        # as the CUDA engine: the hidden kernels' l2 term is part of the gradients only when dense_l2 is set; the
+        # tables' l2 term is added in apply(), after the caller's reduction
         c = o.forward(self.w, users, items)
-        g = o.backward(self.w, c, labels, inv_global_batch, self.params["layers_l2reg"])
+        l2 = list(self.params["layers_l2reg"])
+        g = o.backward(self.w, c, labels, inv_global_batch, [0.0] + (l2[1:] if dense_l2 else [0.0] * (len(l2) - 1)))
         self.g_flat.copy_(torch.from_numpy(np.concatenate([g[k_].reshape(-1) for k_ in self.names]).astype(np.float32)))
         y = np.asarray(labels, np.float32)
         return torch.tensor([float(np.sum(o.bce_from_logits(c["z"], y)))])
@@ -46,6 +49,8 @@ class OracleEngine(object):
         g, off = {}, 0
         for k_, n in zip(self.names, self.sizes):
             g[k_] = flat[off:off + n].reshape(self.w[k_].shape).copy()
+            if "embedding" in k_ and self.params["layers_l2reg"][0]:
+                g[k_] = g[k_] + np.float32(2.0 * self.params["layers_l2reg"][0]) * self.w[k_]
             off += n
         p = self.params
         o.adam_step(self.w, self.state, g, p["lr"], p["beta_1"], p["beta_2"])
@@ -96,7 +101,13 @@ def _global_batch(step):
     return users, items, y
 
 
-def _worker(rank, world, port, out, overlap=False):
+PARAMS_L2 = dict(PARAMS, layers_l2reg=[0.01, 0.02, 0.005])  # the model's own DEFAULT_PARAMS use 0.01
+
+
+def _worker(rank, world, port, out, overlap=False, l2=False):
+    global PARAMS
+    if l2:
+        PARAMS = PARAMS_L2
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     if overlap:
         os.environ["MR_DP_OVERLAP"] = "1"
@@ -118,17 +129,21 @@ def _worker(rank, world, port, out, overlap=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap", [False, True], ids=["one-all-reduce", "region-wise"])
-def test_two_rank_data_parallel_matches_single_process(tmp_path, overlap):
+@pytest.mark.parametrize("overlap,l2", [(False, False), (True, False), (False, True)],
+                         ids=["one-all-reduce", "region-wise", "l2-counted-once"])
+def test_two_rank_data_parallel_matches_single_process(tmp_path, overlap, l2):
+    """l2 != 0: the regulariser gradients must enter the summed gradients ONCE, not once per rank."""
     out = str(tmp_path / "rank0.npz")
-    mp.spawn(_worker, args=(2, _free_port(), out, overlap), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, overlap, l2), nprocs=2, join=True)
     got = np.load(out)
-    w = o.init_weights(9, 13, PARAMS["layers_sizes"], 2, np.random.default_rng(1))
+    params = PARAMS_L2 if l2 else PARAMS
+    w = o.init_weights(9, 13, params["layers_sizes"], 2, np.random.default_rng(1))
     st = o.new_opt_state(w)
     for step in range(3):
         users, items, y = _global_batch(step)
-        loss, _, _ = o.train_step(w, st, users, items, y, PARAMS)
-        assert got["losses"][step] / len(y) == pytest.approx(loss, rel=1e-5)
+        pen = o.l2_penalty(w, params["layers_l2reg"])
+        loss, _, _ = o.train_step(w, st, users, items, y, params)
+        assert got["losses"][step] / len(y) == pytest.approx(loss - pen, rel=1e-5)  # (the workers sum the BCE part)
     for k in w:
         np.testing.assert_allclose(got[k], w[k], rtol=2e-5, atol=1e-7, err_msg=k)
 

@@ -44,6 +44,77 @@ def rel_close(got, want, rtol=RTOL, what="", atol=0.0):
         what, err, rtol, scale, atol)
 
 
+def close_to_truth(got, ref32, ref64, what, rtol=RTOL, k=4.0):
+    """The kernel against the float64 oracle, calibrated by the float32 oracle's own distance from it:
+      per tensor:  max |got - ref64| <= max(k * e32, rtol * max|ref64|),  e32 = max |ref32 - ref64|
+                   (within the north star's tolerance of the tensor's scale, or as close to the truth as a plain
+                   fp32 evaluation of the same formulas gets -- what decides for sums that nearly cancel and for
+                   what Adam's m / (sqrt(v) + eps) makes of them);
+      per element, where |ref64| > 1e-3 * max|ref64|:  |got - ref64| <= rtol * |ref64| + k * e32."""
+    got = np.asarray(got, np.float64).reshape(-1)
+    ref32 = np.asarray(ref32, np.float64).reshape(-1)
+    ref64 = np.asarray(ref64, np.float64).reshape(-1)
+    scale = max(float(np.max(np.abs(ref64))), 1e-30)
+    e32 = float(np.max(np.abs(ref32 - ref64)))
+    err = np.abs(got - ref64)
+    bound = max(k * e32, rtol * scale)
+    assert float(err.max()) <= bound, "{}: max err {:.3e} > max({} x fp32-oracle err {:.3e}, {:.0e} x scale {:.3e})".format(
+        what, float(err.max()), k, e32, rtol, scale)
+    big = np.abs(ref64) > 1e-3 * scale
+    if big.any():
+        excess = err[big] - (rtol * np.abs(ref64[big]) + k * e32)
+        i = int(np.argmax(excess))
+        assert excess[i] <= 0, "{}: element {} got {:.9e} want {:.9e} (fp32-oracle err {:.3e})".format(
+            what, i, got[big][i], ref64[big][i], e32)
+
+
+class OraclePair:
+    """The fp32 oracle and a float64 copy of it stepping through the same batches (the truth `close_to_truth` wants)."""
+
+    def __init__(self, w):
+        self.w = w
+        self.st = o.new_opt_state(w)
+        self.w64 = {k: v.astype(np.float64) for k, v in w.items()}
+        self.st64 = o.new_opt_state(self.w64)
+
+    def grads(self, users, items, y, l2):
+        g = o.backward(self.w, o.forward(self.w, users, items), y, None, l2)
+        g64 = o.backward(self.w64, o.forward(self.w64, users, items), y.astype(np.float64), None, l2)
+        return g, g64
+
+    def step(self, users, items, y, params, adam_mode="dense"):
+        out = o.train_step(self.w, self.st, users, items, y, params, adam_mode=adam_mode)
+        out64 = o.train_step(self.w64, self.st64, users, items, y.astype(np.float64), params, adam_mode=adam_mode)
+        return out, out64
+
+
+def check_step_against_oracles(eng, pair, users, items, y, params, l2, mode, step, grouped, k):
+    """One train step of the engine against both oracles: dense gradients, gradient tables (dense mode), loss,
+    HR / DCG, updated weights."""
+    negs = params["num_negs_per_pos"]
+    B = len(y)
+    g, g64 = pair.grads(users, items, y, l2)
+    w_before, w64_before = pair.w, pair.w64
+    out = eng.train_step(users, items, y, group=negs + 1, k=k, grouped=grouped).cpu().numpy().astype(np.float64)
+    assert out[4] == 0
+    for name, (off, shape) in eng._dense_slices.items():
+        got = eng.g_dense[off:off + int(np.prod(shape))].cpu().numpy()
+        close_to_truth(got, g[name], g64[name], "grad {} step {}".format(name, step))
+    if mode == "dense":
+        for name, t in eng.g_tables.items():  # (the kernel adds the table l2 term in the update, not here)
+            want = g[name] - (2.0 * l2[0]) * w_before[name] if l2[0] else g[name]
+            want64 = g64[name] - (2.0 * l2[0]) * w64_before[name] if l2[0] else g64[name]
+            close_to_truth(t.cpu().numpy(), want, want64, "table grad {} step {}".format(name, step))
+    (loss, hr, dcg), (loss64, _, _) = pair.step(users, items, y, params, adam_mode="lazy" if mode == "sparse" else "dense")
+    got_loss = out[0] / B + out[3]
+    assert abs(got_loss - loss64) <= max(4 * abs(loss - loss64), RTOL * abs(loss64)), (got_loss, loss, loss64)
+    G = B // (negs + 1)
+    assert abs(out[1] / G - hr) <= 1e-3 and abs(out[2] / G - dcg) <= 1e-3
+    got = eng.get_weights()
+    for name in pair.w:
+        close_to_truth(got[name], pair.w[name], pair.w64[name], "weight {} after step {}".format(name, step + 1))
+
+
 CONFIGS = [
     # (num_users, num_items, layers, mf_dim, negs, groups)
     (5, 10, [6, 4], 0, 3, 2),             # reference test params (test/test_model.py:8-26)
@@ -161,36 +232,10 @@ def _train_steps_vs_oracle(eng_mod, case, grouped):
     params = {"layers_sizes": L, "layers_l2reg": l2, "optimizer": opt, "lr": 0.001, "beta_1": 0.9, "beta_2": 0.999,
               "num_negs_per_pos": negs, "k": min(2, negs + 1)}
     eng = eng_mod.NeuMFEngine(nu, ni, L, l2, mf_dim=f, optimizer=opt, lr=0.001, table_mode=mode, seed=7)
-    w = eng.get_weights()
-    st = o.new_opt_state(w)
+    pair = OraclePair(eng.get_weights())
     for step in range(3):
         users, items, y = make_batch(rng, nu, ni, groups, negs)
-        B = len(y)
-        # gradients of this step (dense part), before either side updates
-        c = o.forward(w, users, items)
-        g = o.backward(w, c, y, None, l2)
-        out = eng.train_step(users, items, y, group=negs + 1, k=params["k"], grouped=grouped).cpu().numpy().astype(np.float64)
-        assert out[4] == 0
-        for name, (off, shape) in eng._dense_slices.items():
-            got = eng.g_dense[off:off + int(np.prod(shape))].cpu().numpy().reshape(shape)
-            rel_close(got, g[name].reshape(shape), rtol=2e-5, what="grad {} step {}".format(name, step))
-        if mode == "dense":
-            for name, t in eng.g_tables.items():
-                want = g[name] - (2.0 * l2[0]) * w[name] if l2[0] else g[name]  # kernel adds l2 in the update
-                rel_close(t.cpu().numpy(), want, rtol=2e-5, what="table grad {} step {}".format(name, step))
-        loss, hr, dcg = o.train_step(w, st, users, items, y, params, adam_mode="lazy" if mode == "sparse" else "dense")
-        got_loss = out[0] / B + out[3]
-        assert abs(got_loss - loss) <= 2e-5 * max(abs(loss), 1e-3), (got_loss, loss)
-        G = B // (negs + 1)
-        assert abs(out[1] / G - hr) <= 1e-3 and abs(out[2] / G - dcg) <= 1e-3
-        got = eng.get_weights()
-        # 1e-5 relative on the weights, plus 1e-4 of the distance Adam can have moved an element
-        # (lr per step): Adam's m/(sqrt(v)+eps) turns a summation-order difference in a near-cancelling
-        # gradient entry into a difference of the update itself; zero-initialised biases consist of
-        # nothing but updates, so without this term the test would demand 1e-5 of lr, not of the weight
-        for k in w:
-            rel_close(got[k], w[k], rtol=RTOL * (step + 1), atol=1e-4 * 0.001 * (step + 1),
-                      what="weight {} after step {}".format(k, step + 1))
+        check_step_against_oracles(eng, pair, users, items, y, params, l2, mode, step, grouped, params["k"])
     assert eng.iterations == 3
 
 
@@ -354,35 +399,12 @@ def test_item_projected_train_steps_match_oracle(eng_mod, case):
         eng = eng_mod.NeuMFEngine(nu, ni, L, l2, mf_dim=f, optimizer=opt, lr=0.001, table_mode="dense", seed=11)
         assert eng.uses_tensor_cores() and eng.uses_item_projection(groups * (negs + 1))
         assert eng.uses_user_projection(groups * (negs + 1), negs + 1) == (selector == "on" or nu <= groups)
-        w = eng.get_weights()
-        st = o.new_opt_state(w)
+        pair = OraclePair(eng.get_weights())
         for step in range(3):
             users, items, y = make_batch(rng, nu, ni, groups, negs)
             if step == 1:
                 items[: len(items) // 2] = items[0]  # one hot item: a segment spanning many chunks of the reduction
-            B = len(y)
-            g = o.backward(w, o.forward(w, users, items), y, None, l2)
-            out = eng.train_step(users, items, y, group=negs + 1, k=2, grouped=True).cpu().numpy().astype(np.float64)
-            assert out[4] == 0
-            for name, (off, shape) in eng._dense_slices.items():
-                got = eng.g_dense[off:off + int(np.prod(shape))].cpu().numpy().reshape(shape)
-                rel_close(got, g[name].reshape(shape), rtol=2e-5, what="grad {} step {}".format(name, step))
-            for name, t in eng.g_tables.items():
-                want = g[name] - (2.0 * l2[0]) * w[name] if l2[0] else g[name]
-                rel_close(t.cpu().numpy(), want, rtol=2e-5, what="table grad {} step {}".format(name, step))
-            loss, hr, dcg = o.train_step(w, st, users, items, y, params, adam_mode="dense")
-            got_loss = out[0] / B + out[3]
-            assert abs(got_loss - loss) <= 2e-5 * max(abs(loss), 1e-3), (got_loss, loss)
-            G = B // (negs + 1)
-            assert abs(out[1] / G - hr) <= 1e-3 and abs(out[2] / G - dcg) <= 1e-3
-            got = eng.get_weights()
-            # tolerances as in _train_steps_vs_oracle, except for Adam's amplification term: here the bias gradient of
-            # the first layer is summed per group first, then over groups (the oracle sums rows), and a near-cancelling
-            # entry (|g| ~ 1e-6, both sums within 5e-9 of each other, i.e. 5e-6 of the tensor's scale -- checked above)
-            # moves Adam's normalised update g / (|g| + eps) by up to ~1e-3 of lr
-            for k in w:
-                rel_close(got[k], w[k], rtol=RTOL * (step + 1), atol=(1e-3 if opt == "adam" else 1e-4) * 0.001 * (step + 1),
-                          what="weight {} after step {}".format(k, step + 1))
+            check_step_against_oracles(eng, pair, users, items, y, params, l2, "dense", step, True, 2)
     finally:
         eng_mod.set_item_projection("auto")
 
@@ -517,6 +539,33 @@ def test_rank_scores_reference_vectors(eng_mod, golden_dir):
             assert s[0] == 1.0 and abs(s[1] - np.log(2) / np.log(v["hit_position"] + 2)) < 1e-6
         else:
             assert s[0] == 0.0 and s[1] == 0.0
+
+
+def test_label_column_is_argmax_of_labels(eng_mod):
+    """The reference ranks the column argmax(y_true) of every group (model.py:447-451), wherever the batch puts its
+    positive: the train step's HR / DCG and rank_scores(labels=...) must follow the labels, not the last column."""
+    rng = np.random.default_rng(31)
+    G, group, k = 200, 5, 2
+    scores = rng.random(G * group).astype(np.float32)
+    col = rng.integers(0, group, G)
+    y = np.zeros((G, group), np.float32)
+    y[np.arange(G), col] = 1.0
+    _, pos, sums = eng_mod.rank_scores(scores, group, k, want_rank=False, labels=y.reshape(-1))
+    rank = o.rank_groups(scores, group)
+    assert abs(float(sums[0]) / G - o.hit_rate(y, rank, k)) < 1e-6
+    assert abs(float(sums[1]) / G - o.discounted_cumulative_gain(y, rank, k)) < 1e-6
+    _, pos_lc, _ = eng_mod.rank_scores(scores, group, k, want_rank=False, label_col=col)
+    assert np.array_equal(pos.cpu().numpy(), pos_lc.cpu().numpy())
+    # the train step: same metrics whether the positive is last or anywhere else
+    nu, ni, L, f = 40, 60, [64, 32, 16, 8], 8
+    params = {"layers_sizes": L, "layers_l2reg": [0] * 4, "optimizer": "sgd", "lr": 0.01, "num_negs_per_pos": group - 1, "k": k}
+    eng = eng_mod.NeuMFEngine(nu, ni, L, [0] * 4, mf_dim=f, optimizer="sgd", lr=0.01, seed=3)
+    w = eng.get_weights()
+    users = np.repeat(rng.integers(0, nu, G), group)
+    items = rng.integers(0, ni, G * group)
+    out = eng.train_step(users, items, y.reshape(-1), group=group, k=k).cpu().numpy()
+    loss, hr, dcg = o.train_step(w, o.new_opt_state(w), users, items, y.reshape(-1), params)
+    assert abs(out[1] / G - hr) < 1e-6 and abs(out[2] / G - dcg) < 1e-5, (out[1] / G, hr, out[2] / G, dcg)
 
 
 def test_rank_scores_match_reference_execution(eng_mod, golden_dir):
@@ -718,6 +767,37 @@ def test_full_size_ml20m_properties(eng_mod):
     touched[torch.from_numpy(users).cuda()] = True
     assert torch.equal(eng.user_mlp[~touched], w0_user[~touched])
     assert not torch.equal(eng.user_mlp[touched], w0_user[touched])
+
+
+def test_bench_sequence_ml20m_matches_oracle(eng_mod):
+    """The exact launch sequence bench.py times -- ML-20M tables (BASELINE configs[2]), 1,310,720 rows, grouped batch,
+    item- and user-projected first layer, the fused per-tile kernel, dense Adam -- one step from injected weights
+    against the fp32 and the float64 oracle: loss, every dense gradient, all four gradient tables, updated weights."""
+    nu, ni, L, f, negs = 138493, 26744, [256, 128, 64], 64, 4
+    B = 5 * 2 ** 18
+    groups = B // (negs + 1)
+    rng = np.random.default_rng(42)
+    # bench.py's batch shape: lognormal user activity, Zipf positives over a fixed permutation, uniform negatives
+    act = 20.0 + rng.lognormal(3.0, 1.0, nu)
+    u = np.minimum(np.searchsorted(np.cumsum(act / act.sum()), rng.random(groups)), nu - 1).astype(np.int32)
+    zipf = 1.0 / (np.arange(ni) + 1.0)
+    perm = rng.permutation(ni)
+    pos = perm[np.minimum(np.searchsorted(np.cumsum(zipf / zipf.sum()), rng.random(groups)), ni - 1)].astype(np.int32)
+    items = rng.integers(0, ni, (groups, negs + 1), dtype=np.int32)
+    items[:, -1] = pos
+    users, items = np.repeat(u, negs + 1), items.reshape(-1)
+    y = np.tile(np.array([0] * negs + [1], np.float32), groups)
+    params = {"layers_sizes": L, "layers_l2reg": [0, 0, 0], "optimizer": "adam", "lr": 0.001, "beta_1": 0.9,
+              "beta_2": 0.999, "num_negs_per_pos": negs, "k": negs + 1}
+    eng = eng_mod.NeuMFEngine(nu, ni, L, [0, 0, 0], mf_dim=f, optimizer="adam", lr=0.001, table_mode="dense", seed=1)
+    assert eng.uses_tensor_cores() and eng.uses_item_projection(B) and eng.uses_user_projection(B, negs + 1)
+    w = eng.get_weights()
+    for name in w:  # injected weights: non-zero biases, so that every term of the step is exercised
+        if name.endswith("bias"):
+            w[name] = rng.normal(0, 0.05, w[name].shape).astype(np.float32)
+    eng.set_weights(w)
+    pair = OraclePair(w)
+    check_step_against_oracles(eng, pair, users, items, y, params, [0, 0, 0], "dense", 0, True, negs + 1)
 
 
 def test_full_size_eval_sweep_properties(eng_mod):
