@@ -39,9 +39,9 @@ namespace mr {
 namespace fz {
 
 constexpr int kD1 = 128, kD2 = 64, kF = 64;
-constexpr int kThreads = 13 * 32;
+constexpr int kThreads = 16 * 32;
 constexpr int kProdThreads = 256;
-constexpr int kMmaWarp = 8, kEpiWarp0 = 9;
+constexpr int kE1Warp0 = 8, kE2Warp0 = 12;  // epilogue-1 warps 8-11 (warp 8 also issues the MMAs), epilogue-2 warps 12-15
 constexpr uint32_t kPanel = 16384;        // [128 rows x 64 bf16], rows of 128 bytes
 constexpr uint32_t kH1Part = 2 * kPanel;  // two feature panels per part
 constexpr int kEpiLd = 36;                // floats per row of an epilogue warp's 32 x 32 staging tile
@@ -51,17 +51,21 @@ constexpr uint32_t oH1 = 0;                              // 3 parts x 2 panels
 constexpr uint32_t oZ2 = oH1 + 3 * kH1Part;              // 3 parts x 1 panel
 constexpr uint32_t oW2 = oZ2 + 3 * kPanel;               // 3 parts x 1 panel
 constexpr uint32_t oStage = oW2 + 3 * kPanel;            // 4 warps x 32 x kEpiLd floats (end of kernel: reductions)
-constexpr uint32_t oBits = oStage + 4 * 32 * kEpiLd * 4; // 2 buffers x 128 slots x 16 B of ReLU bits
-constexpr uint32_t oIds = oBits + 2 * 128 * 16;          // 2 buffers x (128 items + 32 users)
-constexpr uint32_t oGdot = oIds + 2 * 160 * 4;           // GMF part of the logit, per slot
+constexpr uint32_t oBits = oStage + 4 * 32 * kEpiLd * 4; // 2 buffers x 128 slots x 16 B: four ReLU bits per 16-byte piece
+constexpr uint32_t oIds = oBits + 2 * 128 * 16;          // 2 buffers x (128 items + 32 users + 128 labels)
+constexpr uint32_t oGdot = oIds + 2 * 288 * 4;           // GMF part of the logit, per slot
 constexpr uint32_t oDz = oGdot + 512;                    // dz per slot
 constexpr uint32_t oFlag = oDz + 512;                    // per slot: 0 = no row, 1 = row, 2 = row with an id out of range
 constexpr uint32_t oConst = oFlag + 512;                 // b2[64] | w_out[f:][64] | w_out[:f][64] | b_out
 constexpr uint32_t oRedG = oConst + 1024;                // end of kernel: the producers' d w_out[:f] partials (256 x float4)
-constexpr uint32_t kSmemBytes = oRedG + 4096;
+constexpr uint32_t oRedE = oRedG + 4096;                 // end of kernel: the epilogue-1 warps' column sums, 4 x 160 floats
+constexpr uint32_t kSmemBytes = oRedE + 4 * 160 * 4;
 
 // TMEM columns
-constexpr uint32_t cFwd = 0, cWg = 64, cBwd = 128, kTmemCols = 256;
+//   cFwd / cBwd: forward / backward accumulators of the tile; cWg: dW2, accumulated over all tiles of the CTA;
+//   cCs: per-lane column sums of dz * H2 (64 columns) and of dZ2 (64), accumulated over the tiles by the epilogue
+//   threads themselves (read-modify-write of their own lane: no shuffles per tile, one reduction at the end)
+constexpr uint32_t cFwd = 0, cWg = 64, cBwd = 128, cCs = 256, kTmemCols = 512;
 
 constexpr uint32_t kLayoutSw128 = 2;
 
@@ -114,6 +118,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // Sum of v[c] over the 32 lanes for every c: lane l returns the total of column l.  31 shuffles, fixed order.
@@ -187,9 +207,12 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
   constexpr int GSLOTS = (NT + kProdThreads - 1) / kProdThreads;
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t h1_full[2], fwd_done, gmf_ready, dz2_full, h1_free, bwd_done, w2_bar;
+  __shared__ uint64_t h1_full[2], fwd_done, gmf_ready, dz2_full, h1_free, bwd_done, e2_done, w2_bar;
   __shared__ uint32_t tmem_slot;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment of the operand tiles, computed in the shared window so that the compiler keeps treating
+  // `smem` as shared memory (through a uintptr_t round trip every access became a generic LD / ST: ncu showed the
+  // producers' stores and the epilogues' staging loads on the long scoreboard)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t ntiles = (p.rows + TR - 1) / TR;
@@ -219,10 +242,11 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
     tc::mbar_init(&dz2_full, 4);
     tc::mbar_init(&h1_free, 1);
     tc::mbar_init(&bwd_done, 1);
+    tc::mbar_init(&e2_done, 4);
     tc::mbar_init(&w2_bar, 1);
     tc::mbar_init_fence();
   }
-  if (warp == kMmaWarp) tc::tmem_alloc(&tmem_slot, kTmemCols);
+  if (warp == kE1Warp0) tc::tmem_alloc(&tmem_slot, kTmemCols);
   tc::fence_proxy_async();  // the zero fill must be visible to the tensor core (padding rows are never written again)
   tc::fence_before_sync();
   __syncthreads();
@@ -240,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
     int32_t* ids_s = reinterpret_cast<int32_t*>(smem + oIds);
     auto load_ids = [&](int64_t tile, int buf, bool async) {
       const int64_t row0 = tile * TR;
-      int32_t* dst = ids_s + buf * 160;
+      int32_t* dst = ids_s + buf * 288;
       if (tid < TR) {
         const int64_t r = row0 + tid;
         if (r < p.rows) {
@@ -258,6 +282,16 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
           dst[tid] = 0;
         }
       }
+      if (tid >= 128 && tid < 128 + TR) {  // the labels of the tile's rows, read by the epilogue warps
+        const int64_t r = row0 + (tid - 128);
+        float* ldst = reinterpret_cast<float*>(dst) + 160 + (tid - 128);
+        if (r < p.rows) {
+          if (async) cp_async4(ldst, p.labels + r);
+          else *ldst = __ldg(p.labels + r);
+        } else {
+          *ldst = 0.f;
+        }
+      }
     };
     if (blockIdx.x < ntiles) load_ids(blockIdx.x, 0, false);
     bar_sync(1, kProdThreads);
@@ -267,106 +301,92 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int buf = (int)(it & 1);
       const int64_t row0 = tile * TR;
-      const int32_t* ids = ids_s + buf * 160;
+      const int32_t* ids = ids_s + buf * 288;
       FZ_T(0)
       if (tile + gridDim.x < ntiles) load_ids(tile + gridDim.x, buf ^ 1, true);
 
-      // ---- H1 = relu(Pi[item] + Pu[user]): all loads of the tile first
-      float4 xu[SLOTS], xi[SLOTS][GROUP];
-#pragma unroll
-      for (int s = 0; s < SLOTS; ++s) {
-        const int T = tid + kProdThreads * s;
+      // the task indices below are re-derived from an opaque copy of the thread index every tile: left to itself the
+      // compiler hoisted ~40 per-task shared-memory offsets out of the tile loop and spilled them (their reloads sat
+      // on the long scoreboard inside the conversion loop)
+      int tidv = tid;
+      asm volatile("" : "+r"(tidv));
+      // ---- H1 = relu(Pi[item] + Pu[user]) and the GMF dot products, software-pipelined over the thread's tasks: the
+      // loads of task s + 2 are issued before task s + 1 is converted, so two tasks (12 x 16 B per thread, 48 KB per
+      // SM) are in flight and at most two tasks' rows are live in registers (the first version issued all 18 loads of
+      // a tile up front: ptxas spilled the loaded rows and every spill store waited for its load)
+      auto h1_issue = [&](int s, float4& xu, float4 (&xi)[GROUP]) {
+        const int T = tidv + kProdThreads * s;
         const int ps = T >= NT ? 1 : 0, idx = T - ps * NT;
         const int gt = idx >> 4, pc = idx & 15;
         const int col = 64 * ps + 4 * pc;
         const bool gvalid = row0 + (int64_t)gt * GROUP < p.rows;
         const int u = ids[128 + gt];
         const bool uok = gvalid && (unsigned)u < (unsigned)p.num_users;
-        xu[s] = uok ? ldg4(p.Pu + (size_t)u * kD1 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xu = uok ? ldg4(p.Pu + (size_t)u * kD1 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < GROUP; ++j) {
           const int itm = ids[gt * GROUP + j];
           const bool iok = uok && (unsigned)itm < (unsigned)p.num_items;
-          xi[s][j] = iok ? ldg4(p.Pi + (size_t)itm * kD1 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xi[j] = iok ? ldg4(p.Pi + (size_t)itm * kD1 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      }
-      FZ_T(1)
-      if (it > 0) {  // the weight-gradient MMAs of the previous tile have read H1
-        tc::mbar_wait(&h1_free, (uint32_t)((it - 1) & 1));
-      }
-      FZ_T(2)
+      };
       uint8_t* bits_b = smem + oBits + buf * (128 * 16);
+      auto h1_store = [&](int s, const float4& xu, const float4 (&xi)[GROUP]) {
+        const int T = tidv + kProdThreads * s;
+        const int ps = T >= NT ? 1 : 0, idx = T - ps * NT;
+        const int gt = idx >> 4, pc = idx & 15;
+        const int sl0 = 32 * (gt / GQ) + GROUP * (gt % GQ);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-          const int T = tid + kProdThreads * s;
-          const int ps = T >= NT ? 1 : 0;
-          if (ps != half) continue;  // warp-uniform
-          const int idx = T - ps * NT;
-          const int gt = idx >> 4, pc = idx & 15;
-          const int sl0 = 32 * (gt / GQ) + GROUP * (gt % GQ);
-#pragma unroll
-          for (int j = 0; j < GROUP; ++j) {
-            const int sl = sl0 + j;
-            const float4 a = xi[s][j], b = xu[s];
-            const float v0 = fmaxf(a.x + b.x, 0.f), v1 = fmaxf(a.y + b.y, 0.f), v2 = fmaxf(a.z + b.z, 0.f),
-                        v3 = fmaxf(a.w + b.w, 0.f);
-            const uint32_t b0 = __ballot_sync(0xffffffffu, v0 > 0.f), b1 = __ballot_sync(0xffffffffu, v1 > 0.f),
-                           b2 = __ballot_sync(0xffffffffu, v2 > 0.f), b3 = __ballot_sync(0xffffffffu, v3 > 0.f);
-            if (pc == 0) {  // lane 0 / 16: the 16 pieces of this half-warp's row
-              const int sh = lane & 16;
-              const uint32_t f0 = (b0 >> sh) & 0xffffu, f1 = (b1 >> sh) & 0xffffu, f2 = (b2 >> sh) & 0xffffu,
-                             f3 = (b3 >> sh) & 0xffffu;
-              *reinterpret_cast<uint2*>(bits_b + sl * 16 + 8 * ps) = make_uint2(f0 | (f1 << 16), f2 | (f3 << 16));
-            }
-            uint32_t w1a, w2a, w3a, w1b, w2b, w3b;
-            split3(v0, v1, w1a, w2a, w3a);
-            split3(v2, v3, w1b, w2b, w3b);
-            const uint32_t off = oH1 + ps * kPanel + (uint32_t)sl * 128 + ((((pc >> 1) ^ (sl & 7)) << 4) | ((pc & 1) << 3));
-            *reinterpret_cast<uint2*>(smem + off) = make_uint2(w1a, w1b);
-            *reinterpret_cast<uint2*>(smem + off + kH1Part) = make_uint2(w2a, w2b);
-            *reinterpret_cast<uint2*>(smem + off + 2 * kH1Part) = make_uint2(w3a, w3b);
-          }
+        for (int j = 0; j < GROUP; ++j) {
+          const int sl = sl0 + j;
+          const float4 a = xi[j], b = xu;
+          const float v0 = fmaxf(a.x + b.x, 0.f), v1 = fmaxf(a.y + b.y, 0.f), v2 = fmaxf(a.z + b.z, 0.f),
+                      v3 = fmaxf(a.w + b.w, 0.f);
+          // four ReLU bits of this 16-byte piece; two neighbouring pieces share a byte (epilogue 2 reads the slot's
+          // 16 bytes).  One shuffle per row: the four ballots + field extraction of the first version cost 3x this.
+          const uint32_t nib = (v0 > 0.f ? 1u : 0u) | (v1 > 0.f ? 2u : 0u) | (v2 > 0.f ? 4u : 0u) | (v3 > 0.f ? 8u : 0u);
+          const uint32_t nib_hi = __shfl_xor_sync(0xffffffffu, nib, 1);
+          if (!(pc & 1)) bits_b[sl * 16 + 8 * ps + (pc >> 1)] = (uint8_t)(nib | (nib_hi << 4));
+          uint32_t w1a, w2a, w3a, w1b, w2b, w3b;
+          split3(v0, v1, w1a, w2a, w3a);
+          split3(v2, v3, w1b, w2b, w3b);
+          const uint32_t off = oH1 + ps * kPanel + (uint32_t)sl * 128 + ((((pc >> 1) ^ (sl & 7)) << 4) | ((pc & 1) << 3));
+          *reinterpret_cast<uint2*>(smem + off) = make_uint2(w1a, w1b);
+          *reinterpret_cast<uint2*>(smem + off + kH1Part) = make_uint2(w2a, w2b);
+          *reinterpret_cast<uint2*>(smem + off + 2 * kH1Part) = make_uint2(w3a, w3b);
         }
+      };
+      auto h1_arrive = [&](int half) {
         tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&h1_full[half]);
-        FZ_T(3 + half)
-      }
-
-      // ---- GMF branch, part 1: gmf_u * gmf_i . w_out[:f] per row (its rows are loaded once and kept for part 2)
-      float4 gu[GSLOTS], gi[GSLOTS][GROUP];
-#pragma unroll
-      for (int s = 0; s < GSLOTS; ++s) {
-        const int idx = tid + kProdThreads * s;
-        if (idx >= NT) continue;  // warp-uniform
+      };
+      auto gmf_issue = [&](int s, float4& gu, float4 (&gi)[GROUP]) {
+        const int idx = tidv + kProdThreads * s;
         const int gt = idx >> 4, pc = idx & 15;
         const bool gvalid = row0 + (int64_t)gt * GROUP < p.rows;
         const int u = ids[128 + gt];
         const bool uok = gvalid && (unsigned)u < (unsigned)p.num_users;
-        gu[s] = uok ? ldg4(p.user_gmf + (size_t)u * kF + 4 * pc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gu = uok ? ldg4(p.user_gmf + (size_t)u * kF + 4 * pc) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < GROUP; ++j) {
           const int itm = ids[gt * GROUP + j];
           const bool iok = uok && (unsigned)itm < (unsigned)p.num_items;
-          gi[s][j] = iok ? ldg4(p.item_gmf + (size_t)itm * kF + 4 * pc) : make_float4(0.f, 0.f, 0.f, 0.f);
+          gi[j] = iok ? ldg4(p.item_gmf + (size_t)itm * kF + 4 * pc) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      }
-#pragma unroll
-      for (int s = 0; s < GSLOTS; ++s) {
-        const int idx = tid + kProdThreads * s;
-        if (idx >= NT) continue;
+      };
+      auto gmf_dot = [&](int s, const float4& gu, const float4 (&gi)[GROUP]) {
+        const int idx = tidv + kProdThreads * s;
         const int gt = idx >> 4, pc = idx & 15;
         const int sl0 = 32 * (gt / GQ) + GROUP * (gt % GQ);
         const bool gvalid = row0 + (int64_t)gt * GROUP < p.rows;
         const bool uok = (unsigned)ids[128 + gt] < (unsigned)p.num_users;
 #pragma unroll
         for (int j = 0; j < GROUP; ++j) {
-          float sdot = wg4.x * (gu[s].x * gi[s][j].x);
-          sdot = fmaf(wg4.y, gu[s].y * gi[s][j].y, sdot);
-          sdot = fmaf(wg4.z, gu[s].z * gi[s][j].z, sdot);
-          sdot = fmaf(wg4.w, gu[s].w * gi[s][j].w, sdot);
+          float sdot = wg4.x * (gu.x * gi[j].x);
+          sdot = fmaf(wg4.y, gu.y * gi[j].y, sdot);
+          sdot = fmaf(wg4.z, gu.z * gi[j].z, sdot);
+          sdot = fmaf(wg4.w, gu.w * gi[j].w, sdot);
           sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
           sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
           sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
@@ -378,7 +398,38 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
             flag_s[sl0 + j] = gvalid ? (bad ? 2 : 1) : 0;
           }
         }
+      };
+      static_assert(SLOTS >= 2, "the producer pipeline keeps two tasks in flight");
+      static_assert(NT >= kProdThreads, "every producer warp must own a task of the first half (its h1_full[0] arrival)");
+      // which half a task belongs to is warp-uniform: T = tid + 256 s >= NT; a warp's LAST task of half 0 is followed
+      // by its arrival on h1_full[0], its last task overall by h1_full[1]
+      const bool g1_live = tid + kProdThreads < NT;  // second GMF task (GSLOTS == 2): warp-uniform
+      static_assert(GSLOTS <= 2, "two GMF tasks per thread at most");
+      float4 xu[2], xi[2][GROUP];
+      float4 gu[GSLOTS], gi[GSLOTS][GROUP];
+      h1_issue(0, xu[0], xi[0]);
+      h1_issue(1, xu[1], xi[1]);
+      FZ_T(1)
+      if (it > 0) {  // the weight-gradient MMAs of the previous tile have read H1
+        tc::mbar_wait(&h1_free, (uint32_t)((it - 1) & 1));
       }
+      FZ_T(2)
+#pragma unroll
+      for (int s = 0; s < SLOTS; ++s) {
+        h1_store(s, xu[s & 1], xi[s & 1]);
+        const bool last_of_half0 = (tidv + kProdThreads * s < NT) && (tidv + kProdThreads * (s + 1) >= NT);
+        if (last_of_half0) h1_arrive(0);
+        // at most two tasks' rows live at any time: the next H1 task takes the registers just converted; the GMF rows
+        // follow once the H1 loads are all issued
+        if (s + 2 < SLOTS) h1_issue(s + 2, xu[s & 1], xi[s & 1]);
+        else if (s + 2 == SLOTS) gmf_issue(0, gu[0], gi[0]);
+        else if (GSLOTS > 1 && g1_live) gmf_issue(1, gu[GSLOTS - 1], gi[GSLOTS - 1]);
+      }
+      h1_arrive(1);
+      FZ_T(4)
+      // ---- GMF branch, part 1: gmf_u * gmf_i . w_out[:f] per row (the rows stay in registers for part 2)
+      gmf_dot(0, gu[0], gi[0]);
+      if (GSLOTS > 1 && g1_live) gmf_dot(1, gu[GSLOTS - 1], gi[GSLOTS - 1]);
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&gmf_ready);
       FZ_T(5)
@@ -388,8 +439,8 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
       FZ_T(6)
 #pragma unroll
       for (int s = 0; s < GSLOTS; ++s) {
-        const int idx = tid + kProdThreads * s;
-        if (idx >= NT) continue;
+        const int idx = tidv + kProdThreads * s;
+        if (s > 0 && !g1_live) continue;
         const int gt = idx >> 4, pc = idx & 15;
         const int sl0 = 32 * (gt / GQ) + GROUP * (gt % GQ);
         const int64_t grow0 = row0 + (int64_t)gt * GROUP;
@@ -422,77 +473,31 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
     FZ_T_FLUSH(0, tid == 0)
     if (any_bad) atomicOr(p.flags, 1);
     *reinterpret_cast<float4*>(smem + oRedG + 16 * tid) = accg;
-  } else if (warp == kMmaWarp) {
-    // ================================ MMA issuer ===================================================================
-    if (tc::elect_one()) {
-      const uint32_t s0 = tc::smem_u32(smem);
-      const uint64_t dk = tc::smem_desc(0, 16, 1024, kLayoutSw128);        // K-major view (LBO unused)
-      const uint64_t dmn = tc::smem_desc(0, kPanel, 1024, kLayoutSw128);   // MN-major view, 64-column blocks kPanel apart
-      const uint32_t id_fwd = idesc_bf16(128, kD2, 0, 1);   // H1 (K-major) x W2 (MN-major: N = output unit)
-      const uint32_t id_bwd = idesc_bf16(128, kD1, 0, 0);   // dZ2 (K-major) x W2 (K-major: N = input unit)
-      const uint32_t id_wg = idesc_bf16(128, kD2, 1, 1);    // H1^T (MN-major) x dZ2 (MN-major)
-      // the six part products of a 3 x bf16 split product (a part, b part)
-      constexpr int PA[6] = {0, 0, 1, 0, 2, 1}, PB[6] = {0, 1, 0, 2, 0, 1};
-      tc::mbar_wait(&w2_bar, 0);
-      int64_t it = 0;
-      FZ_T_DECL
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const uint32_t ph = (uint32_t)(it & 1);
-        // forward: acc_fwd[slot][j] = sum_i H1[slot][i] W2[i][j], one 64-feature half as soon as it has landed
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          tc::mbar_wait(&h1_full[half], ph);
-          tc::fence_after_sync();
-          FZ_T(2 * half)
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-              const uint32_t a = s0 + oH1 + PA[q] * kH1Part + half * kPanel + ks * 32;
-              const uint32_t b = s0 + oW2 + PB[q] * kPanel + (4 * half + ks) * 2048;
-              mma_bf16(tmem_base + cFwd, dk + (a >> 4), dmn + (b >> 4), id_fwd, (half | ks | q) != 0);
-            }
-          }
-          FZ_T(2 * half + 1)
-        }
-        tc::mma_commit(&fwd_done);
-        // weight gradient first (it frees H1 for the producers), then backward
-        tc::mbar_wait(&dz2_full, ph);
-        tc::fence_after_sync();
-        FZ_T(4)
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            const uint32_t a = s0 + oH1 + PA[q] * kH1Part + ks * 2048;
-            const uint32_t b = s0 + oZ2 + PB[q] * kPanel + ks * 2048;
-            mma_bf16(tmem_base + cWg, dmn + (a >> 4), dmn + (b >> 4), id_wg, (it | ks | q) != 0);
-          }
-        }
-        tc::mma_commit(&h1_free);
-        FZ_T(5)
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            const uint32_t a = s0 + oZ2 + PA[q] * kPanel + ks * 32;
-            const uint32_t b = s0 + oW2 + PB[q] * kPanel + ks * 32;
-            mma_bf16(tmem_base + cBwd, dk + (a >> 4), dk + (b >> 4), id_bwd, (ks | q) != 0);
-          }
-        }
-        tc::mma_commit(&bwd_done);
-        FZ_T(6)
-      }
-      FZ_T_FLUSH(1, true)
-    }
-  } else {
-    // ================================ epilogues (thread = row = TMEM lane) ===================================
+  } else if (warp < kE2Warp0) {
+    // ================================ epilogue 1 (thread = row = TMEM lane) + the MMA issuer =================
+    // Warp kE1Warp0 also issues every tcgen05.mma of the CTA, through one elected lane, in the two windows in which
+    // the epilogue-1 warps have nothing to do anyway: before the forward accumulator is ready (forward MMAs) and
+    // after dZ2 has been handed over (weight gradient, backward).  A dedicated issuer warp would be the 17th warp.
     const int quarter = warp & 3;
     const int slot = 32 * quarter + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * quarter) << 16);
-    float* tile_s = reinterpret_cast<float*>(smem + oStage) + (size_t)(warp - kEpiWarp0) * (32 * kEpiLd);
     const float b_out = const_s[192];
-    float cs_w[2] = {0.f, 0.f}, cs_b[2] = {0.f, 0.f};  // column sums (columns lane, lane + 32) of dz * H2 and of dZ2
+    const bool issuer = warp == kE1Warp0;
+    const uint32_t s0 = tc::smem_u32(smem);
+    const uint64_t dk = tc::smem_desc(0, 16, 1024, kLayoutSw128);        // K-major view (LBO unused)
+    const uint64_t dmn = tc::smem_desc(0, kPanel, 1024, kLayoutSw128);   // MN-major view, 64-column blocks kPanel apart
+    const uint32_t id_fwd = idesc_bf16(128, kD2, 0, 1);   // H1 (K-major) x W2 (MN-major: N = output unit)
+    const uint32_t id_bwd = idesc_bf16(128, kD1, 0, 0);   // dZ2 (K-major) x W2 (K-major: N = input unit)
+    const uint32_t id_wg = idesc_bf16(128, kD2, 1, 1);    // H1^T (MN-major) x dZ2 (MN-major)
+    // the six part products of a 3 x bf16 split product (a part, b part)
+    constexpr int PA[6] = {0, 0, 1, 0, 2, 1}, PB[6] = {0, 1, 0, 2, 0, 1};
+    {  // zero this lane's column-sum accumulators
+      float zero[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) zero[i] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_st32(lane_addr + cCs + 32 * c, zero);
+    }
     float accb = 0.f, accl = 0.f;
     int64_t it = 0;
     FZ_T_DECL
@@ -501,33 +506,57 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
       const int64_t row0 = tile * TR;
       const int64_t row = row0 + quarter * RQ + lane;
       const bool live = lane < RQ && row < p.rows;
-      const float y = live ? __ldg(p.labels + row) : 0.f;
 
-      // ---- epilogue 1
+      if (issuer) {
+        // forward: acc_fwd[slot][j] = sum_i H1[slot][i] W2[i][j], one 64-feature half as soon as it has landed
+        if (tc::elect_one()) {
+          if (it == 0) tc::mbar_wait(&w2_bar, 0);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            tc::mbar_wait(&h1_full[half], ph);
+            tc::fence_after_sync();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+              for (int q = 0; q < 6; ++q) {
+                const uint32_t a = s0 + oH1 + PA[q] * kH1Part + half * kPanel + ks * 32;
+                const uint32_t b = s0 + oW2 + PB[q] * kPanel + (4 * half + ks) * 2048;
+                mma_bf16(tmem_base + cFwd, dk + (a >> 4), dmn + (b >> 4), id_fwd, (half | ks | q) != 0);
+              }
+            }
+          }
+          tc::mma_commit(&fwd_done);
+        }
+        __syncwarp();
+      }
+
       tc::mbar_wait(&fwd_done, ph);
       tc::fence_after_sync();
       FZ_T(0)
-      float h[64];
-      tmem_ld32(lane_addr + cFwd, h);
-      tmem_ld32(lane_addr + cFwd + 32, h + 32);
+      // two passes over the accumulator (TMEM reads are cheap, registers are not): the logit first, then -- once dz
+      // is known -- H2 again, 32 columns at a time, for dZ2 and the column sums
       float zdot = 0.f;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const float4 bv = *reinterpret_cast<const float4*>(const_s + 4 * q);
-        const float4 wv = *reinterpret_cast<const float4*>(const_s + 64 + 4 * q);
-        h[4 * q + 0] = fmaxf(h[4 * q + 0] + bv.x, 0.f);
-        h[4 * q + 1] = fmaxf(h[4 * q + 1] + bv.y, 0.f);
-        h[4 * q + 2] = fmaxf(h[4 * q + 2] + bv.z, 0.f);
-        h[4 * q + 3] = fmaxf(h[4 * q + 3] + bv.w, 0.f);
-        zdot = fmaf(h[4 * q + 0], wv.x, zdot);
-        zdot = fmaf(h[4 * q + 1], wv.y, zdot);
-        zdot = fmaf(h[4 * q + 2], wv.z, zdot);
-        zdot = fmaf(h[4 * q + 3], wv.w, zdot);
+      for (int cb = 0; cb < 2; ++cb) {
+        float h[32];
+        tmem_ld32(lane_addr + cFwd + 32 * cb, h);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bv = *reinterpret_cast<const float4*>(const_s + 32 * cb + 4 * q);
+          const float4 wv = *reinterpret_cast<const float4*>(const_s + 64 + 32 * cb + 4 * q);
+          zdot = fmaf(fmaxf(h[4 * q + 0] + bv.x, 0.f), wv.x, zdot);
+          zdot = fmaf(fmaxf(h[4 * q + 1] + bv.y, 0.f), wv.y, zdot);
+          zdot = fmaf(fmaxf(h[4 * q + 2] + bv.z, 0.f), wv.z, zdot);
+          zdot = fmaf(fmaxf(h[4 * q + 3] + bv.w, 0.f), wv.w, zdot);
+        }
       }
       FZ_T(1)
       tc::mbar_wait(&gmf_ready, ph);
       FZ_T(2)
       const int flag = flag_s[slot];
+      // (the label arrived with the tile's ids: a global load here was sunk to its first use by the compiler and
+      // sat on the long scoreboard in the middle of the epilogue)
+      const float y = live ? reinterpret_cast<const float*>(smem + oIds)[(it & 1) * 288 + 160 + quarter * RQ + lane] : 0.f;
       const float z = zdot + gdot_s[slot] + b_out;
       const float pr = sigmoidf_stable(z);
       if (live) p.probs[row] = flag == 2 ? nanf("") : pr;
@@ -537,14 +566,20 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
       dz_s[slot] = dz;
 #pragma unroll
       for (int cb = 0; cb < 2; ++cb) {
-        float g[32];
+        float h[32], g[32];
+        tmem_ld32(lane_addr + cFwd + 32 * cb, h);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
+          const float4 bv = *reinterpret_cast<const float4*>(const_s + 32 * cb + 4 * q);
           const float4 wv = *reinterpret_cast<const float4*>(const_s + 64 + 32 * cb + 4 * q);
-          g[4 * q + 0] = h[32 * cb + 4 * q + 0] > 0.f ? dz * wv.x : 0.f;
-          g[4 * q + 1] = h[32 * cb + 4 * q + 1] > 0.f ? dz * wv.y : 0.f;
-          g[4 * q + 2] = h[32 * cb + 4 * q + 2] > 0.f ? dz * wv.z : 0.f;
-          g[4 * q + 3] = h[32 * cb + 4 * q + 3] > 0.f ? dz * wv.w : 0.f;
+          h[4 * q + 0] = fmaxf(h[4 * q + 0] + bv.x, 0.f);
+          h[4 * q + 1] = fmaxf(h[4 * q + 1] + bv.y, 0.f);
+          h[4 * q + 2] = fmaxf(h[4 * q + 2] + bv.z, 0.f);
+          h[4 * q + 3] = fmaxf(h[4 * q + 3] + bv.w, 0.f);
+          g[4 * q + 0] = h[4 * q + 0] > 0.f ? dz * wv.x : 0.f;
+          g[4 * q + 1] = h[4 * q + 1] > 0.f ? dz * wv.y : 0.f;
+          g[4 * q + 2] = h[4 * q + 2] > 0.f ? dz * wv.z : 0.f;
+          g[4 * q + 3] = h[4 * q + 3] > 0.f ? dz * wv.w : 0.f;
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {  // 16-byte chunk 4 * cb + c of the slot's 128-byte row, in each part
@@ -556,10 +591,16 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
           *reinterpret_cast<uint4*>(smem + off + kPanel) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
           *reinterpret_cast<uint4*>(smem + off + 2 * kPanel) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
         }
-        cs_b[cb] += warp_transpose_sum32(g, lane);
+        // column sums for d w_out[f:] (dz * H2) and d b2 (dZ2): this lane's running sums live in TMEM
+        float acc[32];
+        tmem_ld32(lane_addr + cCs + 32 * cb, acc);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) g[i] = dz * h[32 * cb + i];
-        cs_w[cb] += warp_transpose_sum32(g, lane);
+        for (int i = 0; i < 32; ++i) acc[i] = fmaf(dz, h[i], acc[i]);
+        tmem_st32(lane_addr + cCs + 32 * cb, acc);
+        tmem_ld32(lane_addr + cCs + 64 + 32 * cb, acc);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] += g[i];
+        tmem_st32(lane_addr + cCs + 64 + 32 * cb, acc);
       }
       tc::fence_proxy_async();
       tc::fence_before_sync();
@@ -567,22 +608,105 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
       if (lane == 0) tc::mbar_arrive(&dz2_full);
       FZ_T(3)
 
-      // ---- epilogue 2: dZ1 = acc_bwd * (H1 > 0) -> staged item rows; group sums -> staged user rows
+      if (issuer) {
+        // weight gradient first (it frees H1 for the producers), then backward
+        if (tc::elect_one()) {
+          tc::mbar_wait(&dz2_full, ph);
+          // epilogue 2 of the previous tile has read its accumulator (and long since its ReLU bits)
+          if (it > 0) tc::mbar_wait(&e2_done, (uint32_t)((it - 1) & 1));
+          tc::fence_after_sync();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+              const uint32_t a = s0 + oH1 + PA[q] * kH1Part + ks * 2048;
+              const uint32_t b = s0 + oZ2 + PB[q] * kPanel + ks * 2048;
+              mma_bf16(tmem_base + cWg, dmn + (a >> 4), dmn + (b >> 4), id_wg, (it | ks | q) != 0);
+            }
+          }
+          tc::mma_commit(&h1_free);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+              const uint32_t a = s0 + oZ2 + PA[q] * kPanel + ks * 32;
+              const uint32_t b = s0 + oW2 + PB[q] * kPanel + ks * 32;
+              mma_bf16(tmem_base + cBwd, dk + (a >> 4), dk + (b >> 4), id_bwd, (ks | q) != 0);
+            }
+          }
+          tc::mma_commit(&bwd_done);
+        }
+        __syncwarp();
+      }
+      FZ_T(4)
+    }
+    FZ_T_FLUSH(1, warp == kE1Warp0 && lane == 0)
+    // ---- end of the CTA's tiles: dW2 (TMEM lane = input unit) and the column sums
+    if (it > 0) {
+      tc::mbar_wait(&bwd_done, (uint32_t)((it - 1) & 1));  // every MMA of the CTA has completed
+      tc::fence_after_sync();
+      float* dst = p.partial + (size_t)blockIdx.x * p.partial_stride + p.off_w2 + (size_t)slot * kD2;
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        float v[32];
+        tmem_ld32(lane_addr + cWg + 32 * cb, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o = *reinterpret_cast<float4*>(dst + 32 * cb + 4 * q);
+          o.x += v[4 * q];
+          o.y += v[4 * q + 1];
+          o.z += v[4 * q + 2];
+          o.w += v[4 * q + 3];
+          *reinterpret_cast<float4*>(dst + 32 * cb + 4 * q) = o;
+        }
+      }
+    }
+    // this warp's column sums: the 32 lanes' TMEM accumulators folded once, fixed order; scratch = oRedE (per warp)
+    float* red = reinterpret_cast<float*>(smem + oRedE) + (warp - kE1Warp0) * 160;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // c = 0, 1: d w_out[f:] columns 32 c ..; c = 2, 3: d b2 columns 32 (c - 2) ..
+      float v[32];
+      tmem_ld32(lane_addr + cCs + 32 * c, v);
+      red[32 * c + lane] = warp_transpose_sum32(v, lane);
+    }
+    accb = warp_sum(accb);
+    accl = warp_sum(accl);
+    if (lane == 0) {
+      red[128] = accb;
+      red[129] = accl;
+    }
+  } else {
+    // ================================ epilogue 2 (thread = row = TMEM lane) =====================================
+    // dZ1 = acc_bwd * (H1 > 0) -> staged item rows; group sums -> staged user rows.  Its own four warps: it runs
+    // under the producers' work on the next tile and never delays epilogue 1.
+    const int quarter = warp & 3;
+    const int slot = 32 * quarter + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * quarter) << 16);
+    float* tile_s = reinterpret_cast<float*>(smem + oStage) + (size_t)(warp - kE2Warp0) * (32 * kEpiLd);
+    int64_t it = 0;
+    FZ_T_DECL
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = (uint32_t)(it & 1);
+      const int64_t row0 = tile * TR;
       tc::mbar_wait(&bwd_done, ph);
       tc::fence_after_sync();
-      FZ_T(4)
+      FZ_T(0)
       const uint4 bw = *reinterpret_cast<const uint4*>(smem + oBits + (it & 1) * (128 * 16) + slot * 16);
-      const uint32_t bwv[4] = {bw.x, bw.y, bw.z, bw.w};
+      const uint32_t bwv[4] = {bw.x, bw.y, bw.z, bw.w};  // nibble = piece (4 columns): word cb holds columns 32 cb ..
       const int64_t qrow0 = row0 + quarter * RQ;          // first row of this warp's quarter
       const int64_t qgrp0 = tile * GT + quarter * GQ;     // its first group
 #pragma unroll
       for (int cb = 0; cb < 4; ++cb) {
         float v[32];
         tmem_ld32(lane_addr + cBwd + 32 * cb, v);
+        if (cb == 3) {  // the accumulator is in registers: the next backward pass may overwrite it
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&e2_done);
+        }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const uint32_t field = bwv[2 * (cb >> 1) + ((i & 3) >> 1)] >> (16 * (i & 1));
-          if (!((field >> (8 * (cb & 1) + (i >> 2))) & 1u)) v[i] = 0.f;
+        for (int i = 0; i < 32; ++i) {  // column 32 cb + i: piece 8 cb + i / 4 = nibble i / 4 of word cb, bit i % 4
+          if (!((bwv[cb] >> i) & 1u)) v[i] = 0.f;
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -604,51 +728,19 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
         }
         __syncwarp();
       }
-      tc::fence_before_sync();
-      FZ_T(5)
+      FZ_T(1)
     }
-    FZ_T_FLUSH(2, warp == kEpiWarp0 && lane == 0)
-    // ---- end of the CTA's tiles: dW2 (TMEM lane = input unit) and the column sums
-    if (it > 0) {
-      float* dst = p.partial + (size_t)blockIdx.x * p.partial_stride + p.off_w2 + (size_t)slot * kD2;
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
-        float v[32];
-        tmem_ld32(lane_addr + cWg + 32 * cb, v);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 o = *reinterpret_cast<float4*>(dst + 32 * cb + 4 * q);
-          o.x += v[4 * q];
-          o.y += v[4 * q + 1];
-          o.z += v[4 * q + 2];
-          o.w += v[4 * q + 3];
-          *reinterpret_cast<float4*>(dst + 32 * cb + 4 * q) = o;
-        }
-      }
-    }
-    // reduction scratch = the head of this warp's OWN staging tile (other warps may still be staging rows)
-    float* red = tile_s;
-    __syncwarp();
-    red[lane] = cs_w[0];
-    red[32 + lane] = cs_w[1];
-    red[64 + lane] = cs_b[0];
-    red[96 + lane] = cs_b[1];
-    accb = warp_sum(accb);
-    accl = warp_sum(accl);
-    if (lane == 0) {
-      red[128] = accb;
-      red[129] = accl;
-    }
+    FZ_T_FLUSH(2, warp == kE2Warp0 && lane == 0)
   }
 
   // ---- per-CTA sums into this CTA's partial row, fixed order ---------------------------------------------------
-  // scratch: the head of each epilogue warp's staging tile (160 floats), the producers' d w_out[:f] float4 at oRedG
+  // scratch: the epilogue-1 warps' column sums (160 floats each) at oRedE, the producers' d w_out[:f] float4 at oRedG
   tc::fence_before_sync();
   __syncthreads();
   {
-    const float* red = reinterpret_cast<const float*>(smem + oStage);
+    const float* red = reinterpret_cast<const float*>(smem + oRedE);
     const float4* redg = reinterpret_cast<const float4*>(smem + oRedG);
-    constexpr int RS = 32 * kEpiLd;  // floats between the epilogue warps' scratch rows
+    constexpr int RS = 160;  // floats between the epilogue-1 warps' scratch rows
     float* prow = p.partial + (size_t)blockIdx.x * p.partial_stride;
     if (tid < 64) {  // d w_out[:f]: column tid = piece tid / 4 of the 16 threads tid/4 + 16 k
       float s = 0.f;
@@ -678,7 +770,7 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
     }
   }
   __syncthreads();
-  if (warp == kMmaWarp) tc::tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == kE1Warp0) tc::tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // W2 (128 x 64, Keras (in, out) layout) -> the shared-memory operand image: 3 bf16 parts x [128 rows x 128 B], swizzled.

@@ -14,10 +14,11 @@ import torch  # noqa: E402
 from movierec import _engine, _native as nat  # noqa: E402
 
 SEG = {
-    "producers": ["ids/prefetch", "issue H1 loads", "wait h1_free", "store half A", "store half B", "GMF part 1",
+    "producers": ["ids/prefetch", "issue 2 H1 tasks", "wait h1_free", "-", "H1 convert/store", "GMF part 1",
                   "wait dz2_full", "GMF part 2", "cp.async wait + bar"],
-    "mma": ["wait h1_full[0]", "issue fwd 0", "wait h1_full[1]", "issue fwd 1", "wait dz2_full", "issue wgrad", "issue bwd"],
-    "epilogue": ["wait fwd_done", "E1 ld + zdot", "wait gmf_ready", "E1 rest", "wait bwd_done", "E2"],
+    "epilogue 1 (+ MMA issue)": ["issue fwd + wait fwd_done", "E1 ld + zdot", "wait gmf_ready", "E1 rest",
+                                 "issue wgrad + bwd"],
+    "epilogue 2": ["wait bwd_done", "E2"],
 }
 
 
@@ -36,7 +37,7 @@ def main():
     assert nat.lib.mr_fused_timing_read(out) == 0
     t = np.array(out[:]).reshape(256, 3, 16)[:148]
     tiles = (groups * 5 + 119) // 120 / 148.0
-    for r, role in enumerate(("producers", "mma", "epilogue")):
+    for r, role in enumerate(SEG):
         tot = t[:, r, :].sum(axis=1).mean()
         print("{} (mean over CTAs; {:.0f} cycles per tile)".format(role, tot / tiles))
         for s, name in enumerate(SEG[role]):
