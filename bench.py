@@ -3,14 +3,14 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ml-20m|ml-1m|large-sharded] [--impl reference]
 
-One "step" = one optimisation step (forward + BCE + backward + deterministic embedding-gradient
-reduction + legacy-Keras dense Adam + train-batch HR/DCG) on one synthetic batch.  N > 1 runs under
-torchrun, one rank per GPU, weak scaling (every rank has its own batch of the same size), gradients
-summed with one NCCL all-reduce per step.  Prints ONE JSON line on rank 0.
+One "step" = the device negative sampler over the step's positives + one optimisation step (forward + BCE +
+backward + deterministic embedding-gradient reduction + legacy-Keras dense Adam + train-batch HR/DCG).  `value`
+includes the sampler, `value_excl_sampler` does not.  N > 1 runs under torchrun, one rank per GPU, weak
+scaling (every rank has its own batch of the same size), gradients summed over NCCL.  Prints ONE JSON line on rank 0.
 
-`--impl reference` times the CPU restatement of the reference's Keras path (oracle/, NumPy fp32,
-all host threads BLAS will use) on a bounded sample of the same workload; TensorFlow is not
-installable here, so this is the "port" kind of baseline.
+`--impl reference` times the CPU restatement of the reference's Keras path (oracle/, NumPy fp32, all host threads
+BLAS will use) on a bounded sample of the same workload; TensorFlow is not installable here, so this is the "port"
+kind of baseline.
 """
 
 import argparse
@@ -31,10 +31,10 @@ for _p in (ROOT, PKG):
 
 WORKLOADS = {
     # BASELINE.json configs[2]: ML-20M shape, embed dim 64 (GMF), MLP 256-128-64 (C-20M)
-    "ml-20m": dict(num_users=138493, num_items=26744, layers=[256, 128, 64], mf_dim=64, negs=4,
+    "ml-20m": dict(num_users=138493, num_items=26744, layers=[256, 128, 64], mf_dim=64, negs=4, ratings=20000263,
                    batch=5 * 2 ** 18, eval_negs=99, k_eval=10, cpu_batch=5 * 2 ** 13, cpu_eval_users=2048),
     # BASELINE.json configs[1]: ML-1M shape, reference default tower + GMF 8
-    "ml-1m": dict(num_users=6040, num_items=3706, layers=[64, 32, 16, 8], mf_dim=8, negs=4,
+    "ml-1m": dict(num_users=6040, num_items=3706, layers=[64, 32, 16, 8], mf_dim=8, negs=4, ratings=1000209,
                   batch=5 * 2 ** 16, eval_negs=99, k_eval=10, cpu_batch=5 * 2 ** 14, cpu_eval_users=6040),
     # BASELINE.json configs[4]: synthetic large NeuMF, embed dim 128, tables ROW-SHARDED over the GPUs (owner =
     # row % world), all-to-all of gathered rows and of their gradients; needs --gpus >= 2 (torchrun)
@@ -89,6 +89,24 @@ def synth_batches(wl, n_batches, seed, rows=None):
     return out
 
 
+def synth_ratings(wl, seed):
+    """MovieLens-shaped (user, item) pairs for the negative sampler's per-user item lists: per-user
+    counts 20 + a lognormal tail scaled to the shape's number of ratings, items Zipf(~1) over a fixed permutation
+    (repeats inside a user are dropped by the CSR build).  Returns int32 arrays."""
+    rng = np.random.default_rng(seed)
+    nu, ni, n = wl["num_users"], wl["num_items"], wl["ratings"]
+    tail = rng.lognormal(3.0, 1.0, nu)
+    extra = max(n - 20 * nu, 0)
+    counts = 20 + np.floor(tail * (extra / tail.sum())).astype(np.int64)
+    counts = np.minimum(counts, ni // 2)
+    users = np.repeat(np.arange(nu, dtype=np.int32), counts)
+    zipf = 1.0 / (np.arange(ni) + 1.0)
+    cdf = np.cumsum(zipf / zipf.sum())
+    perm = rng.permutation(ni).astype(np.int32)
+    items = perm[np.minimum(np.searchsorted(cdf, rng.random(users.size)), ni - 1)]
+    return users, items
+
+
 def synth_eval(wl, n_users, seed):
     rng = np.random.default_rng(seed)
     group = wl["eval_negs"] + 1
@@ -122,6 +140,8 @@ def algorithmic_bytes(wl, rows):
 
 
 PHASE_KERNELS = {
+    "fused_tile": "neumf_fused_train_kernel (tcgen05, 3 x bf16: H1 gather, layer-2 forward, head + BCE, dW2, backward, staged rows)",
+    "sampler": "sample_negatives_kernel (Philox4x32-10, uniform without replacement over the complement of the user's items)",
     "tile_train": "neumf_tile_kernel<TM,true> (SIMT fused gather+tower+head+BCE+backward)",
     "tile_forward": "neumf_tile_kernel<TM,false> (SIMT fused forward)",
     "tc_dense_fwd": "tc_dense_kernel<A_GATHER|A_DENSE|A_PROJ,EPI_BIAS_RELU|EPI_HEAD_DOT> (tcgen05 3xTF32 forward layers)",
@@ -199,6 +219,15 @@ def measured_peaks():
             p = json.load(f)
         return float(p["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
+
+
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s sustained inside a long step (MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f).get("bf16_tflops_sustained", 1400.0))
+    return 1400.0
 
 
 class ClockSampler(object):
@@ -297,18 +326,22 @@ def time_oracle_eval(wl, reps=2):
 
 
 def run_reference(args, wl):
+    """The reference arm: the CPU restatement of the reference's Keras train_on_batch (oracle/, NumPy fp32, every host
+    thread BLAS uses) on the SAME workload -- same tables, tower, optimizer, batch layout -- each step a bounded
+    sample of the GPU arm's rows per step (the full 1,310,720-row step takes ~15 s of NumPy), throughput in the same
+    unit.  `config` is the GPU arm's; the sample size is stated in `cpu_baseline.sample` / `sample_rows_per_step`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     value, ms, rows = time_oracle_train(wl, args.steps, args.warmup)
     threads = blas_threads()
     sample = ("oracle (NumPy fp32 restatement of the reference's Keras train_on_batch, dense Adam over the full "
-              "tables) on {} rows/step of the {} workload, {} steps".format(rows, args.workload, args.steps))
+              "tables) on {} of the workload's {} rows per step, {} steps".format(rows, wl["batch"], args.steps))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, wl, rows_override=rows),
+        "config": config_dict(args, wl), "sample_rows_per_step": rows,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -333,12 +366,55 @@ def config_dict(args, wl, rows_override=None):
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
 
+def refuse_diagnostics(args):
+    """A bench value must come from the product build with no diagnostic switch: any MR_* environment variable
+    (variant libraries via MR_LIB_PATH, MR_DP_OVERLAP, ...) makes the run a profiling run, allowed only with --lean."""
+    found = sorted(k for k in os.environ if k.startswith("MR_"))
+    if found and not args.lean:
+        raise SystemExit("refusing to emit a bench value with diagnostic variables set: {} (use --lean for profiling "
+                         "runs; their line is marked and carries no e2e / baseline)".format(", ".join(found)))
+    return found
+
+
+def time_reference_faithful():
+    """the reference's own operating point (trainer.py:8-27: tower 64-32-16-8, batch 100, 4 negatives,
+    Adam) on ML-100k-shaped data, ONE process as Keras' fit_generator default (workers=1): the oracle's NumPy train
+    step fed by the restated generator (data_pipeline.py:99-150: a scan of the ratings and a setdiff per positive)."""
+    from oracle import movierec_oracle as o
+    nu, ni, n, negs, batch = 943, 1682, 100000, 4, 100
+    rng = np.random.default_rng(0)
+    users = rng.integers(0, nu, n)
+    items = rng.integers(0, ni, n)
+    L = [64, 32, 16, 8]
+    params = {"layers_sizes": L, "layers_l2reg": [0, 0, 0, 0], "optimizer": "adam", "lr": 0.001, "beta_1": 0.9,
+              "beta_2": 0.999, "num_negs_per_pos": negs, "k": 5}
+    w = o.init_weights(nu, ni, L, 0, np.random.default_rng(1))
+    st = o.new_opt_state(w)
+    idx = rng.permutation(n)
+    steps, t_gen, t_step = 60, 0.0, 0.0
+    for i in range(steps + 3):
+        t0 = time.perf_counter()
+        (xu, xi), y = o.reference_batch(users, items, idx, i, batch, negs, ni, rng)
+        t1 = time.perf_counter()
+        o.train_step(w, st, xu, xi, y.astype(np.float32), params)
+        t2 = time.perf_counter()
+        if i >= 3:
+            t_gen += t1 - t0
+            t_step += t2 - t1
+    return {"samples_per_sec": batch * steps / (t_gen + t_step), "samples_per_sec_excl_generation": batch * steps / t_step,
+            "batch": batch, "cores": 1, "steps": steps,
+            "config": "reference defaults (trainer.py:8-27): layers [64,32,16,8], batch 100, 4 negatives, Adam; ML-100k "
+                      "shape (943 x 1682, 100,000 ratings); oracle NumPy step + restated generator, one process"}
+
+
 def run_gpu(args, wl):
     import torch
     import torch.distributed as dist
+    from movierec import _engine as eng_mod
     from movierec import _native as nat
     from movierec.model import MovierecModel
 
+    diag_env = refuse_diagnostics(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -353,7 +429,8 @@ def run_gpu(args, wl):
         dist.init_process_group("nccl", device_id=dev)
 
     rows = wl["batch"]
-    group = wl["negs"] + 1
+    negs = wl["negs"]
+    group = negs + 1
     out_dir = tempfile.mkdtemp(prefix="movierec_bench_")
     model = MovierecModel(model_params(wl, rows), "bench", out_dir, verbose=0)
     eng = model.model.engine
@@ -362,17 +439,32 @@ def run_gpu(args, wl):
         dp = DataParallelNeuMF(eng)
         dp.broadcast_parameters(0)
 
+    # ---- synthetic ratings -> per-user item lists on the device (what the sampler excludes); positives of a step
+    # are drawn from the ratings (activity-weighted users, Zipf items), a different stream per rank
+    ru, ri = synth_ratings(wl, seed=0)
+    rowptr, csr = eng_mod.build_user_csr(ru, ri, wl["num_users"], wl["num_items"])
+    P = rows // group
     n_batches = 4
-    host = synth_batches(wl, n_batches, seed=1000 + rank)
-    pinned = [tuple(torch.from_numpy(a).pin_memory() for a in b) for b in host]
-    resident = [tuple(t.to(dev) for t in b) for b in pinned]
+    rng = np.random.default_rng(1000 + rank)
+    positives = []
+    for _ in range(n_batches):
+        sel = rng.integers(0, ru.size, P)
+        positives.append((torch.from_numpy(ru[sel]).to(dev), torch.from_numpy(ri[sel]).to(dev)))
     global_rows = rows * world
+    draw = [0]
 
-    def step_resident(i):
-        u, it, y = resident[i % n_batches]
+    def sample(i):
+        pu, pi = positives[i % n_batches]
+        draw[0] += 1
+        return eng_mod.sample_negatives(rowptr, csr, wl["num_items"], pu, pi, 0, negs, 2 + rank, draw[0])
+
+    def train(u, it, y):
         if dp is None:
             return eng.train_step(u, it, y, group=group, k=group, grouped=True)
         return dp.train_step(u, it, y, global_rows, group=group, k=group, grouped=True)
+
+    resident = [sample(b) for b in range(n_batches)]                       # pre-sampled: the sampler-excluded loop
+    pinned = [tuple(t.cpu().pin_memory() for t in b) for b in resident]     # ... and the end-to-end loop's host batches
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -380,42 +472,62 @@ def run_gpu(args, wl):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for i in range(args.warmup):
-        step_resident(i)
-    sync_all()
+    def timed(step_fn, steps, profile=False):
+        sync_all()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if profile:
+            nat.profile_begin()
+        sync_all()
+        ev0.record()
+        last = None
+        for i in range(steps):
+            last = step_fn(i)
+        ev1.record()
+        sync_all()
+        prof = nat.profile_end() if profile else None
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), last, prof
 
-    # ---- timed region: inputs resident in HBM ------------------------------------------------------
+    for i in range(args.warmup):
+        train(*sample(i))
+    # ---- timed region 1 (the headline): sampler + train step, positives resident in HBM ---------------------------
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nat.profile_begin()
-    sync_all()
-    ev0.record()
-    last = None
-    for i in range(args.steps):
-        last = step_resident(args.warmup + i)
-    ev1.record()
-    sync_all()
-    phases, launches = nat.profile_end()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total, last, (phases, launches) = timed(lambda i: train(*sample(args.warmup + i)), args.steps, profile=True)
     clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    # ---- timed region 2: the train step alone on pre-sampled batches -----------------------------------------------
+    ms_nosampler, _, _ = timed(lambda i: train(*resident[i % n_batches]), args.steps)
     value = global_rows * args.steps / (ms_total / 1e3)
+    value_nosampler = global_rows * args.steps / (ms_nosampler / 1e3)
     final = last.cpu().numpy()
-    if (final[4] != 0 or not np.isfinite(final[0])) and not os.environ.get("MR_TC_DEBUG"):
+    if final[4] != 0 or not np.isfinite(final[0]):
         raise SystemExit("bench produced invalid step outputs: {}".format(final))
 
-    # ---- end to end through the public API: host buffers in, loss out, every step ------------------
+    # ---- the weights the timed steps produced must still score like the oracle says (rank 0) -----------------------
+    check = None
+    if rank == 0:
+        from oracle import movierec_oracle as o
+        w_now = eng.get_weights()
+        u0, i0, _ = resident[0]
+        pick = np.random.default_rng(7).choice(rows, 4096, replace=False)
+        pick_t = torch.from_numpy(pick).to(dev)
+        logits = eng.forward(u0[pick_t], i0[pick_t])[0].cpu().numpy().astype(np.float64)
+        want = o.forward(w_now, u0.cpu().numpy()[pick], i0.cpu().numpy()[pick])["z"].astype(np.float64)
+        err, scale = float(np.max(np.abs(logits - want))), float(np.max(np.abs(want)))
+        check = {"rows": 4096, "max_abs_err": err, "max_abs_logit": scale, "tolerance": 1e-5 * scale}
+        if not np.isfinite(err) or err > 1e-5 * scale:
+            raise SystemExit("bench weights fail the oracle check: logits differ by {:.3e} (scale {:.3e})".format(err, scale))
+
+    # ---- end to end through the public API: host buffers in, loss out, every step ----------------------------------
     def step_e2e(i):
         u, it, y = pinned[i % n_batches]
-        if dp is None:
-            return model.model.train_on_batch([u, it], y)  # uploads, steps, reads the loss back
-        out = dp.train_step(u, it, y, global_rows, group=group, k=group, grouped=True)
-        return out.cpu()
+        if dp is None:  # uploads, steps, reads the loss back; the next batch's upload runs under this step
+            nxt = pinned[(i + 1) % n_batches]
+            return model.model.train_on_batch([u, it], y, prefetch=([nxt[0], nxt[1]], nxt[2]))
+        return dp.train_step(u, it, y, global_rows, group=group, k=group, grouped=True).cpu()
 
     e2e_steps = 0 if args.lean else max(3, min(args.steps, 20))
     if not args.lean:
@@ -431,7 +543,7 @@ def run_gpu(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = global_rows * e2e_steps / float(t.item())
 
-    # ---- ranking eval: HR@10 users/sec (second half of the BASELINE metric), rank 0's replica ------
+    # ---- ranking eval: HR@10 users/sec (second half of the BASELINE metric), rank 0's replica ----------------------
     eval_obj = None
     if rank == 0 and not args.lean:
         n_eval = wl["num_users"]
@@ -443,13 +555,22 @@ def run_gpu(args, wl):
         nat.profile_begin()
         reps = 7
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        for a, b in evs:  # one event pair per sweep; the median is reported (a sweep is ~12 ms, host hiccups show)
+        for a, b in evs:  # one event pair per sweep; the median is reported (host hiccups show in single sweeps)
             a.record()
             pos, sums, _, _ = eng.rank_eval(eu_d, ei_d, egroup, wl["k_eval"])
             b.record()
         torch.cuda.synchronize(dev)
         eph, _ = nat.profile_end()
         ems = float(np.median([a.elapsed_time(b) for a, b in evs]))
+        # end to end: pinned host ids in, HR / NDCG back on the host
+        eu_p, ei_p = torch.from_numpy(eu).pin_memory(), torch.from_numpy(ei).pin_memory()
+        e2e_t = []
+        for _ in range(4):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            pos2, sums2, _, _ = eng.rank_eval(eu_p, ei_p, egroup, wl["k_eval"])
+            hr_host = float(sums2.cpu()[0])
+            e2e_t.append(time.perf_counter() - t0)
         ab = algorithmic_bytes(wl, rows)
         peak, peak_kind = measured_peaks()
         fwd_ms = sum(eph[k][0] for k in ("tile_forward", "tc_dense_fwd", "h1_gather", "head") if k in eph) / reps
@@ -457,10 +578,14 @@ def run_gpu(args, wl):
         eval_obj = {"metric": "hr10_eval_users_per_sec", "value": n_eval / (ems / 1e3), "unit": "users/s",
                     "users": n_eval, "candidates_per_user": egroup, "k": wl["k_eval"], "ms": ems,
                     "hr_at_k": float(sums[0].item()) / n_eval, "ndcg_at_k": float(sums[1].item()) / n_eval,
+                    "e2e": {"value": n_eval / float(np.median(e2e_t[1:])), "unit": "users/s",
+                            "h2d_bytes_per_sweep": int(eu.nbytes + ei.nbytes), "d2h_bytes_per_sweep": 8,
+                            "api": "NeuMFEngine.rank_eval on pinned host ids (MovierecModel.evaluate), sums read back"},
                     "phase_ms": {k: v[0] / reps for k, v in eph.items() if v[1]},
                     "roofline": {"bound": "hbm", "kernel": "forward kernels (tcgen05 layers + head, or the SIMT tile kernel)",
                                  "forward_ms": fwd_ms, "achieved": ach, "peak": peak,
                                  "unit": "GB/s", "frac": ach / peak, "peak_kind": peak_kind, "traffic": None}}
+        assert abs(hr_host - float(sums[0].item())) < 0.5
 
     if world > 1:
         dist.barrier()
@@ -471,11 +596,13 @@ def run_gpu(args, wl):
 
     ab = algorithmic_bytes(wl, rows)
     peak, peak_kind = measured_peaks()
+    tensor_peak = measured_tensor_peak()
     step_ms = ms_total / args.steps
     grouped_seq = bool(eng.uses_tensor_cores()) and wl["mf_dim"] + wl["layers"][-1] <= 128
     projected_seq = grouped_seq and bool(eng.uses_item_projection(rows))
-    uprojected_seq = projected_seq and bool(eng.uses_user_projection(rows, wl["negs"] + 1))
+    uprojected_seq = projected_seq and bool(eng.uses_user_projection(rows, group))
     pbytes = phase_interface_bytes(wl, rows, grouped=grouped_seq, projected=projected_seq, user_projected=uprojected_seq)
+    pbytes["fused_tile"] = ab["tile"]  # B * (4 * (d_U + d_I) + 12), the per-row term of A_train
     phase_table = {}
     for name, (ms, cnt) in phases.items():
         if not cnt:
@@ -487,57 +614,66 @@ def run_gpu(args, wl):
             row["gbs"] = pbytes[name] / (per_step / 1e3) / 1e9
             row["frac_of_hbm_peak"] = row["gbs"] / peak
         phase_table[name] = row
-    dom = max((k for k in phase_table if k in pbytes), key=lambda k: phase_table[k]["ms_per_step"])
+    dom = max(phase_table, key=lambda k: phase_table[k]["ms_per_step"])
     dom_groups = max(phases[dom][1], 1)
-    dom_avg_ms = phases[dom][0] / dom_groups            # one launch group = the kernel(s) of one sub-batch
-    dom_bytes = pbytes[dom] * args.steps / dom_groups
-    achieved = dom_bytes / (dom_avg_ms / 1e3) / 1e9
+    dom_avg_ms = phases[dom][0] / dom_groups            # one launch group = the kernel(s) of one phase interval
+    dominant = {"phase": dom, "kernel": PHASE_KERNELS.get(dom, dom), "avg_launch_ms": dom_avg_ms,
+                "launches_timed": dom_groups, "share_of_step": phase_table[dom]["share_of_step"]}
+    if dom in pbytes:
+        dom_bytes = pbytes[dom] * args.steps / dom_groups
+        dominant.update(algorithmic_bytes_per_launch=dom_bytes, achieved_gbs=dom_bytes / (dom_avg_ms / 1e3) / 1e9,
+                        frac_of_hbm_peak=dom_bytes / (dom_avg_ms / 1e3) / 1e9 / peak)
+    if dom == "fused_tile":
+        # three GEMMs of 2 * 128 * 64 flops per row, each fp32 product = six bf16 part products on the tensor cores
+        tflops = 6.0 * 3 * 2 * 128 * 64 * rows * args.steps / dom_groups / (dom_avg_ms / 1e3) / 1e12
+        dominant.update(bound="hbm (per-row gather + staged gradient rows); tensor time is ~3/4 of the HBM time",
+                        tensor_tflops_bf16=tflops, frac_of_tensor_peak=tflops / tensor_peak)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            per_step = json.load(f).get(args.workload, {}).get(dom + "_dram_bytes_per_step")
-            # ncu measured one step; a "launch" here is one launch group of the phase, like `achieved`
-            traffic = per_step * args.steps / dom_groups if per_step else None
-    tc_flops = 3.0 * ab["flops_step"]  # 3xTF32: every fp32 product is three tensor-core products
+            traffic = json.load(f).get(args.workload, {}).get("step_dram_bytes")
     if args.lean:
-        cpu_value, cpu_ms, cpu_rows, cpu_eval = None, None, 0, None
+        cpu_value, cpu_ms, cpu_rows, cpu_eval, faithful = None, None, 0, None, None
     else:
         cpu_value, cpu_ms, cpu_rows = time_oracle_train(wl, steps=4, warmup=1)
         cpu_eval = time_oracle_eval(wl)
+        faithful = time_reference_faithful()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config_dict(args, wl),
+        "value_excl_sampler": value_nosampler, "ms_per_step_excl_sampler": ms_nosampler / args.steps,
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rows * 12, "d2h_bytes_per_step": 32,
-                "steps": e2e_steps, "api": "MovierecModel.model.train_on_batch([x_users, x_items], y) on pinned host arrays"
+                "steps": e2e_steps,
+                "api": "MovierecModel.model.train_on_batch([x_users, x_items], y, prefetch=next batch) on pinned host arrays: "
+                       "the next batch's upload runs under the current step; the loss is read back every step"
                 if dp is None else "DataParallelNeuMF.train_step on pinned host arrays"},
         "gpu_launches": launches,
-        "launch_sequence": {"grouped": grouped_seq, "item_projection": projected_seq, "user_projection": uprojected_seq},
-        "roofline": {"bound": "hbm", "kernel": PHASE_KERNELS.get(dom, dom), "phase": dom,
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_kind": peak_kind, "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_avg_ms,
-                     "launches_timed": dom_groups, "share_of_step": phase_table[dom]["share_of_step"],
-                     "note": "bytes = what this kernel must move given its interface; one launch = one sub-batch "
-                             "of the step (see DESIGN.md); the tower is 3xTF32 on tcgen05, fp32 TFLOP/s below"},
-        "step_roofline": {"algorithmic_bytes_per_step": ab["step"], "achieved_gbs": ab["step"] / (step_ms / 1e3) / 1e9,
-                          "frac_of_hbm_peak": ab["step"] / (step_ms / 1e3) / 1e9 / peak,
-                          "fp32_tflops": ab["flops_step"] / (step_ms / 1e3) / 1e12,
-                          "tensor_tflops_3xtf32": tc_flops / (step_ms / 1e3) / 1e12},
+        "launch_sequence": {"grouped": grouped_seq, "item_projection": projected_seq, "user_projection": uprojected_seq,
+                            "fused_tile_kernel": "fused_tile" in phase_table},
+        # the whole step's algorithmic bytes over the step time, against the measured copy bandwidth
+        "roofline": {"bound": "hbm", "scope": "whole train step (sampler included), SURVEY 8(d) A_train",
+                     "kernel": PHASE_KERNELS.get(dom, dom), "achieved": ab["step"] / (step_ms / 1e3) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": ab["step"] / (step_ms / 1e3) / 1e9 / peak, "traffic": traffic,
+                     "peak_kind": peak_kind, "algorithmic_bytes_per_step": ab["step"],
+                     "fp32_tflops": ab["flops_step"] / (step_ms / 1e3) / 1e12, "dominant_kernel": dominant},
         "phases": phase_table,
         "phase_ms_per_step": {k: v[0] / args.steps for k, v in phases.items() if v[1]},
+        "oracle_check": check,
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": blas_threads(), "kind": "port",
                          "host_cores": os.cpu_count(),
-                         "sample": "oracle NumPy fp32 train step (dense Adam over the full tables) on {} rows/step, "
-                                   "4 steps after 1 warm-up; eval: {} users x {} candidates".format(
+                         "sample": "oracle NumPy fp32 train step (dense Adam over the full tables) on {} rows/step of the "
+                                   "same workload, 4 steps after 1 warm-up; eval: {} users x {} candidates".format(
                                        cpu_rows, wl["cpu_eval_users"], wl["eval_negs"] + 1),
-                         "eval_users_per_sec": cpu_eval},
+                         "eval_users_per_sec": cpu_eval, "reference_faithful": faithful},
         "eval": eval_obj,
         "final_loss": float(final[0]) / rows,
     }
     if args.lean:
         line["lean"] = True
+        line["diagnostic_env"] = diag_env
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -68,7 +68,29 @@ typedef struct MrModel {
   int32_t L[MR_MAX_LAYERS]; /* layers_sizes */
   int32_t mf_dim;
   float l2[MR_MAX_LAYERS];  /* layers_l2reg: l2[0] on the tables, l2[l] on W[l] (model.py:163,168,178) */
+  /* Kernel selection.  Part of the model description -- not library state -- so that the workspace-size queries and
+   * every launch on this model agree by construction.  Zero-initialised = automatic. */
+  int32_t compute_path;     /* MrComputePath */
+  int32_t item_projection;  /* MrProjection */
+  int32_t fused_train;      /* MrFusedTrain */
 } MrModel;
+
+/* Two implementations of the tower exist: the tcgen05 tensor-core path, used when every layer width is a multiple of
+ * 32 (<= 256), every non-final width a multiple of 128 and layers_sizes[0] a multiple of 64, and the fp32 SIMT tile
+ * kernel for every other shape.  Both are hand-written CUDA. */
+enum { MR_PATH_AUTO = 0, MR_PATH_SIMT = 1, MR_PATH_TENSOR = 2 };
+/* Item-projected first layer (tensor-core path; replaces, like the rest of the tower, the Embedding + Dense of
+ * model.py:154-181).  The first Dense layer is linear before its ReLU, so its item half E_item . W1[item rows] is
+ * computed once per ITEM when a call has at least twice as many rows as there are items (AUTO), and gathered per
+ * row; the backward pass sums dZ1 per item before the item half of its GEMMs.  Used by the grouped train step with
+ * dense gradient tables and by the fused ranking eval when layers_sizes[1] == layers_sizes[0] / 2 and there are at
+ * least three layers.  The train step does the same for the user half when, in addition, there are no more users
+ * than the step has groups.  ON = wherever the model is eligible. */
+enum { MR_PROJECTION_AUTO = 0, MR_PROJECTION_OFF = 1, MR_PROJECTION_ON = 2 };
+/* The fused per-tile train kernel (projected steps of the 256-128-64 / GMF 64 tower in groups of five rows): AUTO =
+ * used wherever it applies; OFF = the kernel-per-layer launch sequence (kept for shapes the fused kernel does not
+ * cover, and for A/B comparisons in the tests). */
+enum { MR_FUSED_AUTO = 0, MR_FUSED_OFF = 1 };
 
 /* Optimizer hyper-parameters and state (model.py:197-204).  m/v mirror MrModel's tables and dense
  * block (NULL for SGD).  `iterations` is the number of steps ALREADY applied (Keras' counter). */
@@ -230,43 +252,16 @@ enum { MR_PHASE_TILE_TRAIN = 0, /* fused gather+tower+head+BCE+backward kernel *
 int mr_profile_begin(void);
 int mr_profile_end(float* phase_ms, int64_t* phase_count, int64_t* kernel_launches);
 
-/* Two implementations of the tower exist: the tcgen05 (3xTF32 tensor-core) path, used when every layer
- * width is a multiple of 32 (<= 256), every non-final width a multiple of 128 and layers_sizes[0] a
- * multiple of 64, and the fp32 SIMT tile kernel for every other shape.  Both are hand-written CUDA; the
- * selector is thread-local: 0 = automatic (default), 1 = always SIMT, 2 = tensor cores where eligible. */
-int mr_set_compute_path(int32_t path);
+/* Which kernels a call on this model takes (see MrModel.compute_path / item_projection). */
 int mr_uses_tensor_cores(const MrModel* model);
 
-/* Item-projected first layer (tensor-core path; replaces, like the rest of the tower, the Embedding + Dense of
- * model.py:154-181).  The first Dense layer is linear before its ReLU, so its item half E_item . W1[item rows] is
- * computed once per ITEM when a call has at least twice as many rows as there are items, and gathered per row; the
- * backward pass sums dZ1 per item before the item half of its GEMMs.  Used by the grouped train step with dense
- * gradient tables and by the fused ranking eval when layers_sizes[1] == layers_sizes[0] / 2 and there are at least
- * three layers.  Thread-local selector: 0 = automatic (default), 1 = off, 2 = on wherever eligible.  Set it before
- * the workspace-size queries: the per-item buffers are part of the workspace. */
-int mr_set_item_projection(int32_t mode);
 int mr_uses_item_projection(const MrModel* model, int64_t rows);
 /* The train step does the same for the user half (E_user . W1[user rows] + b1 once per user, per-user sums of the
  * group sums of dZ1) when, in addition, there are no more users than the step has groups. */
 int mr_uses_user_projection(const MrModel* model, int64_t rows, int32_t group);
 
-/* Building blocks exposed for tests and for data-parallel callers. */
-/* Single-tile tcgen05 GEMM self-test: D[128 x N] = A . B^T on the tensor cores (TF32 or 3xTF32), A given
- * as [128 x K] (a_mn = 0) or [K x 128] (a_mn = 1), B as [N x K] (b_mn = 0) or [K x N] (b_mn = 1).
- * Validates the shared-memory operand layout and descriptors the fused kernels rely on. */
-/* Descriptor explorer used by the tests that pin the operand-layout semantics: raw_a (n_words floats) is
- * the shared-memory image of A, B is the 16x8 identity, one M=128,N=16,K=8 TF32 MMA; D is [128 x 16]. */
-int mr_tc_probe(const float* raw_a, int32_t n_words, int32_t start_off, int32_t lbo, int32_t sbo, int32_t a_mn,
-                float* D, void* stream);
-int mr_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
-                        int32_t three_x, void* stream);
-/* The same single-tile GEMM on the operand form of the fused train kernel: three bf16 parts per operand, six part
- * products, SWIZZLE_128B tiles read K-major (x_mn = 0) or MN-major (x_mn = 1); K % 16 == 0, K <= 256. */
-int mr_bf16x3_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
-                            void* stream);
-/* Diagnostics: sustained tcgen05 issue rate of the 3xTF32 stage pattern on static operands (tools/tc_rate.py). */
-int mr_tc_rate(int32_t N, int32_t iters, int32_t nbuf, int32_t flags, int32_t writers, int32_t write_iters,
-               int64_t* out_cycles, int32_t grid, void* stream);
+/* Building blocks exposed for tests and for data-parallel callers.  (The tcgen05 self-tests, the descriptor probe
+ * and the issue-rate probe are diagnostics: include/movierec_b200_diag.h, libmovierec_b200_diag.so.) */
 /* Dataset preparation on the device.
  * mr_split_last_two replaces the pandas groupby of load_ratings_train_test_sets (movierec/data_pipeline.py:190-198):
  * order[e] = row number of the e-th rating when the ratings are ordered by user, file order kept inside a user (a

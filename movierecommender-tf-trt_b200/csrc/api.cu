@@ -161,8 +161,6 @@ static bool any_l2(const MrModel& m) {
 }
 
 // ---- tensor-core path (tcgen05 3xTF32): eligibility, workspace and launch sequence ----------------------
-static thread_local int g_path = 0;  // 0 auto, 1 force the SIMT tile kernel, 2 require the tensor-core path
-
 static bool tc_eligible(const MrModel& m) {
   if (m.n_layers < 2) return false;
   if (m.L[0] % 64) return false;  // d_u = L0/2 must be a multiple of 32 (K-chunks never straddle the two tables)
@@ -178,7 +176,7 @@ static bool tc_eligible(const MrModel& m) {
   return (a & 15) == 0;
 }
 
-static bool use_tc(const MrModel& m) { return g_path != 1 && tc_eligible(m); }
+static bool use_tc(const MrModel& m) { return m.compute_path != MR_PATH_SIMT && tc_eligible(m); }
 
 // Item-projected first layer (grouped train step, fused ranking eval).  The first Dense layer is linear before its
 // ReLU, so E_item . W1[item rows] is a function of the item alone: with `rows` rows per step and num_items << rows
@@ -187,14 +185,13 @@ static bool use_tc(const MrModel& m) { return g_path != 1 && tc_eligible(m); }
 // segmented reduction that already exists, fed dZ1 instead of dZ1 . W1i^T), then the item half of the backward
 // GEMM and of the weight gradient run on num_items rows instead of `rows`.  Same values up to summation order.
 // Needs L1 == d_i so that the staged item rows keep their width d_i + f, and dense gradient tables.
-static thread_local int g_item_proj = 0;  // 0 auto, 1 never, 2 whenever eligible
-
+// (selector: MrModel.item_projection -- part of the model description, so that workspace sizing and the launch
+// sequence of every call on that model agree)
 static bool item_proj_ok(const MrModel& m, int64_t rows) {
-  static const bool off = getenv("MR_NO_ITEM_PROJECTION") != nullptr;
-  if (off || g_item_proj == 1 || g_path == 1 || !tc_eligible(m) || m.n_layers < 3) return false;
+  if (m.item_projection == MR_PROJECTION_OFF || !use_tc(m) || m.n_layers < 3) return false;
   const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
   if (d_i % 128 || d_i > 256 || m.L[1] != d_i) return false;
-  if (g_item_proj == 2) return true;
+  if (m.item_projection == MR_PROJECTION_ON) return true;
   return 2 * (int64_t)m.num_items <= rows;  // three GEMMs over num_items rows replace three over `rows` rows
 }
 
@@ -203,24 +200,19 @@ static bool item_proj_ok(const MrModel& m, int64_t rows) {
 // backward GEMM and of the weight gradient.  Needs the item projection and L1 == d_u.
 static bool user_proj_ok(const MrModel& m, int64_t rows, int group) {
   if (!item_proj_ok(m, rows) || group < 2) return false;
-  static const bool off = getenv("MR_NO_USER_PROJECTION") != nullptr;
-  if (off || m.L[1] != m.L[0] / 2) return false;
-  return g_item_proj == 2 || (int64_t)m.num_users <= rows / group;
+  if (m.L[1] != m.L[0] / 2) return false;
+  return m.item_projection == MR_PROJECTION_ON || (int64_t)m.num_users <= rows / group;
 }
 
 // Rows per launch of the tensor-core kernels: the whole batch up to 2^21 rows (persistent CTAs need many
 // tiles each to reach steady state: one launch of 1,310,720 rows instead of two of 655,360 takes the ML-20M step
 // from 2.48 to 2.45 ms, and four of 327,680 cost +0.25 ms; intermediates are ~2.3 KB of workspace per row), split
 // evenly above.
-static int64_t sub_batch_cap(const char* env, int64_t dflt) {  // diagnostics: MR_*_SUB_BATCH_ROWS = 2^14 .. 2^20
-  const char* v = getenv(env);
-  if (v == nullptr) return dflt;
-  const long long r = atoll(v);
-  return r >= (1 << 14) && r <= (1 << 22) ? (int64_t)r : dflt;
-}
+constexpr int64_t kTcSubBatchCap = (int64_t)1 << 21;    // train / forward
+constexpr int64_t kEvalSubBatchCap = (int64_t)1 << 22;  // ranking eval
 
 static int64_t tc_sub_batch(int64_t B) {
-  static const int64_t cap = sub_batch_cap("MR_TC_SUB_BATCH_ROWS", (int64_t)1 << 21);
+  const int64_t cap = kTcSubBatchCap;
   const int64_t parts = B <= cap ? 1 : (B + cap - 1) / cap;
   const int64_t sb = ((B < 1 ? 1 : B) + parts - 1) / parts;
   return (sb + 127) / 128 * 128;
@@ -256,7 +248,7 @@ static bool tc_grouped_ok(const MrModel& m, int64_t B, int group) {
   const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
   if (d_u % 128 || d_i % 128 || d_u > 256 || d_i > 256) return false;
   if (B % group) return false;
-  const int64_t cap = sub_batch_cap("MR_TC_SUB_BATCH_ROWS", (int64_t)1 << 21);
+  const int64_t cap = kTcSubBatchCap;
   const int64_t parts = B <= cap ? 1 : (B + cap - 1) / cap;
   if (parts > 1 && (tc_sub_batch(B) % group)) return false;  // sub-batch boundaries must not split a group
   return true;
@@ -298,13 +290,6 @@ static TcWs carve_tc(const MrModel& m, bool train, int64_t B, void* ws) {
   return t;
 }
 
-// Train step without H1 in memory (experiment, MR_TRAIN_NO_H1=1): the second layer's forward producers AND the
-// producers of its weight gradient recompute relu(Pi[item] + Pu[user]) from the L2-resident projections.
-static bool train_without_h1() {
-  static const bool on = getenv("MR_TRAIN_NO_H1") != nullptr;
-  return on;
-}
-
 // Forward of rows [r0, r1) on the tensor cores; leaves H[1..n-1] of the sub-batch in the workspace.
 static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users, const int32_t* items, int user_div,
                            int64_t r0, int64_t r1, cudaStream_t st, int group = 0, bool users_per_group = false,
@@ -315,13 +300,10 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
     // grouped batch: Zu = E_user[user of the group] . W1[user rows] + b1 once per group, then
     // H1 = relu(E_item[item] . W1[item rows] + Zu[row / group]) per row
     const int d_i = m.L[0] - d_u;
-    // the producers of the second layer compute the projected first layer; in the ranking eval H1 then never exists
-    // in memory, in the train step they also write it (and its ReLU bits) for the backward pass
+    // ranking eval: the producers of the second layer compute the projected first layer, H1 never exists in memory;
+    // the (unfused) train step keeps the separate gather kernel, which also writes the ReLU bits of H1
     const bool train_rows = t.bits[1] != nullptr;
-    // (train step: measured 0.08 ms SLOWER than the separate gather kernel -- the extra 64-byte stores land on the
-    // pipe that bounds the layer kernel -- so there it is opt-in, MR_PROJ_PRODUCER_TRAIN=1, and covered by a test)
-    const bool fuse_h1 = t.Pi != nullptr && m.n_layers >= 3 && getenv("MR_NO_PROJ_PRODUCER") == nullptr &&
-                         (!train_rows || getenv("MR_PROJ_PRODUCER_TRAIN") != nullptr || train_without_h1());
+    const bool fuse_h1 = t.Pi != nullptr && m.n_layers >= 3 && !train_rows;
     proj_in_producer = fuse_h1;
     if (fuse_h1 && t.Pu != nullptr) {
     } else if (t.Pu != nullptr) {  // user- and item-projected first layer: H1 = relu(Pi[item] + Pu[user])
@@ -412,10 +394,6 @@ static int tc_forward_rows(const MrModel& m, const TcWs& t, const int32_t* users
         a.proj_u = t.Pu;
         a.proj_ids = users;
         a.proj_u_rows = m.num_users;
-      }
-      if (t.bits[1] != nullptr) {  // training: the ReLU bits for the backward layer; H1 itself only if someone reads it
-        a.h1_out = train_without_h1() ? nullptr : t.H[1];
-        a.h1_bits = t.bits[1];
       }
     }
     if (head_dot && l == m.n_layers - 1) {  // H[l] then holds one float per row: relu(.) . w_out[MLP columns]
@@ -550,7 +528,7 @@ static int64_t eval_sub_batch(int group) {
   int64_t a = 128, b = group;
   while (b) { const int64_t t = a % b; a = b; b = t; }
   const int64_t l = (int64_t)128 / a * group;  // lcm(128, group)
-  static const int64_t cap = sub_batch_cap("MR_EVAL_SUB_BATCH_ROWS", (int64_t)1 << 22);
+  const int64_t cap = kEvalSubBatchCap;
   return l > cap ? 0 : cap / l * l;
 }
 
@@ -778,10 +756,8 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   const bool uproj = proj && user_proj_ok(m, B, group);
   const int64_t n_user_rows = grouped ? B / group : B;  // staged user-gradient rows: one per group or one per row
   // stable sorts of the ids (keys of the segmented reductions below) on the side stream, under the tower
-  // (phase timing then sees only the launch cost of this block on the main stream; MR_NO_SIDE_STREAM=1 keeps
-  // everything on the caller's stream, for diagnostics)
-  static const bool no_side = getenv("MR_NO_SIDE_STREAM") != nullptr;
-  SideStream* side = no_side ? nullptr : side_stream();
+  // (phase timing then sees only the launch cost of this block on the main stream)
+  SideStream* side = side_stream();
   {
     cudaStream_t ss = st;
     if (side != nullptr) {
@@ -849,8 +825,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     }
     // The per-row work of the projected step in ONE kernel (tc_fused.cu): H1, the second layer forward, the head,
     // the second layer's weight gradient and backward, the staged rows and their group sums never leave the SM.
-    static const bool no_fused = getenv("MR_NO_FUSED_TRAIN") != nullptr;
-    const bool fused = uproj && !no_fused && fused_train_supported(m, group);
+    const bool fused = uproj && m.fused_train != MR_FUSED_OFF && fused_train_supported(m, group);
     int fused_grid = 0;
     if (fused) {
       prof_mark(MR_PHASE_FUSED_TILE, st);
@@ -1022,17 +997,6 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
         w.dw_partial = t.dense_partial + (m.W[l] - m.dense);
         w.db_partial = t.dense_partial + (m.b[l] - m.dense);
         w.partial_stride = t.dense_stride;
-        if (proj && l == 2 && train_without_h1() && getenv("MR_NO_PROJ_PRODUCER") == nullptr) {
-          w.a_dense = nullptr;  // H1 was never stored: recomputed from the projections
-          w.proj_i = tw.Pi;
-          w.proj_u = tw.Zu;
-          w.proj_div = group;
-          if (tw.Pu != nullptr) {
-            w.proj_u = tw.Pu;
-            w.proj_ids = users;
-            w.proj_u_rows = m.num_users;
-          }
-        }
         rc = launch_tc_wgrad(w, st);
         if (rc != MR_OK) return rc;
         prof_mark(MR_PHASE_TC_DENSE_BWD, st);
@@ -1395,35 +1359,10 @@ int mr_sample_negatives(const int64_t* csr_rowptr, const int32_t* csr_items, int
   return rc;
 }
 
-int mr_tc_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
-                        int32_t three_x, void* stream) {
-  MR_REQUIRE(A && B && D, "tc selftest: NULL pointer");
-  return launch_tc_selftest(A, B, D, N, K, a_mn, b_mn, three_x, (cudaStream_t)stream);
-}
-
-int mr_bf16x3_gemm_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
-                            void* stream) {
-  MR_REQUIRE(A && B && D, "bf16x3 selftest: NULL pointer");
-  return launch_bf16x3_selftest(A, B, D, N, K, a_mn, b_mn, (cudaStream_t)stream);
-}
-
-int mr_tc_probe(const float* raw_a, int32_t n_words, int32_t start_off, int32_t lbo, int32_t sbo, int32_t a_mn, float* D,
-                void* stream) {
-  MR_REQUIRE(raw_a && D, "tc probe: NULL pointer");
-  return launch_tc_probe(raw_a, n_words, start_off, lbo, sbo, a_mn, D, (cudaStream_t)stream);
-}
-
 int mr_users_grouped(const int32_t* users, int64_t n, int32_t group, int32_t* flag, void* stream) {
   MR_REQUIRE(users != nullptr && flag != nullptr, "users_grouped: NULL pointer");
   MR_REQUIRE(n >= 0 && group >= 1, "users_grouped: bad sizes");
   return launch_check_grouped(users, n, group, flag, (cudaStream_t)stream);
-}
-
-int mr_tc_rate(int32_t N, int32_t iters, int32_t nbuf, int32_t flags, int32_t writers, int32_t write_iters,
-               int64_t* out_cycles, int32_t grid, void* stream) {
-  MR_REQUIRE(out_cycles != nullptr, "tc_rate: NULL output");
-  return launch_tc_rate(N, iters, nbuf, flags, writers, write_iters, reinterpret_cast<long long*>(out_cycles), grid,
-                        (cudaStream_t)stream);
 }
 
 size_t mr_sparse_rows_workspace_bytes(int64_t n, int32_t d0, int32_t d1) {
@@ -1472,18 +1411,6 @@ int mr_sparse_rows_update(float* table0, float* m0, float* v0, int32_t d0, float
   rc = launch_segreduce(skeys, sidx, n, grad_rows, u, seg_ws, seg_bytes, st);
   prof_mark(-1, st);
   return rc;
-}
-
-int mr_set_compute_path(int32_t path) {
-  MR_REQUIRE(path >= 0 && path <= 2, "compute path must be 0 (auto), 1 (SIMT) or 2 (tensor cores)");
-  g_path = path;
-  return MR_OK;
-}
-
-int mr_set_item_projection(int32_t mode) {
-  MR_REQUIRE(mode >= 0 && mode <= 2, "item projection mode must be 0 (auto), 1 (off) or 2 (on where eligible)");
-  g_item_proj = mode;
-  return MR_OK;
 }
 
 int mr_uses_item_projection(const MrModel* model, int64_t rows) {

@@ -3,8 +3,8 @@
 //   D[128 x N] = A . B^T   with A = [128 x K] (K-major) or given as [K x 128] (MN-major),
 //                               B = [N x K]   (K-major) or given as [K x N]   (MN-major),
 // fp32 in/out, computed as 3xTF32 (three_x = 1) or plain TF32 (three_x = 0).
-#include "launchers.h"
-#include "tc_common.cuh"
+#include "../launchers.h"
+#include "../tc_common.cuh"
 
 namespace mr {
 

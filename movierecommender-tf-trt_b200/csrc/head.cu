@@ -7,8 +7,6 @@
 // One warp per row, lanes across columns (every row is read with coalesced 128-byte requests).
 // Algorithmic bytes per row: 4*L_last (h) + 8*f (GMF rows) + 12 (ids, label) read,
 // 4*L_last + 8*f + 8 written.
-#include <stdlib.h>
-
 #include "launchers.h"
 
 namespace mr {
@@ -580,128 +578,6 @@ __global__ void __launch_bounds__(kHeadThreads, 2) head_rank_kernel(const HeadPa
   }
 }
 
-// The same fused score + position kernel, specialised (mf_dim = 32 * FQ, last width = 32 * HQ compile-time) and
-// software-pipelined like head_group_kernel: a warp scores its candidates of a group in two halves of up to KH
-// rows; while one half is reduced the other half's rows -- and, across the group boundary, the next group's first
-// half, ids and user row -- are already in flight.  Requires ceil(group / 8) <= 2 * KH.
-// HQ == 0: p.h_last holds one float per row, the last hidden layer already dotted with its output-unit weights by
-// the layer's own epilogue (tc_dense EPI_HEAD_DOT); only the GMF rows are read here.
-template <int FQ, int HQ, int KH>
-__global__ void __launch_bounds__(kHeadThreads, 2) head_rank_pipe_kernel(const HeadParams p, int group,
-                                                                         int32_t* __restrict__ pos,
-                                                                         float* __restrict__ probs) {
-  constexpr int f = 32 * FQ, Ln = 32 * HQ;
-  constexpr int HA = HQ > 0 ? HQ : 1;  // array extent (HQ == 0: slot 0 carries the row's partial logit)
-  constexpr int kWarps = kHeadThreads / 32;
-  __shared__ float sc[kHeadThreads];
-  const MrModel& m = p.m;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float wg[FQ], wh[HA];
-#pragma unroll
-  for (int q = 0; q < FQ; ++q) wg[q] = __ldg(m.w_out + lane + 32 * q);
-#pragma unroll
-  for (int q = 0; q < HQ; ++q) wh[q] = __ldg(m.w_out + f + lane + 32 * q);
-  const float b_out = __ldg(m.b_out);
-  const int64_t ngroups = p.rows / group;
-  const int per_warp = (group + kWarps - 1) / kWarps;  // candidate j = warp + kWarps * i, i < per_warp
-
-  struct Half {
-    float gi[KH][FQ], h[KH][HA];
-    unsigned bad;  // bit rr: out-of-range item id
-  };
-  // ids of this warp's candidates of group g, lane-distributed (lane i: candidate warp + kWarps * i), and the user
-  auto load_ids = [&](int64_t g, int& idreg, int& u) {
-    const int64_t gg = p.row0 / group + g;
-    const int j = warp + kWarps * lane;
-    idreg = (lane < per_warp && j < group) ? __ldg(p.items + p.row0 + g * group + j) : 0;
-    u = __ldg(p.users + gg);
-  };
-  auto load_half = [&](int64_t g, int half, int idreg, Half& r) {
-    r.bad = 0;
-#pragma unroll
-    for (int rr = 0; rr < KH; ++rr) {
-      const int i = half * KH + rr;
-      int j = warp + kWarps * i;
-      const bool live = i < per_warp && j < group;
-      if (!live) j = group - 1;  // dead slots re-read the positive's row (loads stay unconditional)
-      int it = __shfl_sync(0xffffffffu, idreg, i & 31);
-      if ((unsigned)it >= (unsigned)m.num_items) {
-        if (live) r.bad |= 1u << rr;
-        it = 0;
-      }
-      const float* grow = m.item_gmf + (size_t)it * f;
-      const float* hrow = p.h_last + (size_t)(g * group + j) * (HQ > 0 ? Ln : 1);
-#pragma unroll
-      for (int q = 0; q < FQ; ++q) r.gi[rr][q] = __ldg(grow + lane + 32 * q);
-#pragma unroll
-      for (int q = 0; q < HQ; ++q) r.h[rr][q] = __ldg(hrow + lane + 32 * q);
-      if (HQ == 0) r.h[rr][0] = __ldg(hrow);
-    }
-  };
-  auto score_half = [&](int64_t g, int half, const Half& r, const float (&gu)[FQ], bool bad_u) {
-#pragma unroll
-    for (int rr = 0; rr < KH; ++rr) {
-      const int i = half * KH + rr;
-      const int j = warp + kWarps * i;
-      if (!(i < per_warp && j < group)) continue;  // warp-uniform
-      float s = 0.f;
-#pragma unroll
-      for (int q = 0; q < FQ; ++q) s = fmaf(wg[q], gu[q] * r.gi[rr][q], s);
-#pragma unroll
-      for (int q = 0; q < HQ; ++q) s = fmaf(wh[q], r.h[rr][q], s);
-      s = warp_sum(s);
-      if (HQ == 0) s += r.h[rr][0];
-      const bool bad = bad_u || ((r.bad >> rr) & 1u);
-      const float pr = bad ? nanf("") : sigmoidf_stable(s + b_out);
-      if (lane == 0) {
-        sc[j] = pr;
-        if (probs != nullptr) probs[p.row0 + g * group + j] = pr;
-        if (bad) atomicOr(p.flags, 1);
-      }
-    }
-  };
-  auto load_gu = [&](int u, float (&gu)[FQ], bool& bad_u) {
-    bad_u = (unsigned)u >= (unsigned)m.num_users;
-    const int uu = bad_u ? 0 : u;
-#pragma unroll
-    for (int q = 0; q < FQ; ++q) gu[q] = __ldg(m.user_gmf + (size_t)uu * f + lane + 32 * q);
-  };
-
-  Half ha, hb;
-  int id_cur = 0, u_cur = 0, id_nxt = 0, u_nxt = 0;
-  float gu_cur[FQ], gu_nxt[FQ];
-  bool badu_cur = false, badu_nxt = false;
-  int64_t g = blockIdx.x;
-  if (g < ngroups) {
-    load_ids(g, id_cur, u_cur);
-    load_gu(u_cur, gu_cur, badu_cur);
-    load_half(g, 0, id_cur, ha);
-  }
-  for (; g < ngroups; g += gridDim.x) {
-    const int64_t gn = g + gridDim.x;
-    const bool more = gn < ngroups;
-    if (more) load_ids(gn, id_nxt, u_nxt);
-    load_half(g, 1, id_cur, hb);
-    score_half(g, 0, ha, gu_cur, badu_cur);
-    if (more) {  // the next group's user row and first half: their ids arrived while the first half was reduced
-      load_gu(u_nxt, gu_nxt, badu_nxt);
-      load_half(gn, 0, id_nxt, ha);
-    }
-    score_half(g, 1, hb, gu_cur, badu_cur);
-    __syncthreads();
-    const float key_pos = rank_key(sc[group - 1]);
-    const int j = threadIdx.x;
-    const int above = (j < group - 1) && (rank_key(sc[j]) >= key_pos);  // a negative that ties ranks first
-    const int cnt = __syncthreads_count(above);
-    if (threadIdx.x == 0) pos[p.row0 / group + g] = cnt;
-    id_cur = id_nxt;
-    u_cur = u_nxt;
-    badu_cur = badu_nxt;
-#pragma unroll
-    for (int q = 0; q < FQ; ++q) gu_cur[q] = gu_nxt[q];
-  }
-}
-
 // Score + position with ONE WARP PER GROUP, for the partial-logit form (p.h_last = one float per row: the last
 // hidden layer already dotted with its output-unit weights by tc_dense EPI_HEAD_DOT).  What is left per candidate
 // is the GMF term, a dot product of f = 32 * NV floats: eight lanes take one row (NV 128-bit loads each, 128
@@ -854,13 +730,12 @@ int launch_head(const HeadArgs& a, cudaStream_t st) {
       return MR_ERR_INVALID;
     }
     const bool wide = ncols > 128;  // only the specialisation covers these
-    const bool special = a.labels != nullptr && head_special_widths(m) && (wide || getenv("MR_HEAD_GENERIC") == nullptr);
+    const bool special = a.labels != nullptr && head_special_widths(m);
     const uintptr_t al = reinterpret_cast<uintptr_t>(m.user_gmf) | reinterpret_cast<uintptr_t>(m.item_gmf) |
                          reinterpret_cast<uintptr_t>(m.w_out) | reinterpret_cast<uintptr_t>(a.h_last) |
                          reinterpret_cast<uintptr_t>(a.dz_last) | reinterpret_cast<uintptr_t>(a.stage_u) |
                          reinterpret_cast<uintptr_t>(a.stage_i);
-    if (special && m.mf_dim == 64 && a.group <= 5 && (al & 15) == 0 && (m.L[0] / 2) % 4 == 0 &&
-        getenv("MR_HEAD_PIPE") == nullptr) {  // eight lanes per row (BASELINE configs[2])
+    if (special && m.mf_dim == 64 && a.group <= 5 && (al & 15) == 0 && (m.L[0] / 2) % 4 == 0) {  // eight lanes per row
       const int64_t want = (a.rows / a.group + 15) / 16;  // 16 groups per CTA iteration
       const unsigned qgrid = (unsigned)(want < grid ? want : grid);
       switch (a.group) {
@@ -910,13 +785,9 @@ int launch_head(const HeadArgs& a, cudaStream_t st) {
 
 bool head_rank_supported(const MrModel& m) { return m.mf_dim + m.L[m.n_layers - 1] <= 128; }
 
-static bool head_rank_pipe_ok(const MrModel& m, int group) {
-  return m.mf_dim == 64 && m.L[m.n_layers - 1] == 64 && (group + 7) / 8 <= 14 && getenv("MR_HEAD_GENERIC") == nullptr;
-}
-
 bool head_rank_takes_dot(const MrModel& m, int group) {
   const bool widths = m.mf_dim == 32 || m.mf_dim == 64 || m.mf_dim == 128;  // head_rank_warp_kernel<1 | 2 | 4>
-  return widths && group >= 2 && group <= 256 && getenv("MR_NO_HEAD_DOT") == nullptr &&
+  return widths && group >= 2 && group <= 256 &&
          (reinterpret_cast<uintptr_t>(m.user_gmf) | reinterpret_cast<uintptr_t>(m.item_gmf) |
           reinterpret_cast<uintptr_t>(m.w_out)) % 16 == 0;
 }
@@ -949,18 +820,15 @@ int launch_head_rank(const HeadArgs& a, int group, int32_t* pos, float* probs, c
     const int64_t wcap = (int64_t)sm_count() * 8;
     const int64_t want = (ngroups + kHeadThreads / 32 - 1) / (kHeadThreads / 32);
     const unsigned wgrid = (unsigned)(want < wcap ? want : wcap);
-    if (m.mf_dim == 64 && head_rank_pipe_ok(m, group) && getenv("MR_HEAD_RANK_PIPE") != nullptr)  // diagnostics (A/B)
-      head_rank_pipe_kernel<2, 0, 7><<<grid, kHeadThreads, 0, st>>>(p, group, pos, probs);
-    else if (m.mf_dim == 32)
+    if (m.mf_dim == 32)
       head_rank_warp_kernel<1><<<wgrid, kHeadThreads, 0, st>>>(p, group, pos, probs);
     else if (m.mf_dim == 64)
       head_rank_warp_kernel<2><<<wgrid, kHeadThreads, 0, st>>>(p, group, pos, probs);
     else
       head_rank_warp_kernel<4><<<wgrid, kHeadThreads, 0, st>>>(p, group, pos, probs);
-  } else if (head_rank_pipe_ok(m, group))
-    head_rank_pipe_kernel<2, 2, 7><<<grid, kHeadThreads, 0, st>>>(p, group, pos, probs);
-  else
+  } else {
     head_rank_kernel<4><<<grid, kHeadThreads, 0, st>>>(p, group, pos, probs);
+  }
   MR_LAUNCH_CHECK("head_rank_kernel");
   return MR_OK;
 }

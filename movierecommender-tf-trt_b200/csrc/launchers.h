@@ -84,8 +84,6 @@ struct TcDenseArgs {
   int32_t proj_div;
   const int32_t* proj_ids;  // optional: row r reads proj_u[proj_ids[row0 + r]] (proj_u_rows rows) instead of r / proj_div
   int32_t proj_u_rows;
-  float* h1_out;            // optional (training): the A rows [rows x K] and their ReLU bits [rows x K/32]
-  uint32_t* h1_bits;
   const float* user_tab;
   const float* item_tab;
   const int32_t* users;
@@ -122,10 +120,6 @@ struct TcWgradArgs {
   const int32_t* items;
   int32_t num_users, num_items, d_u;
   int32_t user_mul;       // gather: user rows read users[(row0 + r) * user_mul]; d_u = 0 / Fa selects one table
-  const float* proj_i;    // A row r = relu(proj_i[items[row0 + r]] + proj_u[...]): the projected first layer recomputed
-  const float* proj_u;    // by the producers (Fa = 128); user-side row = proj_ids[row0 + r] (proj_u_rows rows) or r / proj_div
-  const int32_t* proj_ids;
-  int32_t proj_u_rows, proj_div;
   const float* z;         // [rows x Fb] launch-local rows
   int32_t Fa, Fb;
   int64_t rows, row0;

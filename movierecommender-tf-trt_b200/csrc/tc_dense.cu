@@ -26,8 +26,6 @@
 //   warp 13    L2 prefetch of the A rows two tiles ahead
 // Stages are recycled with mbarriers: full[s] (8 producer arrivals + the bulk copy's bytes),
 // empty[s] (tcgen05.commit), acc_full/acc_empty per TMEM buffer.
-#include <stdlib.h>
-
 #include "launchers.h"
 #include "tc_common.cuh"
 
@@ -66,8 +64,6 @@ struct TcDenseParams {
   int32_t proj_div;      //          with proj_ids: [proj_u_rows x K], row r reads row proj_ids[row0 + r]
   const int32_t* proj_ids;
   int32_t proj_u_rows;
-  float* h1_out;         // (A_PROJ, optional) [rows x K] launch-local rows: the A rows, for the backward pass
-  uint32_t* h1_bits;     // (A_PROJ, optional) [rows x K/32] their ReLU bits
   const float* user_tab; // (A_GATHER) user rows of width d_u, item rows of width K - d_u
   const float* item_tab;
   const int32_t* users;
@@ -92,7 +88,6 @@ struct TcDenseParams {
   float* stage_i;
   int32_t su, si;
   int32_t stages;        // pipeline depth
-  int32_t debug;         // MR_TC_DEBUG (diagnostics only): 1 = skip weight copies after the first pass, 2 = skip A loads
 };
 
 template <int AMODE, int EPI, int NPROD = 8, int NEPI = 4>
@@ -207,7 +202,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
         for (int h = 0; h < 2; ++h) {
           const int col = col0 + 4 * (4 * h + csub);
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok[g] && !(p.debug & 2)) {
+          if (ok[g]) {
             if (AMODE == A_GATHER) v = (col < p.d_u) ? ldg4(src_u[g] + col) : ldg4(src_i[g] + (col - p.d_u));
             else if (AMODE == A_DENSE || src_u[g] != nullptr) v = ldg4(src_u[g] + col);  // A_PROJ: the user-side row
           }
@@ -227,7 +222,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
         }
       }
     };
-    auto store_chunk = [&](bool first_pass, const float4(&x)[2 * RG]) {
+    auto store_chunk = [&](const float4(&x)[2 * RG]) {
       const int c = st_c;
       const int stage = st_stage;
       const uint32_t phase = st_phase;
@@ -238,14 +233,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       tc::mbar_wait(&empty_bar[stage], phase ^ 1);
       uint8_t* st = smem + (size_t)stage * stage_bytes;
       if (pw == 0 && lane == 0) {
-        if ((p.debug & 1) && !first_pass) {
-          tc::mbar_arrive(&full_bar[stage]);
-        } else {
-          tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * b_bytes);
-          tc::bulk_g2s(st + 2 * a_bytes, p.b_packed + (size_t)c * 2 * N * kTcKC, 2 * b_bytes, &full_bar[stage]);
-        }
+        tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * b_bytes);
+        tc::bulk_g2s(st + 2 * a_bytes, p.b_packed + (size_t)c * 2 * N * kTcKC, 2 * b_bytes, &full_bar[stage]);
       }
-      if (!(p.debug & 4))
 #pragma unroll
       for (int g = 0; g < RG; ++g) {
         const int r = 8 * RG * pw + 8 * g + rsub;
@@ -259,7 +249,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
           *reinterpret_cast<float4*>(st + a_bytes + off) = lo;
         }
       }
-      if (!(p.debug & 16)) tc::fence_proxy_async();
+      tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&full_bar[stage]);
     };
@@ -281,28 +271,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
           buf[0][e].z = fmaxf(buf[0][e].z + buf[NB - 1][e].z, 0.f);
           buf[0][e].w = fmaxf(buf[0][e].w + buf[NB - 1][e].w, 0.f);
         }
-        if (p.h1_out != nullptr || p.h1_bits != nullptr) {
-          // training: the backward pass wants these rows (A of the weight gradient) and their ReLU bits.  A row's 32
-          // columns of the chunk sit in four lanes (csub) x two pieces (h): 64-byte stores, bits OR-ed over the lanes
-          const int64_t trow0 = (blockIdx.x + cached_tile * gridDim.x) * kTcTileRows;
-#pragma unroll
-          for (int g = 0; g < RG; ++g) {
-            const int64_t lr = trow0 + 8 * RG * pw + 8 * g + rsub;
-            uint32_t w = 0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float4 v = buf[0][2 * g + h];
-              if (ok[g] && p.h1_out != nullptr)
-                *reinterpret_cast<float4*>(p.h1_out + (size_t)lr * K + c * kTcKC + 4 * (4 * h + csub)) = v;
-              const uint32_t nib = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
-              w |= nib << (4 * (4 * h + csub));
-            }
-            w |= __shfl_xor_sync(0xffffffffu, w, 8);
-            w |= __shfl_xor_sync(0xffffffffu, w, 16);
-            if (csub == 0 && ok[g] && p.h1_bits != nullptr) p.h1_bits[(size_t)lr * (K >> 5) + c] = w;
-          }
-        }
-        store_chunk(i * G < S, buf[0]);
+        store_chunk(buf[0]);
       }
     } else {
 #pragma unroll
@@ -314,7 +283,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
         const int64_t i = i0 + j;
         if (i < mine) {
           if (i + D < mine) issue_loads(buf[(j + D) % NB]);
-          store_chunk(i * G < S, buf[j]);
+          store_chunk(buf[j]);
         }
       }
     }
@@ -362,7 +331,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
     // The producers keep one chunk per group in flight in registers (32 KB per SM), which covers L2 latency
     // but not DRAM latency at full bandwidth.  This warp pulls the A rows of the tile kTcPrefetchAhead tiles
     // ahead of the MMA issuer into L2 (prefetch.global.L2 holds no registers), so the producers' loads hit L2.
-    if (!(p.debug & 128) && AMODE != A_PROJ) {  // (A_PROJ reads L2-resident projections)
+    if (AMODE != A_PROJ) {  // (A_PROJ reads L2-resident projections)
       int64_t it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         while (it >= (int64_t)*reinterpret_cast<volatile int*>(&tiles_started) + kTcPrefetchAhead) __nanosleep(256);
@@ -417,7 +386,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
       // fully unrolled over the (at most 8) 32-column blocks so that mbits[] is indexed at compile time: with a
       // run-time index the array lived in local memory and ncu showed the epilogue warps of the backward layers,
       // which bound that kernel, waiting on those loads for a third of their time
-      const int ncols_epi = (p.debug & 32) ? 0 : N;
+      const int ncols_epi = N;
 #pragma unroll
       for (int cb = 0; cb < 8; ++cb) {
         const int c0 = 32 * cb;
@@ -473,7 +442,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_dense_kernel(const TcDensePa
           *reinterpret_cast<float4*>(tile_s + lane * kEpiLd + 4 * q) =
               make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
-        if (!(p.debug & 8)) {
+        {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int idx = lane + 32 * j, r = idx >> 3, c = c0 + 4 * (idx & 7);
@@ -540,10 +509,6 @@ static int launch_dense_t(TcDenseParams p, cudaStream_t st) {
     return MR_ERR_INVALID;
   }
   p.stages = stages;
-  {
-    const char* dbg = getenv("MR_TC_DEBUG");
-    p.debug = dbg ? atoi(dbg) : 0;
-  }
   const size_t smem = sb * stages + epi_bytes;
   auto kern = tc_dense_kernel<AMODE, EPI, NPROD, NEPI>;
   MR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -573,8 +538,6 @@ int launch_tc_dense(const TcDenseArgs& a, cudaStream_t st) {
   p.proj_div = a.proj_div < 1 ? 1 : a.proj_div;
   p.proj_ids = a.proj_ids;
   p.proj_u_rows = a.proj_u_rows;
-  p.h1_out = a.h1_out;
-  p.h1_bits = a.h1_bits;
   p.addend = a.addend;
   p.addend_div = a.addend_div < 1 ? 1 : a.addend_div;
   p.relu = a.linear ? 0 : 1;
@@ -608,16 +571,10 @@ int launch_tc_dense(const TcDenseArgs& a, cudaStream_t st) {
     return MR_ERR_INVALID;
   }
   switch (a.epilogue) {
-    case TC_EPI_BIAS_RELU: {
-      static const bool eight = getenv("MR_TC_EPI8_FWD") != nullptr;  // experiment: N = 128 plain layers (Pi, Pu, dE = S . W^T)
-      if (eight && a.N >= 128) return launch_dense_t<A_DENSE, EPI_BIAS_RELU, 4, 8>(p, st);
-      return launch_dense_t<A_DENSE, EPI_BIAS_RELU>(p, st);
-    }
-    case TC_EPI_MASK: {
-      static const bool four = getenv("MR_TC_EPI4") != nullptr;  // diagnostics: the 8 + 4 warp shape everywhere
-      if (four || a.N < 64) return launch_dense_t<A_DENSE, EPI_MASK>(p, st);
+    case TC_EPI_BIAS_RELU: return launch_dense_t<A_DENSE, EPI_BIAS_RELU>(p, st);
+    case TC_EPI_MASK:  // epilogue-bound (K = 64, N = 128 in the ML-20M tower): 4 producer + 8 epilogue warps
+      if (a.N < 64) return launch_dense_t<A_DENSE, EPI_MASK>(p, st);
       return launch_dense_t<A_DENSE, EPI_MASK, 4, 8>(p, st);
-    }
     case TC_EPI_STAGE: return launch_dense_t<A_DENSE, EPI_STAGE>(p, st);
     case TC_EPI_HEAD_DOT:
       if (a.bias == nullptr || a.head_w == nullptr || a.out == nullptr) return MR_ERR_INVALID;

@@ -33,6 +33,7 @@
 //               group sums), thread = row = TMEM lane
 // Everything is single-buffered; the overlap is producers(t + 1) under backward + epilogue 2 of tile t.
 #include "launchers.h"
+#include "tc_bf16x3.cuh"
 #include "tc_common.cuh"
 
 namespace mr {
@@ -62,79 +63,14 @@ constexpr uint32_t oRedE = oRedG + 4096;                 // end of kernel: the e
 constexpr uint32_t kSmemBytes = oRedE + 4 * 160 * 4;
 
 // TMEM columns
-//   cFwd / cBwd: forward / backward accumulators of the tile; cWg: dW2, accumulated over all tiles of the CTA;
+//   cFwd / cBwd: forward / backward accumulators of the tile; cWg: dW2 of the tile.  The tensor core's fp32
+//   accumulation truncates: n chained MMAs leave ~n x 2^-24 of relative error (measured, tests/test_gpu_tc.py), so a
+//   chain over all of a CTA's tiles (3,500 MMAs at the ML-20M batch) would cost 4e-5 -- every tile's dW2 is
+//   therefore added to cWgSum by the epilogue-2 warps with ordinary round-to-nearest adds (48 MMAs per chain);
 //   cCs: per-lane column sums of dz * H2 (64 columns) and of dZ2 (64), accumulated over the tiles by the epilogue
 //   threads themselves (read-modify-write of their own lane: no shuffles per tile, one reduction at the end)
-constexpr uint32_t cFwd = 0, cWg = 64, cBwd = 128, cCs = 256, kTmemCols = 512;
-
-constexpr uint32_t kLayoutSw128 = 2;
-
-__device__ __forceinline__ uint32_t sw128_off(int row, int col) {  // col = bf16 element 0..63 of the panel row
-  return (uint32_t)(row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1)));
-}
-
-// d = {upper: bf16(hi_elem), lower: bf16(lo_elem)}
-__device__ __forceinline__ uint32_t cvt_bf16x2(float lo_elem, float hi_elem) {
-  uint32_t d;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
-  return d;
-}
-// two fp32 values -> three packed bf16 pairs (round to nearest at each level; the remainders are exact in fp32)
-__device__ __forceinline__ void split3(float x0, float x1, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
-  w1 = cvt_bf16x2(x0, x1);
-  const float r0 = x0 - __uint_as_float(w1 << 16), r1 = x1 - __uint_as_float(w1 & 0xffff0000u);
-  w2 = cvt_bf16x2(r0, r1);
-  const float s0 = r0 - __uint_as_float(w2 << 16), s1 = r1 - __uint_as_float(w2 & 0xffff0000u);
-  w3 = cvt_bf16x2(s0, s1);
-}
-
-__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// thread t of warp w gets 32 consecutive columns of TMEM lane 32 * (w % 4) + t
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
-      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
-      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
-      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
+//   cWgSum: dW2 summed over the tiles in fp32 registers (below)
+constexpr uint32_t cFwd = 0, cWg = 64, cBwd = 128, cCs = 256, cWgSum = 384, kTmemCols = 512;
 
 // Sum of v[c] over the 32 lanes for every c: lane l returns the total of column l.  31 shuffles, fixed order.
 __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
@@ -207,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
   constexpr int GSLOTS = (NT + kProdThreads - 1) / kProdThreads;
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t h1_full[2], fwd_done, gmf_ready, dz2_full, h1_free, bwd_done, e2_done, w2_bar;
+  __shared__ uint64_t h1_full[2], fwd_done, gmf_ready, dz2_full, h1_free, bwd_done, e2_done, wg_read, w2_bar;
   __shared__ uint32_t tmem_slot;
   // 1024-byte alignment of the operand tiles, computed in the shared window so that the compiler keeps treating
   // `smem` as shared memory (through a uintptr_t round trip every access became a generic LD / ST: ncu showed the
@@ -243,6 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
     tc::mbar_init(&h1_free, 1);
     tc::mbar_init(&bwd_done, 1);
     tc::mbar_init(&e2_done, 4);
+    tc::mbar_init(&wg_read, 4);
     tc::mbar_init(&w2_bar, 1);
     tc::mbar_init_fence();
   }
@@ -612,8 +549,12 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
         // weight gradient first (it frees H1 for the producers), then backward
         if (tc::elect_one()) {
           tc::mbar_wait(&dz2_full, ph);
-          // epilogue 2 of the previous tile has read its accumulator (and long since its ReLU bits)
-          if (it > 0) tc::mbar_wait(&e2_done, (uint32_t)((it - 1) & 1));
+          // epilogue 2 of the previous tile has read its accumulator (and long since its ReLU bits), and the previous
+          // tile's dW2 has been taken out of cWg
+          if (it > 0) {
+            tc::mbar_wait(&e2_done, (uint32_t)((it - 1) & 1));
+            tc::mbar_wait(&wg_read, (uint32_t)((it - 1) & 1));
+          }
           tc::fence_after_sync();
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
@@ -621,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
             for (int q = 0; q < 6; ++q) {
               const uint32_t a = s0 + oH1 + PA[q] * kH1Part + ks * 2048;
               const uint32_t b = s0 + oZ2 + PB[q] * kPanel + ks * 2048;
-              mma_bf16(tmem_base + cWg, dmn + (a >> 4), dmn + (b >> 4), id_wg, (it | ks | q) != 0);
+              mma_bf16(tmem_base + cWg, dmn + (a >> 4), dmn + (b >> 4), id_wg, (ks | q) != 0);
             }
           }
           tc::mma_commit(&h1_free);
@@ -641,26 +582,6 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
       FZ_T(4)
     }
     FZ_T_FLUSH(1, warp == kE1Warp0 && lane == 0)
-    // ---- end of the CTA's tiles: dW2 (TMEM lane = input unit) and the column sums
-    if (it > 0) {
-      tc::mbar_wait(&bwd_done, (uint32_t)((it - 1) & 1));  // every MMA of the CTA has completed
-      tc::fence_after_sync();
-      float* dst = p.partial + (size_t)blockIdx.x * p.partial_stride + p.off_w2 + (size_t)slot * kD2;
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
-        float v[32];
-        tmem_ld32(lane_addr + cWg + 32 * cb, v);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 o = *reinterpret_cast<float4*>(dst + 32 * cb + 4 * q);
-          o.x += v[4 * q];
-          o.y += v[4 * q + 1];
-          o.z += v[4 * q + 2];
-          o.w += v[4 * q + 3];
-          *reinterpret_cast<float4*>(dst + 32 * cb + 4 * q) = o;
-        }
-      }
-    }
     // this warp's column sums: the 32 lanes' TMEM accumulators folded once, fixed order; scratch = oRedE (per warp)
     float* red = reinterpret_cast<float*>(smem + oRedE) + (warp - kE1Warp0) * 160;
 #pragma unroll
@@ -683,11 +604,35 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
     const int slot = 32 * quarter + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * quarter) << 16);
     float* tile_s = reinterpret_cast<float*>(smem + oStage) + (size_t)(warp - kE2Warp0) * (32 * kEpiLd);
+    {  // zero this lane's (= input unit's) row of the dW2 sum
+      float zero[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) zero[i] = 0.f;
+      tmem_st32(lane_addr + cWgSum, zero);
+      tmem_st32(lane_addr + cWgSum + 32, zero);
+    }
     int64_t it = 0;
     FZ_T_DECL
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
       const int64_t row0 = tile * TR;
+      // this tile's dW2 out of the tensor core's accumulator as soon as its MMAs are done (h1_free), into the sum
+      tc::mbar_wait(&h1_free, ph);
+      tc::fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float w[32], acc[32];
+        tmem_ld32(lane_addr + cWg + 32 * c, w);
+        if (c == 1) {  // cWg is in registers: the next tile's weight-gradient MMAs may overwrite it
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&wg_read);
+        }
+        tmem_ld32(lane_addr + cWgSum + 32 * c, acc);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] += w[i];
+        tmem_st32(lane_addr + cWgSum + 32 * c, acc);
+      }
       tc::mbar_wait(&bwd_done, ph);
       tc::fence_after_sync();
       FZ_T(0)
@@ -731,6 +676,24 @@ __global__ void __launch_bounds__(kThreads, 1) neumf_fused_train_kernel(const Fu
       FZ_T(1)
     }
     FZ_T_FLUSH(2, warp == kE2Warp0 && lane == 0)
+    // ---- end of the CTA's tiles: dW2 (TMEM lane = input unit) into this CTA's partial row
+    if (it > 0) {
+      float* dst = p.partial + (size_t)blockIdx.x * p.partial_stride + p.off_w2 + (size_t)slot * kD2;
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        float v[32];
+        tmem_ld32(lane_addr + cWgSum + 32 * cb, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o = *reinterpret_cast<float4*>(dst + 32 * cb + 4 * q);
+          o.x += v[4 * q];
+          o.y += v[4 * q + 1];
+          o.z += v[4 * q + 2];
+          o.w += v[4 * q + 3];
+          *reinterpret_cast<float4*>(dst + 32 * cb + 4 * q) = o;
+        }
+      }
+    }
   }
 
   // ---- per-CTA sums into this CTA's partial row, fixed order ---------------------------------------------------
@@ -850,102 +813,5 @@ extern "C" int mr_fused_timing_read(long long* out_host) {
   return cudaMemcpyFromSymbol(out_host, fz::g_fused_timing, sizeof(long long) * 256 * 48) == cudaSuccess ? 0 : -1;
 }
 #endif
-
-// ---- single-tile GEMM on the same operand layout, descriptors and split (tests/test_gpu_tc.py) ----------------------
-//   D[128 x N] = A . B^T,  A = [128 x K] (K-major) or given as [K x 128] (MN-major), B = [N x K] or given as [K x N].
-namespace fz {
-__global__ void __launch_bounds__(128) bf16x3_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                                                              float* __restrict__ D, int N, int K, int a_mn, int b_mn) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t done_bar;
-  __shared__ uint32_t tmem_slot;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // operand image: row-major source [R x C] -> panels of 64 columns, each [R x 128 B] (R padded to 8)
-  const int Ra = a_mn ? K : 128, Ca = a_mn ? 128 : K;
-  const int Rb = b_mn ? K : N, Cb = b_mn ? N : K;
-  const uint32_t pa = (uint32_t)((Ra + 7) / 8 * 8) * 128, pb = (uint32_t)((Rb + 7) / 8 * 8) * 128;  // panel bytes
-  const uint32_t parta = pa * ((Ca + 63) / 64), partb = pb * ((Cb + 63) / 64);
-  uint8_t* a_img = smem;
-  uint8_t* b_img = smem + 3 * parta;
-  for (uint32_t e = tid; e < (3 * parta + 3 * partb) / 16; e += blockDim.x) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0u, 0u, 0u, 0u);
-  __syncthreads();
-  for (int e = tid; e < Ra * Ca / 2; e += blockDim.x) {
-    const int r = e / (Ca / 2), c = 2 * (e - r * (Ca / 2));
-    uint32_t w1, w2, w3;
-    split3(A[(size_t)r * Ca + c], A[(size_t)r * Ca + c + 1], w1, w2, w3);
-    const uint32_t off = (uint32_t)(c >> 6) * pa + sw128_off(r, c & 63);
-    *reinterpret_cast<uint32_t*>(a_img + off) = w1;
-    *reinterpret_cast<uint32_t*>(a_img + parta + off) = w2;
-    *reinterpret_cast<uint32_t*>(a_img + 2 * parta + off) = w3;
-  }
-  for (int e = tid; e < Rb * Cb / 2; e += blockDim.x) {
-    const int r = e / (Cb / 2), c = 2 * (e - r * (Cb / 2));
-    uint32_t w1, w2, w3;
-    split3(B[(size_t)r * Cb + c], B[(size_t)r * Cb + c + 1], w1, w2, w3);
-    const uint32_t off = (uint32_t)(c >> 6) * pb + sw128_off(r, c & 63);
-    *reinterpret_cast<uint32_t*>(b_img + off) = w1;
-    *reinterpret_cast<uint32_t*>(b_img + partb + off) = w2;
-    *reinterpret_cast<uint32_t*>(b_img + 2 * partb + off) = w3;
-  }
-  uint32_t ncols = 32;
-  while (ncols < (uint32_t)N) ncols <<= 1;
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, ncols);
-  if (tid == 0) {
-    tc::mbar_init(&done_bar, 1);
-    tc::mbar_init_fence();
-  }
-  tc::fence_proxy_async();
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem_base = tmem_slot;
-  if (tid == 0) {
-    const uint32_t idesc = idesc_bf16(128, N, a_mn, b_mn);
-    const uint64_t da = tc::smem_desc(0, a_mn ? pa : 16, 1024, kLayoutSw128);
-    const uint64_t db = tc::smem_desc(0, b_mn ? pb : 16, 1024, kLayoutSw128);
-    constexpr int PA[6] = {0, 0, 1, 0, 2, 1}, PB[6] = {0, 1, 0, 2, 0, 1};
-    for (int ks = 0; ks < K / 16; ++ks) {
-      const uint32_t ao = a_mn ? (uint32_t)ks * 2048 : (uint32_t)(ks >> 2) * pa + (ks & 3) * 32;
-      const uint32_t bo = b_mn ? (uint32_t)ks * 2048 : (uint32_t)(ks >> 2) * pb + (ks & 3) * 32;
-      for (int q = 0; q < 6; ++q) {
-        const uint32_t a = tc::smem_u32(a_img) + PA[q] * parta + ao;
-        const uint32_t b = tc::smem_u32(b_img) + PB[q] * partb + bo;
-        mma_bf16(tmem_base, da + (a >> 4), db + (b >> 4), idesc, (ks | q) != 0);
-      }
-    }
-    tc::mma_commit(&done_bar);
-  }
-  tc::mbar_wait(&done_bar, 0);
-  tc::fence_after_sync();
-  const int row = 32 * warp + lane;
-  for (int c0 = 0; c0 < N; c0 += 16) {
-    float v[16];
-    tc::tmem_ld16(tmem_base + ((uint32_t)(32 * warp) << 16) + c0, v);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) D[(size_t)row * N + c0 + i] = v[i];
-  }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base, ncols);
-}
-}  // namespace fz
-
-int launch_bf16x3_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn, int b_mn, cudaStream_t st) {
-  if (N % 16 || N < 16 || N > 256 || K % 16 || K < 16 || K > 256 || (b_mn && N % 64)) {
-    set_error("bf16x3 selftest: unsupported N=%d K=%d", N, K);
-    return MR_ERR_INVALID;
-  }
-  const int Ra = a_mn ? K : 128, Ca = a_mn ? 128 : K, Rb = b_mn ? K : N, Cb = b_mn ? N : K;
-  const size_t smem = 3 * ((size_t)((Ra + 7) / 8 * 8) * 128 * ((Ca + 63) / 64) + (size_t)((Rb + 7) / 8 * 8) * 128 * ((Cb + 63) / 64)) + 1024;
-  if (smem > 220 * 1024) {
-    set_error("bf16x3 selftest: operands too large");
-    return MR_ERR_INVALID;
-  }
-  MR_CUDA(cudaFuncSetAttribute(fz::bf16x3_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fz::bf16x3_selftest_kernel<<<1, 128, smem, st>>>(A, B, D, N, K, a_mn, b_mn);
-  MR_LAUNCH_CHECK("bf16x3_selftest_kernel");
-  return MR_OK;
-}
 
 }  // namespace mr

@@ -65,8 +65,14 @@ class NeuMFEngine(object):
 
     def __init__(self, num_users, num_items, layers_sizes, layers_l2reg, mf_dim=0, optimizer="adam",
                  lr=1e-3, beta_1=0.9, beta_2=0.999, table_mode="dense", device=None, seed=None,
-                 table_state=True):
+                 table_state=True, compute_path=None, item_projection=None, fused_train=None):
+        """compute_path: 'auto' | 'simt' | 'tc'; item_projection: 'auto' | 'off' | 'on'; fused_train: 'auto' | 'off'
+        (include/movierec_b200.h: MrModel.compute_path / item_projection / fused_train).  None = the module defaults
+        (`set_compute_path`, `set_item_projection`, `set_fused_train`), which start as 'auto'."""
         require_cuda()
+        self.compute_path = _PATHS[compute_path if compute_path is not None else _DEFAULTS["compute_path"]]
+        self.item_projection = _PROJECTIONS[item_projection if item_projection is not None else _DEFAULTS["item_projection"]]
+        self.fused_train = _FUSED[fused_train if fused_train is not None else _DEFAULTS["fused_train"]]
         self.device = torch.device(device if device is not None else "cuda:{}".format(torch.cuda.current_device()))
         self.num_users, self.num_items = int(num_users), int(num_items)
         self.L = [int(x) for x in layers_sizes]
@@ -226,6 +232,7 @@ class NeuMFEngine(object):
             m.L[i] = w
             m.l2[i] = self.l2[i]
         m.mf_dim = self.mf_dim
+        m.compute_path, m.item_projection, m.fused_train = self.compute_path, self.item_projection, self.fused_train
         self._model = m
 
         o = nat.MrOptState()
@@ -419,17 +426,34 @@ class NeuMFEngine(object):
         return pos, sums, rank, probs
 
 
+# Kernel selection is part of the model description handed to the library (MrModel), not library state.  These
+# module-level defaults only decide what an engine constructed WITHOUT explicit arguments asks for.
+_PATHS = {"auto": 0, "simt": 1, "tc": 2}
+_PROJECTIONS = {"auto": 0, "off": 1, "on": 2}
+_FUSED = {"auto": 0, "off": 1}
+_DEFAULTS = {"compute_path": "auto", "item_projection": "auto", "fused_train": "auto"}
+
+
 def set_compute_path(path):
-    """'auto' (tensor cores where the layer widths allow, else the SIMT kernel), 'simt' or 'tc'."""
-    code = {"auto": 0, "simt": 1, "tc": 2}[path]
-    nat.check(nat.lib.mr_set_compute_path(code), "mr_set_compute_path")
+    """Default for engines constructed from now on: 'auto' (tensor cores where the layer widths allow, else the SIMT
+    kernel), 'simt' or 'tc'."""
+    _PATHS[path]
+    _DEFAULTS["compute_path"] = path
 
 
 def set_item_projection(mode):
-    """Item half of the first layer once per item instead of once per row: 'auto' (when a call has at least twice
-    as many rows as there are items), 'off' or 'on' (wherever the model is eligible)."""
-    code = {"auto": 0, "off": 1, "on": 2}[mode]
-    nat.check(nat.lib.mr_set_item_projection(code), "mr_set_item_projection")
+    """Default for engines constructed from now on.  Item half of the first layer once per item instead of once per
+    row: 'auto' (when a call has at least twice as many rows as there are items), 'off' or 'on' (wherever the model is
+    eligible)."""
+    _PROJECTIONS[mode]
+    _DEFAULTS["item_projection"] = mode
+
+
+def set_fused_train(mode):
+    """Default for engines constructed from now on: 'auto' (the fused per-tile train kernel wherever it applies) or
+    'off' (the kernel-per-layer launch sequence)."""
+    _FUSED[mode]
+    _DEFAULTS["fused_train"] = mode
 
 
 def rank_scores(scores, group, k, label_col=None, want_rank=True, device=None, labels=None):

@@ -44,6 +44,7 @@ class MrModel(C.Structure):
         ("L", C.c_int32 * MR_MAX_LAYERS),
         ("mf_dim", C.c_int32),
         ("l2", C.c_float * MR_MAX_LAYERS),
+        ("compute_path", C.c_int32), ("item_projection", C.c_int32), ("fused_train", C.c_int32),
     ]
 
 
@@ -86,10 +87,6 @@ SIGNATURES = {
     "mr_sample_negatives": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i64, _i64, _i32, _u64, _u64, _vp, _vp, _vp, _vp]),
     "mr_sort_workspace_bytes": (_sz, [_i64]),
     "mr_sort_pairs": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
-    "mr_tc_probe": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
-    "mr_tc_gemm_selftest": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
-    "mr_bf16x3_gemm_selftest": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
-    "mr_tc_rate": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "mr_gather_rows_sharded": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _i64, _vp, _vp]),
     "mr_sparse_rows_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "mr_sparse_rows_update": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _i32, _f, _f, _f, _f,
@@ -100,9 +97,7 @@ SIGNATURES = {
     "mr_split_last_two": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "mr_user_csr_workspace_bytes": (C.c_size_t, [_i64]),
     "mr_build_user_csr": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "mr_set_compute_path": (C.c_int, [_i32]),
     "mr_uses_tensor_cores": (C.c_int, [_PM]),
-    "mr_set_item_projection": (C.c_int, [_i32]),
     "mr_uses_item_projection": (C.c_int, [_PM, _i64]),
     "mr_uses_user_projection": (C.c_int, [_PM, _i64, _i32]),
     "mr_profile_begin": (C.c_int, []),

@@ -168,21 +168,48 @@ class NeuMFModel(object):
         return {"loss": loss, OUTPUT_PRED + "_loss": out[0] / rows,
                 OUTPUT_PRED + "_" + HIT_RATE: out[1] / (rows // group), OUTPUT_PRED + "_" + DCG: out[2] / (rows // group)}
 
-    def train_on_batch(self, x, y):
-        """One optimisation step; returns [loss, output_loss, output_hr, output_dcg] like Keras."""
+    def train_on_batch(self, x, y, prefetch=None):
+        """One optimisation step; returns [loss, output_loss, output_hr, output_dcg] like Keras.
+
+        prefetch=([x_users, x_items], y) (optional, not in Keras): the NEXT batch.  Its host-to-device copies are
+        issued on a copy stream before this step's loss is read back, so they run under this step; the next call
+        finds them by the identity of the host arrays and skips its own upload.  Pinned host tensors make the
+        copies asynchronous."""
         x_users, x_items = x
         o = self._owner
         group = o._num_negs_per_pos + 1
         # the reference accepts any users per row; the once-per-group fast path is taken only when the batch
         # really has the generator's layout (checked on the device before the step: one tiny kernel)
         eng = self.engine
-        x_users = _engine_module().as_device_i32(x_users, eng.device)
-        grouped = eng.users_grouped(x_users, group)
-        out = eng.train_step(x_users, x_items, y, group=group, k=o._k, grouped=grouped).cpu().numpy().astype(np.float64)
+        mod = _engine_module()
+        rows = int(np.asarray(y).size if not hasattr(y, "numel") else y.numel())
+        staged = getattr(self, "_prefetched", None)
+        if staged is not None and staged[0] == (id(x_users), id(x_items), id(y)):
+            _, d_users, d_items, d_y, ready = staged
+            import torch
+            torch.cuda.current_stream(eng.device).wait_event(ready)
+        else:
+            d_users = mod.as_device_i32(x_users, eng.device)
+            d_items, d_y = x_items, y
+        self._prefetched = None
+        grouped = eng.users_grouped(d_users, group)
+        out_dev = eng.train_step(d_users, d_items, d_y, group=group, k=o._k, grouped=grouped)
+        if prefetch is not None:
+            import torch
+            (n_users, n_items), n_y = prefetch
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=eng.device)
+            with torch.cuda.stream(self._copy_stream):
+                staged = (mod.as_device_i32(n_users, eng.device), mod.as_device_i32(n_items, eng.device),
+                          mod.as_device_f32(n_y, eng.device))
+                ready = torch.cuda.Event()
+                ready.record(self._copy_stream)
+            self._prefetched = ((id(n_users), id(n_items), id(n_y)),) + staged + (ready,)
+        out = out_dev.cpu().numpy().astype(np.float64)
         if int(out[4]) & 1:
             raise IndexError("user/item id out of range in batch (num_users={}, num_items={})".format(
                 o._num_users, o._num_items))
-        logs = self._step_logs(out, int(np.asarray(y).size if not hasattr(y, "numel") else y.numel()), group)
+        logs = self._step_logs(out, rows, group)
         return [logs[n] for n in self.metrics_names]
 
     def test_on_batch(self, x, y):

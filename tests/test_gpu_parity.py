@@ -376,26 +376,27 @@ def test_grouped_and_ungrouped_steps_agree(eng_mod):
             rel_close(weights[True][0][k], weights[False][0][k], rtol=1e-4, what="{} grouped vs ungrouped {}".format(mode, k))
 
 
-def test_wgrad_ts_variant_matches_default(eng_mod, monkeypatch):
-    """MR_WGRAD_TS=1 selects the weight-gradient kernel whose A operand lives in tensor memory (tcgen05.st +
-    A-from-TMEM MMAs); it must produce the same dense gradients as the default shared-memory-operand kernel."""
-    nu, ni, L, f, negs = 900, 700, [256, 128, 64], 64, 4
-    rng = np.random.default_rng(23)
-    users, items, y = make_batch(rng, nu, ni, 777, negs)  # 3885 rows: ragged last chunk and tile
-    grads = {}
-    for ts in (False, True):
-        if ts:
-            monkeypatch.setenv("MR_WGRAD_TS", "1")
-        else:
-            monkeypatch.delenv("MR_WGRAD_TS", raising=False)
-        for grouped in (False, True):
-            eng = eng_mod.NeuMFEngine(nu, ni, L, [0, 0, 0], mf_dim=f, seed=8)
-            eng.train_grads(users, items, y, group=negs + 1, k=3, grouped=grouped)
-            grads[(ts, grouped)] = eng.g_dense.cpu().numpy().copy()
-    monkeypatch.delenv("MR_WGRAD_TS", raising=False)
-    w64 = None
-    for grouped in (False, True):
-        rel_close(grads[(True, grouped)], grads[(False, grouped)], rtol=4e-6, what="TS vs SS dense gradients, grouped={}".format(grouped))
+def test_fused_and_unfused_train_steps_agree(eng_mod):
+    """The fused per-tile kernel (tc_fused.cu) against the kernel-per-layer launch sequence it replaces: same batches,
+    three dense-Adam steps, Zipf-hot users and items, a ragged last tile."""
+    nu, ni, L, f, negs, groups = 700, 300, [256, 128, 64], 64, 4, 2077
+    runs = {}
+    for mode in ("auto", "off"):
+        rng = np.random.default_rng(29)
+        eng = eng_mod.NeuMFEngine(nu, ni, L, [0, 0, 0], mf_dim=f, table_mode="dense", optimizer="sgd", lr=0.5, seed=6,
+                                  fused_train=mode)
+        assert eng.uses_user_projection(groups * (negs + 1), negs + 1)
+        outs = []
+        for _ in range(3):
+            users = np.repeat(np.minimum(rng.zipf(1.3, groups) - 1, nu - 1), negs + 1)
+            items = np.minimum(rng.zipf(1.2, groups * (negs + 1)) - 1, ni - 1)
+            y = np.tile([0] * negs + [1], groups).astype(np.float32)
+            outs.append(eng.train_step(users, items, y, group=negs + 1, k=3, grouped=True).cpu().numpy())
+        runs[mode] = (eng.get_weights(), outs)
+    for a, b in zip(runs["auto"][1], runs["off"][1]):
+        assert abs(a[0] - b[0]) <= 1e-5 * abs(a[0]) and a[1] == b[1] and a[4] == 0 and b[4] == 0
+    for k in runs["auto"][0]:  # SGD at lr 0.5 over three steps: see test_grouped_and_ungrouped_steps_agree
+        rel_close(runs["auto"][0][k], runs["off"][0][k], rtol=1e-4, what="fused vs unfused " + k)
 
 
 def test_out_of_range_ids_are_flagged(eng_mod):
@@ -443,11 +444,8 @@ def test_item_projection_on_and_off_agree_and_are_deterministic(eng_mod, monkeyp
     nu, ni, L, f, negs, groups = 5000, 3000, [256, 128, 64], 64, 4, 6000
     runs = {}
     try:
-        # "producers": H1 and its ReLU bits written by the second layer's producers (opt-in variant of the train step)
-        for tag, selector in (("off", "off"), ("on", "auto"), ("again", "auto"), ("producers", "auto")):
+        for tag, selector in (("off", "off"), ("on", "auto"), ("again", "auto")):
             eng_mod.set_item_projection(selector)
-            if tag == "producers":
-                monkeypatch.setenv("MR_PROJ_PRODUCER_TRAIN", "1")
             rng = np.random.default_rng(23)
             eng = eng_mod.NeuMFEngine(nu, ni, L, [0, 0, 0], mf_dim=f, table_mode="dense", optimizer="sgd", lr=0.5, seed=6)
             assert eng.uses_item_projection(groups * (negs + 1)) == (selector != "off")
@@ -464,7 +462,6 @@ def test_item_projection_on_and_off_agree_and_are_deterministic(eng_mod, monkeyp
         assert abs(a[0] - b[0]) <= 1e-5 * abs(a[0]) and a[1] == b[1] and a[4] == 0 and b[4] == 0
     for k in runs["off"][0]:  # SGD at lr 0.5 over three steps: see test_grouped_and_ungrouped_steps_agree
         rel_close(runs["on"][0][k], runs["off"][0][k], rtol=1e-4, what="projected vs per-row " + k)
-        rel_close(runs["producers"][0][k], runs["on"][0][k], rtol=1e-5, what="H1 from the producers vs the gather kernel " + k)
         assert np.array_equal(runs["on"][0][k], runs["again"][0][k]), k
     for a, b in zip(runs["on"][1], runs["again"][1]):
         assert np.array_equal(a, b)
@@ -483,17 +480,10 @@ def test_item_projected_rank_eval_matches_oracle(eng_mod, monkeypatch):
     hr_o, dcg_o, pos_o, p_o = o.evaluate_groups(w, users, items, group, k)
     got = {}
     try:
-        # third pass: the last hidden layer written out and dotted by the score kernel (MR_NO_HEAD_DOT) instead of
-        # folded into the output unit's dot product by the layer's own epilogue
-        # fourth pass: H1 written by the gather kernel (MR_NO_PROJ_PRODUCER) instead of computed by the second layer's
-        # producers
-        for selector in ("auto", "off", "auto-nodot", "auto-noprod"):
-            eng_mod.set_item_projection(selector.split("-")[0])
-            if selector.endswith("nodot"):
-                monkeypatch.setenv("MR_NO_HEAD_DOT", "1")
-            if selector.endswith("noprod"):
-                monkeypatch.delenv("MR_NO_HEAD_DOT")
-                monkeypatch.setenv("MR_NO_PROJ_PRODUCER", "1")
+        for selector in ("auto", "off"):
+            eng_mod.set_item_projection(selector)
+            eng = eng_mod.NeuMFEngine(nu, ni, L, [0] * 3, mf_dim=f, seed=5)
+            assert eng.uses_item_projection(G * group) == (selector == "auto")
             # positions only: the fused sequence (a full permutation request takes the forward + rank kernels)
             pos, sums, _, probs = eng.rank_eval(users, items, group, k, want_probs=True)
             p = probs.cpu().numpy()
@@ -506,8 +496,6 @@ def test_item_projected_rank_eval_matches_oracle(eng_mod, monkeypatch):
     finally:
         eng_mod.set_item_projection("auto")
     rel_close(got["auto"], got["off"], what="eval probs projected vs per-row")
-    rel_close(got["auto"], got["auto-nodot"], what="eval probs, last layer folded into the dot vs written out")
-    rel_close(got["auto"], got["auto-noprod"], what="eval probs, H1 in the producers vs written out")
 
 
 @pytest.mark.parametrize("f,group,L", [(32, 7, [256, 128, 32]), (128, 100, [256, 128, 64]), (64, 256, [256, 128, 128, 64]),

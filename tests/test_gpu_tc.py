@@ -16,7 +16,7 @@ CASES = [
 
 
 def run_case(N, K, a_mn, b_mn, three_x, seed=0):
-    from movierec import _native as nat
+    from movierec import _diag as nat
     rng = np.random.default_rng(seed)
     A = rng.normal(size=(128, K)).astype(np.float32)
     B = rng.normal(size=(N, K)).astype(np.float32)
@@ -74,7 +74,7 @@ BF16_CASES = [
 def test_tc_gemm_bf16x3_is_fp32_accurate(case):
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
-    from movierec import _native as nat
+    from movierec import _diag as nat
     N, K, a_mn, b_mn = case
     rng = np.random.default_rng(7)
     A = (rng.normal(size=(128, K)) * np.exp(rng.normal(size=(128, K)) * 3)).astype(np.float32)  # wide dynamic range

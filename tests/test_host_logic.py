@@ -40,11 +40,20 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert nat.version() == int(re.search(r"#define MR_VERSION (\d+)", header).group(1))
+    # the product library exports no diagnostics; those live in their own library with their own header
+    from movierec import _diag
+    diag_header = open(os.path.join(ROOT, "include", "movierec_b200_diag.h")).read()
+    diag_declared = set(re.findall(r"\b(mr_[a-z_0-9]+)\s*\(", diag_header))
+    assert diag_declared == set(_diag.SIGNATURES), diag_declared ^ set(_diag.SIGNATURES)
+    dlib = ctypes.CDLL(_diag.LIB_PATH)
+    for name in diag_declared:
+        assert hasattr(dlib, name), name
+        assert name == "mr_diag_last_error" or not hasattr(lib, name), name
 
 
 def test_struct_layouts_match_header():
     # sizes follow from the header's field lists (8-byte pointers, natural alignment)
-    assert ctypes.sizeof(nat.MrModel) == 5 * 8 + 8 * 8 * 2 + 2 * 8 + 8 + 3 * 4 + 8 * 4 + 4 + 8 * 4
+    assert ctypes.sizeof(nat.MrModel) == 5 * 8 + 8 * 8 * 2 + 2 * 8 + 8 + 3 * 4 + 8 * 4 + 4 + 8 * 4 + 3 * 4 + 4  # (+ tail padding)
     assert ctypes.sizeof(nat.MrOptState) == 2 * 4 + 4 * 4 + 8 + 10 * 8
     assert ctypes.sizeof(nat.MrGrads) == 5 * 8
     assert nat.MrModel.dense_count.offset == 5 * 8 + 16 * 8 + 2 * 8

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "movierecommender-tf-trt_b200"))
-from movierec import _native as nat  # noqa: E402
+from movierec import _diag as nat  # noqa: E402
 
 NW = 8192
 

@@ -9,7 +9,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "movierecommender-tf-trt_b200"))
-from movierec import _native as nat  # noqa: E402
+from movierec import _diag as nat  # noqa: E402
 
 
 def rate(N, iters=2000, nbuf=3, flags=0, writers=0, write_iters=0, grid=148):
