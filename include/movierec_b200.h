@@ -113,6 +113,11 @@ typedef struct MrGrads {
   float* item_mlp;
   float* user_gmf;
   float* item_gmf;
+  /* Optional cudaEvent_t (NULL = none), recorded by mr_neumf_train_grads at the point of its launch sequence from
+   * which user_mlp and user_gmf are final -- in the projected grouped step that is well before the call's last
+   * kernel, on an internal stream.  A data-parallel caller makes its communication stream wait on it and starts
+   * the all-reduce of the user tables' gradients under the rest of the step. */
+  void* user_tables_ready;
 } MrGrads;
 
 /* `flags` of the train step.  MR_TRAIN_USERS_GROUPED: the caller states that the batch has the layout the

@@ -744,6 +744,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   cudaStream_t st = (cudaStream_t)stream;
   TrainWs t = carve_train(m, B, ws);
   const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
+  bool user_event_recorded = false;  // grads->user_tables_ready: recorded early where the launch sequence allows
 
   prof_mark(MR_PHASE_MISC, st);
   MR_CUDA(cudaMemsetAsync(t.flags, 0, 256, st));
@@ -1059,6 +1060,25 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
         uu.g1 = grads->user_gmf;
         rc = launch_segreduce(t.sorted_keys, t.sorted_index, n_user_rows, t.stage_u, uu, t.seg_ws_u, t.seg_ws_u_bytes, su_st);
         if (rc != MR_OK) return rc;
+        // d E_user = Su . W1u^T right behind it on the side stream: both user-side gradient tables (83 % of the
+        // table-gradient bytes at the ML-20M shape) are then final while the item side is still being reduced, and
+        // a data-parallel caller starts their all-reduce on grads->user_tables_ready
+        TcDenseArgs bu{};
+        bu.a_dense = tw.Su;
+        bu.b_packed = tw.pack_bu;
+        bu.N = d_u;
+        bu.K = m.L[1];
+        bu.rows = m.num_users;
+        bu.row0 = 0;
+        bu.epilogue = TC_EPI_BIAS_RELU;
+        bu.linear = true;
+        bu.out = grads->user_mlp;
+        rc = launch_tc_dense(bu, su_st);
+        if (rc != MR_OK) return rc;
+        if (grads->user_tables_ready != nullptr) {
+          MR_CUDA(cudaEventRecord((cudaEvent_t)grads->user_tables_ready, su_st));
+          user_event_recorded = true;
+        }
         MR_CUDA(cudaEventRecord(side->join2, su_st));
       }
       prof_mark(MR_PHASE_SEGREDUCE, st);
@@ -1104,20 +1124,22 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       rc = launch_tc_wgrad(wi, st);
       if (rc != MR_OK) return rc;
       if (uproj && su_st != st) MR_CUDA(cudaStreamWaitEvent(st, side->join2, 0));
-      if (uproj) {  // d E_user = Su . W1u^T, d W1u = E_user^T . Su, d b1 = column sums of Su
-        prof_mark(MR_PHASE_TC_DENSE_BWD, st);
-        TcDenseArgs bu{};
-        bu.a_dense = tw.Su;
-        bu.b_packed = tw.pack_bu;
-        bu.N = d_u;
-        bu.K = m.L[1];
-        bu.rows = m.num_users;
-        bu.row0 = 0;
-        bu.epilogue = TC_EPI_BIAS_RELU;
-        bu.linear = true;
-        bu.out = grads->user_mlp;
-        rc = launch_tc_dense(bu, st);
-        if (rc != MR_OK) return rc;
+      if (uproj) {  // d E_user = Su . W1u^T (above, or here without a side stream), d W1u = E_user^T . Su, d b1 = colsum(Su)
+        if (su_st == st) {
+          prof_mark(MR_PHASE_TC_DENSE_BWD, st);
+          TcDenseArgs bu{};
+          bu.a_dense = tw.Su;
+          bu.b_packed = tw.pack_bu;
+          bu.N = d_u;
+          bu.K = m.L[1];
+          bu.rows = m.num_users;
+          bu.row0 = 0;
+          bu.epilogue = TC_EPI_BIAS_RELU;
+          bu.linear = true;
+          bu.out = grads->user_mlp;
+          rc = launch_tc_dense(bu, st);
+          if (rc != MR_OK) return rc;
+        }
         prof_mark(MR_PHASE_TC_WGRAD, st);
         TcWgradArgs wu{};
         wu.a_dense = m.user_mlp;
@@ -1231,6 +1253,8 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     prof_mark(MR_PHASE_SEGREDUCE, st);
     rc = launch_segreduce(t.sorted_keys_i, t.sorted_index_i, B, t.stage_i, u, t.seg_ws, t.seg_ws_bytes, st);
   }
+  if (grads->user_tables_ready != nullptr && !user_event_recorded)  // other launch sequences: final at the end
+    MR_CUDA(cudaEventRecord((cudaEvent_t)grads->user_tables_ready, st));
   prof_mark(-1, st);
   return rc;
 }

@@ -48,6 +48,11 @@ class DataParallelNeuMF(object):
         # next.  Parity-checked (tools/dp_gpu_check.py), but on 2 GPUs the five smaller collectives cost what the
         # overlap saves (2.86 against 2.84 ms per step), so the default stays one all-reduce, then one apply.
         self.overlap = os.environ.get("MR_DP_OVERLAP") is not None
+        # default on GPUs: start the all-reduce of the user tables' gradients as soon as they are final (train_step)
+        self.early_user = os.environ.get("MR_DP_NO_EARLY_USER") is None and getattr(engine, "device", None) is not None \
+            and str(getattr(engine, "device", "cpu")).startswith("cuda")
+        self._comm = None
+        self._ready = None
         self.world_size = dist.get_world_size(process_group)
         self.rank = dist.get_rank(process_group)
 
@@ -64,8 +69,27 @@ class DataParallelNeuMF(object):
         e = self.engine
         # the hidden kernels' l2 term 2*l2*W is part of the gradients this call returns; the all-reduce below SUMS the
         # ranks' gradients, so only rank 0 adds it (the tables' l2 term is added by apply(), after the reduction)
-        out = e.train_grads(users, items, labels, group=group, k=k, inv_global_batch=1.0 / float(global_rows),
-                            grouped=grouped, dense_l2=(self.rank == 0))
+        kw = dict(group=group, k=k, inv_global_batch=1.0 / float(global_rows), grouped=grouped, dense_l2=(self.rank == 0))
+        if self.early_user and hasattr(e, "gradient_parts") and e.gradient_parts()[0].numel() > 0:
+            # The user tables' gradients (five sixths of the bytes at the ML-20M shape) are final well before the end
+            # of the step: their all-reduce starts on the communication stream as soon as the library signals it and
+            # runs under the item-side reduction and GEMMs; only the rest is reduced after the step's last kernel.
+            import torch
+            if self._comm is None:
+                self._comm = torch.cuda.Stream(device=e.device)
+                self._ready = torch.cuda.Event()
+                self._ready.record()  # (creates the CUDA event the library records into)
+            out = e.train_grads(users, items, labels, user_ready=self._ready, **kw)
+            g_user, g_rest = e.gradient_parts()
+            with torch.cuda.stream(self._comm):
+                self._comm.wait_event(self._ready)
+                w_user = dist.all_reduce(g_user, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            w_rest = dist.all_reduce(g_rest, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            w_user.wait()
+            w_rest.wait()
+            e.apply()
+            return out
+        out = e.train_grads(users, items, labels, **kw)
         if self.overlap and hasattr(e, "gradient_regions"):
             # region by region, largest first: the Adam sweep of one region runs (on the compute stream) under the
             # all-reduce of the next ones (on NCCL's stream); work.wait() orders the streams, the host never blocks

@@ -131,17 +131,24 @@ class NeuMFEngine(object):
         self.v = {k: z(t) for k, t in self._tables.items()} if (adam and table_state) else {}
         self.m_dense = z(self.dense) if adam else None
         self.v_dense = z(self.dense) if adam else None
-        # one flat gradient buffer [dense | tables...] so a data-parallel caller all-reduces once
-        sizes = [self.dense_count] + ([t.numel() for t in self._tables.values()] if table_mode == "dense" else [])
+        # one flat gradient buffer so that a data-parallel caller all-reduces it in one or two calls: the user tables'
+        # gradients first (final early in the projected step: MrGrads.user_tables_ready), then dense + item tables
+        order = [k for k in (K_USER, K_GMF_USER) if k in self._tables] + ["dense"] + \
+                [k for k in (K_ITEM, K_GMF_ITEM) if k in self._tables]
+        if table_mode != "dense":
+            order = ["dense"]
         pad = lambda x: (x + 63) // 64 * 64  # keep every slice 256-byte aligned (128-bit kernel accesses)
-        self.g_flat = torch.zeros(sum(pad(x) for x in sizes), dtype=f32, device=dev)
-        self.g_dense = self.g_flat[:self.dense_count]
+        numel = lambda k: self.dense_count if k == "dense" else self._tables[k].numel()
+        self.g_flat = torch.zeros(sum(pad(numel(k)) for k in order), dtype=f32, device=dev)
         self.g_tables = {}
-        off = pad(self.dense_count)
-        if table_mode == "dense":
-            for k, t in self._tables.items():
-                self.g_tables[k] = self.g_flat[off:off + t.numel()].view_as(t)
-                off += pad(t.numel())
+        off = 0
+        for k in order:
+            if k == "dense":
+                self.g_dense = self.g_flat[off:off + self.dense_count]
+                self._g_user_end = off  # [0, _g_user_end): the user tables' gradients
+            else:
+                self.g_tables[k] = self.g_flat[off:off + numel(k)].view_as(self._tables[k])
+            off += pad(numel(k))
         self.step_out = torch.zeros(nat.MR_STEP_OUT_FLOATS, dtype=f32, device=dev)
         self._ws = None
         self._structs()
@@ -284,6 +291,12 @@ class NeuMFEngine(object):
         """The flat gradient buffer a data-parallel caller all-reduces between train_grads and apply."""
         return [self.g_flat]
 
+    def gradient_parts(self):
+        """(user part, rest) of the flat gradient buffer: the user tables' gradients, which the projected grouped
+        step finishes early (see train_grads(user_ready=...)), and everything else.  The user part is empty in
+        sparse table mode."""
+        return self.g_flat[:self._g_user_end], self.g_flat[self._g_user_end:]
+
     # ---- hot path ---------------------------------------------------------------------------------
     def forward(self, users, items, user_div=1, labels=None, want_logits=True, want_probs=True):
         """Fused forward (model.py:154-188).  Returns (logits, probs, loss_sum) device tensors
@@ -345,11 +358,17 @@ class NeuMFEngine(object):
         self.iterations = int(self._opt.iterations)
         return self.step_out.clone()
 
-    def train_grads(self, users, items, labels, group=0, k=0, inv_global_batch=None, grouped=False, dense_l2=True):
+    def train_grads(self, users, items, labels, group=0, k=0, inv_global_batch=None, grouped=False, dense_l2=True,
+                    user_ready=None):
         """Gradients only (no update).  dense_l2=False leaves the hidden kernels' 2*l2*W term out of g_dense: a
-        data-parallel caller that sums the ranks' gradients lets exactly one rank add it."""
+        data-parallel caller that sums the ranks' gradients lets exactly one rank add it.
+        user_ready: a torch.cuda.Event the library records (on one of its streams) as soon as the user tables'
+        gradients -- gradient_parts()[0] -- are final; a stream that waits on it may all-reduce them while the rest
+        of the call is still running."""
         args, keep = self._train_args(users, items, labels, group, k, inv_global_batch, grouped, dense_l2)
+        self._grads.user_tables_ready = user_ready.cuda_event if user_ready is not None else None
         nat.check(nat.lib.mr_neumf_train_grads(*args), "mr_neumf_train_grads")
+        self._grads.user_tables_ready = None
         return self.step_out.clone()
 
     def apply(self):
