@@ -587,6 +587,14 @@ def run_gpu(args, wl):
                                  "unit": "GB/s", "frac": ach / peak, "peak_kind": peak_kind, "traffic": None}}
         assert abs(hr_host - float(sums[0].item())) < 0.5
 
+    # ---- N >= 2: the row-sharded configuration (BASELINE.json configs[4]) rides on the same line, the way the ranking
+    # eval rides on the N = 1 line, so that the scaling record sees it at every N
+    sharded_obj = None
+    if world > 1 and not args.lean:
+        resident = pinned = positives = None  # (free the replicated run's batches)
+        torch.cuda.empty_cache()
+        sharded_obj = sharded_measure(WORKLOADS["large-sharded"], steps=max(5, min(args.steps, 10)), warmup=3, dev=dev,
+                                      rank=rank, world=world, e2e=False)
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -669,6 +677,7 @@ def run_gpu(args, wl):
                                        cpu_rows, wl["cpu_eval_users"], wl["eval_negs"] + 1),
                          "eval_users_per_sec": cpu_eval, "reference_faithful": faithful},
         "eval": eval_obj,
+        "sharded": sharded_obj,
         "final_loss": float(final[0]) / rows,
     }
     if args.lean:
@@ -679,25 +688,15 @@ def run_gpu(args, wl):
         dist.destroy_process_group()
 
 
-def run_sharded(args, wl):
-    """BASELINE.json configs[4]: tables row-sharded over the ranks (owner = row % world), every rank trains on its
-    own batch of `batch` rows (weak scaling): all-to-all of ids, gathered rows and gradient rows (NCCL over
-    NVLink), owner-side deterministic sparse-row Adam, all-reduce of the replicated dense tower."""
+def sharded_measure(wl, steps, warmup, dev, rank, world, e2e=True):
+    """The row-sharded step (BASELINE.json configs[4]) on an initialised process group: returns rank 0's summary
+    (all ranks must call).  Tables row-sharded over the ranks (owner = row % world), every rank trains on its own
+    batch of `batch` rows (weak scaling)."""
     import torch
     import torch.distributed as dist
     from movierec import _native as nat
     from movierec._distributed import ShardedNeuMF
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world < 2:
-        raise SystemExit("--workload large-sharded shards the tables over the ranks: run it under torchrun with "
-                         "--gpus >= 2 (python -m torch.distributed.run --nproc-per-node N bench.py --gpus N --workload large-sharded)")
-    args.gpus = world
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist.init_process_group("nccl", device_id=dev)
     rows, group = wl["batch"], wl["negs"] + 1
     groups = rows // group
     global_rows = rows * world
@@ -723,95 +722,106 @@ def run_sharded(args, wl):
         dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(resident, i)
     sync_all()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nat.profile_begin()
     sync_all()
     ev0.record()
     last = None
-    for i in range(args.steps):
-        last = step(resident, args.warmup + i)
+    for i in range(steps):
+        last = step(resident, warmup + i)
     ev1.record()
     sync_all()
     phases, launches = nat.profile_end()
-    clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     final = last.cpu().numpy()
     if int(final[4]) != 0 or not np.isfinite(final[0]):
-        raise SystemExit("bench produced invalid step outputs: {}".format(final))
-    # end to end: pinned host arrays in, step outputs back, every step
-    e2e_steps = max(3, min(args.steps, 10))
-    step(pinned, 0).cpu()
-    sync_all()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        step(pinned, i + 1).cpu()
-    sync_all()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = global_rows * e2e_steps / float(t.item())
+        raise SystemExit("sharded bench produced invalid step outputs: {}".format(final))
+    e2e_value, e2e_steps = None, 0
+    if e2e:  # end to end: pinned host arrays in, step outputs back, every step
+        e2e_steps = max(3, min(steps, 10))
+        step(pinned, 0).cpu()
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            step(pinned, i + 1).cpu()
+        sync_all()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = global_rows * e2e_steps / float(t.item())
     dist.barrier()
+    del sh
+    torch.cuda.empty_cache()
+    step_ms = ms_total / steps
+    L, f = wl["layers"], wl["mf_dim"]
+    row_bytes = 4 * (L[0] + 2 * f)  # one user row + one item row (MLP + GMF parts)
+    kernel_ms = sum(ms / steps for ms, cnt in phases.values() if cnt)
+    return {"value": global_rows * steps / (ms_total / 1e3), "unit": UNIT, "ms_per_step": step_ms, "steps": steps,
+            "warmup": warmup, "n_gpus": world, "rows_per_step_per_gpu": rows, "global_rows_per_step": global_rows,
+            "workload": "large-sharded: {} users x {} items, NeuMF layers {} mf_dim {}, {} negatives/positive, sparse-row "
+                        "Adam at the owners (BASELINE.json configs[4])".format(wl["num_users"], wl["num_items"], L, f, wl["negs"]),
+            "parallelism": "tables row-sharded over {} ranks (owner = row % world)".format(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rows * 12, "d2h_bytes_per_step": 32,
+                    "steps": e2e_steps, "api": "ShardedNeuMF.train_step on pinned host arrays"},
+            "gpu_launches": launches, "final_loss": float(final[0]) / rows,
+            "exchange": {"bytes_per_step_per_rank_upper_bound": 2 * 2 * rows * row_bytes // 2,
+                         "library_kernel_ms_per_step": kernel_ms,
+                         "routing_and_collectives_ms_per_step": step_ms - kernel_ms},
+            "phase_ms_per_step": {k: v[0] / steps for k, v in phases.items() if v[1]}}
+
+
+def run_sharded(args, wl):
+    """BASELINE.json configs[4] as the headline of the line (`--workload large-sharded`, torchrun, --gpus >= 2)."""
+    import torch
+    import torch.distributed as dist
+
+    refuse_diagnostics(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world < 2:
+        raise SystemExit("--workload large-sharded shards the tables over the ranks: run it under torchrun with "
+                         "--gpus >= 2 (python -m torch.distributed.run --nproc-per-node N bench.py --gpus N --workload large-sharded)")
+    args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    r = sharded_measure(wl, args.steps, args.warmup, dev, rank, world)
+    clk = clocks.stop() if rank == 0 else None
     if rank != 0:
         dist.destroy_process_group()
         return
-    step_ms = ms_total / args.steps
     peak, peak_kind = measured_peaks()
-    pbytes = phase_interface_bytes(wl, rows)
-    phase_table = {}
-    for name, (ms, cnt) in phases.items():
-        if not cnt:
-            continue
-        per_step = ms / args.steps
-        row = {"ms_per_step": per_step, "launch_groups_per_step": cnt / args.steps, "share_of_step": per_step / step_ms}
-        if name in pbytes and name not in ("segreduce", "sort", "optimizer"):  # those run on other sizes here
-            row["interface_bytes_per_step"] = pbytes[name]
-            row["gbs"] = pbytes[name] / (per_step / 1e3) / 1e9
-            row["frac_of_hbm_peak"] = row["gbs"] / peak
-        phase_table[name] = row
-    cand = [k for k in phase_table if "gbs" in phase_table[k]]
-    dom = max(cand, key=lambda k: phase_table[k]["ms_per_step"])
-    dom_groups = max(phases[dom][1], 1)
-    dom_avg_ms = phases[dom][0] / dom_groups
-    dom_bytes = pbytes[dom] * args.steps / dom_groups
-    achieved = dom_bytes / (dom_avg_ms / 1e3) / 1e9
     L, f = wl["layers"], wl["mf_dim"]
-    row_bytes = 4 * (L[0] + 2 * f)  # one user row + one item row (MLP + GMF parts)
-    kernel_ms = sum(v["ms_per_step"] for v in phase_table.values())
+    # SURVEY 8(d), sparse-row form: per-row gathers + Adam on the touched rows (every id distinct at this table size)
+    a_step = wl["batch"] * (4 * (L[0] + 2 * f) + 12) + 24 * (wl["batch"] // (wl["negs"] + 1) + wl["batch"]) * (L[0] // 2 + f)
     line = {
-        "metric": METRIC, "value": global_rows * args.steps / (ms_total / 1e3), "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "large-sharded: {} users x {} items, NeuMF layers {} mf_dim {}, {} negatives/positive, "
-                               "sparse-row Adam at the owners".format(wl["num_users"], wl["num_items"], L, f, wl["negs"]),
-                   "baseline_config": "BASELINE.json configs[4]", "rows_per_step_per_gpu": rows,
-                   "global_rows_per_step": global_rows,
-                   "parallelism": "tables row-sharded over {} ranks (owner = row % world); per step and side: all-to-all of "
-                                  "ids, of gathered rows and of gradient rows, all-reduce of the dense tower".format(world),
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": r["workload"], "baseline_config": "BASELINE.json configs[4]",
+                   "rows_per_step_per_gpu": r["rows_per_step_per_gpu"], "global_rows_per_step": r["global_rows_per_step"],
+                   "parallelism": r["parallelism"] + "; per step and side: ids to the owners, rows gathered over peer "
+                                  "pointers (NVLink), gradient rows back to the owners, all-reduce of the dense tower",
                    "table_bytes_total": 4 * (wl["num_users"] + wl["num_items"]) * (L[0] // 2 + f) * 3,
                    "l2_policy": "working set larger than L2: 4 rotating batches of uniformly drawn ids over 11 GB of tables"},
-        "clocks": clk,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rows * 12, "d2h_bytes_per_step": 32,
-                "steps": e2e_steps, "api": "ShardedNeuMF.train_step on pinned host arrays"},
-        "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": PHASE_KERNELS.get(dom, dom), "phase": dom, "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
-                     "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_avg_ms, "launches_timed": dom_groups,
-                     "share_of_step": phase_table[dom]["share_of_step"]},
-        "exchange": {"bytes_per_step_per_rank_upper_bound": 2 * 2 * rows * row_bytes // 2,
-                     "note": "rows + gradient rows of the distinct ids of the batch, both directions, (world-1)/world of them "
-                             "remote; routing (unique / owner grouping) runs in torch ops between the library's kernels",
-                     "library_kernel_ms_per_step": kernel_ms, "routing_and_collectives_ms_per_step": step_ms - kernel_ms},
-        "phases": phase_table,
+        "clocks": clk, "e2e": r["e2e"], "gpu_launches": r["gpu_launches"],
+        "roofline": {"bound": "hbm", "scope": "whole step per GPU, SURVEY 8(d) A_train in sparse-row form",
+                     "kernel": "row-sharded step (exchange + cache-slot train step + owner-side sparse-row Adam)",
+                     "achieved": a_step / (r["ms_per_step"] / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": a_step / (r["ms_per_step"] / 1e3) / 1e9 / peak, "traffic": None, "peak_kind": peak_kind,
+                     "algorithmic_bytes_per_step": a_step},
+        "exchange": r["exchange"], "phase_ms_per_step": r["phase_ms_per_step"],
         "cpu_baseline": {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                          "sample": "not timed: the CPU baseline leg runs at N=1 only and this workload needs N >= 2"},
-        "final_loss": float(final[0]) / rows,
+        "final_loss": r["final_loss"],
     }
     emit(line)
     dist.destroy_process_group()

@@ -802,12 +802,17 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     TcWs tw = carve_tc(m, true, B, t.tc_ws);
     if (!proj) tw.Pi = tw.Si = nullptr;
     if (!uproj) tw.Pu = tw.Su = nullptr;
+    // The per-row work of the projected step in ONE kernel (tc_fused.cu): H1, the second layer forward, the head,
+    // the second layer's weight gradient and backward, the staged rows and their group sums never leave the SM.
+    const bool fused = uproj && m.fused_train != MR_FUSED_OFF && fused_train_supported(m, group);
     MR_CUDA(cudaMemsetAsync(t.dense_partial, 0, (size_t)P * t.dense_stride * sizeof(float), st));
-    MR_CUDA(cudaMemsetAsync(tw.head_partial, 0, head_partial_floats(m) * sizeof(float), st));
-    for (int l = grouped ? 2 : 1; l < n; ++l) {
-      rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 0, tw.pack_f[l], st);
-      if (rc == MR_OK) rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 1, tw.pack_b[l], st);
-      if (rc != MR_OK) return rc;
+    if (!fused) {  // (the fused kernel packs its own operand image of W[2] and keeps the head's sums itself)
+      MR_CUDA(cudaMemsetAsync(tw.head_partial, 0, head_partial_floats(m) * sizeof(float), st));
+      for (int l = grouped ? 2 : 1; l < n; ++l) {
+        rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 0, tw.pack_f[l], st);
+        if (rc == MR_OK) rc = launch_pack_weights(m.W[l], m.L[l - 1], m.L[l], 1, tw.pack_b[l], st);
+        if (rc != MR_OK) return rc;
+      }
     }
     if (grouped) {  // W[1] is (L0, L1) row-major: rows [0, d_u) multiply the user row, rows [d_u, L0) the item row
       const float* Wu = m.W[1];
@@ -824,9 +829,6 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       if (rc == MR_OK && uproj) rc = tc_project_users(m, tw, st);
       if (rc != MR_OK) return rc;
     }
-    // The per-row work of the projected step in ONE kernel (tc_fused.cu): H1, the second layer forward, the head,
-    // the second layer's weight gradient and backward, the staged rows and their group sums never leave the SM.
-    const bool fused = uproj && m.fused_train != MR_FUSED_OFF && fused_train_supported(m, group);
     int fused_grid = 0;
     if (fused) {
       prof_mark(MR_PHASE_FUSED_TILE, st);

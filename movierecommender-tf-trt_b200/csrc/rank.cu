@@ -62,6 +62,70 @@ __global__ void __launch_bounds__(kRankThreads) rank_positions_kernel(const floa
   }
 }
 
+// Small groups (the train step: one positive + a few negatives): ONE THREAD per group -- a warp-per-group launch leaves
+// 27 of 32 lanes idle at group = 5 and spends its time in shuffles.  A warp's 32 groups are 32 * group consecutive
+// floats, so the `group` strided loads of a thread hit the lines its neighbours load too (L1).  The CTA's
+// kRankGroupsPerCta groups are folded into partial[blockIdx] = {hits, dcg} in a fixed order, as below.
+template <int MAXG>
+__global__ void __launch_bounds__(kRankThreads) rank_small_kernel(const float* __restrict__ scores, int64_t G, int group,
+                                                                  const int32_t* __restrict__ label_col,
+                                                                  const float* __restrict__ labels, int k,
+                                                                  int32_t* __restrict__ pos, float* __restrict__ partial) {
+  __shared__ float red_h[kRankThreads / 32], red_d[kRankThreads / 32];
+  const int64_t lo = (int64_t)blockIdx.x * kRankGroupsPerCta;
+  const int64_t hi = min(G, lo + kRankGroupsPerCta);
+  float h = 0.f, d = 0.f;
+  const float ln2 = logf(2.f);
+  for (int64_t g = lo + threadIdx.x; g < hi; g += blockDim.x) {
+    float sc[MAXG];
+    int lc = label_col != nullptr ? __ldg(label_col + g) : group - 1;
+    float best = -INFINITY;
+    int bi = group;
+#pragma unroll
+    for (int j = 0; j < MAXG; ++j) {
+      if (j < group) {
+        sc[j] = rank_key(__ldg(scores + g * group + j));
+        if (label_col == nullptr && labels != nullptr) {
+          const float v = __ldg(labels + g * group + j);
+          if (v > best) { best = v; bi = j; }
+        }
+      }
+    }
+    if (label_col == nullptr && labels != nullptr) lc = bi >= group ? 0 : bi;
+    lc = min(max(lc, 0), group - 1);
+    float sp = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXG; ++j)
+      if (j == lc) sp = sc[j];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < MAXG; ++j)
+      if (j < group) cnt += (sc[j] > sp) || (sc[j] == sp && j < lc);
+    pos[g] = cnt;
+    if (cnt < k) {
+      h += 1.f;
+      d += ln2 / logf((float)cnt + 2.f);
+    }
+  }
+  if (partial == nullptr) return;
+  h = warp_sum(h);
+  d = warp_sum(d);
+  if ((threadIdx.x & 31) == 0) {
+    red_h[threadIdx.x >> 5] = h;
+    red_d[threadIdx.x >> 5] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float hh = 0.f, dd = 0.f;
+    for (int w = 0; w < kRankThreads / 32; ++w) {
+      hh += red_h[w];
+      dd += red_d[w];
+    }
+    partial[2 * blockIdx.x] = hh;
+    partial[2 * blockIdx.x + 1] = dd;
+  }
+}
+
 // partial[b] = {hits, dcg} of groups [b*1024, (b+1)*1024): fixed strided order + shuffle tree.
 __global__ void __launch_bounds__(kRankThreads) rank_metric_partial_kernel(const int32_t* __restrict__ pos, int64_t G,
                                                                            int k, float* __restrict__ partial) {
@@ -147,6 +211,17 @@ int launch_rank_scores(const float* scores, int64_t G, int group, int k, const i
                        int32_t* pos, float* sums, float* partials, cudaStream_t st, const float* labels) {
   if (G == 0) {
     if (sums != nullptr) MR_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(float), st));
+    return MR_OK;
+  }
+  if (group <= 8 && rank == nullptr) {  // thread per group, positions + metric partials in one kernel
+    const int64_t nb = (G + kRankGroupsPerCta - 1) / kRankGroupsPerCta;
+    rank_small_kernel<8><<<(unsigned)nb, kRankThreads, 0, st>>>(scores, G, group, label_col, labels, k, pos,
+                                                               sums != nullptr ? partials : nullptr);
+    MR_LAUNCH_CHECK("rank_small_kernel");
+    if (sums != nullptr) {
+      rank_metric_final_kernel<<<1, 1024, 0, st>>>(partials, nb, sums);
+      MR_LAUNCH_CHECK("rank_metric_final_kernel");
+    }
     return MR_OK;
   }
   int64_t blocks = (G + 7) / 8;
