@@ -36,7 +36,7 @@ def dur_us(r):
     return v / 1e3 if u.startswith("n") else v * (1e3 if u.startswith("m") else 1.0)
 
 
-PHASE = [("tc_wgrad_kernel", "tc_wgrad"), ("tc_dense_kernel<1, 1>", "tc_dense_bwd"), ("tc_dense_kernel<1, 2>", "tc_dense_bwd"),
+PHASE = [("neumf_fused_train", "fused_tile"), ("sample_negatives", "sampler"), ("rank_", "rank"), ("tc_wgrad_kernel", "tc_wgrad"), ("tc_dense_kernel<1, 1>", "tc_dense_bwd"), ("tc_dense_kernel<1, 2>", "tc_dense_bwd"),
          ("tc_dense_kernel", "tc_dense_fwd"), ("head_", "head"), ("h1_from", "h1_gather"), ("segreduce", "segreduce"),
          ("group_sum", "misc"), ("optimizer", "optimizer")]
 out, phase_bytes = [], {}
@@ -57,7 +57,7 @@ for r in rows[2:]:
             e[key] = round(v, 2)
     out.append(e)
     # B1 / B1u (plain dense over the item / user table into the gradient tables) belong to the backward phase
-    ph = next(p for k, p in PHASE if k in name)
+    ph = next((p for k, p in PHASE if k in name), "misc")
     if ph == "tc_dense_fwd" and out and len([x for x in out if x["kernel"].startswith("tc_dense_kernel<1, 0>")]) > 4:
         ph = "tc_dense_bwd"
     phase_bytes[ph] = phase_bytes.get(ph, 0.0) + rd + wr
