@@ -357,7 +357,11 @@ def config_dict(args, wl, rows_override=None):
             "baseline_config": "BASELINE.json configs[{}]".format({"ml-20m": 2, "ml-1m": 1}.get(args.workload, 4)),
             "rows_per_step_per_gpu": wl["batch"] if rows_override is None else rows_override,
             "global_rows_per_step": (wl["batch"] if rows_override is None else rows_override) * args.gpus,
-            "parallelism": "dp{} replicated tables, one all-reduce of dense+table gradients".format(args.gpus),
+            "parallelism": "single GPU" if args.gpus == 1 else
+                           "dp{} replicated tables; gradient sum + Adam + weight distribution in one kernel over NVLink "
+                           "peer pointers (mr_dp_reduce_apply), optimizer state sharded by owner".format(args.gpus)
+                           if args.dp_exchange != "nccl" else
+                           "dp{} replicated tables, NCCL all-reduce of dense+table gradients, full Adam sweep per rank".format(args.gpus),
             "l2_policy": "working set larger than L2: 4 rotating batches; staged row gradients (~{:.1f} GB/step) and "
                          "tables+Adam state exceed the 126 MB L2".format(wl["batch"] * 4 * (sum(wl["layers"][:1]) + 2 * wl["mf_dim"]) / 1e9)}
 
@@ -436,7 +440,7 @@ def run_gpu(args, wl):
     eng = model.model.engine
     if world > 1:
         from movierec._distributed import DataParallelNeuMF
-        dp = DataParallelNeuMF(eng)
+        dp = DataParallelNeuMF(eng, exchange=args.dp_exchange)
         dp.broadcast_parameters(0)
 
     # ---- synthetic ratings -> per-user item lists on the device (what the sampler excludes); positives of a step
@@ -833,6 +837,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)   # ~0.3 s timed at N=1: several nvidia-smi clock samples
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dp-exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: fused peer-memory reduce + optimizer kernel (default) or NCCL all-reduce + full sweep")
     ap.add_argument("--workload", default="ml-20m", choices=sorted(WORKLOADS))
     ap.add_argument("--lean", action="store_true",
                     help="profiling runs (ncu): skip the e2e, eval and CPU-baseline legs; not a bench value")

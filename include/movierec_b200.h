@@ -114,9 +114,10 @@ typedef struct MrGrads {
   float* user_gmf;
   float* item_gmf;
   /* Optional cudaEvent_t (NULL = none), recorded by mr_neumf_train_grads at the point of its launch sequence from
-   * which user_mlp and user_gmf are final -- in the projected grouped step that is well before the call's last
-   * kernel, on an internal stream.  A data-parallel caller makes its communication stream wait on it and starts
-   * the all-reduce of the user tables' gradients under the rest of the step. */
+   * which the gradients user_mlp and user_gmf are final AND the call no longer reads the model's user tables -- in
+   * the projected grouped step that is well before the call's last kernel, on an internal stream.  A data-parallel
+   * caller makes its communication stream wait on it and reduces the user tables' gradients -- and may update the user
+   * tables in place (mr_dp_reduce_apply) -- under the rest of the step. */
   void* user_tables_ready;
 } MrGrads;
 
@@ -293,6 +294,21 @@ int mr_build_user_csr(const int32_t* users, const int32_t* items, int64_t n, int
 size_t mr_sort_workspace_bytes(int64_t n);
 int mr_sort_pairs(const int32_t* keys, int64_t n, int32_t key_bits, int32_t* sorted_keys,
                   int32_t* sorted_index, void* ws, size_t ws_bytes, void* stream);
+/* Data-parallel replicas on ONE box: all-reduce(sum) of the gradients + optimizer step + all-gather of the
+ * new weights as one kernel over NVLink peer memory.  grad_peers / param_peers are HOST arrays of `world` device
+ * pointers: rank r's flat gradient buffer and flat parameter buffer (same layout on every rank, 16-byte aligned,
+ * mapped into this process by peer access -- e.g. torch symmetric memory; entry `rank` is this rank's own buffer).
+ * For the elements [lo, hi) this rank owns (multiples of 4):
+ *     g = grad_peers[0][i] + grad_peers[1][i] + ... (rank order, the same on every rank) + 2*l2*p[i]
+ *     Adam / SGD step of mr_optimizer_flat with THIS rank's m[i], v[i] (optimizer state is sharded by owner)
+ *     param_peers[r][i] = new value, for every r.
+ * The caller orders the launch against the other ranks with cross-rank barriers: every rank's gradients of the region
+ * final and its reads of the region's parameters done before, all owners' launches complete before the parameters
+ * are read again.  No reference counterpart (the reference is single-process). */
+int mr_dp_reduce_apply(const float* const* grad_peers, float* const* param_peers, int32_t world, int32_t rank,
+                       float* m, float* v, int64_t lo, int64_t hi, int32_t optimizer, float lr_t, float beta_1,
+                       float beta_2, float epsilon, float l2, void* stream);
+
 /* Elementwise legacy-Keras Adam / SGD over a flat buffer (l2 adds 2*l2*p to the gradient). */
 int mr_optimizer_flat(float* p, const float* g, float* m, float* v, int64_t n, int32_t optimizer,
                       float lr_t, float beta_1, float beta_2, float epsilon, float l2, void* stream);

@@ -749,6 +749,23 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   prof_mark(MR_PHASE_MISC, st);
   MR_CUDA(cudaMemsetAsync(t.flags, 0, 256, st));
   MR_CUDA(cudaMemsetAsync(step_out, 0, MR_STEP_OUT_FLOATS * sizeof(float), st));
+  // l2 penalty of the step's weights: first, so that nothing reads the tables after grads->user_tables_ready
+  if (any_l2(m)) {
+    float* pen = step_out + MR_OUT_L2_PENALTY;
+    if (m.l2[0] != 0.f) {
+      rc = launch_l2_penalty(m.user_mlp, (int64_t)m.num_users * d_u, m.l2[0], pen, st);
+      if (rc == MR_OK) rc = launch_l2_penalty(m.item_mlp, (int64_t)m.num_items * d_i, m.l2[0], pen, st);
+      if (rc == MR_OK && m.mf_dim > 0) rc = launch_l2_penalty(m.user_gmf, (int64_t)m.num_users * m.mf_dim, m.l2[0], pen, st);
+      if (rc == MR_OK && m.mf_dim > 0) rc = launch_l2_penalty(m.item_gmf, (int64_t)m.num_items * m.mf_dim, m.l2[0], pen, st);
+      if (rc != MR_OK) return rc;
+    }
+    for (int l = 1; l < m.n_layers; ++l)
+      if (m.l2[l] != 0.f) {
+        rc = launch_l2_penalty(m.W[l], (int64_t)m.L[l - 1] * m.L[l], m.l2[l], pen, st);
+        if (rc != MR_OK) return rc;
+      }
+  }
+
   // grouped batch (MR_TRAIN_USERS_GROUPED): user-only work once per group; the promise is checked on the device
   const bool grouped = (flags & MR_TRAIN_USERS_GROUPED) && use_tc(m) && tc_grouped_ok(m, B, group);
   const int gdiv = grouped ? group : 0;
@@ -1077,6 +1094,20 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
         bu.out = grads->user_mlp;
         rc = launch_tc_dense(bu, su_st);
         if (rc != MR_OK) return rc;
+        // d W1u = E_user^T . Su, d b1 = colsum(Su): the step's last read of the user table, so it goes before the event
+        // (its columns of the partial buffer are disjoint from the item half's, which the caller's stream adds to)
+        TcWgradArgs wu{};
+        wu.a_dense = m.user_mlp;
+        wu.z = tw.Su;
+        wu.Fa = d_u;
+        wu.Fb = m.L[1];
+        wu.rows = m.num_users;
+        wu.row0 = 0;
+        wu.dw_partial = t.dense_partial + (m.W[1] - m.dense);
+        wu.db_partial = t.dense_partial + (m.b[1] - m.dense);
+        wu.partial_stride = t.dense_stride;
+        rc = launch_tc_wgrad(wu, su_st);
+        if (rc != MR_OK) return rc;
         if (grads->user_tables_ready != nullptr) {
           MR_CUDA(cudaEventRecord((cudaEvent_t)grads->user_tables_ready, su_st));
           user_event_recorded = true;
@@ -1126,8 +1157,8 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
       rc = launch_tc_wgrad(wi, st);
       if (rc != MR_OK) return rc;
       if (uproj && su_st != st) MR_CUDA(cudaStreamWaitEvent(st, side->join2, 0));
-      if (uproj) {  // d E_user = Su . W1u^T (above, or here without a side stream), d W1u = E_user^T . Su, d b1 = colsum(Su)
-        if (su_st == st) {
+      if (uproj && su_st == st) {  // without a side stream: d E_user = Su . W1u^T, d W1u = E_user^T . Su, d b1 here
+        {
           prof_mark(MR_PHASE_TC_DENSE_BWD, st);
           TcDenseArgs bu{};
           bu.a_dense = tw.Su;
@@ -1200,22 +1231,6 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   if (side != nullptr) MR_CUDA(cudaStreamWaitEvent(st, side->join, 0));  // sorts and the group check are done
   flag_to_float_kernel<<<1, 1, 0, st>>>(t.flags, step_out + MR_OUT_BAD_IDS);
   MR_LAUNCH_CHECK("flag_to_float_kernel");
-
-  if (any_l2(m)) {
-    float* pen = step_out + MR_OUT_L2_PENALTY;
-    if (m.l2[0] != 0.f) {
-      rc = launch_l2_penalty(m.user_mlp, (int64_t)m.num_users * d_u, m.l2[0], pen, st);
-      if (rc == MR_OK) rc = launch_l2_penalty(m.item_mlp, (int64_t)m.num_items * d_i, m.l2[0], pen, st);
-      if (rc == MR_OK && m.mf_dim > 0) rc = launch_l2_penalty(m.user_gmf, (int64_t)m.num_users * m.mf_dim, m.l2[0], pen, st);
-      if (rc == MR_OK && m.mf_dim > 0) rc = launch_l2_penalty(m.item_gmf, (int64_t)m.num_items * m.mf_dim, m.l2[0], pen, st);
-      if (rc != MR_OK) return rc;
-    }
-    for (int l = 1; l < m.n_layers; ++l)
-      if (m.l2[l] != 0.f) {
-        rc = launch_l2_penalty(m.W[l], (int64_t)m.L[l - 1] * m.L[l], m.l2[l], pen, st);
-        if (rc != MR_OK) return rc;
-      }
-  }
 
   if (group > 0) {
     prof_mark(MR_PHASE_RANK, st);
@@ -1528,6 +1543,21 @@ int mr_optimizer_flat(float* p, const float* g, float* m, float* v, int64_t n, i
   MR_REQUIRE(p && g && n >= 0, "optimizer_flat: NULL pointer");
   MR_REQUIRE(optimizer == MR_OPT_SGD || (m && v), "optimizer_flat: Adam needs m and v");
   return launch_optimizer_flat(p, g, m, v, n, optimizer, lr_t, beta_1, beta_2, epsilon, l2, (cudaStream_t)stream);
+}
+
+int mr_dp_reduce_apply(const float* const* grad_peers, float* const* param_peers, int32_t world, int32_t rank, float* m,
+                       float* v, int64_t lo, int64_t hi, int32_t optimizer, float lr_t, float beta_1, float beta_2,
+                       float epsilon, float l2, void* stream) {
+  MR_REQUIRE(grad_peers && param_peers, "dp_reduce_apply: NULL pointer array");
+  MR_REQUIRE(world >= 1 && rank >= 0 && rank < world, "dp_reduce_apply: rank %d of %d", rank, world);
+  MR_REQUIRE(lo >= 0 && hi >= lo && (lo & 3) == 0 && (hi & 3) == 0, "dp_reduce_apply: [lo, hi) must be multiples of 4");
+  MR_REQUIRE(optimizer == MR_OPT_SGD || (m && v), "dp_reduce_apply: Adam needs m and v");
+  for (int r = 0; r < world; ++r)
+    MR_REQUIRE(grad_peers[r] && param_peers[r] && ((reinterpret_cast<uintptr_t>(grad_peers[r]) |
+                                                     reinterpret_cast<uintptr_t>(param_peers[r])) & 15) == 0,
+               "dp_reduce_apply: rank %d's pointers must be non-NULL and 16-byte aligned", r);
+  return launch_dp_reduce_apply(grad_peers, param_peers, world, rank, m, v, lo, hi, optimizer, lr_t, beta_1, beta_2,
+                                epsilon, l2, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -3,11 +3,22 @@
 One process per GPU (`torch.distributed`, NCCL over NVLink 5 / NVSwitch on GPUs, gloo in CPU
 tests).  Tables are replicated.  A global batch is split across ranks BY WHOLE GROUPS (a group = one
 positive and its negatives, so the ranking metrics stay rank-local); every rank runs the fused
-forward/backward on its groups with the gradient scale 1/B_global, the flat gradient buffer
-(dense-layer gradients + the embedding gradient tables) is summed with ONE all-reduce, and every
-rank applies the identical optimizer update.  The result equals the single-GPU step on the global
-batch up to summation order.  The reference is single-process: there is no reference
-collective to mirror; this is the exchange step the data-parallel path needs and nothing more.
+forward/backward on its groups with the gradient scale 1/B_global, the ranks' flat gradient buffers
+(dense-layer gradients + the embedding gradient tables) are summed, and every replica receives the
+identical optimizer update.  The result equals the single-GPU step on the global batch up to summation
+order.  The reference is single-process: there is no reference collective to mirror; this
+is the exchange step the data-parallel path needs and nothing more.
+
+Two exchanges:
+  "peer" (default on the GPUs of one box): parameters and gradients live in symmetric memory; the sum of the
+      gradients, the optimizer step and the distribution of the new weights are ONE kernel over NVLink peer pointers
+      (`mr_dp_reduce_apply`, csrc/dp_exchange.cu): every rank owns 1/world of every region, adds the ranks' gradient
+      values in rank order, steps its slice with its own slice of the Adam state and stores the result into every
+      replica.  The user tables' part (five sixths of the bytes at the ML-20M shape) runs on a communication stream
+      as soon as every rank's user-side gradients are final (MrGrads.user_tables_ready), under the item-side half
+      of the step; cross-rank barriers (symmetric-memory signal pads) order it.
+  "nccl": all-reduce of the flat gradient buffer (the user part early, as above), then the full optimizer sweep on
+      every rank.  Used with gloo on CPUs and when symmetric memory is not available.
 """
 
 import os
@@ -36,25 +47,103 @@ def shard_batch(users, items, labels, group, world_size, rank):
 class DataParallelNeuMF(object):
     """Wraps a NeuMFEngine replica; `train_step` takes the RANK-LOCAL rows of a global batch."""
 
-    def __init__(self, engine, process_group=None):
+    def __init__(self, engine, process_group=None, exchange=None):
+        """exchange: "peer" | "nccl" | None (= "peer" on CUDA devices with the NCCL backend and more than one rank;
+        MR_DP_EXCHANGE overrides the default for A/B runs)."""
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         if engine.table_mode != "dense":
-            raise NotImplementedError("replicated data parallelism all-reduces dense gradient tables; "
-                                      "use table_mode='dense'")
+            raise NotImplementedError("replicated data parallelism sums dense gradient tables; use table_mode='dense'")
         self.engine = engine
         self.group = process_group
-        # MR_DP_OVERLAP=1: all-reduce region by region with the Adam sweep of one region under the all-reduce of the
-        # next.  Parity-checked (tools/dp_gpu_check.py), but on 2 GPUs the five smaller collectives cost what the
-        # overlap saves (2.86 against 2.84 ms per step), so the default stays one all-reduce, then one apply.
-        self.overlap = os.environ.get("MR_DP_OVERLAP") is not None
-        # default on GPUs: start the all-reduce of the user tables' gradients as soon as they are final (train_step)
-        self.early_user = os.environ.get("MR_DP_NO_EARLY_USER") is None and getattr(engine, "device", None) is not None \
-            and str(getattr(engine, "device", "cpu")).startswith("cuda")
-        self._comm = None
-        self._ready = None
         self.world_size = dist.get_world_size(process_group)
         self.rank = dist.get_rank(process_group)
+        on_gpu = str(getattr(engine, "device", "cpu")).startswith("cuda")
+        # MR_DP_OVERLAP=1 (nccl exchange): all-reduce region by region with the Adam sweep of one region under the
+        # all-reduce of the next.  Parity-checked (tools/dp_gpu_check.py); not faster than the default on 2 GPUs.
+        self.overlap = os.environ.get("MR_DP_OVERLAP") is not None
+        # nccl exchange on GPUs: the all-reduce of the user tables' gradients starts as soon as they are final
+        self.early_user = os.environ.get("MR_DP_NO_EARLY_USER") is None and on_gpu
+        if exchange is None:
+            exchange = os.environ.get("MR_DP_EXCHANGE") or (
+                "peer" if on_gpu and self.world_size > 1 and dist.get_backend(process_group) == "nccl"
+                and hasattr(engine, "rebind_flat") else "nccl")
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl', found {!r}".format(exchange))
+        self.exchange = exchange
+        self._comm = None
+        self._ready = None
+        if exchange == "peer":
+            self._setup_peer()
+
+    def _setup_peer(self):
+        """Parameters and gradients into symmetric memory (values kept), peer pointers, this rank's slices."""
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        e = self.engine
+        pg = self.group if self.group is not None else dist.group.WORLD
+        e.rebind_flat(lambda count: symm.empty(count, dtype=torch.float32, device=e.device))
+        self._hp = symm.rendezvous(e.p_flat, pg.group_name)
+        self._hg = symm.rendezvous(e.g_flat, pg.group_name)
+        w = self.world_size
+        self._p_peers = (C.c_void_p * w)(*[int(x) for x in self._hp.buffer_ptrs])
+        self._g_peers = (C.c_void_p * w)(*[int(x) for x in self._hg.buffer_ptrs])
+        self._slices = []  # (lo, hi, l2, is_user_region) of the elements this rank owns
+        for off, count, l2 in e.flat_regions():
+            per = ((count // 4 + w - 1) // w) * 4
+            lo, hi = off + min(count, per * self.rank), off + min(count, per * (self.rank + 1))
+            self._slices.append((lo, hi, l2, off < e._g_user_end))
+        self._comm = torch.cuda.Stream(device=e.device)
+        self._ready = torch.cuda.Event()
+        self._ready.record()  # (creates the CUDA event the library records into)
+        self._comm_done = torch.cuda.Event()
+
+    def _reduce_apply(self, lo, hi, l2, lr_t):
+        import ctypes as C
+        from . import _engine
+        e = self.engine
+        nat = _engine.nat
+        adam = e.optimizer == "adam"
+        nat.check(nat.lib.mr_dp_reduce_apply(self._g_peers, self._p_peers, self.world_size, self.rank,
+                                             C.c_void_p(e.m_flat.data_ptr()) if adam else None,
+                                             C.c_void_p(e.v_flat.data_ptr()) if adam else None, lo, hi,
+                                             nat.OPT_ADAM if adam else nat.OPT_SGD, lr_t, e.beta_1, e.beta_2,
+                                             _engine.ADAM_EPSILON, l2, e._stream()), "mr_dp_reduce_apply")
+
+    def _peer_step(self, users, items, labels, kw):
+        e = self.engine
+        out = e.train_grads(users, items, labels, user_ready=self._ready, **kw)
+        lr_t = e.step_lr_t()
+        main = torch.cuda.current_stream(e.device)
+        # user tables: as soon as EVERY rank's user-side gradients are final and its step no longer reads the tables
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(self._ready)
+            self._hg.barrier(channel=1)
+            for lo, hi, l2, user in self._slices:
+                if user:
+                    self._reduce_apply(lo, hi, l2, lr_t)
+            self._comm_done.record(self._comm)
+        # dense block and item tables: after every rank's step
+        self._hg.barrier(channel=0)
+        for lo, hi, l2, user in self._slices:
+            if not user:
+                self._reduce_apply(lo, hi, l2, lr_t)
+        main.wait_event(self._comm_done)
+        self._hg.barrier(channel=0)  # all owners' stores have landed: the replicas are whole again
+        e.finish_apply()
+        return out
+
+    def sync_optimizer_state(self):
+        """peer exchange: the Adam state is sharded by owner; this makes every rank hold all of it (checkpoints)."""
+        e = self.engine
+        if self.exchange != "peer" or e.optimizer != "adam":
+            return
+        for buf in (e.m_flat, e.v_flat):
+            own = torch.zeros_like(buf)
+            for lo, hi, _, _ in self._slices:
+                own[lo:hi].copy_(buf[lo:hi])
+            dist.all_reduce(own, op=dist.ReduceOp.SUM, group=self.group)
+            buf.copy_(own)
 
     def broadcast_parameters(self, src=0):
         """Make every replica start from rank `src`'s weights."""
@@ -70,11 +159,12 @@ class DataParallelNeuMF(object):
         # the hidden kernels' l2 term 2*l2*W is part of the gradients this call returns; the all-reduce below SUMS the
         # ranks' gradients, so only rank 0 adds it (the tables' l2 term is added by apply(), after the reduction)
         kw = dict(group=group, k=k, inv_global_batch=1.0 / float(global_rows), grouped=grouped, dense_l2=(self.rank == 0))
+        if self.exchange == "peer":
+            return self._peer_step(users, items, labels, kw)
         if self.early_user and hasattr(e, "gradient_parts") and e.gradient_parts()[0].numel() > 0:
             # The user tables' gradients (five sixths of the bytes at the ML-20M shape) are final well before the end
             # of the step: their all-reduce starts on the communication stream as soon as the library signals it and
             # runs under the item-side reduction and GEMMs; only the rest is reduced after the step's last kernel.
-            import torch
             if self._comm is None:
                 self._comm = torch.cuda.Stream(device=e.device)
                 self._ready = torch.cuda.Event()

@@ -141,6 +141,7 @@ class NeuMFEngine(object):
         numel = lambda k: self.dense_count if k == "dense" else self._tables[k].numel()
         self.g_flat = torch.zeros(sum(pad(numel(k)) for k in order), dtype=f32, device=dev)
         self.g_tables = {}
+        self._flat_layout = []  # (name, offset, elements) of every region of g_flat, in order
         off = 0
         for k in order:
             if k == "dense":
@@ -148,7 +149,9 @@ class NeuMFEngine(object):
                 self._g_user_end = off  # [0, _g_user_end): the user tables' gradients
             else:
                 self.g_tables[k] = self.g_flat[off:off + numel(k)].view_as(self._tables[k])
+            self._flat_layout.append((k, off, numel(k)))
             off += pad(numel(k))
+        self.p_flat = self.m_flat = self.v_flat = None  # set by rebind_flat()
         self.step_out = torch.zeros(nat.MR_STEP_OUT_FLOATS, dtype=f32, device=dev)
         self._ws = None
         self._structs()
@@ -217,6 +220,64 @@ class NeuMFEngine(object):
                 for tag, tabs, dense in (("m/", self.m, self.m_dense), ("v/", self.v, self.v_dense)):
                     dst = tabs[k] if k in tabs else self._view(k, dense)
                     dst.copy_(torch.from_numpy(np.ascontiguousarray(st[tag + k], dtype=np.float32)).view_as(dst))
+
+    def rebind_flat(self, alloc=None):
+        """Moves the parameters, the gradients and the optimizer state into flat buffers that share ONE layout (that of
+        g_flat: [user tables | dense block | item tables], regions 256-byte aligned), keeping every value, and re-seats
+        all views and C structs.  `alloc(numel)` allocates the parameter and the gradient buffer (a data-parallel
+        caller passes a symmetric-memory allocator so that peers can address them: DataParallelNeuMF); the optimizer
+        state is rank-private.  Element i of p_flat, g_flat, m_flat and v_flat belong together."""
+        if self.table_mode != "dense" or not self.table_state:
+            raise RuntimeError("rebind_flat needs dense gradient tables and table state on this engine")
+        dev, f32 = self.device, torch.float32
+        n = self.g_flat.numel()
+        alloc = alloc or (lambda count: torch.empty(count, dtype=f32, device=dev))
+        adam = self.optimizer == "adam"
+        p_flat, g_flat = alloc(n), alloc(n)
+        p_flat.zero_()
+        g_flat.copy_(self.g_flat)
+        m_flat = torch.zeros(n, dtype=f32, device=dev) if adam else None
+        v_flat = torch.zeros(n, dtype=f32, device=dev) if adam else None
+        for k, off, cnt in self._flat_layout:
+            sl = slice(off, off + cnt)
+            if k == "dense":
+                p_flat[sl].copy_(self.dense)
+                if adam:
+                    m_flat[sl].copy_(self.m_dense)
+                    v_flat[sl].copy_(self.v_dense)
+                self.dense, self.g_dense = p_flat[sl], g_flat[sl]
+                if adam:
+                    self.m_dense, self.v_dense = m_flat[sl], v_flat[sl]
+            else:
+                shape = self._tables[k].shape
+                p_flat[sl].copy_(self._tables[k].reshape(-1))
+                if adam:
+                    m_flat[sl].copy_(self.m[k].reshape(-1))
+                    v_flat[sl].copy_(self.v[k].reshape(-1))
+                    self.m[k], self.v[k] = m_flat[sl].view(shape), v_flat[sl].view(shape)
+                self._tables[k] = p_flat[sl].view(shape)
+                self.g_tables[k] = g_flat[sl].view(shape)
+        self.user_mlp, self.item_mlp = self._tables[K_USER], self._tables[K_ITEM]
+        if self.mf_dim:
+            self.user_gmf, self.item_gmf = self._tables[K_GMF_USER], self._tables[K_GMF_ITEM]
+        self.p_flat, self.g_flat, self.m_flat, self.v_flat = p_flat, g_flat, m_flat, v_flat
+        self._structs()
+
+    def flat_regions(self):
+        """[(offset, padded elements, l2 coefficient)] of the flat layout: user tables, dense block, item tables."""
+        out = []
+        for i, (k, off, cnt) in enumerate(self._flat_layout):
+            end = self._flat_layout[i + 1][1] if i + 1 < len(self._flat_layout) else self.g_flat.numel()
+            out.append((off, end - off, 0.0 if k == "dense" else self.l2[0]))
+        return out
+
+    def step_lr_t(self):
+        """Step size of the NEXT update as mr_neumf_apply computes it (legacy-Keras Adam folds the bias correction in)."""
+        f32 = lambda x: float(np.float32(x))  # the C side holds lr and the betas as floats
+        if self.optimizer != "adam":
+            return f32(self.lr)
+        t = self.iterations + 1
+        return f32(self.lr) * math.sqrt(1.0 - f32(self.beta_2) ** t) / (1.0 - f32(self.beta_1) ** t)
 
     # ---- C structs ------------------------------------------------------------------------------
     def _structs(self):
@@ -391,12 +452,8 @@ class NeuMFEngine(object):
         advances the step counter once every region is done."""
         if not self.table_state:
             raise RuntimeError("this engine caches rows owned by other ranks; use apply_dense_only()")
-        t = self.iterations + 1
         adam = self.optimizer == "adam"
-        f32 = lambda x: float(np.float32(x))  # the C side holds lr and the betas as floats
-        lr_t = f32(self.lr)
-        if adam:  # adam_lr_t of api.cu: double arithmetic on the float-valued hyper-parameters
-            lr_t = f32(self.lr) * math.sqrt(1.0 - f32(self.beta_2) ** t) / (1.0 - f32(self.beta_1) ** t)
+        lr_t = self.step_lr_t()  # adam_lr_t of api.cu: double arithmetic on the float-valued hyper-parameters
         if name == "dense":
             p, g, m, v, l2 = self.dense, self.g_dense, self.m_dense, self.v_dense, 0.0
         else:

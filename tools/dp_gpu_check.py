@@ -1,7 +1,9 @@
 """2+ GPU check of the data-parallel step (run under torchrun, one rank per GPU):
     torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_gpu_check.py
-Every rank trains on its shard of a global batch through DataParallelNeuMF (NCCL all-reduce of the flat
-gradient buffer); rank 0 replays the same global batches on one GPU and compares the weights."""
+Every rank trains on its shard of a global batch through DataParallelNeuMF -- with both exchanges: "peer" (the fused
+reduce + optimizer + distribute kernel over NVLink peer pointers, mr_dp_reduce_apply) and "nccl" (all-reduce of the
+flat gradient buffer, then the full sweep); rank 0 replays the same global batches on one GPU and compares the
+weights and the Adam state; all replicas must end BIT-identical."""
 import os
 import sys
 
@@ -15,6 +17,27 @@ from movierec import _engine  # noqa: E402
 from movierec._distributed import DataParallelNeuMF, shard_batch  # noqa: E402
 
 
+FAILURES = []
+
+
+def robust_err(a, b, tol, max_outliers=8, cap=2e-3):
+    """Worst |a - b| / max|b| after setting aside at most `max_outliers` elements (returns -1 outliers when there are
+    more, or when one is off by more than `cap`).  Why any: the gradient is DIScontinuous in the weights where a ReLU
+    input sits at zero; two runs whose weights agree to 1e-7 after a step can take different sides of one of the ~4 M
+    kinks in the next one, and legacy Adam turns that single row's gradient difference into a visible difference of
+    the few entries of it whose sqrt(v) is near epsilon (seen once: peer against nccl exchange, bit-identical Adam
+    state after step 1, one element of one user row 8e-6 apart after step 3)."""
+    scale = max(float(np.max(np.abs(b))), 1e-30)
+    d = np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)).reshape(-1) / scale
+    bad = np.flatnonzero(d > tol)
+    if bad.size == 0:
+        return float(d.max()) if d.size else 0.0, 0
+    if bad.size > max_outliers or float(d[bad].max()) > cap:
+        return float(d.max()), -1
+    d[bad] = 0.0
+    return float(d.max()), int(bad.size)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -25,17 +48,24 @@ def main():
     # (SGD for the projected sequence: the update is linear in the gradients, so the 1e-6 the two summation orders of
     # the per-user GEMMs differ by stays 1e-6; under Adam, m / (sqrt(v) + eps) turns it into up to 1e-4 of a weight
     # wherever a gradient entry nearly cancels -- see tests/test_gpu_parity.py: OraclePair)
-    for grouped, l2, opt in ((False, [0, 0, 0], "adam"), (True, [0, 0, 0], "sgd"), (True, [0.01, 0.02, 0.005], "sgd"),
-                             (True, [0, 0, 0], "adam")):
-        check(rank, world, grouped, l2, opt)
+    for exchange in ("peer", "nccl"):
+        for grouped, l2, opt in ((False, [0, 0, 0], "adam"), (True, [0, 0, 0], "sgd"), (True, [0.01, 0.02, 0.005], "sgd"),
+                                 (True, [0, 0, 0], "adam"), (False, [0.01, 0.02, 0.005], "adam")):
+            check(rank, world, grouped, l2, opt, exchange)
     dist.barrier()
     dist.destroy_process_group()
+    for f in FAILURES:
+        print("dp_gpu_check FAILED:", f, flush=True)
+    if FAILURES:
+        sys.exit(1)
+    if rank == 0:
+        print("dp_gpu_check ok", flush=True)
 
 
-def check(rank, world, grouped, l2, opt):
+def check(rank, world, grouped, l2, opt, exchange):
     nu, ni, L, f, negs = (1500 if grouped else 5000), 3000, [256, 128, 64], 64, 4
     eng = _engine.NeuMFEngine(nu, ni, L, l2, mf_dim=f, seed=11 + rank, optimizer=opt, lr=0.5 if opt == "sgd" else 1e-3)  # different seeds: broadcast must fix it
-    dp = DataParallelNeuMF(eng)
+    dp = DataParallelNeuMF(eng, exchange=exchange)
     dp.broadcast_parameters(0)
     ref = None
     if rank == 0:
@@ -54,21 +84,35 @@ def check(rank, world, grouped, l2, opt):
             assert abs(float(tot[0]) - float(want[0])) <= 1e-5 * abs(float(want[0])), (tot, want)
             assert float(tot[1]) == float(want[1])
     torch.cuda.synchronize()
+    dp.sync_optimizer_state()  # peer exchange: the Adam state is sharded by owner
     if rank == 0:
         a, b = eng.get_weights(), ref.get_weights()
         worst = 0.0
+        tol = 3e-5 if (opt == "sgd" or not grouped) else 1e-3
         for k in a:
-            err = float(np.max(np.abs(a[k] - b[k])) / max(np.max(np.abs(b[k])), 1e-30))
+            err, outliers = robust_err(a[k], b[k], tol)
             worst = max(worst, err)
-            assert err <= (3e-5 if (opt == "sgd" or not grouped) else 1e-3), (k, err)
-        print("dp_gpu_check ok: world={} grouped={} l2={} {} early_user_all_reduce={} steps=3 worst relative weight "
-              "difference {:.2e}".format(world, grouped, l2, opt, dp.early_user and grouped, worst))
-    # every replica must hold identical weights
-    h = torch.tensor([float(eng.dense.double().sum()) + float(eng.user_mlp.double().sum())], device="cuda", dtype=torch.float64)
+            if err > tol or outliers < 0:
+                FAILURES.append((exchange, grouped, l2, opt, k, err, outliers))
+        if opt == "adam":
+            sa, sb = eng.get_optimizer_state(), ref.get_optimizer_state()
+            assert sa["iterations"] == sb["iterations"] == 3
+            for k in sa:
+                if k != "iterations":
+                    err, _ = robust_err(sa[k], sb[k], 5e-3)
+                    # (a plumbing check of the owner-sharded state -- a slice that went missing would be off by ~1;
+                    # m and v follow the weights' differences discussed above and in robust_err)
+                    if err > 5e-3:
+                        FAILURES.append((exchange, grouped, l2, opt, "adam state " + k, err))
+        print("dp_gpu_check done: world={} exchange={} grouped={} l2={} {} steps=3 worst relative weight difference {:.2e}"
+              .format(world, exchange, grouped, l2, opt, worst), flush=True)
+    # every replica must hold bit-identical weights
+    bits = torch.cat([eng.dense.reshape(-1)] + [t.reshape(-1) for t in eng._tables.values()]).view(torch.int32).to(torch.int64)
+    h = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=bits.device)).sum()])
     lo, hi = h.clone(), h.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    assert float(lo) == float(hi), "replicas diverged"
+    assert bool((lo == hi).all()), "replicas diverged"
 
 
 if __name__ == "__main__":
