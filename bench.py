@@ -531,7 +531,8 @@ def run_gpu(args, wl):
         if dp is None:  # uploads, steps, reads the loss back; the next batch's upload runs under this step
             nxt = pinned[(i + 1) % n_batches]
             return model.model.train_on_batch([u, it], y, prefetch=([nxt[0], nxt[1]], nxt[2]))
-        return dp.train_step(u, it, y, global_rows, group=group, k=group, grouped=True).cpu()
+        return dp.train_step(u, it, y, global_rows, group=group, k=group, grouped=True,
+                             prefetch=pinned[(i + 1) % n_batches]).cpu()
 
     e2e_steps = 0 if args.lean else max(3, min(args.steps, 20))
     if not args.lean:

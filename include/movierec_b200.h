@@ -302,12 +302,17 @@ int mr_sort_pairs(const int32_t* keys, int64_t n, int32_t key_bits, int32_t* sor
  *     g = grad_peers[0][i] + grad_peers[1][i] + ... (rank order, the same on every rank) + 2*l2*p[i]
  *     Adam / SGD step of mr_optimizer_flat with THIS rank's m[i], v[i] (optimizer state is sharded by owner)
  *     param_peers[r][i] = new value, for every r.
+ * grad_multicast / param_multicast (both or neither; NULL = peer loads and stores): NVSwitch multicast addresses of the
+ * same two buffers (cuMulticast* / torch symmetric memory's multicast_ptr).  The sum is then one multimem.ld_reduce
+ * and the distribution one multimem.st per 16 bytes -- the switch adds and replicates -- which halves the NVLink bytes
+ * per rank; the order of the switch's additions is its own, the replicas still end bit-identical.
  * The caller orders the launch against the other ranks with cross-rank barriers: every rank's gradients of the region
  * final and its reads of the region's parameters done before, all owners' launches complete before the parameters
  * are read again.  No reference counterpart (the reference is single-process). */
 int mr_dp_reduce_apply(const float* const* grad_peers, float* const* param_peers, int32_t world, int32_t rank,
                        float* m, float* v, int64_t lo, int64_t hi, int32_t optimizer, float lr_t, float beta_1,
-                       float beta_2, float epsilon, float l2, void* stream);
+                       float beta_2, float epsilon, float l2, const float* grad_multicast, float* param_multicast,
+                       void* stream);
 
 /* Elementwise legacy-Keras Adam / SGD over a flat buffer (l2 adds 2*l2*p to the gradient). */
 int mr_optimizer_flat(float* p, const float* g, float* m, float* v, int64_t n, int32_t optimizer,

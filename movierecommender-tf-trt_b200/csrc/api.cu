@@ -1547,7 +1547,7 @@ int mr_optimizer_flat(float* p, const float* g, float* m, float* v, int64_t n, i
 
 int mr_dp_reduce_apply(const float* const* grad_peers, float* const* param_peers, int32_t world, int32_t rank, float* m,
                        float* v, int64_t lo, int64_t hi, int32_t optimizer, float lr_t, float beta_1, float beta_2,
-                       float epsilon, float l2, void* stream) {
+                       float epsilon, float l2, const float* grad_multicast, float* param_multicast, void* stream) {
   MR_REQUIRE(grad_peers && param_peers, "dp_reduce_apply: NULL pointer array");
   MR_REQUIRE(world >= 1 && rank >= 0 && rank < world, "dp_reduce_apply: rank %d of %d", rank, world);
   MR_REQUIRE(lo >= 0 && hi >= lo && (lo & 3) == 0 && (hi & 3) == 0, "dp_reduce_apply: [lo, hi) must be multiples of 4");
@@ -1556,8 +1556,11 @@ int mr_dp_reduce_apply(const float* const* grad_peers, float* const* param_peers
     MR_REQUIRE(grad_peers[r] && param_peers[r] && ((reinterpret_cast<uintptr_t>(grad_peers[r]) |
                                                      reinterpret_cast<uintptr_t>(param_peers[r])) & 15) == 0,
                "dp_reduce_apply: rank %d's pointers must be non-NULL and 16-byte aligned", r);
+  MR_REQUIRE((grad_multicast == nullptr) == (param_multicast == nullptr) &&
+                 ((reinterpret_cast<uintptr_t>(grad_multicast) | reinterpret_cast<uintptr_t>(param_multicast)) & 15) == 0,
+             "dp_reduce_apply: multicast addresses come as a 16-byte aligned pair or not at all");
   return launch_dp_reduce_apply(grad_peers, param_peers, world, rank, m, v, lo, hi, optimizer, lr_t, beta_1, beta_2,
-                                epsilon, l2, (cudaStream_t)stream);
+                                epsilon, l2, grad_multicast, param_multicast, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -172,7 +172,8 @@ int launch_gather_rows_sharded(const float* const* shards, int world, int64_t to
 // elements [lo, hi) of a region; grad_peers / param_peers are HOST arrays of `world` peer-mapped device pointers
 int launch_dp_reduce_apply(const float* const* grad_peers, float* const* param_peers, int world, int rank, float* m,
                            float* v, int64_t lo, int64_t hi, int optimizer, float lr_t, float beta_1, float beta_2,
-                           float epsilon, float l2, cudaStream_t st);
+                           float epsilon, float l2, const float* grad_multicast, float* param_multicast,
+                           cudaStream_t st);
 
 // ---- grouped batches (gather.cu): one positive and its negatives share the user ----------------------------
 // out[g] = sum_{j < group} in[g * group + j]  (rows of `width` floats, width % 4 == 0, row strides in_ld / out_ld

@@ -47,9 +47,10 @@ def shard_batch(users, items, labels, group, world_size, rank):
 class DataParallelNeuMF(object):
     """Wraps a NeuMFEngine replica; `train_step` takes the RANK-LOCAL rows of a global batch."""
 
-    def __init__(self, engine, process_group=None, exchange=None):
+    def __init__(self, engine, process_group=None, exchange=None, multicast=None):
         """exchange: "peer" | "nccl" | None (= "peer" on CUDA devices with the NCCL backend and more than one rank;
-        MR_DP_EXCHANGE overrides the default for A/B runs)."""
+        MR_DP_EXCHANGE overrides the default for A/B runs).  multicast (peer exchange): None = NVSwitch multicast on
+        more than four ranks when the buffers have a multicast address, False = peer loads / stores, True = insist."""
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         if engine.table_mode != "dense":
@@ -71,6 +72,9 @@ class DataParallelNeuMF(object):
         if exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' or 'nccl', found {!r}".format(exchange))
         self.exchange = exchange
+        if os.environ.get("MR_DP_MULTICAST") is not None:  # A/B runs: 0 = peer loads / stores, 1 = insist
+            multicast = os.environ["MR_DP_MULTICAST"] not in ("0", "")
+        self.multicast = multicast
         self._comm = None
         self._ready = None
         if exchange == "peer":
@@ -88,6 +92,17 @@ class DataParallelNeuMF(object):
         w = self.world_size
         self._p_peers = (C.c_void_p * w)(*[int(x) for x in self._hp.buffer_ptrs])
         self._g_peers = (C.c_void_p * w)(*[int(x) for x in self._hg.buffer_ptrs])
+        # NVSwitch multicast addresses of the two buffers, when the box has them (NVLS): the switch then does the sum
+        # and the replication (csrc/dp_exchange.cu); MR_DP_NO_MULTICAST keeps the peer loads / stores for A/B runs
+        mc_g, mc_p = int(getattr(self._hg, "multicast_ptr", 0) or 0), int(getattr(self._hp, "multicast_ptr", 0) or 0)
+        # measured (ML-20M shape, ms per step, multicast / peer): 2 GPUs 2.06 / 1.90, 4 GPUs 2.02 / 2.00, 8 GPUs
+        # 2.02 / 2.09 -- the switch's reduction pays once the peer form would fetch more than four copies
+        use_mc = bool(mc_g and mc_p) and (self.multicast is True or (self.multicast is None and w > 4))
+        if self.multicast is True and not use_mc:
+            raise RuntimeError("multicast=True, but the symmetric-memory buffers have no multicast address on this box")
+        self.multicast = use_mc
+        self._mc_g = C.c_void_p(mc_g) if use_mc else None
+        self._mc_p = C.c_void_p(mc_p) if use_mc else None
         self._slices = []  # (lo, hi, l2, is_user_region) of the elements this rank owns
         for off, count, l2 in e.flat_regions():
             per = ((count // 4 + w - 1) // w) * 4
@@ -108,7 +123,8 @@ class DataParallelNeuMF(object):
                                              C.c_void_p(e.m_flat.data_ptr()) if adam else None,
                                              C.c_void_p(e.v_flat.data_ptr()) if adam else None, lo, hi,
                                              nat.OPT_ADAM if adam else nat.OPT_SGD, lr_t, e.beta_1, e.beta_2,
-                                             _engine.ADAM_EPSILON, l2, e._stream()), "mr_dp_reduce_apply")
+                                             _engine.ADAM_EPSILON, l2, self._mc_g, self._mc_p, e._stream()),
+                  "mr_dp_reduce_apply")
 
     def _peer_step(self, users, items, labels, kw):
         e = self.engine
@@ -151,10 +167,42 @@ class DataParallelNeuMF(object):
         for t in [e.dense] + list(e._tables.values()):
             dist.broadcast(t, src, group=self.group)
 
-    def train_step(self, users, items, labels, global_rows, group=0, k=0, grouped=False):
-        """Local forward/backward -> all-reduce(sum) of the flat gradients -> identical update.
-        Returns the rank-local step outputs (loss/hit/dcg sums over the local rows).
-        grouped: see NeuMFEngine.train_step (batches are split by whole groups, so the layout survives)."""
+    def _staged(self, users, items, labels):
+        """The device copies of a batch uploaded by the previous call's `prefetch`, found by the host arrays' identity."""
+        staged, self._prefetched = getattr(self, "_prefetched", None), None
+        if staged is not None and staged[0] == (id(users), id(items), id(labels)):
+            torch.cuda.current_stream(self.engine.device).wait_event(staged[4])
+            return staged[1], staged[2], staged[3]
+        return users, items, labels
+
+    def _upload(self, batch):
+        from . import _engine
+        e = self.engine
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=e.device)
+        users, items, labels = batch
+        with torch.cuda.stream(self._copy_stream):
+            dev = (_engine.as_device_i32(users, e.device), _engine.as_device_i32(items, e.device),
+                   _engine.as_device_f32(labels, e.device))
+            ready = torch.cuda.Event()
+            ready.record(self._copy_stream)
+        self._prefetched = ((id(users), id(items), id(labels)),) + dev + (ready,)
+
+    def train_step(self, users, items, labels, global_rows, group=0, k=0, grouped=False, prefetch=None):
+        """Local forward/backward -> sum of the ranks' gradients -> identical update on every replica.
+        Returns the rank-local step outputs (loss/hit/dcg sums over the local rows), a device tensor.
+        grouped: see NeuMFEngine.train_step (batches are split by whole groups, so the layout survives).
+        prefetch=(users, items, labels): the NEXT rank-local batch (host arrays, pinned for asynchronous copies); it is
+        uploaded on a copy stream under this step, and the next call finds it by the identity of the arrays."""
+        on_gpu = str(getattr(self.engine, "device", "cpu")).startswith("cuda")
+        if on_gpu:
+            users, items, labels = self._staged(users, items, labels)
+        out = self._step(users, items, labels, global_rows, group, k, grouped)
+        if prefetch is not None and on_gpu:
+            self._upload(prefetch)
+        return out
+
+    def _step(self, users, items, labels, global_rows, group, k, grouped):
         e = self.engine
         # the hidden kernels' l2 term 2*l2*W is part of the gradients this call returns; the all-reduce below SUMS the
         # ranks' gradients, so only rank 0 adds it (the tables' l2 term is added by apply(), after the reduction)

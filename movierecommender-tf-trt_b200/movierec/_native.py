@@ -103,7 +103,7 @@ SIGNATURES = {
     "mr_profile_begin": (C.c_int, []),
     "mr_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mr_optimizer_flat": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _f, _f, _f, _vp]),
-    "mr_dp_reduce_apply": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64, _i32, _f, _f, _f, _f, _f, _vp]),
+    "mr_dp_reduce_apply": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _i64, _i64, _i32, _f, _f, _f, _f, _f, _vp, _vp, _vp]),
 }
 
 

@@ -48,10 +48,18 @@ def main():
     # (SGD for the projected sequence: the update is linear in the gradients, so the 1e-6 the two summation orders of
     # the per-user GEMMs differ by stays 1e-6; under Adam, m / (sqrt(v) + eps) turns it into up to 1e-4 of a weight
     # wherever a gradient entry nearly cancels -- see tests/test_gpu_parity.py: OraclePair)
-    for exchange in ("peer", "nccl"):
+    # "peer-mc": the peer exchange through NVSwitch multicast (its default on more than four ranks); "peer-p2p": plain
+    # peer loads / stores
+    for exchange in ("peer-mc", "peer-p2p", "nccl"):
         for grouped, l2, opt in ((False, [0, 0, 0], "adam"), (True, [0, 0, 0], "sgd"), (True, [0.01, 0.02, 0.005], "sgd"),
                                  (True, [0, 0, 0], "adam"), (False, [0.01, 0.02, 0.005], "adam")):
-            check(rank, world, grouped, l2, opt, exchange)
+            h1 = check(rank, world, grouped, l2, opt, exchange)
+            if exchange == "peer-mc" and grouped and opt == "adam":  # run to run: the same bits
+                h2 = check(rank, world, grouped, l2, opt, exchange, quiet=True)
+                if not bool((h1 == h2).all()):
+                    FAILURES.append((exchange, grouped, l2, opt, "two runs differ", h1.tolist(), h2.tolist()))
+                elif rank == 0:
+                    print("dp_gpu_check: exchange=peer-mc run twice: bit-identical weights", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     for f in FAILURES:
@@ -62,10 +70,10 @@ def main():
         print("dp_gpu_check ok", flush=True)
 
 
-def check(rank, world, grouped, l2, opt, exchange):
+def check(rank, world, grouped, l2, opt, exchange, quiet=False):
     nu, ni, L, f, negs = (1500 if grouped else 5000), 3000, [256, 128, 64], 64, 4
     eng = _engine.NeuMFEngine(nu, ni, L, l2, mf_dim=f, seed=11 + rank, optimizer=opt, lr=0.5 if opt == "sgd" else 1e-3)  # different seeds: broadcast must fix it
-    dp = DataParallelNeuMF(eng, exchange=exchange)
+    dp = DataParallelNeuMF(eng, exchange=exchange.split("-")[0], multicast=exchange == "peer-mc")
     dp.broadcast_parameters(0)
     ref = None
     if rank == 0:
@@ -104,8 +112,10 @@ def check(rank, world, grouped, l2, opt, exchange):
                     # m and v follow the weights' differences discussed above and in robust_err)
                     if err > 5e-3:
                         FAILURES.append((exchange, grouped, l2, opt, "adam state " + k, err))
-        print("dp_gpu_check done: world={} exchange={} grouped={} l2={} {} steps=3 worst relative weight difference {:.2e}"
-              .format(world, exchange, grouped, l2, opt, worst), flush=True)
+        if not quiet:
+            print("dp_gpu_check done: world={} exchange={}{} grouped={} l2={} {} steps=3 worst relative weight difference "
+                  "{:.2e}".format(world, exchange, "",
+                                  grouped, l2, opt, worst), flush=True)
     # every replica must hold bit-identical weights
     bits = torch.cat([eng.dense.reshape(-1)] + [t.reshape(-1) for t in eng._tables.values()]).view(torch.int32).to(torch.int64)
     h = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=bits.device)).sum()])
@@ -113,6 +123,7 @@ def check(rank, world, grouped, l2, opt, exchange):
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     assert bool((lo == hi).all()), "replicas diverged"
+    return h.cpu()
 
 
 if __name__ == "__main__":
