@@ -265,6 +265,12 @@ int mr_uses_item_projection(const MrModel* model, int64_t rows);
 /* The train step does the same for the user half (E_user . W1[user rows] + b1 once per user, per-user sums of the
  * group sums of dZ1) when, in addition, there are no more users than the step has groups. */
 int mr_uses_user_projection(const MrModel* model, int64_t rows, int32_t group);
+/* 1 when a grouped train step (MR_TRAIN_USERS_GROUPED, dense gradient tables) over `rows` rows in groups of `group` on
+ * this model takes the default-tower kernel: the reference's DEFAULT_PARAMS tower 64-32-16-8 (trainer.py) with GMF 8,
+ * both halves of the first layer projected over the tables and everything per row in one thread-per-group kernel on
+ * CUDA cores (the widths are below the tensor-core tiles).  Same results as the generic kernel up to summation order.
+ * MR_PROJECTION_OFF or MR_FUSED_OFF on the model keep the generic kernel. */
+int mr_uses_small_tower(const MrModel* model, int64_t rows, int32_t group);
 
 /* Building blocks exposed for tests and for data-parallel callers.  (The tcgen05 self-tests, the descriptor probe
  * and the issue-rate probe are diagnostics: include/movierec_b200_diag.h, libmovierec_b200_diag.so.) */

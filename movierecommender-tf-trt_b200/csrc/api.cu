@@ -204,6 +204,31 @@ static bool user_proj_ok(const MrModel& m, int64_t rows, int group) {
   return m.item_projection == MR_PROJECTION_ON || (int64_t)m.num_users <= rows / group;
 }
 
+// The reference's default tower (64-32-16-8, GMF 8) takes the same two projections on CUDA cores (small_tower.cu):
+// grouped batches of five rows, dense gradient tables, at least twice as many rows as items and no more users than
+// groups (or MR_PROJECTION_ON).  MR_PROJECTION_OFF / MR_FUSED_OFF keep the generic tile kernel (A/B runs, tests).
+static bool small_proj_ok(const MrModel& m, int64_t rows, int group) {
+  if (use_tc(m) || m.item_projection == MR_PROJECTION_OFF || m.fused_train == MR_FUSED_OFF) return false;
+  if (group < 1 || !small_tower_supported(m, group) || rows % group) return false;
+  if (m.item_projection == MR_PROJECTION_ON) return true;
+  return 2 * (int64_t)m.num_items <= rows && (int64_t)m.num_users <= rows / group;
+}
+
+struct SmallWs {
+  float *Pi, *Pu, *Si, *Su;
+  size_t total;
+};
+static SmallWs carve_small(const MrModel& m, void* ws) {
+  SmallWs w{};
+  Carver cv(ws);
+  w.Pi = cv.take<float>((size_t)m.num_items * m.L[1]);
+  w.Pu = cv.take<float>((size_t)m.num_users * m.L[1]);
+  w.Si = cv.take<float>((size_t)m.num_items * m.L[1]);
+  w.Su = cv.take<float>((size_t)m.num_users * m.L[1]);
+  w.total = cv.off;
+  return w;
+}
+
 // Rows per launch of the tensor-core kernels: the whole batch up to 2^21 rows (persistent CTAs need many
 // tiles each to reach steady state: one launch of 1,310,720 rows instead of two of 655,360 takes the ML-20M step
 // from 2.48 to 2.45 ms, and four of 327,680 cost +0.25 ms; intermediates are ~2.3 KB of workspace per row), split
@@ -459,6 +484,8 @@ struct TrainWs {
   size_t seg_ws_u_bytes;
   void* tc_ws;
   size_t tc_ws_bytes;
+  void* small_ws;  // projected tables and per-item / per-user sums of the default-tower step
+  size_t small_ws_bytes;
   int32_t* pos;
   float* rank_partials;
   int32_t* group_users;  // grouped batches: the user of each group
@@ -493,6 +520,8 @@ static TrainWs carve_train(const MrModel& m, int64_t B, void* ws) {
   t.group_users = cv.take<int32_t>(B / 2 + 1);
   t.tc_ws_bytes = tc_eligible(m) ? carve_tc(m, true, B, nullptr).total : 0;
   t.tc_ws = cv.take<char>(t.tc_ws_bytes);
+  t.small_ws_bytes = (!tc_eligible(m) && small_tower_supported(m, 5)) ? carve_small(m, nullptr).total : 0;
+  t.small_ws = cv.take<char>(t.small_ws_bytes);
   t.total = cv.off;
   return t;
 }
@@ -772,7 +801,10 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   // item-projected first layer: item half of the first layer once per item (see item_proj_ok)
   const bool proj = grouped && opt->table_mode == MR_TABLES_DENSE && item_proj_ok(m, B);
   const bool uproj = proj && user_proj_ok(m, B, group);
-  const int64_t n_user_rows = grouped ? B / group : B;  // staged user-gradient rows: one per group or one per row
+  // default tower: both projections on CUDA cores, thread per group (small_tower.cu)
+  const bool small = (flags & MR_TRAIN_USERS_GROUPED) && opt->table_mode == MR_TABLES_DENSE && small_proj_ok(m, B, group);
+  const bool by_group = grouped || small;
+  const int64_t n_user_rows = by_group ? B / group : B;  // staged user-gradient rows: one per group or one per row
   // stable sorts of the ids (keys of the segmented reductions below) on the side stream, under the tower
   // (phase timing then sees only the launch cost of this block on the main stream)
   SideStream* side = side_stream();
@@ -787,10 +819,14 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     if (opt->table_mode == MR_TABLES_DENSE) {  // the gradient tables the segmented reductions write into
       if (uproj)
         MR_CUDA(cudaMemsetAsync(carve_tc(m, true, B, t.tc_ws).Su, 0, (size_t)m.num_users * m.L[1] * sizeof(float), ss));
+      else if (small)
+        MR_CUDA(cudaMemsetAsync(carve_small(m, t.small_ws).Su, 0, (size_t)m.num_users * m.L[1] * sizeof(float), ss));
       else
         MR_CUDA(cudaMemsetAsync(grads->user_mlp, 0, (size_t)m.num_users * d_u * sizeof(float), ss));
       if (proj)  // the per-item sums of dZ[1]; grads->item_mlp is then written whole by a GEMM on them
         MR_CUDA(cudaMemsetAsync(carve_tc(m, true, B, t.tc_ws).Si, 0, (size_t)m.num_items * m.L[1] * sizeof(float), ss));
+      else if (small)
+        MR_CUDA(cudaMemsetAsync(carve_small(m, t.small_ws).Si, 0, (size_t)m.num_items * m.L[1] * sizeof(float), ss));
       else
         MR_CUDA(cudaMemsetAsync(grads->item_mlp, 0, (size_t)m.num_items * d_i * sizeof(float), ss));
       if (m.mf_dim > 0) {
@@ -798,12 +834,12 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
         MR_CUDA(cudaMemsetAsync(grads->item_gmf, 0, (size_t)m.num_items * m.mf_dim * sizeof(float), ss));
       }
     }
-    if (grouped) {
+    if (by_group) {
       rc = launch_check_grouped(users, B, group, t.flags + 1, ss);
       if (rc == MR_OK) rc = launch_group_heads(users, B / group, group, t.group_users, ss);
       if (rc != MR_OK) return rc;
     }
-    rc = launch_sort_pairs(grouped ? t.group_users : users, n_user_rows, bits_for(m.num_users), t.sorted_keys,
+    rc = launch_sort_pairs(by_group ? t.group_users : users, n_user_rows, bits_for(m.num_users), t.sorted_keys,
                            t.sorted_index, t.sort_ws, t.sort_ws_bytes, ss);
     if (rc == MR_OK)
       rc = launch_sort_pairs(items, B, bits_for(m.num_items), t.sorted_keys_i, t.sorted_index_i, t.sort_ws,
@@ -1197,6 +1233,73 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     if (rc != MR_OK) return rc;
     rc = launch_dense_reduce(m, t.dense_partial, t.dense_stride, P, grads->dense, st, !(flags & MR_TRAIN_NO_DENSE_L2));
     if (rc != MR_OK) return rc;
+  } else if (small) {
+    // ---- default tower, projected: Pi / Pu over the tables, one thread-per-group kernel for everything per row,
+    // segment sums of the staged rows per item / per user, then the first layer's backward on the sums
+    const int L1 = m.L[1], f = m.mf_dim, cap = max_tile_ctas();
+    const SmallWs w = carve_small(m, t.small_ws);
+    const float* W1u = m.W[1];
+    const float* W1i = m.W[1] + (size_t)d_u * L1;
+    MR_CUDA(cudaMemsetAsync(t.dense_partial, 0, (size_t)cap * t.dense_stride * sizeof(float), st));
+    prof_mark(MR_PHASE_TC_DENSE_FWD, st);
+    rc = launch_small_rows_gemm(m.item_mlp, m.num_items, d_i, W1i, L1, L1, false, nullptr, w.Pi, st);
+    if (rc == MR_OK) rc = launch_small_rows_gemm(m.user_mlp, m.num_users, d_u, W1u, L1, L1, false, m.b[1], w.Pu, st);
+    if (rc != MR_OK) return rc;
+    SmallTowerArgs a{};
+    a.model = model;
+    a.Pi = w.Pi;
+    a.Pu = w.Pu;
+    a.users = users;
+    a.items = items;
+    a.labels = labels;
+    a.B = B;
+    a.inv_batch = inv_global_batch;
+    a.probs = t.probs;
+    a.stage_i = t.stage_i;
+    a.stage_u = t.stage_u;
+    a.dense_partial = t.dense_partial;
+    a.dense_stride = t.dense_stride;
+    a.loss_partial = t.loss_partial;
+    a.flags = t.flags;
+    a.max_ctas = cap;
+    int grid = 0, grid_i = 0, grid_u = 0;
+    prof_mark(MR_PHASE_FUSED_TILE, st);
+    rc = launch_small_tower_train(a, st, &grid);
+    if (rc != MR_OK) return rc;
+    if (side != nullptr) MR_CUDA(cudaStreamWaitEvent(st, side->join, 0));  // sorted keys, cleared Si / Su / GMF tables
+    prof_mark(MR_PHASE_SEGREDUCE, st);
+    RowUpdate ru{};
+    ru.mode = MR_TABLES_DENSE;
+    ru.optimizer = opt->optimizer;
+    ru.d0 = L1;
+    ru.d1 = f;
+    ru.num_rows = m.num_items;
+    ru.g0 = w.Si;
+    ru.g1 = grads->item_gmf;
+    rc = launch_segreduce(t.sorted_keys_i, t.sorted_index_i, B, t.stage_i, ru, t.seg_ws, t.seg_ws_bytes, st);
+    if (rc != MR_OK) return rc;
+    ru.num_rows = m.num_users;
+    ru.g0 = w.Su;
+    ru.g1 = grads->user_gmf;
+    rc = launch_segreduce(t.sorted_keys, t.sorted_index, n_user_rows, t.stage_u, ru, t.seg_ws_u, t.seg_ws_u_bytes, st);
+    if (rc != MR_OK) return rc;
+    prof_mark(MR_PHASE_TC_DENSE_BWD, st);  // d E = S . W1^T over the tables
+    rc = launch_small_rows_gemm(w.Si, m.num_items, L1, W1i, L1, d_i, true, nullptr, grads->item_mlp, st);
+    if (rc == MR_OK) rc = launch_small_rows_gemm(w.Su, m.num_users, L1, W1u, L1, d_u, true, nullptr, grads->user_mlp, st);
+    if (rc != MR_OK) return rc;
+    prof_mark(MR_PHASE_TC_WGRAD, st);  // d W1 = E^T . S, d b1 = colsum(Su)
+    rc = launch_small_table_wgrad(m.item_mlp, w.Si, m.num_items, t.dense_partial + (W1i - m.dense), nullptr,
+                                  t.dense_stride, cap, st, &grid_i);
+    if (rc == MR_OK)
+      rc = launch_small_table_wgrad(m.user_mlp, w.Su, m.num_users, t.dense_partial + (W1u - m.dense),
+                                    t.dense_partial + (m.b[1] - m.dense), t.dense_stride, cap, st, &grid_u);
+    if (rc != MR_OK) return rc;
+    prof_mark(MR_PHASE_MISC, st);
+    const int nrows = grid > grid_i ? (grid > grid_u ? grid : grid_u) : (grid_i > grid_u ? grid_i : grid_u);
+    rc = launch_dense_reduce(m, t.dense_partial, t.dense_stride, nrows, grads->dense, st, !(flags & MR_TRAIN_NO_DENSE_L2));
+    if (rc != MR_OK) return rc;
+    rc = launch_sum_partials(t.loss_partial, grid, step_out + MR_OUT_LOSS_SUM, st);
+    if (rc != MR_OK) return rc;
   } else {
   rc = launch_transpose_kernels(m, t.wt, st);
   if (rc != MR_OK) return rc;
@@ -1256,7 +1359,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   u.num_rows = m.num_users;
   u.p0 = m.user_mlp; u.m0 = opt->m_user_mlp; u.v0 = opt->v_user_mlp; u.g0 = grads->user_mlp;
   u.p1 = m.user_gmf; u.m1 = opt->m_user_gmf; u.v1 = opt->v_user_gmf; u.g1 = grads->user_gmf;
-  if (!uproj) {
+  if (!uproj && !small) {
     prof_mark(MR_PHASE_SEGREDUCE, st);
     rc = launch_segreduce(t.sorted_keys, t.sorted_index, n_user_rows, t.stage_u, u, t.seg_ws, t.seg_ws_bytes, st);
     if (rc != MR_OK) return rc;
@@ -1266,7 +1369,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   u.num_rows = m.num_items;
   u.p0 = m.item_mlp; u.m0 = opt->m_item_mlp; u.v0 = opt->v_item_mlp; u.g0 = grads->item_mlp;
   u.p1 = m.item_gmf; u.m1 = opt->m_item_gmf; u.v1 = opt->v_item_gmf; u.g1 = grads->item_gmf;
-  if (!proj) {  // (the item-projected step reduced the item rows before its per-item GEMMs)
+  if (!proj && !small) {  // (the item-projected step reduced the item rows before its per-item GEMMs)
     prof_mark(MR_PHASE_SEGREDUCE, st);
     rc = launch_segreduce(t.sorted_keys_i, t.sorted_index_i, B, t.stage_i, u, t.seg_ws, t.seg_ws_bytes, st);
   }
@@ -1462,6 +1565,11 @@ int mr_uses_item_projection(const MrModel* model, int64_t rows) {
 int mr_uses_user_projection(const MrModel* model, int64_t rows, int32_t group) {
   if (model == nullptr || model->n_layers < 1 || model->n_layers > MR_MAX_LAYERS) return 0;
   return user_proj_ok(*model, rows, group) ? 1 : 0;
+}
+
+int mr_uses_small_tower(const MrModel* model, int64_t rows, int32_t group) {
+  if (model == nullptr || model->n_layers < 1 || model->n_layers > MR_MAX_LAYERS) return 0;
+  return small_proj_ok(*model, rows, group) ? 1 : 0;
 }
 
 int mr_uses_tensor_cores(const MrModel* model) {

@@ -175,6 +175,31 @@ int launch_dp_reduce_apply(const float* const* grad_peers, float* const* param_p
                            float epsilon, float l2, const float* grad_multicast, float* param_multicast,
                            cudaStream_t st);
 
+// ---- the reference's default tower 64-32-16-8 + GMF 8 as a projected grouped step on CUDA cores (small_tower.cu) ----
+struct SmallTowerArgs {
+  const MrModel* model;
+  const float *Pi, *Pu;  // E_item . W1i (num_items x L1), E_user . W1u + b1 (num_users x L1)
+  const int32_t *users, *items;
+  const float* labels;
+  int64_t B;
+  float inv_batch;
+  float* probs;
+  float *stage_i, *stage_u;  // [dZ1 | GMF row gradient] per row / per group
+  float* dense_partial;      // rows of dense_stride floats, one per CTA: layers >= 2 and the output unit
+  int64_t dense_stride;
+  float* loss_partial;
+  int32_t* flags;
+  int max_ctas;
+};
+bool small_tower_supported(const MrModel& m, int group);
+int launch_small_tower_train(const SmallTowerArgs& a, cudaStream_t st, int* grid_out);
+// out = A (rows x K) . W (K x N, or its transpose read from an N x K array when `transpose`) (+ bias)
+int launch_small_rows_gemm(const float* A, int64_t rows, int K, const float* W, int ldw, int N, bool transpose,
+                           const float* bias, float* out, cudaStream_t st);
+// dW (32 x 32) = E^T . S, db = colsum(S) into per-CTA rows of a partial buffer
+int launch_small_table_wgrad(const float* E, const float* S, int64_t rows, float* dw_partial, float* db_partial,
+                             int64_t stride, int max_ctas, cudaStream_t st, int* grid_out);
+
 // ---- grouped batches (gather.cu): one positive and its negatives share the user ----------------------------
 // out[g] = sum_{j < group} in[g * group + j]  (rows of `width` floats, width % 4 == 0, row strides in_ld / out_ld
 // floats, 0 = width), fixed order

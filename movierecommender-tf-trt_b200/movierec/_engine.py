@@ -340,6 +340,10 @@ class NeuMFEngine(object):
         """True when a grouped train step over `rows` rows also computes the user half once per user."""
         return bool(nat.lib.mr_uses_user_projection(C.byref(self._model), int(rows), int(group)))
 
+    def uses_small_tower(self, rows, group):
+        """True when a grouped train step takes the default-tower (64-32-16-8 + GMF 8) thread-per-group kernel."""
+        return bool(nat.lib.mr_uses_small_tower(C.byref(self._model), int(rows), int(group)))
+
     def _workspace(self, nbytes):
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)

@@ -100,6 +100,7 @@ SIGNATURES = {
     "mr_uses_tensor_cores": (C.c_int, [_PM]),
     "mr_uses_item_projection": (C.c_int, [_PM, _i64]),
     "mr_uses_user_projection": (C.c_int, [_PM, _i64, _i32]),
+    "mr_uses_small_tower": (C.c_int, [_PM, _i64, _i32]),
     "mr_profile_begin": (C.c_int, []),
     "mr_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mr_optimizer_flat": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _f, _f, _f, _vp]),

@@ -537,6 +537,65 @@ def test_item_projection_treats_bad_item_ids_like_the_per_row_path(eng_mod):
     assert int(eng.train_step(users, items, y, group=negs + 1, k=3, grouped=True).cpu().numpy()[4]) & 1
 
 
+# ---- the reference's default tower 64-32-16-8 (+ GMF 8): projected thread-per-group kernel (small_tower.cu) --------
+
+SMALL_TOWER_CASES = [
+    # (num_users, num_items, layers, mf_dim, negs, groups), optimizer, l2, selector
+    ((60, 40, [64, 32, 16, 8], 8, 4, 301), "adam", [0, 0, 0, 0], "auto"),            # ragged last warp
+    ((200, 300, [64, 32, 16, 8], 8, 4, 77), "sgd", [0.001, 0.01, 0, 0.02], "on"),   # forced; table and kernel l2
+    ((700, 90, [64, 32, 16, 8], 8, 4, 2000), "adam", [0, 0, 0, 0], "auto"),          # several CTAs
+]
+
+
+@pytest.mark.parametrize("case", SMALL_TOWER_CASES, ids=lambda c: "nu{}-{}-{}".format(c[0][0], c[1], c[3]))
+def test_small_tower_train_steps_match_oracle(eng_mod, case):
+    (nu, ni, L, f, negs, groups), opt, l2, selector = case
+    rng = np.random.default_rng(500 + nu)
+    params = {"layers_sizes": L, "layers_l2reg": l2, "optimizer": opt, "lr": 0.001, "beta_1": 0.9, "beta_2": 0.999,
+              "num_negs_per_pos": negs, "k": 2}
+    eng = eng_mod.NeuMFEngine(nu, ni, L, l2, mf_dim=f, optimizer=opt, lr=0.001, table_mode="dense", seed=13,
+                              item_projection=selector)
+    assert not eng.uses_tensor_cores() and eng.uses_small_tower(groups * (negs + 1), negs + 1)
+    pair = OraclePair(eng.get_weights())
+    for step in range(3):
+        users, items, y = make_batch(rng, nu, ni, groups, negs)
+        if step == 1:
+            items[: len(items) // 2] = items[0]  # one hot item: a segment spanning many chunks of the reduction
+        check_step_against_oracles(eng, pair, users, items, y, params, l2, "dense", step, True, 2)
+    assert eng.iterations == 3
+
+
+def test_small_tower_and_tile_kernel_agree_and_are_deterministic(eng_mod):
+    """The default tower at a size where the automatic choice projects (20,000 rows, 1,500 items, 3,000 users):
+    thread-per-group kernel against the generic tile kernel, and against itself; a bad id is flagged by both."""
+    nu, ni, L, f, negs, groups = 3000, 1500, [64, 32, 16, 8], 8, 4, 4000
+    runs = {}
+    for tag, fused in (("tile", "off"), ("small", "auto"), ("again", "auto")):
+        rng = np.random.default_rng(29)
+        eng = eng_mod.NeuMFEngine(nu, ni, L, [0, 0, 0, 0], mf_dim=f, table_mode="dense", optimizer="sgd", lr=0.5, seed=6,
+                                  fused_train=fused)
+        assert eng.uses_small_tower(groups * (negs + 1), negs + 1) == (fused != "off")
+        outs = []
+        for step in range(4):
+            users = np.repeat(np.minimum(rng.zipf(1.3, groups) - 1, nu - 1), negs + 1)
+            items = np.minimum(rng.zipf(1.2, groups * (negs + 1)) - 1, ni - 1)
+            y = np.tile([0] * negs + [1], groups).astype(np.float32)
+            if step == 3:
+                items[4321] = ni + 7  # the last step only tests the flag (its weights are not compared)
+            outs.append(eng.train_step(users, items, y, group=negs + 1, k=3, grouped=True).cpu().numpy())
+            if step == 2:
+                weights = eng.get_weights()
+        runs[tag] = (weights, outs)
+    for a, b in zip(runs["tile"][1][:3], runs["small"][1][:3]):
+        assert abs(a[0] - b[0]) <= 1e-5 * abs(a[0]) and a[1] == b[1] and a[4] == 0 and b[4] == 0
+    assert int(runs["tile"][1][3][4]) & 1 and int(runs["small"][1][3][4]) & 1
+    for k in runs["tile"][0]:  # SGD at lr 0.5 over three steps: see test_grouped_and_ungrouped_steps_agree
+        rel_close(runs["small"][0][k], runs["tile"][0][k], rtol=1e-4, what="small tower vs tile kernel " + k)
+        assert np.array_equal(runs["small"][0][k], runs["again"][0][k]), k
+    for a, b in zip(runs["small"][1][:3], runs["again"][1][:3]):
+        assert np.array_equal(a, b)
+
+
 # ---- ranking ------------------------------------------------------------------------------------
 
 def test_rank_scores_reference_vectors(eng_mod, golden_dir):
