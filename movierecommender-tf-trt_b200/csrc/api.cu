@@ -1267,33 +1267,49 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     rc = launch_small_tower_train(a, st, &grid);
     if (rc != MR_OK) return rc;
     if (side != nullptr) MR_CUDA(cudaStreamWaitEvent(st, side->join, 0));  // sorted keys, cleared Si / Su / GMF tables
-    prof_mark(MR_PHASE_SEGREDUCE, st);
+    // the user-side chain (per-user sums, d E_user, d W1u / d b1) runs on the side stream next to the item-side one:
+    // both are short launches whose cost is latency, not bytes
+    cudaStream_t su_st = st;
+    if (side != nullptr) {
+      MR_CUDA(cudaEventRecord(side->fork2, st));
+      MR_CUDA(cudaStreamWaitEvent(side->stream, side->fork2, 0));
+      su_st = side->stream;
+    }
     RowUpdate ru{};
     ru.mode = MR_TABLES_DENSE;
     ru.optimizer = opt->optimizer;
     ru.d0 = L1;
     ru.d1 = f;
+    ru.num_rows = m.num_users;
+    ru.g0 = w.Su;
+    ru.g1 = grads->user_gmf;
+    rc = launch_segreduce(t.sorted_keys, t.sorted_index, n_user_rows, t.stage_u, ru, t.seg_ws_u, t.seg_ws_u_bytes, su_st);
+    if (rc == MR_OK) rc = launch_small_rows_gemm(w.Su, m.num_users, L1, W1u, L1, d_u, true, nullptr, grads->user_mlp, su_st);
+    if (rc == MR_OK)
+      rc = launch_small_table_wgrad(m.user_mlp, w.Su, m.num_users, t.dense_partial + (W1u - m.dense),
+                                    t.dense_partial + (m.b[1] - m.dense), t.dense_stride, cap, su_st, &grid_u);
+    if (rc != MR_OK) return rc;
+    if (su_st != st) {
+      if (grads->user_tables_ready != nullptr) {  // gradients final, user tables no longer read
+        MR_CUDA(cudaEventRecord((cudaEvent_t)grads->user_tables_ready, su_st));
+        user_event_recorded = true;
+      }
+      MR_CUDA(cudaEventRecord(side->join2, su_st));
+    }
+    prof_mark(MR_PHASE_SEGREDUCE, st);
     ru.num_rows = m.num_items;
     ru.g0 = w.Si;
     ru.g1 = grads->item_gmf;
     rc = launch_segreduce(t.sorted_keys_i, t.sorted_index_i, B, t.stage_i, ru, t.seg_ws, t.seg_ws_bytes, st);
     if (rc != MR_OK) return rc;
-    ru.num_rows = m.num_users;
-    ru.g0 = w.Su;
-    ru.g1 = grads->user_gmf;
-    rc = launch_segreduce(t.sorted_keys, t.sorted_index, n_user_rows, t.stage_u, ru, t.seg_ws_u, t.seg_ws_u_bytes, st);
-    if (rc != MR_OK) return rc;
-    prof_mark(MR_PHASE_TC_DENSE_BWD, st);  // d E = S . W1^T over the tables
+    prof_mark(MR_PHASE_TC_DENSE_BWD, st);  // d E_item = Si . W1i^T over the table
     rc = launch_small_rows_gemm(w.Si, m.num_items, L1, W1i, L1, d_i, true, nullptr, grads->item_mlp, st);
-    if (rc == MR_OK) rc = launch_small_rows_gemm(w.Su, m.num_users, L1, W1u, L1, d_u, true, nullptr, grads->user_mlp, st);
     if (rc != MR_OK) return rc;
-    prof_mark(MR_PHASE_TC_WGRAD, st);  // d W1 = E^T . S, d b1 = colsum(Su)
+    prof_mark(MR_PHASE_TC_WGRAD, st);  // d W1i = E_item^T . Si
     rc = launch_small_table_wgrad(m.item_mlp, w.Si, m.num_items, t.dense_partial + (W1i - m.dense), nullptr,
                                   t.dense_stride, cap, st, &grid_i);
-    if (rc == MR_OK)
-      rc = launch_small_table_wgrad(m.user_mlp, w.Su, m.num_users, t.dense_partial + (W1u - m.dense),
-                                    t.dense_partial + (m.b[1] - m.dense), t.dense_stride, cap, st, &grid_u);
     if (rc != MR_OK) return rc;
+    if (su_st != st) MR_CUDA(cudaStreamWaitEvent(st, side->join2, 0));
     prof_mark(MR_PHASE_MISC, st);
     const int nrows = grid > grid_i ? (grid > grid_u ? grid : grid_u) : (grid_i > grid_u ? grid_i : grid_u);
     rc = launch_dense_reduce(m, t.dense_partial, t.dense_stride, nrows, grads->dense, st, !(flags & MR_TRAIN_NO_DENSE_L2));

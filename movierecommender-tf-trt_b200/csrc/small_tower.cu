@@ -16,6 +16,8 @@
 //                                 in a fixed order; CTAs write their sums to their row of the partial buffer.
 //   small_table_wgrad_kernel      dW1 = E^T . S (and db1 = colsum(Su)) over the tables, per-CTA partial rows.
 // No atomics on floats; results are bit-identical run to run.
+#include <mutex>
+
 #include "launchers.h"
 
 namespace mr {
@@ -23,15 +25,25 @@ namespace st {
 
 constexpr int L1 = 32, L2 = 16, L3 = 8, F = 8;
 constexpr int SW = L1 + F;          // staged row: [dZ1 | GMF row gradient]
+#ifndef MR_ST_CTAS
+#define MR_ST_CTAS 4  // resident CTAs per SM the register budget is set for (A/B: tools/build_variant.sh)
+#endif
 constexpr int kWarps = 4, kThreads = kWarps * 32;
 constexpr int H1S = 33, DS = 28, H2S = 17, HDS = 17;  // row strides of the per-warp staging tiles (floats)
-constexpr int kWeightFloats = 688;                    // W2 512, b2 16, W3 128, b3 8, w_out 16, b_out 1, padded to 16 B
 constexpr int kWarpFloats = 32 * (H1S + DS + H2S + HDS);
 constexpr int kSlots = 22;                            // per-lane accumulators: dW2 row 16, dW3 part 4, d w_out, bias sums
 
+// The 681 weights behind the first layer -- W2 (32x16), b2, W3 (16x8), b3, w_out (16), b_out: contiguous in the model's
+// dense block from W[2] on -- are copied into constant memory before every launch (one 2.7 KB device-to-device copy on
+// the caller's stream) and enter the FMAs as constant-bank operands.  From shared memory the broadcast reads of the
+// weights alone were 1,280 of the kernel's 2,100 shared-memory wavefronts per 32 rows, and the LSU bound it (0.135 ms
+// for 327,680 rows).
+constexpr int kConstFloats = L1 * L2 + L2 + L2 * L3 + L3 + F + L3 + 1;
+__constant__ float c_w[kConstFloats];
+constexpr int cW2 = 0, cB2 = cW2 + L1 * L2, cW3 = cB2 + L2, cB3 = cW3 + L2 * L3, cWO = cB3 + L3, cBO = cWO + F + L3;
+
 struct Params {
   const float *Pi, *Pu, *gmf_u, *gmf_i;
-  const float *W2, *b2, *W3, *b3, *w_out, *b_out;
   const int32_t *users, *items;
   const float* labels;
   int64_t G;
@@ -46,26 +58,13 @@ struct Params {
 };
 
 template <int GROUP>
-__global__ void __launch_bounds__(kThreads, 4) small_tower_train_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, MR_ST_CTAS) small_tower_train_kernel(const Params p) {
   extern __shared__ __align__(16) float smem[];
-  float* W2_s = smem;
-  float* b2_s = W2_s + L1 * L2;
-  float* W3_s = b2_s + L2;
-  float* b3_s = W3_s + L2 * L3;
-  float* wo_s = b3_s + L3;
-  float* bo_s = wo_s + F + L3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* h1_s = smem + kWeightFloats + warp * kWarpFloats;
+  float* h1_s = smem + warp * kWarpFloats;
   float* d_s = h1_s + 32 * H1S;   // per row: dZ2 [0,16), dZ3 [16,24), dz [24]
   float* h2_s = d_s + 32 * DS;
   float* hd_s = h2_s + 32 * H2S;  // per row: GMF products [0,8), h3 [8,16)
-  for (int i = tid; i < L1 * L2; i += kThreads) W2_s[i] = p.W2[i];
-  for (int i = tid; i < L2 * L3; i += kThreads) W3_s[i] = p.W3[i];
-  if (tid < L2) b2_s[tid] = p.b2[tid];
-  if (tid < L3) b3_s[tid] = p.b3[tid];
-  if (tid < F + L3) wo_s[tid] = p.w_out[tid];
-  if (tid == 0) bo_s[0] = p.b_out[0];
-  __syncthreads();
 
   float acc2[L2], acc3[4], dwo = 0.f, misc = 0.f, loss = 0.f;
 #pragma unroll
@@ -80,21 +79,19 @@ __global__ void __launch_bounds__(kThreads, 4) small_tower_train_kernel(const Pa
     const bool live = g < p.G;
     float gu[F], gug[F], gsum[L1];
     bool bad_u = false;
-    const float4* pu4 = reinterpret_cast<const float4*>(p.Pu);  // the group's user row: re-read per row (L1 hits)
+    int u = 0, it_next = 0;
     if (live) {
-      int u = __ldg(p.users + g * GROUP);
+      u = __ldg(p.users + g * GROUP);
+      it_next = __ldg(p.items + g * GROUP);
       bad_u = (unsigned)u >= (unsigned)p.num_users;
       if (bad_u) u = 0;
-      pu4 = reinterpret_cast<const float4*>(p.Pu + (size_t)u * L1);
       const float4* gu4 = reinterpret_cast<const float4*>(p.gmf_u + (size_t)u * F);
 #pragma unroll
       for (int c = 0; c < F / 4; ++c) {
         const float4 a = __ldg(gu4 + c);
         gu[4 * c] = a.x; gu[4 * c + 1] = a.y; gu[4 * c + 2] = a.z; gu[4 * c + 3] = a.w;
       }
-    } else {  // idle lane of the last iteration: its staged rows contribute zeros
-#pragma unroll
-      for (int k = 0; k < L1; ++k) h1_s[lane * H1S + k] = 0.f;
+    } else {  // idle lane of the last iteration: zero pre-activation gradients, so its rows add nothing below
 #pragma unroll
       for (int k = 0; k < DS; ++k) d_s[lane * DS + k] = 0.f;
 #pragma unroll
@@ -109,14 +106,29 @@ __global__ void __launch_bounds__(kThreads, 4) small_tower_train_kernel(const Pa
 
 #pragma unroll 1
     for (int j = 0; j < GROUP; ++j) {
+      const int64_t row = g * GROUP + j;
+      int it = it_next;
+      if (live && j + 1 < GROUP) it_next = __ldg(p.items + row + 1);  // one row ahead of its use
+      const bool bad = live && (bad_u || (unsigned)it >= (unsigned)p.num_items);
+      if (bad || !live) it = 0;
+      // h1 = relu(Pi[item] + Pu[user]) of the warp's 32 rows: lane = unit, a row is one coalesced 128-byte load of each
+      // table; eight rows in flight
+#pragma unroll
+      for (int r0 = 0; r0 < 32; r0 += 8) {
+        float a[8], b[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int ir = __shfl_sync(0xffffffffu, it, r0 + q), ur = __shfl_sync(0xffffffffu, u, r0 + q);
+          a[q] = __ldg(p.Pi + (size_t)ir * L1 + lane);
+          b[q] = __ldg(p.Pu + (size_t)ur * L1 + lane);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) h1_s[(r0 + q) * H1S + lane] = fmaxf(a[q] + b[q], 0.f);
+      }
+      __syncwarp();
       if (live) {
-        const int64_t row = g * GROUP + j;
-        int it = __ldg(p.items + row);
-        const bool bad = bad_u || (unsigned)it >= (unsigned)p.num_items;
-        if (bad) it = 0;
         any_bad |= bad;
         const float y = __ldg(p.labels + row);
-        const float4* pi4 = reinterpret_cast<const float4*>(p.Pi + (size_t)it * L1);
         const float4* gi4 = reinterpret_cast<const float4*>(p.gmf_i + (size_t)it * F);
         float gi[F];
 #pragma unroll
@@ -127,56 +139,41 @@ __global__ void __launch_bounds__(kThreads, 4) small_tower_train_kernel(const Pa
         // ---- forward ----
         float z2[L2];
 #pragma unroll
-        for (int o = 0; o < L2; ++o) z2[o] = b2_s[o];
+        for (int o = 0; o < L2; ++o) z2[o] = c_w[cB2 + o];
         uint32_t m1 = 0;
 #pragma unroll
-        for (int c = 0; c < L1 / 4; ++c) {
-          const float4 a = __ldg(pi4 + c), b = __ldg(pu4 + c);
-          const float hv[4] = {fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f)};
+        for (int k = 0; k < L1; ++k) {
+          const float hv = h1_s[lane * H1S + k];
+          if (hv > 0.f) m1 |= 1u << k;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int k = 4 * c + q;
-            h1_s[lane * H1S + k] = hv[q];
-            if (hv[q] > 0.f) m1 |= 1u << k;
-            const float4* w = reinterpret_cast<const float4*>(W2_s + k * L2);
-#pragma unroll
-            for (int o4 = 0; o4 < L2 / 4; ++o4) {
-              const float4 wv = w[o4];
-              z2[4 * o4] = fmaf(hv[q], wv.x, z2[4 * o4]);
-              z2[4 * o4 + 1] = fmaf(hv[q], wv.y, z2[4 * o4 + 1]);
-              z2[4 * o4 + 2] = fmaf(hv[q], wv.z, z2[4 * o4 + 2]);
-              z2[4 * o4 + 3] = fmaf(hv[q], wv.w, z2[4 * o4 + 3]);
-            }
-          }
+          for (int o = 0; o < L2; ++o) z2[o] = fmaf(hv, c_w[cW2 + k * L2 + o], z2[o]);
         }
         uint32_t m2 = 0;
         float z3[L3];
 #pragma unroll
-        for (int o = 0; o < L3; ++o) z3[o] = b3_s[o];
+        for (int o = 0; o < L3; ++o) z3[o] = c_w[cB3 + o];
 #pragma unroll
         for (int k = 0; k < L2; ++k) {
           const float h = fmaxf(z2[k], 0.f);
           h2_s[lane * H2S + k] = h;
           if (h > 0.f) m2 |= 1u << k;
-          const float4* w = reinterpret_cast<const float4*>(W3_s + k * L3);
-          const float4 w0 = w[0], w1 = w[1];
-          z3[0] = fmaf(h, w0.x, z3[0]); z3[1] = fmaf(h, w0.y, z3[1]); z3[2] = fmaf(h, w0.z, z3[2]); z3[3] = fmaf(h, w0.w, z3[3]);
-          z3[4] = fmaf(h, w1.x, z3[4]); z3[5] = fmaf(h, w1.y, z3[5]); z3[6] = fmaf(h, w1.z, z3[6]); z3[7] = fmaf(h, w1.w, z3[7]);
+#pragma unroll
+          for (int o = 0; o < L3; ++o) z3[o] = fmaf(h, c_w[cW3 + k * L3 + o], z3[o]);
         }
         uint32_t m3 = 0;
-        float s = bo_s[0];
+        float s = c_w[cBO];
 #pragma unroll
         for (int f = 0; f < F; ++f) {
           const float gp = gu[f] * gi[f];
           hd_s[lane * HDS + f] = gp;
-          s = fmaf(wo_s[f], gp, s);
+          s = fmaf(c_w[cWO + f], gp, s);
         }
 #pragma unroll
         for (int o = 0; o < L3; ++o) {
           const float h = fmaxf(z3[o], 0.f);
           hd_s[lane * HDS + F + o] = h;
           if (h > 0.f) m3 |= 1u << o;
-          s = fmaf(wo_s[F + o], h, s);
+          s = fmaf(c_w[cWO + F + o], h, s);
         }
         const float pr = sigmoidf_stable(s);
         const float dz = bad ? 0.f : (pr - y) * p.inv_batch;
@@ -185,13 +182,13 @@ __global__ void __launch_bounds__(kThreads, 4) small_tower_train_kernel(const Pa
         // ---- backward ----
         float dz3[L3];
 #pragma unroll
-        for (int o = 0; o < L3; ++o) dz3[o] = ((m3 >> o) & 1u) ? dz * wo_s[F + o] : 0.f;
+        for (int o = 0; o < L3; ++o) dz3[o] = ((m3 >> o) & 1u) ? dz * c_w[cWO + F + o] : 0.f;
         float* si = p.stage_i + (size_t)row * SW;
         {
           float gq[F];
 #pragma unroll
           for (int f = 0; f < F; ++f) {
-            const float gv = dz * wo_s[f];
+            const float gv = dz * c_w[cWO + f];
             gug[f] = fmaf(gv, gi[f], gug[f]);
             gq[f] = gv * gu[f];
           }
@@ -201,11 +198,9 @@ __global__ void __launch_bounds__(kThreads, 4) small_tower_train_kernel(const Pa
         float dz2[L2];
 #pragma unroll
         for (int k = 0; k < L2; ++k) {
-          const float4* w = reinterpret_cast<const float4*>(W3_s + k * L3);
-          const float4 w0 = w[0], w1 = w[1];
-          float v = dz3[0] * w0.x;
-          v = fmaf(dz3[1], w0.y, v); v = fmaf(dz3[2], w0.z, v); v = fmaf(dz3[3], w0.w, v);
-          v = fmaf(dz3[4], w1.x, v); v = fmaf(dz3[5], w1.y, v); v = fmaf(dz3[6], w1.z, v); v = fmaf(dz3[7], w1.w, v);
+          float v = 0.f;
+#pragma unroll
+          for (int o = 0; o < L3; ++o) v = fmaf(dz3[o], c_w[cW3 + k * L3 + o], v);
           dz2[k] = ((m2 >> k) & 1u) ? v : 0.f;
         }
         float4* dq = reinterpret_cast<float4*>(d_s + lane * DS);
@@ -222,14 +217,9 @@ __global__ void __launch_bounds__(kThreads, 4) small_tower_train_kernel(const Pa
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int k = 4 * c + q;
-            const float4* w = reinterpret_cast<const float4*>(W2_s + k * L2);
             float v = 0.f;
 #pragma unroll
-            for (int o = 0; o < L2 / 4; ++o) {
-              const float4 wv = w[o];
-              v = fmaf(dz2[4 * o], wv.x, v); v = fmaf(dz2[4 * o + 1], wv.y, v);
-              v = fmaf(dz2[4 * o + 2], wv.z, v); v = fmaf(dz2[4 * o + 3], wv.w, v);
-            }
+            for (int o = 0; o < L2; ++o) v = fmaf(dz2[o], c_w[cW2 + k * L2 + o], v);
             v = ((m1 >> k) & 1u) ? v : 0.f;
             gsum[k] += v;
             o4[q] = v;
@@ -272,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 4) small_tower_train_kernel(const Pa
 
   // ---- per-CTA sums, fixed order over the warps, into this CTA's row of the partial buffer ----
   __syncthreads();
-  float* red = smem + kWeightFloats;  // [warp][slot][lane]
+  float* red = smem;  // [warp][slot][lane]
   {
     float* rw = red + warp * kSlots * 32;
 #pragma unroll
@@ -341,9 +331,9 @@ __global__ void __launch_bounds__(256) small_rows_gemm_kernel(const float* __res
   }
 }
 
-// dW[i][j] = sum_r E[r][i] * S[r][j] (i < 32, j < 32), db[j] = sum_r S[r][j]: CTA = chunks of 128 rows staged in
+// dW[i][j] = sum_r E[r][i] * S[r][j] (i < 32, j < 32), db[j] = sum_r S[r][j]: CTA = chunks of 32 rows staged in
 // shared memory, thread = (i, four j); the CTA's sum goes to its row of the partial buffer.
-constexpr int kWgRows = 128;
+constexpr int kWgRows = 32;
 __global__ void __launch_bounds__(256) small_table_wgrad_kernel(const float* __restrict__ E, const float* __restrict__ S,
                                                                 int64_t rows, float* __restrict__ dw_partial,
                                                                 float* __restrict__ db_partial, int64_t stride) {
@@ -377,6 +367,9 @@ __global__ void __launch_bounds__(256) small_table_wgrad_kernel(const float* __r
 
 }  // namespace st
 
+static std::mutex g_const_mutex;
+static cudaEvent_t g_const_free = nullptr;  // recorded after the kernel that reads st::c_w (one device per process)
+
 bool small_tower_supported(const MrModel& m, int group) {
   return m.n_layers == 4 && m.L[0] == 2 * st::L1 && m.L[1] == st::L1 && m.L[2] == st::L2 && m.L[3] == st::L3 &&
          m.mf_dim == st::F && group == 5;
@@ -386,7 +379,6 @@ int launch_small_tower_train(const SmallTowerArgs& a, cudaStream_t stream, int* 
   const MrModel& m = *a.model;
   st::Params p{};
   p.Pi = a.Pi; p.Pu = a.Pu; p.gmf_u = m.user_gmf; p.gmf_i = m.item_gmf;
-  p.W2 = m.W[2]; p.b2 = m.b[2]; p.W3 = m.W[3]; p.b3 = m.b[3]; p.w_out = m.w_out; p.b_out = m.b_out;
   p.users = a.users; p.items = a.items; p.labels = a.labels;
   p.G = a.B / 5;
   p.num_users = m.num_users; p.num_items = m.num_items;
@@ -397,7 +389,7 @@ int launch_small_tower_train(const SmallTowerArgs& a, cudaStream_t stream, int* 
   p.off_W3 = (int)(m.W[3] - m.dense); p.off_b3 = (int)(m.b[3] - m.dense);
   p.off_wout = (int)(m.w_out - m.dense); p.off_bout = (int)(m.b_out - m.dense);
   p.loss_partial = a.loss_partial; p.flags = a.flags;
-  const size_t smem = (size_t)(st::kWeightFloats + st::kWarps * st::kWarpFloats) * sizeof(float);
+  const size_t smem = (size_t)(st::kWarps * st::kWarpFloats) * sizeof(float);
   auto kern = st::small_tower_train_kernel<5>;
   static thread_local bool attr_set = false;
   if (!attr_set) {
@@ -411,8 +403,18 @@ int launch_small_tower_train(const SmallTowerArgs& a, cudaStream_t stream, int* 
   const int64_t cap = (int64_t)sm_count() * occ < a.max_ctas ? (int64_t)sm_count() * occ : a.max_ctas;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  kern<<<(unsigned)grid, st::kThreads, smem, stream>>>(p);
-  MR_LAUNCH_CHECK("small_tower_train_kernel");
+  // the constant image belongs to one launch at a time: a launch on another stream waits for the previous kernel
+  {
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (g_const_free == nullptr) MR_CUDA(cudaEventCreateWithFlags(&g_const_free, cudaEventDisableTiming));
+    MR_CUDA(cudaStreamWaitEvent(stream, g_const_free, 0));
+    MR_CUDA(cudaMemcpyToSymbolAsync(st::c_w, m.W[2], st::kConstFloats * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream));
+    kern<<<(unsigned)grid, st::kThreads, smem, stream>>>(p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "small_tower_train_kernel");
+    count_launch();
+    MR_CUDA(cudaEventRecord(g_const_free, stream));
+  }
   *grid_out = (int)grid;
   return MR_OK;
 }
