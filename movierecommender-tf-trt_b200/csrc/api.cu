@@ -1406,26 +1406,23 @@ int mr_neumf_apply(MrModel* model, MrOptState* opt, const MrGrads* grads, void* 
   const bool adam = opt->optimizer == MR_OPT_ADAM;
   const float lr_t = adam ? adam_lr_t(*opt, opt->iterations + 1) : opt->lr;
   prof_mark(MR_PHASE_OPTIMIZER, st);
-  rc = launch_optimizer_flat(m.dense, grads->dense, opt->m_dense, opt->v_dense, m.dense_count, opt->optimizer, lr_t,
-                             opt->beta_1, opt->beta_2, opt->epsilon, 0.f, st);
-  if (rc != MR_OK) return rc;
+  OptRegions r{};
+  auto add = [&](float* p, const float* g, float* mm, float* vv, int64_t n, float l2) {
+    r.p[r.count] = p; r.g[r.count] = g; r.m[r.count] = mm; r.v[r.count] = vv; r.n[r.count] = n; r.l2[r.count] = l2;
+    ++r.count;
+  };
+  add(m.dense, grads->dense, opt->m_dense, opt->v_dense, m.dense_count, 0.f);
   if (opt->table_mode == MR_TABLES_DENSE) {
     const float l2 = m.l2[0];
-    rc = launch_optimizer_flat(m.user_mlp, grads->user_mlp, opt->m_user_mlp, opt->v_user_mlp, (int64_t)m.num_users * d_u,
-                               opt->optimizer, lr_t, opt->beta_1, opt->beta_2, opt->epsilon, l2, st);
-    if (rc == MR_OK)
-      rc = launch_optimizer_flat(m.item_mlp, grads->item_mlp, opt->m_item_mlp, opt->v_item_mlp, (int64_t)m.num_items * d_i,
-                                 opt->optimizer, lr_t, opt->beta_1, opt->beta_2, opt->epsilon, l2, st);
-    if (rc == MR_OK && m.mf_dim > 0)
-      rc = launch_optimizer_flat(m.user_gmf, grads->user_gmf, opt->m_user_gmf, opt->v_user_gmf,
-                                 (int64_t)m.num_users * m.mf_dim, opt->optimizer, lr_t, opt->beta_1, opt->beta_2,
-                                 opt->epsilon, l2, st);
-    if (rc == MR_OK && m.mf_dim > 0)
-      rc = launch_optimizer_flat(m.item_gmf, grads->item_gmf, opt->m_item_gmf, opt->v_item_gmf,
-                                 (int64_t)m.num_items * m.mf_dim, opt->optimizer, lr_t, opt->beta_1, opt->beta_2,
-                                 opt->epsilon, l2, st);
-    if (rc != MR_OK) return rc;
+    add(m.user_mlp, grads->user_mlp, opt->m_user_mlp, opt->v_user_mlp, (int64_t)m.num_users * d_u, l2);
+    add(m.item_mlp, grads->item_mlp, opt->m_item_mlp, opt->v_item_mlp, (int64_t)m.num_items * d_i, l2);
+    if (m.mf_dim > 0) {
+      add(m.user_gmf, grads->user_gmf, opt->m_user_gmf, opt->v_user_gmf, (int64_t)m.num_users * m.mf_dim, l2);
+      add(m.item_gmf, grads->item_gmf, opt->m_item_gmf, opt->v_item_gmf, (int64_t)m.num_items * m.mf_dim, l2);
+    }
   }
+  rc = launch_optimizer_regions(r, opt->optimizer, lr_t, opt->beta_1, opt->beta_2, opt->epsilon, st);
+  if (rc != MR_OK) return rc;
   prof_mark(-1, st);
   opt->iterations += 1;
   return MR_OK;

@@ -59,6 +59,20 @@ int launch_segreduce(const int32_t* sorted_keys, const int32_t* sorted_index, in
                      const RowUpdate& u, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // ---- optimizer.cu ----------------------------------------------------------------------------
+constexpr int kMaxOptRegions = 5;
+struct OptRegions {
+  float* p[kMaxOptRegions];
+  const float* g[kMaxOptRegions];
+  float* m[kMaxOptRegions];
+  float* v[kMaxOptRegions];
+  int64_t n[kMaxOptRegions];
+  float l2[kMaxOptRegions];
+  int count;
+  int block_start[kMaxOptRegions + 1];
+};
+// the sweep of launch_optimizer_flat over several buffers in one launch
+int launch_optimizer_regions(OptRegions r, int optimizer, float lr_t, float beta_1, float beta_2, float epsilon,
+                             cudaStream_t st);
 int launch_optimizer_flat(float* p, const float* g, float* m, float* v, int64_t n, int optimizer, float lr_t,
                           float beta_1, float beta_2, float epsilon, float l2, cudaStream_t st);
 
