@@ -54,6 +54,8 @@ def main():
         for grouped, l2, opt in ((False, [0, 0, 0], "adam"), (True, [0, 0, 0], "sgd"), (True, [0.01, 0.02, 0.005], "sgd"),
                                  (True, [0, 0, 0], "adam"), (False, [0.01, 0.02, 0.005], "adam")):
             h1 = check(rank, world, grouped, l2, opt, exchange)
+            if grouped and opt == "sgd" and not any(l2):  # the default tower's projected step (small_tower.cu)
+                check(rank, world, grouped, [0, 0, 0, 0], opt, exchange, small=True)
             if exchange == "peer-mc" and grouped and opt == "adam":  # run to run: the same bits
                 h2 = check(rank, world, grouped, l2, opt, exchange, quiet=True)
                 if not bool((h1 == h2).all()):
@@ -70,8 +72,10 @@ def main():
         print("dp_gpu_check ok", flush=True)
 
 
-def check(rank, world, grouped, l2, opt, exchange, quiet=False):
+def check(rank, world, grouped, l2, opt, exchange, quiet=False, small=False):
     nu, ni, L, f, negs = (1500 if grouped else 5000), 3000, [256, 128, 64], 64, 4
+    if small:
+        nu, ni, L, f = 700, 900, [64, 32, 16, 8], 8
     eng = _engine.NeuMFEngine(nu, ni, L, l2, mf_dim=f, seed=11 + rank, optimizer=opt, lr=0.5 if opt == "sgd" else 1e-3)  # different seeds: broadcast must fix it
     dp = DataParallelNeuMF(eng, exchange=exchange.split("-")[0], multicast=exchange == "peer-mc")
     dp.broadcast_parameters(0)
@@ -114,7 +118,7 @@ def check(rank, world, grouped, l2, opt, exchange, quiet=False):
                         FAILURES.append((exchange, grouped, l2, opt, "adam state " + k, err))
         if not quiet:
             print("dp_gpu_check done: world={} exchange={}{} grouped={} l2={} {} steps=3 worst relative weight difference "
-                  "{:.2e}".format(world, exchange, "",
+                  "{:.2e}".format(world, exchange, " default tower" if small else "",
                                   grouped, l2, opt, worst), flush=True)
     # every replica must hold bit-identical weights
     bits = torch.cat([eng.dense.reshape(-1)] + [t.reshape(-1) for t in eng._tables.values()]).view(torch.int32).to(torch.int64)
