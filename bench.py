@@ -630,13 +630,25 @@ def run_gpu(args, wl):
     dom = max(phase_table, key=lambda k: phase_table[k]["ms_per_step"])
     dom_groups = max(phases[dom][1], 1)
     dom_avg_ms = phases[dom][0] / dom_groups            # one launch group = the kernel(s) of one phase interval
-    dominant = {"phase": dom, "kernel": PHASE_KERNELS.get(dom, dom), "avg_launch_ms": dom_avg_ms,
+    small_tower = bool(eng.uses_small_tower(rows, group))
+    kernels = dict(PHASE_KERNELS)
+    if small_tower:  # the default tower's step reuses the phase slots of the tensor-core sequence
+        kernels.update(fused_tile="small_tower_train_kernel<5> (fp32 CUDA cores, thread per group: projected first layer, "
+                                  "layers 2-3, head + BCE, backward, weight gradients, staged rows) + wait for the id sorts",
+                       tc_dense_fwd="small_rows_gemm_kernel (Pi, Pu over the tables)",
+                       tc_dense_bwd="small_rows_gemm_kernel (dE = S . W1^T over the tables)",
+                       tc_wgrad="small_table_wgrad_kernel (dW1 = E^T . S)")
+    dominant = {"phase": dom, "kernel": kernels.get(dom, dom), "avg_launch_ms": dom_avg_ms,
                 "launches_timed": dom_groups, "share_of_step": phase_table[dom]["share_of_step"]}
     if dom in pbytes:
         dom_bytes = pbytes[dom] * args.steps / dom_groups
         dominant.update(algorithmic_bytes_per_launch=dom_bytes, achieved_gbs=dom_bytes / (dom_avg_ms / 1e3) / 1e9,
                         frac_of_hbm_peak=dom_bytes / (dom_avg_ms / 1e3) / 1e9 / peak)
-    if dom == "fused_tile":
+    if dom == "fused_tile" and small_tower:
+        # per row: 656 multiply-adds forward, the same again for the data gradients and for the weight gradients
+        dominant.update(bound="instruction issue / launch latency (fp32 CUDA cores); HBM traffic is ~0.1 GB per step",
+                        fp32_tflops=3 * 2 * 656.0 * rows * args.steps / dom_groups / (dom_avg_ms / 1e3) / 1e12)
+    elif dom == "fused_tile":
         # three GEMMs of 2 * 128 * 64 flops per row, each fp32 product = six bf16 part products on the tensor cores
         tflops = 6.0 * 3 * 2 * 128 * 64 * rows * args.steps / dom_groups / (dom_avg_ms / 1e3) / 1e12
         dominant.update(bound="hbm (per-row gather + staged gradient rows); tensor time is ~3/4 of the HBM time",
@@ -665,10 +677,11 @@ def run_gpu(args, wl):
                 if dp is None else "DataParallelNeuMF.train_step on pinned host arrays"},
         "gpu_launches": launches,
         "launch_sequence": {"grouped": grouped_seq, "item_projection": projected_seq, "user_projection": uprojected_seq,
-                            "fused_tile_kernel": "fused_tile" in phase_table},
+                            "fused_tile_kernel": "fused_tile" in phase_table and not small_tower,
+                            "small_tower_kernel": small_tower},
         # the whole step's algorithmic bytes over the step time, against the measured copy bandwidth
         "roofline": {"bound": "hbm", "scope": "whole train step (sampler included), SURVEY 8(d) A_train",
-                     "kernel": PHASE_KERNELS.get(dom, dom), "achieved": ab["step"] / (step_ms / 1e3) / 1e9, "peak": peak,
+                     "kernel": kernels.get(dom, dom), "achieved": ab["step"] / (step_ms / 1e3) / 1e9, "peak": peak,
                      "unit": "GB/s", "frac": ab["step"] / (step_ms / 1e3) / 1e9 / peak, "traffic": traffic,
                      "peak_kind": peak_kind, "algorithmic_bytes_per_step": ab["step"],
                      "fp32_tflops": ab["flops_step"] / (step_ms / 1e3) / 1e12, "dominant_kernel": dominant},

@@ -214,6 +214,14 @@ static bool small_proj_ok(const MrModel& m, int64_t rows, int group) {
   return 2 * (int64_t)m.num_items <= rows && (int64_t)m.num_users <= rows / group;
 }
 
+// ranking eval of the default tower: one user id per group of candidates, Pi / Pu over the tables first
+static bool small_eval_ok(const MrModel& m, int64_t rows) {
+  if (use_tc(m) || m.item_projection == MR_PROJECTION_OFF || m.fused_train == MR_FUSED_OFF) return false;
+  if (!small_tower_supported(m, 5)) return false;
+  if (m.item_projection == MR_PROJECTION_ON) return true;
+  return 2 * ((int64_t)m.num_items + m.num_users) <= rows;
+}
+
 struct SmallWs {
   float *Pi, *Pu, *Si, *Su;
   size_t total;
@@ -1443,7 +1451,11 @@ size_t mr_rank_eval_workspace_bytes(const MrModel* model, int64_t G, int32_t gro
   if (model != nullptr && model->n_layers >= 1 && model->n_layers <= MR_MAX_LAYERS && tc_eligible(*model) && group >= 2 &&
       eval_sub_batch(group) > 0 && model->n_layers >= 2)
     fused = carve_eval(*model, group, G * group, nullptr).total + 512;
-  const size_t plain = mr_forward_workspace_bytes(model, G * group) + align_up((size_t)G * group * sizeof(float), 256);
+  size_t plain = mr_forward_workspace_bytes(model, G * group) + align_up((size_t)G * group * sizeof(float), 256);
+  if (model != nullptr && model->n_layers >= 1 && model->n_layers <= MR_MAX_LAYERS && !tc_eligible(*model) &&
+      small_tower_supported(*model, 5))  // Pi, Pu of the default-tower eval
+    plain += align_up((size_t)model->num_items * model->L[1] * sizeof(float), 256) +
+             align_up((size_t)model->num_users * model->L[1] * sizeof(float), 256);
   return (plain > fused ? plain : fused) + align_up(rank_partials_count(G) * sizeof(float), 256) + 512;
 }
 
@@ -1477,7 +1489,21 @@ int mr_rank_eval(const MrModel* model, const int32_t* users, const int32_t* item
   float* probs_buf = cv.take<float>((size_t)G * group);
   float* partials = cv.take<float>(rank_partials_count(G));
   float* pr = probs != nullptr ? probs : probs_buf;
-  int rc = mr_neumf_forward(model, users, items, G * group, group, nullptr, pr, nullptr, nullptr, ws, fwd_bytes, stream);
+  int rc;
+  if (small_eval_ok(*model, G * group)) {  // default tower: projected tables, thread-per-row forward (small_tower.cu)
+    const MrModel& m = *model;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u, L1 = m.L[1];
+    float* Pi = cv.take<float>((size_t)m.num_items * L1);
+    float* Pu = cv.take<float>((size_t)m.num_users * L1);
+    prof_mark(MR_PHASE_TC_DENSE_FWD, st);
+    rc = launch_small_rows_gemm(m.item_mlp, m.num_items, d_i, m.W[1] + (size_t)d_u * L1, L1, L1, false, nullptr, Pi, st);
+    if (rc == MR_OK) rc = launch_small_rows_gemm(m.user_mlp, m.num_users, d_u, m.W[1], L1, L1, false, m.b[1], Pu, st);
+    prof_mark(MR_PHASE_FUSED_TILE, st);
+    if (rc == MR_OK) rc = launch_small_tower_forward(m, Pi, Pu, users, items, G * group, group, pr, st);
+  } else {
+    rc = mr_neumf_forward(model, users, items, G * group, group, nullptr, pr, nullptr, nullptr, ws, fwd_bytes, stream);
+  }
   if (rc != MR_OK) return rc;
   prof_mark(MR_PHASE_RANK, (cudaStream_t)stream);
   rc = launch_rank_scores(pr, G, group, k, nullptr, rank, pos, sums, partials, (cudaStream_t)stream);

@@ -207,6 +207,9 @@ struct SmallTowerArgs {
 };
 bool small_tower_supported(const MrModel& m, int group);
 int launch_small_tower_train(const SmallTowerArgs& a, cudaStream_t st, int* grid_out);
+// forward of the same tower: probs[row] for rows whose user is users[row / group]
+int launch_small_tower_forward(const MrModel& m, const float* Pi, const float* Pu, const int32_t* users,
+                               const int32_t* items, int64_t rows, int group, float* probs, cudaStream_t st);
 // out = A (rows x K) . W (K x N, or its transpose read from an N x K array when `transpose`) (+ bias)
 int launch_small_rows_gemm(const float* A, int64_t rows, int K, const float* W, int ldw, int N, bool transpose,
                            const float* bias, float* out, cudaStream_t st);

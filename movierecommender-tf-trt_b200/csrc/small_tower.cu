@@ -300,6 +300,59 @@ __global__ void __launch_bounds__(kThreads, MR_ST_CTAS) small_tower_train_kernel
   }
 }
 
+// Ranking eval / forward: thread = candidate row, `group` consecutive rows share users[row / group].  The row's Pi and
+// Pu are read as eight 16-byte pieces (the user's row hits L1 for the group's other candidates), layers 2-3 and the
+// output unit run in registers on constant-bank weights, one probability is stored per row (NaN for a bad id).
+__global__ void __launch_bounds__(256) small_tower_forward_kernel(const float* __restrict__ Pi, const float* __restrict__ Pu,
+                                                                  const float* __restrict__ gmf_u,
+                                                                  const float* __restrict__ gmf_i,
+                                                                  const int32_t* __restrict__ users,
+                                                                  const int32_t* __restrict__ items, int64_t rows, int group,
+                                                                  int num_users, int num_items, float* __restrict__ probs) {
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
+    int u = __ldg(users + row / group), it = __ldg(items + row);
+    const bool bad = (unsigned)u >= (unsigned)num_users || (unsigned)it >= (unsigned)num_items;
+    if (bad) u = it = 0;
+    const float4* pi4 = reinterpret_cast<const float4*>(Pi + (size_t)it * L1);
+    const float4* pu4 = reinterpret_cast<const float4*>(Pu + (size_t)u * L1);
+    float z2[L2];
+#pragma unroll
+    for (int o = 0; o < L2; ++o) z2[o] = c_w[cB2 + o];
+#pragma unroll
+    for (int c = 0; c < L1 / 4; ++c) {
+      const float4 a = __ldg(pi4 + c), b = __ldg(pu4 + c);
+      const float hv[4] = {fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f)};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int o = 0; o < L2; ++o) z2[o] = fmaf(hv[q], c_w[cW2 + (4 * c + q) * L2 + o], z2[o]);
+    }
+    float z3[L3];
+#pragma unroll
+    for (int o = 0; o < L3; ++o) z3[o] = c_w[cB3 + o];
+#pragma unroll
+    for (int k = 0; k < L2; ++k) {
+      const float h = fmaxf(z2[k], 0.f);
+#pragma unroll
+      for (int o = 0; o < L3; ++o) z3[o] = fmaf(h, c_w[cW3 + k * L3 + o], z3[o]);
+    }
+    float s = c_w[cBO];
+    const float4* gu4 = reinterpret_cast<const float4*>(gmf_u + (size_t)u * F);
+    const float4* gi4 = reinterpret_cast<const float4*>(gmf_i + (size_t)it * F);
+#pragma unroll
+    for (int c = 0; c < F / 4; ++c) {
+      const float4 a = __ldg(gu4 + c), b = __ldg(gi4 + c);
+      s = fmaf(c_w[cWO + 4 * c], a.x * b.x, s);
+      s = fmaf(c_w[cWO + 4 * c + 1], a.y * b.y, s);
+      s = fmaf(c_w[cWO + 4 * c + 2], a.z * b.z, s);
+      s = fmaf(c_w[cWO + 4 * c + 3], a.w * b.w, s);
+    }
+#pragma unroll
+    for (int o = 0; o < L3; ++o) s = fmaf(c_w[cWO + F + o], fmaxf(z3[o], 0.f), s);
+    probs[row] = bad ? nanf("") : sigmoidf_stable(s);
+  }
+}
+
 // out[r][j] = (bias ? bias[j] : 0) + sum_k A[r][k] * Wv(k, j), Wv(k, j) = transpose ? W[j * ldw + k] : W[k * ldw + j];
 // K, N multiples of 4, K * N <= 4096.  256 threads = 256 / (N / 4) rows per CTA, four outputs per thread.
 __global__ void __launch_bounds__(256) small_rows_gemm_kernel(const float* __restrict__ A, int64_t rows, int K,
@@ -370,6 +423,14 @@ __global__ void __launch_bounds__(256) small_table_wgrad_kernel(const float* __r
 static std::mutex g_const_mutex;
 static cudaEvent_t g_const_free = nullptr;  // recorded after the kernel that reads st::c_w (one device per process)
 
+// (call with g_const_mutex held) waits for the last reader of the constant image, then copies this model's weights
+static int upload_weights(const MrModel& m, cudaStream_t stream) {
+  if (g_const_free == nullptr) MR_CUDA(cudaEventCreateWithFlags(&g_const_free, cudaEventDisableTiming));
+  MR_CUDA(cudaStreamWaitEvent(stream, g_const_free, 0));
+  MR_CUDA(cudaMemcpyToSymbolAsync(st::c_w, m.W[2], st::kConstFloats * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream));
+  return MR_OK;
+}
+
 bool small_tower_supported(const MrModel& m, int group) {
   return m.n_layers == 4 && m.L[0] == 2 * st::L1 && m.L[1] == st::L1 && m.L[2] == st::L2 && m.L[3] == st::L3 &&
          m.mf_dim == st::F && group == 5;
@@ -406,9 +467,8 @@ int launch_small_tower_train(const SmallTowerArgs& a, cudaStream_t stream, int* 
   // the constant image belongs to one launch at a time: a launch on another stream waits for the previous kernel
   {
     std::lock_guard<std::mutex> lock(g_const_mutex);
-    if (g_const_free == nullptr) MR_CUDA(cudaEventCreateWithFlags(&g_const_free, cudaEventDisableTiming));
-    MR_CUDA(cudaStreamWaitEvent(stream, g_const_free, 0));
-    MR_CUDA(cudaMemcpyToSymbolAsync(st::c_w, m.W[2], st::kConstFloats * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream));
+    int rc = upload_weights(m, stream);
+    if (rc != MR_OK) return rc;
     kern<<<(unsigned)grid, st::kThreads, smem, stream>>>(p);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "small_tower_train_kernel");
@@ -416,6 +476,24 @@ int launch_small_tower_train(const SmallTowerArgs& a, cudaStream_t stream, int* 
     MR_CUDA(cudaEventRecord(g_const_free, stream));
   }
   *grid_out = (int)grid;
+  return MR_OK;
+}
+
+int launch_small_tower_forward(const MrModel& m, const float* Pi, const float* Pu, const int32_t* users,
+                               const int32_t* items, int64_t rows, int group, float* probs, cudaStream_t stream) {
+  if (rows == 0) return MR_OK;
+  int64_t grid = (rows + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  std::lock_guard<std::mutex> lock(g_const_mutex);
+  int rc = upload_weights(m, stream);
+  if (rc != MR_OK) return rc;
+  st::small_tower_forward_kernel<<<(unsigned)grid, 256, 0, stream>>>(Pi, Pu, m.user_gmf, m.item_gmf, users, items, rows,
+                                                                     group, m.num_users, m.num_items, probs);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "small_tower_forward_kernel");
+  count_launch();
+  MR_CUDA(cudaEventRecord(g_const_free, stream));
   return MR_OK;
 }
 

@@ -666,10 +666,13 @@ def test_rank_scores_nan_and_label_col(eng_mod):
     assert pos.cpu().numpy().tolist() == [2, 1]
 
 
-def test_rank_eval_matches_oracle(eng_mod):
+@pytest.mark.parametrize("fused", ["auto", "off"], ids=["projected-thread-per-row", "tile-kernel"])
+def test_rank_eval_matches_oracle(eng_mod, fused):
+    """The default tower's eval: 25,700 rows over 300 + 500 table rows, so the automatic choice projects the first layer
+    over the tables and runs the thread-per-row forward (small_tower.cu); fused_train='off' keeps the tile kernel."""
     nu, ni, L, f = 300, 500, [64, 32, 16, 8], 8
     rng = np.random.default_rng(4)
-    eng = eng_mod.NeuMFEngine(nu, ni, L, [0] * 4, mf_dim=f, seed=5)
+    eng = eng_mod.NeuMFEngine(nu, ni, L, [0] * 4, mf_dim=f, seed=5, fused_train=fused)
     w = eng.get_weights()
     G, group, k = 257, 100, 10
     users = rng.integers(0, nu, G)
