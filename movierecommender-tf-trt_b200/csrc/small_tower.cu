@@ -420,12 +420,22 @@ __global__ void __launch_bounds__(256) small_table_wgrad_kernel(const float* __r
 
 }  // namespace st
 
+// __constant__ memory is per device; so is the event recorded after the kernel that reads the image
+constexpr int kMaxDevices = 64;
 static std::mutex g_const_mutex;
-static cudaEvent_t g_const_free = nullptr;  // recorded after the kernel that reads st::c_w (one device per process)
+static cudaEvent_t g_const_free_of[kMaxDevices] = {};
 
 // (call with g_const_mutex held) waits for the last reader of the constant image, then copies this model's weights
-static int upload_weights(const MrModel& m, cudaStream_t stream) {
+static int upload_weights(const MrModel& m, cudaStream_t stream, cudaEvent_t* free_event) {
+  int dev = 0;
+  MR_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) {
+    set_error("small tower: device ordinal %d out of range", dev);
+    return MR_ERR_INVALID;
+  }
+  cudaEvent_t& g_const_free = g_const_free_of[dev];
   if (g_const_free == nullptr) MR_CUDA(cudaEventCreateWithFlags(&g_const_free, cudaEventDisableTiming));
+  *free_event = g_const_free;
   MR_CUDA(cudaStreamWaitEvent(stream, g_const_free, 0));
   MR_CUDA(cudaMemcpyToSymbolAsync(st::c_w, m.W[2], st::kConstFloats * sizeof(float), 0, cudaMemcpyDeviceToDevice, stream));
   return MR_OK;
@@ -452,11 +462,7 @@ int launch_small_tower_train(const SmallTowerArgs& a, cudaStream_t stream, int* 
   p.loss_partial = a.loss_partial; p.flags = a.flags;
   const size_t smem = (size_t)(st::kWarps * st::kWarpFloats) * sizeof(float);
   auto kern = st::small_tower_train_kernel<5>;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    MR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static_assert((size_t)(st::kWarps * st::kWarpFloats) * sizeof(float) <= 48 * 1024, "fits the default dynamic shared memory");
   int occ = 0;
   MR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, st::kThreads, smem));
   if (occ < 1) occ = 1;
@@ -467,7 +473,8 @@ int launch_small_tower_train(const SmallTowerArgs& a, cudaStream_t stream, int* 
   // the constant image belongs to one launch at a time: a launch on another stream waits for the previous kernel
   {
     std::lock_guard<std::mutex> lock(g_const_mutex);
-    int rc = upload_weights(m, stream);
+    cudaEvent_t g_const_free = nullptr;
+    int rc = upload_weights(m, stream, &g_const_free);
     if (rc != MR_OK) return rc;
     kern<<<(unsigned)grid, st::kThreads, smem, stream>>>(p);
     const cudaError_t e = cudaGetLastError();
@@ -486,7 +493,8 @@ int launch_small_tower_forward(const MrModel& m, const float* Pi, const float* P
   const int64_t cap = (int64_t)sm_count() * 8;
   if (grid > cap) grid = cap;
   std::lock_guard<std::mutex> lock(g_const_mutex);
-  int rc = upload_weights(m, stream);
+  cudaEvent_t g_const_free = nullptr;
+  int rc = upload_weights(m, stream, &g_const_free);
   if (rc != MR_OK) return rc;
   st::small_tower_forward_kernel<<<(unsigned)grid, 256, 0, stream>>>(Pi, Pu, m.user_gmf, m.item_gmf, users, items, rows,
                                                                      group, m.num_users, m.num_items, probs);
