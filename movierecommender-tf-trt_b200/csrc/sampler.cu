@@ -46,8 +46,19 @@ __global__ void __launch_bounds__(128) sample_negatives_kernel(
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
     const int u = __ldg(pos_users + p);
     const int64_t lo = __ldg(rowptr + u), hi = __ldg(rowptr + u + 1);
-    const int deg = (int)(hi - lo);
+    int deg = (int)(hi - lo);
     const int32_t* seen = csr + lo;
+    // the candidates are arange(num_items) minus the seen items (np.setdiff1d, data_pipeline.py:104-108): seen ids at
+    // or beyond num_items (raw id spaces, a patched num_items) take no candidate away
+    if (deg > 0 && __ldg(seen + deg - 1) >= num_items) {
+      int a = 0, b = deg;
+      while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (__ldg(seen + mid) < num_items) a = mid + 1;
+        else b = mid;
+      }
+      deg = a;
+    }
     const int C = num_items - deg;
     const bool replace = C < negs;
     const uint64_t index = (uint64_t)(first_index + p);

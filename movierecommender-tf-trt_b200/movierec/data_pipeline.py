@@ -112,6 +112,18 @@ class MovieLensDataGenerator(object):
             "degree_max": int((rowptr[1:] - rowptr[:-1]).max().item()) if rowptr.numel() > 1 else 0,
         }
 
+    def _max_seen_below(self, num_items):
+        """Largest number of DISTINCT seen items below `num_items` any user has (only those take candidates away)."""
+        import torch
+        d = self._device
+        key = ("seen_below", int(num_items))
+        if key not in d:
+            below = torch.cat([torch.zeros(1, dtype=torch.int64, device=d["dev"]),
+                               (d["csr"] < num_items).to(torch.int64).cumsum(0)])
+            rp = d["rowptr"].to(torch.int64)
+            d[key] = int((below[rp[1:]] - below[rp[:-1]]).max().item()) if rp.numel() > 1 else 0
+        return d[key]
+
     def device_batch(self, idx):
         """Batch `idx` as device tensors ([x_user int32, x_item int32], y float32), layout of the
         reference's __getitem__ (:136-150): users repeated, negatives first, positive last."""
@@ -121,7 +133,7 @@ class MovieLensDataGenerator(object):
             self._upload()
         d = self._device
         num_items = self.num_items  # read through the property: the reference's tests patch it
-        if d["degree_max"] >= num_items:
+        if d["degree_max"] >= num_items and self._max_seen_below(num_items) >= num_items:
             raise ValueError("a user has interacted with every item: no candidate negatives "
                              "(np.random.choice would raise 'a cannot be empty' in the reference)")
         P = self.num_positives_per_batch

@@ -6,9 +6,11 @@ reference; the Keras graph (model.py:135-215) is replaced by `_engine.NeuMFEngin
 the device tensors and calls libmovierec_b200.so.  Optional new parameters keep the reference
 behaviour by default: `mf_dim` (0 = the reference's MLP-only model), `adam_mode` ("dense" =
 legacy-Keras Adam over every table row, "sparse" = touched rows only), `seed`.
-Deviations, each deliberate: weights are saved as `.npz` (no h5py here; the reference writes
-`.h5`, model.py:245), and `load_from_files` passes name and directory in the declared order (the
-reference swaps them, model.py:301).
+Deviations, each deliberate: weights are saved under the reference's `.h5` file names in the Keras
+HDF5 layout when h5py is installed (util/keras_h5.py) and as NumPy `.npz` payloads under the same
+names otherwise (this image has no h5py; `load_weights` tells the two apart by the file signature),
+and `load_from_files` passes name and directory in the declared order (the reference swaps them,
+model.py:301).
 """
 
 import json
@@ -145,7 +147,9 @@ class NeuMFModel(object):
             raise ValueError("batch of {} rows is not divisible by (num_negs_per_pos_eval + 1) = {}".format(
                 probs.numel(), group))
         rank, _, _ = _engine_module().rank_scores(probs, group, o._k, want_rank=True, device=self.engine.device)
-        return [probs.cpu().numpy().reshape(-1, 1), rank.cpu().numpy()]
+        out = probs.cpu().numpy().reshape(-1, 1)
+        self._raise_on_bad_ids(bool(np.isnan(out).any()))  # the kernels mark rows with an out-of-range id with NaN
+        return [out, rank.cpu().numpy()]
 
     def recommend(self, user_id, candidate_items, top_k=10):
         """Serving-shaped scoring (reference client, trt_client.py:47-57: one user, N candidate items, the K best):
@@ -217,6 +221,7 @@ class NeuMFModel(object):
         sums, rows = self._eval_batch_sums(x, y)
         o = self._owner
         out = sums.cpu().numpy().astype(np.float64)
+        self._raise_on_bad_ids(out[3])
         group = o._num_negs_per_pos_eval + 1
         logs = self._step_logs([out[0], out[1], out[2], 0.0], rows, group)
         return [logs[n] for n in self.metrics_names]
@@ -231,7 +236,10 @@ class NeuMFModel(object):
         rows = probs.numel()
         # the label column is the argmax of y_true per group (model.py:447-448), wherever the batch puts its positive
         _, _, sums = _engine_module().rank_scores(probs, group, o._k, want_rank=False, device=eng.device, labels=y)
-        return torch.cat([loss, sums]), rows
+        # an out-of-range id makes its row's probability NaN (and is left out of the loss): reported with the sums so
+        # that callers raise instead of returning metrics of a partly invalid batch
+        bad = torch.isnan(probs).any().to(loss.dtype).reshape(1)
+        return torch.cat([loss, sums, bad]), rows
 
     def evaluate_generator(self, generator, steps=None):
         """Keras `evaluate_generator`: batch-size-weighted mean of the per-batch values over
@@ -240,7 +248,7 @@ class NeuMFModel(object):
         steps = len(generator) if steps is None else steps
         o = self._owner
         group = o._num_negs_per_pos_eval + 1
-        acc = torch.zeros(3, dtype=torch.float64, device=self.engine.device)
+        acc = torch.zeros(4, dtype=torch.float64, device=self.engine.device)
         rows = 0
         for b in range(steps):
             x, y = _device_batch(generator, b)
@@ -250,8 +258,15 @@ class NeuMFModel(object):
         if rows == 0:
             return [float("nan")] * 4
         out = acc.cpu().numpy()
+        self._raise_on_bad_ids(out[3])
         logs = self._step_logs([out[0], out[1], out[2], self._l2_penalty()], rows, group)
         return [logs[n] for n in self.metrics_names]
+
+    def _raise_on_bad_ids(self, flag):
+        if flag:
+            o = self._owner
+            raise IndexError("user/item id out of range in an evaluation batch (num_users={}, num_items={})".format(
+                o._num_users, o._num_items))
 
     def _l2_penalty(self):
         o = self._owner
@@ -545,8 +560,19 @@ class MovierecModel(object):
         (negs_eval+1) candidate items per user with the positive last.  Returns (hr, dcg)."""
         group = self._num_negs_per_pos_eval + 1
         k = self._k if k is None else k
-        pos, sums, _, _ = self.model.engine.rank_eval(users, items, group, k)
-        s = sums.cpu().numpy().astype(np.float64)
+        import torch
+        eng = self.model.engine
+        mod = _engine_module()
+        d_users, d_items = mod.as_device_i32(users, eng.device), mod.as_device_i32(items, eng.device)
+        pos, sums, _, _ = eng.rank_eval(d_users, d_items, group, k)
+        # (the fused eval kernels rank a candidate with an out-of-range id last and say nothing: check the ids here,
+        # two reductions next to a sweep of millions of rows, and read the verdict back with the sums)
+        bad = torch.zeros(1, dtype=sums.dtype, device=sums.device)
+        if d_users.numel():
+            bad = ((d_users.min() < 0) | (d_users.max() >= self._num_users) | (d_items.min() < 0) |
+                   (d_items.max() >= self._num_items)).to(sums.dtype).reshape(1)
+        s = torch.cat([sums.reshape(-1), bad]).cpu().numpy().astype(np.float64)
+        self.model._raise_on_bad_ids(s[2])
         G = max(int(pos.numel()), 1)
         return s[0] / G, s[1] / G
 

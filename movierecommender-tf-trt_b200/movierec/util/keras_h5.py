@@ -67,9 +67,15 @@ def read(path):
                           ".npz payloads when h5py is missing".format(path))
     weights, opt = {}, {}
     with h5py.File(path, "r") as f:
-        for layer in f.attrs["layer_names"]:
+        # `save_weights` files carry layer_names at the root; full-model files (ModelCheckpoint with
+        # save_weights_only=False, the reference's callback at model.py:317-320) keep them under 'model_weights'
+        root = f if "layer_names" in f.attrs else (f["model_weights"] if "model_weights" in f else None)
+        if root is None:
+            raise ValueError("{} is not a Keras weight file: no layer_names attribute at the root or under "
+                             "'model_weights'".format(path))
+        for layer in root.attrs["layer_names"]:
             layer = layer.decode("utf8") if isinstance(layer, bytes) else str(layer)
-            g = f[layer]
+            g = root[layer]
             for wn in g.attrs.get("weight_names", []):
                 wn = wn.decode("utf8") if isinstance(wn, bytes) else str(wn)
                 key = wn[:-2] if wn.endswith(":0") else wn

@@ -720,6 +720,35 @@ def test_sampler_bit_exact_vs_oracle(eng_mod):
                 assert len(set(got[p, :negs].tolist())) == negs
 
 
+def test_sampler_ignores_seen_items_beyond_num_items(eng_mod):
+    """Candidates are arange(num_items) minus the seen items (np.setdiff1d, data_pipeline.py:104-108): seen ids at or
+    beyond num_items -- raw id spaces, a num_items smaller than the lists' range -- take no candidate away, so every
+    valid unseen item can still be drawn and the draws equal the oracle's bit for bit."""
+    rng = np.random.default_rng(9)
+    nu, ni_lists, ni = 30, 90, 50  # the lists hold ids up to 89, the sampler is asked for items below 50
+    users = np.repeat(np.arange(nu), 20)
+    items = np.concatenate([rng.choice(ni_lists, 20, replace=False) for _ in range(nu)])
+    rowptr, csr = o.build_csr(nu, users, items)
+    pu = rng.integers(0, nu, 256).astype(np.int32)
+    pi = rng.integers(0, ni, 256).astype(np.int32)
+    d_rowptr, d_csr = torch.from_numpy(rowptr).cuda(), torch.from_numpy(csr).cuda()
+    drawn = {u: set() for u in range(nu)}
+    for epoch in range(40):
+        xu, xi, _ = eng_mod.sample_negatives(d_rowptr, d_csr, ni, pu, pi, 0, 4, 5, epoch)
+        if epoch < 3:
+            np.testing.assert_array_equal(xi.cpu().numpy(), o.device_sample_batch(rowptr, csr, ni, pu, pi, 0, 4, 5, epoch))
+        got = xi.cpu().numpy().reshape(256, 5)
+        assert got[:, :4].max() < ni
+        for p in range(256):
+            drawn[int(pu[p])].update(got[p, :4].tolist())
+    for u in set(pu.tolist()):
+        seen = set(csr[rowptr[u]:rowptr[u + 1]].tolist())
+        cand = set(range(ni)) - seen
+        assert not drawn[u] & seen
+        if sum(pu == u) * 40 * 4 >= 40 * len(cand):  # enough draws that every candidate is all but certain to appear
+            assert drawn[u] == cand, (u, sorted(cand - drawn[u]))
+
+
 # ---- dataset preparation on the device: split and per-user item lists (SURVEY 8 (f) 2) ---------------------------
 
 def _ratings(rng, nu, ni, n, min_per_user=2):

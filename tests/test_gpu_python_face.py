@@ -251,3 +251,29 @@ def test_recommend_top_k_matches_oracle(mods, tmp_path, layers, mf_dim, n):
     if np.all(sep):
         assert np.array_equal(items, cand[order])
     assert np.all(np.diff(scores) <= 0)
+
+
+def test_evaluation_paths_raise_on_out_of_range_ids(mods, tmp_path):
+    """An id beyond the tables is an IndexError in every evaluation path (the kernels mark such rows with NaN and
+    rank them last; without the check the metrics of a partly invalid batch would be returned): predict_on_batch,
+    test_on_batch, evaluate_generator's batches, and the full-sweep evaluate()."""
+    model_mod, _, _ = mods
+    m = model_mod.MovierecModel(copy.deepcopy(TEST_PARAMS), "bad_ids", str(tmp_path), verbose=0)
+    group = TEST_PARAMS["num_negs_per_pos_eval"] + 1
+    users = np.repeat(np.array([0, 4], dtype=np.int32), group)
+    items = np.arange(2 * group, dtype=np.int32) % TEST_PARAMS["num_items"]
+    y = np.tile([0.0] * (group - 1) + [1.0], 2).astype(np.float32)
+    m.model.predict_on_batch([users, items])           # in range: fine
+    m.model.test_on_batch([users, items], y)
+    m.evaluate(users[::group], items)
+    bad_items = items.copy()
+    bad_items[3] = TEST_PARAMS["num_items"]
+    bad_users = users.copy()
+    bad_users[group:] = TEST_PARAMS["num_users"] + 2
+    for u, i in ((users, bad_items), (bad_users, items)):
+        with pytest.raises(IndexError):
+            m.model.predict_on_batch([u, i])
+        with pytest.raises(IndexError):
+            m.model.test_on_batch([u, i], y)
+        with pytest.raises(IndexError):
+            m.evaluate(u[::group], i)
