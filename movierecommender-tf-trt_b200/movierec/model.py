@@ -562,15 +562,11 @@ class MovierecModel(object):
         k = self._k if k is None else k
         import torch
         eng = self.model.engine
-        mod = _engine_module()
-        d_users, d_items = mod.as_device_i32(users, eng.device), mod.as_device_i32(items, eng.device)
-        pos, sums, _, _ = eng.rank_eval(d_users, d_items, group, k)
-        # (the fused eval kernels rank a candidate with an out-of-range id last and say nothing: check the ids here,
-        # two reductions next to a sweep of millions of rows, and read the verdict back with the sums)
-        bad = torch.zeros(1, dtype=sums.dtype, device=sums.device)
-        if d_users.numel():
-            bad = ((d_users.min() < 0) | (d_users.max() >= self._num_users) | (d_items.min() < 0) |
-                   (d_items.max() >= self._num_items)).to(sums.dtype).reshape(1)
+        # (the fused eval kernels rank a candidate with an out-of-range id last and say nothing: the engine checks the
+        # ids on the device -- four reductions next to a sweep of millions of rows -- and the verdict is read back
+        # with the sums; host arrays are uploaded in chunks under the sweep, see NeuMFEngine.rank_eval)
+        pos, sums, _, _ = eng.rank_eval(users, items, group, k, check_ids=True)
+        bad = eng.last_eval_bad.to(sums.dtype)
         s = torch.cat([sums.reshape(-1), bad]).cpu().numpy().astype(np.float64)
         self.model._raise_on_bad_ids(s[2])
         G = max(int(pos.numel()), 1)

@@ -692,6 +692,30 @@ def test_rank_eval_matches_oracle(eng_mod, fused):
     assert s[0] == hs and abs(s[1] - ds) <= 1e-4 * max(ds, 1)
 
 
+@pytest.mark.parametrize("L,f", [([256, 128, 64], 64), ([64, 32, 16, 8], 8)], ids=["ml20m-tower", "default-tower"])
+def test_rank_eval_from_host_arrays_is_pipelined_and_identical(eng_mod, monkeypatch, L, f):
+    """Host inputs above EVAL_PIPELINE_MIN_ROWS are uploaded in chunks under the sweep: same positions, same sums (to
+    the order of the chunks' partial sums) as one call on device tensors; the id check sees a bad id in any chunk."""
+    nu, ni, G, group, k = 500, 300, 1003, 100, 10
+    rng = np.random.default_rng(12)
+    eng = eng_mod.NeuMFEngine(nu, ni, L, [0] * len(L), mf_dim=f, seed=9)
+    users = rng.integers(0, nu, G).astype(np.int32)
+    items = rng.integers(0, ni, G * group).astype(np.int32)
+    pos_d, sums_d, _, _ = eng.rank_eval(torch.from_numpy(users).cuda(), torch.from_numpy(items).cuda(), group, k)
+    monkeypatch.setattr(eng_mod.NeuMFEngine, "EVAL_PIPELINE_MIN_ROWS", 1000)
+    for host_u, host_i in ((users, items), (torch.from_numpy(users).pin_memory(), torch.from_numpy(items).pin_memory()),
+                           (users.astype(np.int64), items.astype(np.int64))):
+        pos_h, sums_h, _, _ = eng.rank_eval(host_u, host_i, group, k, check_ids=True)
+        np.testing.assert_array_equal(pos_h.cpu().numpy(), pos_d.cpu().numpy())
+        assert sums_h.cpu().numpy()[0] == sums_d.cpu().numpy()[0]
+        assert abs(sums_h.cpu().numpy()[1] - sums_d.cpu().numpy()[1]) <= 1e-5 * abs(sums_d.cpu().numpy()[1])
+        assert float(eng.last_eval_bad.item()) == 0.0
+    bad = items.copy()
+    bad[-7] = ni + 1  # in the last chunk
+    eng.rank_eval(users, bad, group, k, check_ids=True)
+    assert float(eng.last_eval_bad.item()) != 0.0
+
+
 # ---- sampler --------------------------------------------------------------------------------------
 
 def test_sampler_bit_exact_vs_oracle(eng_mod):
