@@ -119,6 +119,10 @@ typedef struct MrGrads {
    * caller makes its communication stream wait on it and reduces the user tables' gradients -- and may update the user
    * tables in place (mr_dp_reduce_apply) -- under the rest of the step. */
   void* user_tables_ready;
+  /* Optional cudaEvent_t (NULL = none): the same for user_gmf ALONE -- its gradients are final and the call no longer
+   * reads the model's user_gmf table -- which in the projected grouped step is earlier still (right after the per-user
+   * segment sums, before the first layer's per-user GEMMs).  Recorded no later than user_tables_ready. */
+  void* user_gmf_ready;
 } MrGrads;
 
 /* `flags` of the train step.  MR_TRAIN_USERS_GROUPED: the caller states that the batch has the layout the

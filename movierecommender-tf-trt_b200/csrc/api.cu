@@ -782,6 +782,7 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
   TrainWs t = carve_train(m, B, ws);
   const int d_u = m.L[0] / 2, d_i = m.L[0] - d_u;
   bool user_event_recorded = false;  // grads->user_tables_ready: recorded early where the launch sequence allows
+  bool user_gmf_event_recorded = false;  // grads->user_gmf_ready likewise
 
   prof_mark(MR_PHASE_MISC, st);
   MR_CUDA(cudaMemsetAsync(t.flags, 0, 256, st));
@@ -1123,6 +1124,10 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
         uu.g1 = grads->user_gmf;
         rc = launch_segreduce(t.sorted_keys, t.sorted_index, n_user_rows, t.stage_u, uu, t.seg_ws_u, t.seg_ws_u_bytes, su_st);
         if (rc != MR_OK) return rc;
+        if (grads->user_gmf_ready != nullptr) {  // user_gmf: gradients final, table last read by the fused kernel
+          MR_CUDA(cudaEventRecord((cudaEvent_t)grads->user_gmf_ready, su_st));
+          user_gmf_event_recorded = true;
+        }
         // d E_user = Su . W1u^T right behind it on the side stream: both user-side gradient tables (83 % of the
         // table-gradient bytes at the ML-20M shape) are then final while the item side is still being reduced, and
         // a data-parallel caller starts their all-reduce on grads->user_tables_ready
@@ -1292,6 +1297,10 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     ru.g0 = w.Su;
     ru.g1 = grads->user_gmf;
     rc = launch_segreduce(t.sorted_keys, t.sorted_index, n_user_rows, t.stage_u, ru, t.seg_ws_u, t.seg_ws_u_bytes, su_st);
+    if (rc == MR_OK && su_st != st && grads->user_gmf_ready != nullptr) {
+      MR_CUDA(cudaEventRecord((cudaEvent_t)grads->user_gmf_ready, su_st));
+      user_gmf_event_recorded = true;
+    }
     if (rc == MR_OK) rc = launch_small_rows_gemm(w.Su, m.num_users, L1, W1u, L1, d_u, true, nullptr, grads->user_mlp, su_st);
     if (rc == MR_OK)
       rc = launch_small_table_wgrad(m.user_mlp, w.Su, m.num_users, t.dense_partial + (W1u - m.dense),
@@ -1397,7 +1406,9 @@ int mr_neumf_train_grads(MrModel* model, MrOptState* opt, MrGrads* grads, const 
     prof_mark(MR_PHASE_SEGREDUCE, st);
     rc = launch_segreduce(t.sorted_keys_i, t.sorted_index_i, B, t.stage_i, u, t.seg_ws, t.seg_ws_bytes, st);
   }
-  if (grads->user_tables_ready != nullptr && !user_event_recorded)  // other launch sequences: final at the end
+  if (grads->user_gmf_ready != nullptr && !user_gmf_event_recorded)  // other launch sequences: final at the end
+    MR_CUDA(cudaEventRecord((cudaEvent_t)grads->user_gmf_ready, st));
+  if (grads->user_tables_ready != nullptr && !user_event_recorded)
     MR_CUDA(cudaEventRecord((cudaEvent_t)grads->user_tables_ready, st));
   prof_mark(-1, st);
   return rc;

@@ -103,14 +103,22 @@ class DataParallelNeuMF(object):
         self.multicast = use_mc
         self._mc_g = C.c_void_p(mc_g) if use_mc else None
         self._mc_p = C.c_void_p(mc_p) if use_mc else None
-        self._slices = []  # (lo, hi, l2, is_user_region) of the elements this rank owns
-        for off, count, l2 in e.flat_regions():
+        # (lo, hi, l2, stage) of the elements this rank owns; stage 0: the user GMF table (final first), 1: the user MLP
+        # table, 2: dense block and item tables (after the step)
+        from . import _engine
+        self._slices = []
+        for name, off, count, l2 in e.flat_regions():
             per = ((count // 4 + w - 1) // w) * 4
             lo, hi = off + min(count, per * self.rank), off + min(count, per * (self.rank + 1))
-            self._slices.append((lo, hi, l2, off < e._g_user_end))
+            stage = 0 if name == _engine.K_GMF_USER else (1 if name == _engine.K_USER else 2)
+            if stage == 0 and os.environ.get("MR_DP_NO_GMF_SPLIT") is not None:  # A/B runs: one early exchange
+                stage = 1
+            self._slices.append((lo, hi, l2, stage))
         self._comm = torch.cuda.Stream(device=e.device)
         self._ready = torch.cuda.Event()
-        self._ready.record()  # (creates the CUDA event the library records into)
+        self._ready.record()  # (creates the CUDA events the library records into)
+        self._gmf_ready = torch.cuda.Event()
+        self._gmf_ready.record()
         self._comm_done = torch.cuda.Event()
 
     def _reduce_apply(self, lo, hi, l2, lr_t):
@@ -128,21 +136,27 @@ class DataParallelNeuMF(object):
 
     def _peer_step(self, users, items, labels, kw):
         e = self.engine
-        out = e.train_grads(users, items, labels, user_ready=self._ready, **kw)
+        out = e.train_grads(users, items, labels, user_ready=self._ready, user_gmf_ready=self._gmf_ready, **kw)
         lr_t = e.step_lr_t()
         main = torch.cuda.current_stream(e.device)
-        # user tables: as soon as EVERY rank's user-side gradients are final and its step no longer reads the tables
+        # user tables: as soon as EVERY rank's gradients of a table are final and its step no longer reads the table --
+        # the GMF table right after the per-user sums, the MLP table after the first layer's per-user GEMMs.  The
+        # exchange must be over before the step's item-side table GEMMs start (persistent tcgen05 kernels that need whole
+        # SMs wait for the exchange CTAs to leave), so every microsecond of head start counts.
         with torch.cuda.stream(self._comm):
-            self._comm.wait_event(self._ready)
-            self._hg.barrier(channel=1)
-            for lo, hi, l2, user in self._slices:
-                if user:
+            for stage, event, channel in ((0, self._gmf_ready, 2), (1, self._ready, 1)):
+                mine = [sl for sl in self._slices if sl[3] == stage]
+                if not mine:
+                    continue
+                self._comm.wait_event(event)
+                self._hg.barrier(channel=channel)
+                for lo, hi, l2, _ in mine:
                     self._reduce_apply(lo, hi, l2, lr_t)
             self._comm_done.record(self._comm)
         # dense block and item tables: after every rank's step
         self._hg.barrier(channel=0)
-        for lo, hi, l2, user in self._slices:
-            if not user:
+        for lo, hi, l2, stage in self._slices:
+            if stage == 2:
                 self._reduce_apply(lo, hi, l2, lr_t)
         main.wait_event(self._comm_done)
         self._hg.barrier(channel=0)  # all owners' stores have landed: the replicas are whole again

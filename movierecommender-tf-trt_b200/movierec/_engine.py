@@ -264,11 +264,11 @@ class NeuMFEngine(object):
         self._structs()
 
     def flat_regions(self):
-        """[(offset, padded elements, l2 coefficient)] of the flat layout: user tables, dense block, item tables."""
+        """[(name, offset, padded elements, l2 coefficient)] of the flat layout: user tables, dense block, item tables."""
         out = []
         for i, (k, off, cnt) in enumerate(self._flat_layout):
             end = self._flat_layout[i + 1][1] if i + 1 < len(self._flat_layout) else self.g_flat.numel()
-            out.append((off, end - off, 0.0 if k == "dense" else self.l2[0]))
+            out.append((k, off, end - off, 0.0 if k == "dense" else self.l2[0]))
         return out
 
     def step_lr_t(self):
@@ -424,16 +424,19 @@ class NeuMFEngine(object):
         return self.step_out.clone()
 
     def train_grads(self, users, items, labels, group=0, k=0, inv_global_batch=None, grouped=False, dense_l2=True,
-                    user_ready=None):
+                    user_ready=None, user_gmf_ready=None):
         """Gradients only (no update).  dense_l2=False leaves the hidden kernels' 2*l2*W term out of g_dense: a
         data-parallel caller that sums the ranks' gradients lets exactly one rank add it.
         user_ready: a torch.cuda.Event the library records (on one of its streams) as soon as the user tables'
         gradients -- gradient_parts()[0] -- are final; a stream that waits on it may all-reduce them while the rest
-        of the call is still running."""
+        of the call is still running.  user_gmf_ready: the same for the user GMF table alone (MrGrads.user_gmf_ready),
+        which is final earlier still."""
         args, keep = self._train_args(users, items, labels, group, k, inv_global_batch, grouped, dense_l2)
         self._grads.user_tables_ready = user_ready.cuda_event if user_ready is not None else None
+        self._grads.user_gmf_ready = user_gmf_ready.cuda_event if user_gmf_ready is not None else None
         nat.check(nat.lib.mr_neumf_train_grads(*args), "mr_neumf_train_grads")
         self._grads.user_tables_ready = None
+        self._grads.user_gmf_ready = None
         return self.step_out.clone()
 
     def apply(self):

@@ -62,7 +62,8 @@ class MrOptState(C.Structure):
 
 class MrGrads(C.Structure):
     _fields_ = [("dense", C.c_void_p), ("user_mlp", C.c_void_p), ("item_mlp", C.c_void_p),
-                ("user_gmf", C.c_void_p), ("item_gmf", C.c_void_p), ("user_tables_ready", C.c_void_p)]
+                ("user_gmf", C.c_void_p), ("item_gmf", C.c_void_p), ("user_tables_ready", C.c_void_p),
+                ("user_gmf_ready", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/movierec_b200.h

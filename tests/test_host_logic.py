@@ -55,7 +55,7 @@ def test_struct_layouts_match_header():
     # sizes follow from the header's field lists (8-byte pointers, natural alignment)
     assert ctypes.sizeof(nat.MrModel) == 5 * 8 + 8 * 8 * 2 + 2 * 8 + 8 + 3 * 4 + 8 * 4 + 4 + 8 * 4 + 3 * 4 + 4  # (+ tail padding)
     assert ctypes.sizeof(nat.MrOptState) == 2 * 4 + 4 * 4 + 8 + 10 * 8
-    assert ctypes.sizeof(nat.MrGrads) == 6 * 8
+    assert ctypes.sizeof(nat.MrGrads) == 7 * 8
     assert nat.MrModel.dense_count.offset == 5 * 8 + 16 * 8 + 2 * 8
 
 
