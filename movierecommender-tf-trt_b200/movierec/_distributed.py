@@ -44,6 +44,18 @@ def shard_batch(users, items, labels, group, world_size, rank):
     return users[sl], items[sl], labels[sl]
 
 
+def owner_slices(regions, world_size, rank, stage_of):
+    """The elements of the flat parameter layout rank `rank` owns in the peer exchange: for every region
+    (name, offset, padded count, l2) a contiguous [lo, hi) whose bounds are multiples of four elements (the kernel works
+    on 16-byte pieces); over the ranks the slices of a region tile it exactly.  -> [(lo, hi, l2, stage_of(name))]."""
+    out = []
+    for name, off, count, l2 in regions:
+        per = ((count // 4 + world_size - 1) // world_size) * 4
+        lo, hi = off + min(count, per * rank), off + min(count, per * (rank + 1))
+        out.append((lo, hi, l2, stage_of(name)))
+    return out
+
+
 class DataParallelNeuMF(object):
     """Wraps a NeuMFEngine replica; `train_step` takes the RANK-LOCAL rows of a global batch."""
 
@@ -106,14 +118,9 @@ class DataParallelNeuMF(object):
         # (lo, hi, l2, stage) of the elements this rank owns; stage 0: the user GMF table (final first), 1: the user MLP
         # table, 2: dense block and item tables (after the step)
         from . import _engine
-        self._slices = []
-        for name, off, count, l2 in e.flat_regions():
-            per = ((count // 4 + w - 1) // w) * 4
-            lo, hi = off + min(count, per * self.rank), off + min(count, per * (self.rank + 1))
-            stage = 0 if name == _engine.K_GMF_USER else (1 if name == _engine.K_USER else 2)
-            if stage == 0 and os.environ.get("MR_DP_NO_GMF_SPLIT") is not None:  # A/B runs: one early exchange
-                stage = 1
-            self._slices.append((lo, hi, l2, stage))
+        one_early = os.environ.get("MR_DP_NO_GMF_SPLIT") is not None  # A/B runs: one early exchange instead of two
+        stage_of = lambda name: (1 if one_early else 0) if name == _engine.K_GMF_USER else (1 if name == _engine.K_USER else 2)
+        self._slices = owner_slices(e.flat_regions(), w, self.rank, stage_of)
         self._comm = torch.cuda.Stream(device=e.device)
         self._ready = torch.cuda.Event()
         self._ready.record()  # (creates the CUDA events the library records into)

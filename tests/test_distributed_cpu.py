@@ -209,3 +209,21 @@ def test_sharded_routing_round_trip(tmp_path, world):
     mp.spawn(_sharded_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     r = np.load(out)
     assert np.array_equal(r["got"], r["want"])
+
+
+def test_owner_slices_tile_every_region():
+    """The peer exchange's ownership map: per region the ranks' slices are disjoint, in rank order, 16-byte aligned and
+    cover the region exactly -- for region sizes that do and do not divide by the world size."""
+    from movierec._distributed import owner_slices
+    regions = [("user", 0, 64 * 1000, 0.01), ("gmf_user", 64000, 64 * 7, 0.01), ("dense", 64448, 64, 0.0),
+               ("item", 64512, 64 * 333, 0.01)]
+    for world in (1, 2, 3, 4, 7, 8, 16):
+        per_rank = [owner_slices(regions, world, r, lambda n: {"user": 1, "gmf_user": 0}.get(n, 2)) for r in range(world)]
+        for i, (name, off, count, l2) in enumerate(regions):
+            cur = off
+            for r in range(world):
+                lo, hi, got_l2, stage = per_rank[r][i]
+                assert lo == cur and hi >= lo and lo % 4 == 0 and hi % 4 == 0
+                assert got_l2 == l2 and stage == {"user": 1, "gmf_user": 0}.get(name, 2)
+                cur = hi
+            assert cur == off + count
