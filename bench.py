@@ -440,7 +440,8 @@ def run_gpu(args, wl):
     eng = model.model.engine
     if world > 1:
         from movierec._distributed import DataParallelNeuMF
-        dp = DataParallelNeuMF(eng, exchange=args.dp_exchange)
+        dp = DataParallelNeuMF(eng, exchange=None if args.dp_exchange == "auto" else args.dp_exchange)
+        args.dp_exchange = dp.exchange  # what the wrapper took ("auto" falls back to NCCL without symmetric memory)
         dp.broadcast_parameters(0)
 
     # ---- synthetic ratings -> per-user item lists on the device (what the sampler excludes); positives of a step
@@ -851,8 +852,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100)   # ~0.3 s timed at N=1: several nvidia-smi clock samples
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--dp-exchange", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: fused peer-memory reduce + optimizer kernel (default) or NCCL all-reduce + full sweep")
+    ap.add_argument("--dp-exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: fused peer-memory reduce + optimizer kernel (auto: wherever torch symmetric memory works) "
+                         "or NCCL all-reduce + full sweep")
     ap.add_argument("--workload", default="ml-20m", choices=sorted(WORKLOADS))
     ap.add_argument("--lean", action="store_true",
                     help="profiling runs (ncu): skip the e2e, eval and CPU-baseline legs; not a bench value")

@@ -77,6 +77,7 @@ class DataParallelNeuMF(object):
         self.overlap = os.environ.get("MR_DP_OVERLAP") is not None
         # nccl exchange on GPUs: the all-reduce of the user tables' gradients starts as soon as they are final
         self.early_user = os.environ.get("MR_DP_NO_EARLY_USER") is None and on_gpu
+        explicit = exchange is not None
         if exchange is None:
             exchange = os.environ.get("MR_DP_EXCHANGE") or (
                 "peer" if on_gpu and self.world_size > 1 and dist.get_backend(process_group) == "nccl"
@@ -84,6 +85,8 @@ class DataParallelNeuMF(object):
         if exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' or 'nccl', found {!r}".format(exchange))
         self.exchange = exchange
+        if exchange == "peer" and not self._symmetric_memory_available(explicit):
+            self.exchange = exchange = "nccl"
         if os.environ.get("MR_DP_MULTICAST") is not None:  # A/B runs: 0 = peer loads / stores, 1 = insist
             multicast = os.environ["MR_DP_MULTICAST"] not in ("0", "")
         self.multicast = multicast
@@ -91,6 +94,28 @@ class DataParallelNeuMF(object):
         self._ready = None
         if exchange == "peer":
             self._setup_peer()
+
+    def _symmetric_memory_available(self, explicit):
+        """True when EVERY rank can allocate symmetric memory on its device (the decision must be the same everywhere:
+        the rendezvous that follows is a collective).  An explicit exchange="peer" raises instead of falling back."""
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm
+            probe = symm.empty(1024, dtype=torch.float32, device=self.engine.device)
+            del probe
+        except Exception as err:  # noqa: BLE001 -- any failure means "not on this box"
+            ok, why = 0, err
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.engine.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            return True
+        if explicit:
+            raise RuntimeError("exchange='peer' needs torch symmetric memory on every rank" +
+                               ("" if ok else ": {}".format(why)))
+        import sys
+        print("movierec: symmetric memory is not available on every rank; data-parallel exchange falls back to NCCL",
+              file=sys.stderr)
+        return False
 
     def _setup_peer(self):
         """Parameters and gradients into symmetric memory (values kept), peer pointers, this rank's slices."""
