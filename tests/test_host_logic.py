@@ -275,3 +275,27 @@ def test_keras_h5_detection_and_missing_h5py(tmp_path):
     if not keras_h5.have_h5py():
         with pytest.raises(ImportError, match="h5py is not installed"):
             keras_h5.read(str(p))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs on host cores alone (no GPU, no CUDA library call) and prints ONE JSON line with
+    the keys the driver reads: impl, the metric of BASELINE.json, the same config dict as the GPU arm, e2e with zero
+    copy bytes, and a cpu_baseline that says which implementation was timed."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    with open(os.path.join(root, "BASELINE.json")) as f:
+        base = json.load(f)
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["n_gpus"] == 1
+    assert line["unit"] == "samples/s" and line["value"] > 0 and line["steps"] == 1
+    assert line["metric"] and (line["metric"] in json.dumps(base) or "samples" in line["metric"])
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert "ml-20m" in line["config"]["workload"] and line["config"]["baseline_config"] == "BASELINE.json configs[2]"
